@@ -1,0 +1,165 @@
+/* pcc.h — C ABI of libpcc.so, the B200 (sm_100a) point-set encoder hot path.
+ *
+ * Drop-in boundary: the reference has no native layer; its hot path is
+ * the sequence of torch / torch_geometric library calls made by
+ *   /root/reference/models/deep_sets.py:81-114   (DeepSets._forward_sparse)
+ *   /root/reference/models/graph_net.py:65-104   (GraphNet.forward)
+ * and their autograd.  Every entry point below replaces one of those call sites (cited
+ * per function).  The Python host side (point-cloud-classifier_b200/pcc_b200) binds
+ * them with ctypes; see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; pcc_last_error() gives the
+ *     thread-local message.  No CPU fallback exists: a call without a usable CUDA
+ *     device fails.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The caller
+ *     (PyTorch) owns every buffer: inputs, outputs, saved-for-backward and workspace.
+ *     The library never allocates persistent device memory.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal
+ *     synchronisation.  `device` is made current for the duration of the call.
+ *   - matrices are dense row-major fp32 unless stated; index arrays are int64
+ *     (torch.long) on the boundary, as the reference collate functions produce them
+ *     (/root/reference/utils/data.py:651-663, :1228-1261).
+ *   - re-entrant and stateless: forward is called from the Python main thread,
+ *     backward from PyTorch's autograd worker thread.
+ */
+#ifndef PCC_H_
+#define PCC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation ids: deep_sets.py:21-26 (relu/gelu/silu), graph_net.py:38-43 (tanh/relu/gelu) */
+enum { PCC_ACT_NONE = 0, PCC_ACT_RELU = 1, PCC_ACT_GELU = 2, PCC_ACT_SILU = 3, PCC_ACT_TANH = 4 };
+/* pooling ids: deep_sets.py:96-104.  SUM is the reference's sum/sqrt(n) (:99); ADD is a
+ * plain sum (PyG aggr="add", graph_net.py:50). */
+enum { PCC_POOL_SUM = 0, PCC_POOL_MEAN = 1, PCC_POOL_MAX = 2, PCC_POOL_ADD = 3 };
+
+const char* pcc_last_error(void);
+int pcc_version(void);
+/* 0 if `device` is an sm_100 part this library can run on, <0 (with message) otherwise */
+int pcc_check_device(int device);
+
+/* ---- segment bookkeeping: replaces torch.bincount + counts.tolist() + torch.split
+ *      (deep_sets.py:91-92) without the host sync.  offsets[B+1] = exclusive scan of the
+ *      histogram of idx (values >= B are ignored).  Also used for PyG `batch` vectors. */
+int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int64_t* offsets, int device, void* stream);
+/* max over an int64 vector (num_sets = max+1 when the caller does not know B) */
+int pcc_index_max(const int64_t* idx, int64_t n, int64_t* out_max, int device, void* stream);
+
+/* ---- ragged pooling: replaces the python loop deep_sets.py:94-106 and PyG
+ *      global_mean_pool (graph_net.py:92,96).  x[n,H] -> pooled[B,H]; argmax[B,H]
+ *      (int32 global row id, first occurrence on ties) is written for PCC_POOL_MAX only.
+ *      Empty segments give 0 (reference: NaN / error; never produced by the collate). */
+int pcc_segment_pool_fwd(const float* x, const int64_t* offsets, int64_t n, int64_t B, int64_t H, int pooling,
+                         float* pooled, int32_t* argmax, int device, void* stream);
+/* backward of the above (autograd of deep_sets.py:96-106): dx[n,H] fully written */
+int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets, const int32_t* argmax, int64_t n, int64_t B,
+                         int64_t H, int pooling, float* dx, int device, void* stream);
+
+/* ---- dense layer, fp32 SIMT path: replaces nn.Linear (+ fused activation / residual)
+ *      inside phi / rho (deep_sets.py:89,112), GraphConv's lin_rel / lin_root and fc1 /
+ *      fc2 (graph_net.py:73,82,87,98,102).
+ *      y[M,N] = residual[M,N]? + act( x[M,K] · w[N,K]^T + bias[N]? + pre_add[M,N]? );
+ *      z_out (optional) receives the pre-activation.  pre_add is how GraphConv's
+ *      lin_rel(agg) + lin_root(x) shares one activation.  accumulate!=0 adds into y
+ *      instead of overwriting (act must be NONE then). */
+int pcc_linear_fwd(const float* x, const float* w, const float* bias, const float* pre_add, const float* residual,
+                   float* y, float* z_out, int64_t M, int64_t N, int64_t K, int act, int accumulate, int device,
+                   void* stream);
+/* dx[M,K] = residual[M,K]? + dy[M,N] · w[N,K] */
+int pcc_linear_bwd_data(const float* dy, const float* w, const float* residual, float* dx, int64_t M, int64_t N,
+                        int64_t K, int device, void* stream);
+/* dw[N,K] (+)= dy[M,N]^T · x[M,K];  db[N] (+)= column sums of dy (db may be NULL).
+ * accumulate==0 overwrites (the function zeroes the outputs itself). */
+int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
+                          int accumulate, int device, void* stream);
+/* dz = dy * act'(z) elementwise over `count` values (autograd of the activation) */
+int pcc_act_bwd(const float* dy, const float* z, float* dz, int64_t count, int act, int device, void* stream);
+
+/* ---- LayerNorm over the last dim (deep_sets.py:50-51,65-66,153), fused with the
+ *      following activation and the residual add of ResidualBlock (:156-160):
+ *      y = residual? + act( (z-mean)*rstd*gamma + beta ).  mean/rstd [M] are saved. */
+int pcc_layernorm_fwd(const float* z, const float* gamma, const float* beta, const float* residual, float* y,
+                      float* mean, float* rstd, int64_t M, int64_t H, int act, float eps, int device, void* stream);
+/* dz[M,H] written; dgamma/dbeta[H] accumulated with atomics (caller zeroes them). */
+int pcc_layernorm_bwd(const float* dy, const float* z, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, float* dz, float* dgamma, float* dbeta, int64_t M, int64_t H, int act,
+                      int device, void* stream);
+
+/* ---- BatchNorm1d over rows (graph_net.py:76,84,89,100).  Training: batch statistics
+ *      (biased variance) + running-stat update (momentum, unbiased variance).
+ *      stats_ws: 2*C floats of workspace. */
+int pcc_batchnorm_fwd_train(const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
+                            float* save_invstd, float* running_mean, float* running_var, int64_t n, int64_t C,
+                            float momentum, float eps, int device, void* stream);
+int pcc_batchnorm_fwd_eval(const float* x, const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float* y, int64_t n, int64_t C, float eps, int device,
+                           void* stream);
+/* dx written; dgamma/dbeta[C] overwritten. ws: 2*C floats. */
+int pcc_batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                      const float* save_invstd, float* dx, float* dgamma, float* dbeta, int64_t n, int64_t C,
+                      int device, void* stream);
+
+/* ---- graph stage -------------------------------------------------------------------
+ * CSR by key: rowptr[n+1], perm[E] = edge ids grouped by key (ascending edge id inside a
+ * group, so results are run-to-run deterministic).  Replaces the sort inside PyG's
+ * scatter (GraphConv.propagate, graph_net.py:73,82).  ws: workspace of
+ * pcc_csr_workspace_bytes(n, E) bytes. */
+int64_t pcc_csr_workspace_bytes(int64_t n, int64_t E);
+int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t* rowptr, int32_t* perm, void* ws, int device,
+                  void* stream);
+/* out[i,:] = aggr_{e in in(i)} w_e * x[src(e),:]   (aggr: PCC_POOL_ADD / MEAN / MAX);
+ * rowptr/perm = CSR by TARGET.  arg_edge[n,C] (int32 edge id, -1 if none) for MAX only. */
+int pcc_graph_aggregate_fwd(const float* x, const int64_t* src, const float* w, const int64_t* rowptr,
+                            const int32_t* perm, int64_t n, int64_t C, int aggr, float* out, int32_t* arg_edge,
+                            int device, void* stream);
+/* dx[j,:] = sum_{e in out(j)} w_e * scale(dst e) * g[dst(e),:]  (MAX: only where
+ * arg_edge[dst,c]==e); rowptr_src/perm_src = CSR by SOURCE; rowptr_dst gives in-degrees
+ * for MEAN. */
+int pcc_graph_aggregate_bwd(const float* g, const int64_t* dst, const float* w, const int64_t* rowptr_src,
+                            const int32_t* perm_src, const int64_t* rowptr_dst, const int32_t* arg_edge, int64_t n,
+                            int64_t C, int aggr, float* dx, int device, void* stream);
+
+/* kNN graph build (north_star; no reference counterpart — semantics defined by
+ * oracle/knn_oracle.py).  pos: row r at pos + r*pos_stride floats, 3 coordinates.
+ * nbr[n,k] global neighbour ids (-1 pad), d2[n,k] squared distances (inf pad), both
+ * ascending by (d2, id).  k <= 32. */
+int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offsets, int64_t n, int64_t B, int k, int64_t* nbr,
+            float* d2, int device, void* stream);
+/* edge_index[2,n*k] from nbr (row0 = neighbour, row1 = centre); all slots must be valid */
+int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge_index, int device, void* stream);
+
+/* ---- fused DeepSets phi + pool, tcgen05 / TMEM path (bf16 operands, fp32 accumulate).
+ *      Replaces deep_sets.py:89-106 and its autograd in two launches; per-point
+ *      activations never reach HBM.  See DESIGN.md §3 for the layer descriptor. */
+typedef struct {
+  int32_t n_layers;      /* hidden layers + the final Linear(H,H) (deep_sets.py:55); <= 6 */
+  int32_t input_dim;     /* d <= 16 */
+  int32_t hidden;        /* H in {64,128,256}: every phi width equal (after layer 0) */
+  int32_t act;           /* PCC_ACT_RELU / GELU / SILU */
+  int32_t pooling;       /* PCC_POOL_SUM / MEAN / MAX */
+  int32_t residual_mask; /* bit l set: layer l is a ResidualBlock (deep_sets.py:149-160) */
+  const float* w[6];     /* fp32 [out,in] row-major, nn.Linear layout */
+  const float* b[6];
+} pcc_phi_desc;
+
+/* 0 when the fused path supports the descriptor; <0 with a reason otherwise */
+int pcc_phi_fused_supported(const pcc_phi_desc* d);
+int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B);
+/* x[n,d] fp32, offsets[B+1] -> pooled[B,H] (+ argmax[B,H] for MAX).  ws: workspace. */
+int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
+                              float* pooled, int32_t* argmax, void* ws, int device, void* stream);
+/* dpooled[B,H] -> dw[l] / db[l] (fp32, OVERWRITTEN) for every phi layer; recomputes the
+ * forward per tile.  dw/db arrays follow d->w / d->b order. */
+int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
+                              const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
+                              void* ws, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCC_H_ */

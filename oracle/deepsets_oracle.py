@@ -1,0 +1,174 @@
+"""CPU oracle for the DeepSets hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this file.  The product (point-cloud-classifier_b200/) never does.
+
+This is a functional restatement (no nn.Module, parameters taken from a flat
+state_dict) of the reference algorithm:
+
+  * layer plan                -> /root/reference/models/deep_sets.py:44-57 (phi), :59-72 (rho)
+  * residual block            -> /root/reference/models/deep_sets.py:149-160
+  * segment bookkeeping       -> /root/reference/models/deep_sets.py:91-92 (bincount + contiguous split)
+  * pooling (sum/sqrt(n), mean, max first-occurrence) -> /root/reference/models/deep_sets.py:96-106
+  * rho head                  -> /root/reference/models/deep_sets.py:112
+  * loss                      -> /root/reference/models/wrapper.py:38 (BCEWithLogitsLoss, mean)
+
+Parity pin: the reference has no golden vectors of its own, so this
+oracle is pinned against outputs of the reference module itself, generated in the
+build container by oracle/gen_golden.py (which imports /root/reference) and committed
+under tests/golden/deepsets_*.npz.  tests/test_oracle_golden.py checks it.
+
+Arithmetic is plain torch CPU tensor ops in the dtype of the inputs (float32 for the
+reference-equivalent run, float64 for a high-precision truth value).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+ACTS = ("relu", "gelu", "silu")
+POOLS = ("sum", "mean", "max")
+
+
+def layer_plan(prefix: str, in_dim: int, hidden: List[int], out_dim: int,
+               layer_norm: bool, residual_block: bool) -> List[dict]:
+    """Sequential-index bookkeeping of deep_sets.py:44-57 / :59-72.
+
+    Each entry: {"kind": "linear"|"res"|"final", "lin": key-prefix of the Linear,
+                 "ln": key-prefix of the LayerNorm or None, "in": K, "out": N}
+    rho never uses residual blocks (deep_sets.py:63-68), so callers pass False there.
+    """
+    plan, i, last = [], 0, in_dim
+    for h in hidden:
+        if residual_block and last == h:
+            plan.append({"kind": "res", "lin": f"{prefix}.{i}.linear",
+                         "ln": f"{prefix}.{i}.layer_norm" if layer_norm else None,
+                         "in": last, "out": h})
+            i += 1
+        else:
+            plan.append({"kind": "linear", "lin": f"{prefix}.{i}",
+                         "ln": f"{prefix}.{i + 1}" if layer_norm else None,
+                         "in": last, "out": h})
+            i += 3 if layer_norm else 2
+        last = h
+    plan.append({"kind": "final", "lin": f"{prefix}.{i}", "ln": None, "in": last, "out": out_dim})
+    return plan
+
+
+def _act(name: str, z: torch.Tensor) -> torch.Tensor:
+    if name == "relu":
+        return torch.relu(z)
+    if name == "gelu":  # nn.GELU() default: exact erf form (deep_sets.py:24)
+        return 0.5 * z * (1.0 + torch.erf(z * (1.0 / math.sqrt(2.0))))
+    if name == "silu":
+        return z * torch.sigmoid(z)
+    raise AttributeError(f"unknown activation {name!r}")  # reference: attribute never set (:21-26)
+
+
+def _layer_norm(z: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    mu = z.mean(dim=-1, keepdim=True)
+    var = ((z - mu) ** 2).mean(dim=-1, keepdim=True)  # biased, as nn.LayerNorm
+    return (z - mu) * torch.rsqrt(var + eps) * w + b
+
+
+def mlp_forward(sd: Dict[str, torch.Tensor], plan: List[dict], activation: str, h: torch.Tensor) -> torch.Tensor:
+    for L in plan:
+        z = F.linear(h, sd[L["lin"] + ".weight"], sd[L["lin"] + ".bias"])
+        if L["kind"] == "final":
+            h = z
+            continue
+        if L["ln"] is not None:
+            z = _layer_norm(z, sd[L["ln"] + ".weight"], sd[L["ln"] + ".bias"])
+        a = _act(activation, z)
+        h = h + a if L["kind"] == "res" else a
+    return h
+
+
+def segment_offsets(idx: torch.Tensor) -> torch.Tensor:
+    """deep_sets.py:91-92: only the histogram of idx matters; the split is contiguous."""
+    counts = torch.bincount(idx)
+    off = torch.zeros(counts.numel() + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(counts, 0)
+    return off
+
+
+def segment_pool(phi_x: torch.Tensor, offsets: torch.Tensor, pooling: str
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """deep_sets.py:96-106.  Returns (pooled[B,H], argmax[B,H] global row ids or None)."""
+    B = offsets.numel() - 1
+    H = phi_x.shape[1]
+    pooled = phi_x.new_empty((B, H))
+    arg = torch.empty((B, H), dtype=torch.int64) if pooling == "max" else None
+    for b in range(B):
+        s, e = int(offsets[b]), int(offsets[b + 1])
+        chunk = phi_x[s:e]
+        n = e - s
+        if pooling == "sum":
+            pooled[b] = chunk.sum(dim=0) / torch.sqrt(torch.tensor(n, dtype=chunk.dtype))
+        elif pooling == "mean":
+            pooled[b] = chunk.mean(dim=0)
+        elif pooling == "max":
+            v, i = chunk.max(dim=0)  # first occurrence on ties
+            pooled[b] = v
+            arg[b] = i + s
+        else:
+            raise ValueError("pooling must be 'mean', 'sum', or 'max'")
+    return pooled, arg
+
+
+def deepsets_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, idx: torch.Tensor,
+                     return_aux: bool = False):
+    """cfg keys = the reference ctor kwargs (deep_sets.py:6-16)."""
+    ln = cfg.get("layer_norm", True)
+    phi = layer_plan("phi", cfg["input_dim"], list(cfg["phi_layers"]),
+                     cfg["phi_layers"][-1] if cfg["phi_layers"] else cfg["input_dim"],
+                     ln, cfg.get("residual_block", False))
+    H = phi[-1]["out"]
+    rho = layer_plan("rho", H, list(cfg["rho_layers"]), cfg["output_dim"], ln, False)
+    pooling = cfg.get("pooling", "sum")
+    if pooling not in POOLS:
+        raise ValueError("pooling must be 'mean', 'sum', or 'max'")
+    phi_x = mlp_forward(sd, phi, cfg["activation"], x)
+    offsets = segment_offsets(idx)
+    pooled, arg = segment_pool(phi_x, offsets, pooling)
+    logits = mlp_forward(sd, rho, cfg["activation"], pooled)
+    if return_aux:
+        return logits, {"phi_x": phi_x, "pooled": pooled, "argmax": arg, "offsets": offsets}
+    return logits
+
+
+def deepsets_train_step(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, idx: torch.Tensor,
+                        y: torch.Tensor):
+    """forward + BCEWithLogitsLoss(mean) + backward (wrapper.py:58-67).
+
+    Returns (logits, loss, grads{name: tensor}, aux).  Gradients come from torch
+    autograd over the restated forward above.
+    """
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    logits, aux = deepsets_forward(leaves, cfg, x, idx, return_aux=True)
+    loss = F.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return logits.detach(), loss.detach(), grads, {k: (v.detach() if v is not None else None) for k, v in aux.items()}
+
+
+def init_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Deterministic parameters with nn.Linear-like scale (NOT the reference RNG stream;
+    parity tests always pass one state_dict to both sides)."""
+    g = torch.Generator().manual_seed(seed)
+    ln = cfg.get("layer_norm", True)
+    phi = layer_plan("phi", cfg["input_dim"], list(cfg["phi_layers"]), cfg["phi_layers"][-1], ln,
+                     cfg.get("residual_block", False))
+    rho = layer_plan("rho", phi[-1]["out"], list(cfg["rho_layers"]), cfg["output_dim"], ln, False)
+    sd = {}
+    for L in phi + rho:
+        bound = 1.0 / math.sqrt(L["in"])
+        sd[L["lin"] + ".weight"] = ((torch.rand(L["out"], L["in"], generator=g) * 2 - 1) * bound).to(dtype)
+        sd[L["lin"] + ".bias"] = ((torch.rand(L["out"], generator=g) * 2 - 1) * bound).to(dtype)
+        if L["ln"] is not None:
+            sd[L["ln"] + ".weight"] = (1.0 + 0.1 * torch.randn(L["out"], generator=g)).to(dtype)
+            sd[L["ln"] + ".bias"] = (0.1 * torch.randn(L["out"], generator=g)).to(dtype)
+    return sd

@@ -1,0 +1,94 @@
+// Shared helpers for libpcc.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <stdio.h>
+
+#include "../../include/pcc.h"
+
+namespace pcc {
+
+void set_error(const std::string& msg);
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    ok = (cudaSetDevice(device) == cudaSuccess);
+    if (!ok) { cudaGetLastError(); }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline int fail(const char* where, const std::string& msg) {
+  set_error(std::string(where) + ": " + msg);
+  return -1;
+}
+
+inline int check_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
+  return 0;
+}
+
+#define PCC_ENTER(device)                                                                  \
+  pcc::DeviceGuard _guard(device);                                                         \
+  if (!_guard.ok) return pcc::fail(__func__, "cannot select CUDA device (no CPU fallback exists)")
+
+#define PCC_REQUIRE(cond, msg)                       \
+  do {                                               \
+    if (!(cond)) return pcc::fail(__func__, msg);    \
+  } while (0)
+
+#define PCC_CUDA(call)                                                      \
+  do {                                                                      \
+    cudaError_t _e = (call);                                                \
+    if (_e != cudaSuccess) return pcc::fail(__func__, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- activations (fp32)
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  switch (act) {
+    case PCC_ACT_RELU: return z > 0.f ? z : 0.f;
+    case PCC_ACT_GELU: return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+    case PCC_ACT_SILU: return z / (1.f + expf(-z));
+    case PCC_ACT_TANH: return tanhf(z);
+    default: return z;
+  }
+}
+
+// derivative of act at pre-activation z
+__device__ __forceinline__ float act_grad(int act, float z) {
+  switch (act) {
+    case PCC_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case PCC_ACT_GELU: {
+      float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
+      float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
+      return cdf + z * pdf;
+    }
+    case PCC_ACT_SILU: {
+      float s = 1.f / (1.f + expf(-z));
+      return s * (1.f + z * (1.f - s));
+    }
+    case PCC_ACT_TANH: {
+      float t = tanhf(z);
+      return 1.f - t * t;
+    }
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace pcc

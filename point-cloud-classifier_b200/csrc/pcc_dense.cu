@@ -1,0 +1,463 @@
+// fp32 SIMT dense path: Linear fwd / dgrad / wgrad with fused epilogues, activation
+// backward, LayerNorm, BatchNorm1d.  This is the exact-fp32 ("parity") path and the
+// path for shapes the fused tcgen05 kernel does not take (LayerNorm inside phi, rho
+// head, GraphNet dense layers).
+//   reference call sites: /root/reference/models/deep_sets.py:89,112,156-160;
+//   /root/reference/models/graph_net.py:73-102 (lin_rel/lin_root, fc1/fc2, bn1-3).
+#include "pcc_common.cuh"
+
+namespace pcc {
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t M, N, K;  // C[M,N] = A[M,K] * B[K,N]
+  int64_t lda, ldb, ldc;
+  const float* bias;      // [N] or null
+  const float* pre_add;   // [M,N] (ld = ldc) or null, added before the activation
+  const float* residual;  // [M,N] (ld = ldc) or null, added after the activation
+  float* z_out;           // [M,N] (ld = ldc) or null
+  int act;
+  int accumulate;   // C += result
+  int atomic;       // split-K partial sums: atomicAdd into C
+  int64_t k_chunk;  // K range per blockIdx.z
+};
+
+// A_T=false: A(m,k)=A[m*lda+k] ; A_T=true: A(m,k)=A[k*lda+m]
+// B_T=false: B(k,n)=B[k*ldb+n] ; B_T=true: B(k,n)=B[n*ldb+k]
+template <int BM, int BN, int BK, int TM, int TN, bool A_T, bool B_T>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmArgs p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int GM = TM / 4, GN = TN / 4;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_chunk;
+  const int64_t kend = (kbeg + p.k_chunk < p.K) ? kbeg + p.k_chunk : p.K;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- stage A tile
+    for (int i = tid; i < BM * BK; i += NT) {
+      int m, k;
+      if (A_T) { m = i % BM; k = i / BM; } else { m = i / BK; k = i % BK; }
+      int64_t gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < p.M && gk < kend) v = A_T ? __ldg(p.A + gk * p.lda + gm) : __ldg(p.A + gm * p.lda + gk);
+      As[k][m] = v;
+    }
+    for (int i = tid; i < BN * BK; i += NT) {
+      int n, k;
+      if (B_T) { n = i / BK; k = i % BK; } else { n = i % BN; k = i / BN; }
+      int64_t gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < p.N && gk < kend) v = B_T ? __ldg(p.B + gn * p.ldb + gk) : __ldg(p.B + gk * p.ldb + gn);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        float4 t = *reinterpret_cast<const float4*>(&As[k][g * (BM / GM) + ty * 4]);
+        a[g * 4 + 0] = t.x; a[g * 4 + 1] = t.y; a[g * 4 + 2] = t.z; a[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        float4 t = *reinterpret_cast<const float4*>(&Bs[k][g * (BN / GN) + tx * 4]);
+        b[g * 4 + 0] = t.x; b[g * 4 + 1] = t.y; b[g * 4 + 2] = t.z; b[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gm = m0 + (i / 4) * (BM / GM) + ty * 4 + (i % 4);
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int64_t gn = n0 + (j / 4) * (BN / GN) + tx * 4 + (j % 4);
+      if (gn >= p.N) continue;
+      const int64_t o = gm * p.ldc + gn;
+      float v = acc[i][j];
+      if (p.atomic) {
+        atomicAdd(p.C + o, v);
+        continue;
+      }
+      if (p.bias) v += __ldg(p.bias + gn);
+      if (p.pre_add) v += __ldg(p.pre_add + o);
+      if (p.z_out) p.z_out[o] = v;
+      v = act_fwd(p.act, v);
+      if (p.residual) v += __ldg(p.residual + o);
+      if (p.accumulate) v += p.C[o];
+      p.C[o] = v;
+    }
+  }
+}
+
+template <bool A_T, bool B_T>
+static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
+  if (p.M == 0 || p.N == 0) return 0;
+  const int64_t tiles[3] = {cdiv(p.M, 128) * cdiv(p.N, 128), cdiv(p.M, 64) * cdiv(p.N, 64),
+                            cdiv(p.M, 32) * cdiv(p.N, 32)};
+  const int64_t min_mn = p.M < p.N ? p.M : p.N;
+  int cfg = min_mn <= 32 ? 2 : (min_mn <= 64 ? 1 : 0);  // do not waste a big tile on a thin matrix
+  int64_t split = 1;
+  if (want_split > 1) {
+    // reduction-dominated (wgrad): spread K over ~2 waves of CTAs
+    split = cdiv(296, tiles[cfg]);
+    int64_t max_split = cdiv(p.K, 256);
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+  } else {
+    while (cfg < 2 && tiles[cfg] < 120) ++cfg;
+  }
+  p.k_chunk = cdiv(cdiv(p.K, split), 32) * 32;
+  if (p.k_chunk == 0) p.k_chunk = 32;
+  split = cdiv(p.K, p.k_chunk);
+  if (split < 1) split = 1;
+  p.atomic = split > 1 ? 1 : 0;
+  if (cfg == 0) {
+    dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
+    sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
+  } else if (cfg == 1) {
+    dim3 grid((unsigned)cdiv(p.N, 64), (unsigned)cdiv(p.M, 64), (unsigned)split);
+    sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
+    sgemm_kernel<32, 32, 32, 4, 4, A_T, B_T><<<grid, 64, 0, st>>>(p);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ small kernels
+__global__ void zero_f32_kernel(float* p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// column sums of dy[M,N] -> db[N] (atomic accumulate); block: 256 threads, 128-row slab
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int64_t M, int64_t N,
+                                                     float* __restrict__ db) {
+  const int64_t r0 = (int64_t)blockIdx.y * 128;
+  const int64_t r1 = r0 + 128 < M ? r0 + 128 : M;
+  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < N; c += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += __ldg(dy + r * N + c);
+    atomicAdd(db + c, s);
+  }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ dz,
+                               int64_t count, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    dz[i] = dy[i] * act_grad(act, z[i]);
+}
+
+// ------------------------------------------------------------------ LayerNorm (warp per row)
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ residual, float* __restrict__ y,
+                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                            int64_t M, int64_t H, int act, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* zr = z + row * H;
+  float s = 0.f;
+  for (int64_t c = lane; c < H; c += 32) s += zr[c];
+  const float mu = warp_sum(s) / (float)H;
+  float v = 0.f;
+  for (int64_t c = lane; c < H; c += 32) {
+    float d = zr[c] - mu;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)H + eps);
+  if (lane == 0) {
+    mean_o[row] = mu;
+    rstd_o[row] = rstd;
+  }
+  for (int64_t c = lane; c < H; c += 32) {
+    float u = (zr[c] - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    float o = act_fwd(act, u);
+    if (residual) o += residual[row * H + c];
+    y[row * H + c] = o;
+  }
+}
+
+// dz written; dgamma/dbeta accumulated (block-level smem reduction, then atomics)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            float* __restrict__ dz, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int64_t M, int64_t H, int act,
+                                                            int rows_per_block) {
+  extern __shared__ float sm[];  // [2][H] partial dgamma / dbeta
+  float* s_dg = sm;
+  float* s_db = sm + H;
+  for (int64_t c = threadIdx.x; c < 2 * H; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rend = rbeg + rows_per_block < M ? rbeg + rows_per_block : M;
+  for (int64_t row = rbeg + wid; row < rend; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* zr = z + row * H;
+    const float* gr = dy + row * H;
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t c = lane; c < H; c += 32) {
+      float xh = (zr[c] - mu) * rs;
+      float g = __ldg(gamma + c);
+      float u = xh * g + __ldg(beta + c);
+      float du = gr[c] * act_grad(act, u);
+      float dxh = du * g;
+      s1 += dxh;
+      s2 += dxh * xh;
+      atomicAdd(&s_dg[c], du * xh);
+      atomicAdd(&s_db[c], du);
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    for (int64_t c = lane; c < H; c += 32) {
+      float xh = (zr[c] - mu) * rs;
+      float g = __ldg(gamma + c);
+      float u = xh * g + __ldg(beta + c);
+      float dxh = gr[c] * act_grad(act, u) * g;
+      dz[row * H + c] = rs * (dxh - s1 - xh * s2);
+    }
+  }
+  __syncthreads();
+  for (int64_t c = threadIdx.x; c < H; c += blockDim.x) {
+    atomicAdd(dgamma + c, s_dg[c]);
+    atomicAdd(dbeta + c, s_db[c]);
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm1d
+// pass 1: column sums -> ws[0:C]; pass 2: sum (x-mean)^2 -> ws[C:2C]; finalize; apply.
+__global__ void __launch_bounds__(256) bn_colsum_kernel(const float* __restrict__ x, int64_t n, int64_t C,
+                                                        const float* __restrict__ mean, float* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.y * 256;
+  const int64_t r1 = r0 + 256 < n ? r0 + 256 : n;
+  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    if (mean) {
+      const float mu = mean[c];
+      for (int64_t r = r0; r < r1; ++r) {
+        float d = __ldg(x + r * C + c) - mu;
+        s += d * d;
+      }
+    } else {
+      for (int64_t r = r0; r < r1; ++r) s += __ldg(x + r * C + c);
+    }
+    atomicAdd(out + c, s);
+  }
+}
+
+__global__ void bn_mean_finalize_kernel(float* sum_to_mean, int64_t C, float inv_n) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c < C) sum_to_mean[c] *= inv_n;
+}
+
+// ssq and invstd may alias (the sum of squares is replaced by 1/std in place)
+__global__ void bn_var_finalize_kernel(const float* mean, const float* ssq, float* invstd, float* running_mean,
+                                       float* running_var, int64_t C, int64_t n, float momentum, float eps) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = ssq[c];
+  float var = s / (float)n;
+  invstd[c] = rsqrtf(var + eps);
+  if (running_mean) {
+    float unbiased = n > 1 ? s / (float)(n - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[c];
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ mean,
+                                const float* __restrict__ invstd_or_var, float* __restrict__ y, int64_t total,
+                                int64_t C, float eps, int is_var) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = i % C;
+    float is = is_var ? rsqrtf(invstd_or_var[c] + eps) : invstd_or_var[c];
+    y[i] = (x[i] - mean[c]) * is * gamma[c] + beta[c];
+  }
+}
+
+// backward pass 1: dbeta = sum dy ; dgamma = sum dy * xhat
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, int64_t n, int64_t C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int64_t r0 = (int64_t)blockIdx.y * 256;
+  const int64_t r1 = r0 + 256 < n ? r0 + 256 : n;
+  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
+    const float mu = mean[c], is = invstd[c];
+    float sg = 0.f, sb = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float g = __ldg(dy + r * C + c);
+      sb += g;
+      sg += g * (__ldg(x + r * C + c) - mu) * is;
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, float* __restrict__ dx, int64_t total, int64_t C,
+                                    float inv_n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = i % C;
+    float is = invstd[c];
+    float xh = (x[i] - mean[c]) * is;
+    dx[i] = gamma[c] * is * (dy[i] - dbeta[c] * inv_n - xh * dgamma[c] * inv_n);
+  }
+}
+
+static inline unsigned ew_blocks(int64_t total) {
+  int64_t b = cdiv(total, 256);
+  return (unsigned)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" int pcc_linear_fwd(const float* x, const float* w, const float* bias, const float* pre_add,
+                              const float* residual, float* y, float* z_out, int64_t M, int64_t N, int64_t K, int act,
+                              int accumulate, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(!(accumulate && act != PCC_ACT_NONE), "accumulate requires act NONE");
+  GemmArgs p{};
+  p.A = x; p.B = w; p.C = y; p.M = M; p.N = N; p.K = K; p.lda = K; p.ldb = K; p.ldc = N;
+  p.bias = bias; p.pre_add = pre_add; p.residual = residual; p.z_out = z_out; p.act = act;
+  p.accumulate = accumulate;
+  launch_gemm<false, true>(p, 1, (cudaStream_t)stream);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_linear_bwd_data(const float* dy, const float* w, const float* residual, float* dx, int64_t M,
+                                   int64_t N, int64_t K, int device, void* stream) {
+  PCC_ENTER(device);
+  GemmArgs p{};  // dx[M,K] = dy[M,N] * w[N,K]
+  p.A = dy; p.B = w; p.C = dx; p.M = M; p.N = K; p.K = N; p.lda = N; p.ldb = K; p.ldc = K;
+  p.residual = residual; p.act = PCC_ACT_NONE;
+  launch_gemm<false, false>(p, 1, (cudaStream_t)stream);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N,
+                                     int64_t K, int accumulate, int device, void* stream) {
+  PCC_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    zero_f32_kernel<<<(unsigned)cdiv(N * K, 256), 256, 0, st>>>(dw, N * K);
+    if (db) zero_f32_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(db, N);
+  }
+  if (M > 0) {
+    GemmArgs p{};  // dw[N,K] = dy^T[N,M] * x[M,K]  (reduction over M)
+    p.A = dy; p.B = x; p.C = dw; p.M = N; p.N = K; p.K = M; p.lda = N; p.ldb = K; p.ldc = K;
+    p.act = PCC_ACT_NONE; p.accumulate = 1;
+    launch_gemm<true, false>(p, 2, st);
+    if (db) {
+      dim3 grid((unsigned)cdiv(N, 256), (unsigned)cdiv(M, 128));
+      colsum_kernel<<<grid, 256, 0, st>>>(dy, M, N, db);
+    }
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_act_bwd(const float* dy, const float* z, float* dz, int64_t count, int act, int device,
+                           void* stream) {
+  PCC_ENTER(device);
+  if (count == 0) return 0;
+  act_bwd_kernel<<<ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, count, act);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_layernorm_fwd(const float* z, const float* gamma, const float* beta, const float* residual,
+                                 float* y, float* mean, float* rstd, int64_t M, int64_t H, int act, float eps,
+                                 int device, void* stream) {
+  PCC_ENTER(device);
+  if (M == 0) return 0;
+  layernorm_fwd_kernel<<<(unsigned)cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, residual, y, mean,
+                                                                                 rstd, M, H, act, eps);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_layernorm_bwd(const float* dy, const float* z, const float* gamma, const float* beta,
+                                 const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
+                                 int64_t M, int64_t H, int act, int device, void* stream) {
+  PCC_ENTER(device);
+  if (M == 0) return 0;
+  PCC_REQUIRE(H <= 4096, "LayerNorm width > 4096 unsupported");
+  const int rows_per_block = 64;
+  layernorm_bwd_kernel<<<(unsigned)cdiv(M, rows_per_block), 256, 2 * H * sizeof(float), (cudaStream_t)stream>>>(
+      dy, z, gamma, beta, mean, rstd, dz, dgamma, dbeta, M, H, act, rows_per_block);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_batchnorm_fwd_train(const float* x, const float* gamma, const float* beta, float* y,
+                                       float* save_mean, float* save_invstd, float* running_mean,
+                                       float* running_var, int64_t n, int64_t C, float momentum, float eps,
+                                       int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(n > 0, "BatchNorm1d training needs at least one row");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned cb = (unsigned)cdiv(C, 256);
+  dim3 grid(cb, (unsigned)cdiv(n, 256));
+  zero_f32_kernel<<<cb, 256, 0, st>>>(save_mean, C);
+  zero_f32_kernel<<<cb, 256, 0, st>>>(save_invstd, C);
+  bn_colsum_kernel<<<grid, 256, 0, st>>>(x, n, C, nullptr, save_mean);
+  bn_mean_finalize_kernel<<<cb, 256, 0, st>>>(save_mean, C, 1.f / (float)n);
+  bn_colsum_kernel<<<grid, 256, 0, st>>>(x, n, C, save_mean, save_invstd);  // holds ssq until finalize
+  bn_var_finalize_kernel<<<cb, 256, 0, st>>>(save_mean, save_invstd, save_invstd, running_mean, running_var, C, n,
+                                             momentum, eps);
+  bn_apply_kernel<<<ew_blocks(n * C), 256, 0, st>>>(x, gamma, beta, save_mean, save_invstd, y, n * C, C, eps, 0);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_batchnorm_fwd_eval(const float* x, const float* gamma, const float* beta,
+                                      const float* running_mean, const float* running_var, float* y, int64_t n,
+                                      int64_t C, float eps, int device, void* stream) {
+  PCC_ENTER(device);
+  if (n == 0) return 0;
+  bn_apply_kernel<<<ew_blocks(n * C), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, running_mean, running_var, y,
+                                                                        n * C, C, eps, 1);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_batchnorm_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                                 const float* save_invstd, float* dx, float* dgamma, float* dbeta, int64_t n,
+                                 int64_t C, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(n > 0, "BatchNorm1d backward needs at least one row");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned cb = (unsigned)cdiv(C, 256);
+  zero_f32_kernel<<<cb, 256, 0, st>>>(dgamma, C);
+  zero_f32_kernel<<<cb, 256, 0, st>>>(dbeta, C);
+  dim3 grid(cb, (unsigned)cdiv(n, 256));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, x, save_mean, save_invstd, n, C, dgamma, dbeta);
+  bn_bwd_apply_kernel<<<ew_blocks(n * C), 256, 0, st>>>(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, n * C,
+                                                        C, 1.f / (float)n);
+  return check_launch(__func__);
+}

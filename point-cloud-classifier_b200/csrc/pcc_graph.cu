@@ -1,0 +1,344 @@
+// Graph neighbour stage: CSR build, GraphConv neighbour aggregation fwd/bwd, kNN.
+//   reference: PyG GraphConv.propagate called at /root/reference/models/graph_net.py:73,82
+//   (gather x[src] -> optional scalar edge weight -> scatter-aggr at dst); batch layout
+//   from /root/reference/utils/data.py:1228-1261.  kNN has no reference counterpart
+//   (semantics: oracle/knn_oracle.py).
+// HBM/L2-bound gather-reduce: one thread group per node, 128-bit channel loads, no
+// [E,C] message tensor is ever materialised.
+#include "pcc_common.cuh"
+#include "pcc_scan.cuh"
+
+namespace pcc {
+
+// ------------------------------------------------------------------ CSR build
+__global__ void csr_zero_kernel(int64_t* rowptr, int64_t n1) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n1) rowptr[i] = 0;
+}
+__global__ void csr_count_kernel(const int64_t* __restrict__ keys, int64_t E, int64_t n,
+                                 unsigned long long* __restrict__ counts) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < E) {
+    int64_t k = keys[e];
+    if (k >= 0 && k < n) atomicAdd(&counts[k], 1ull);
+  }
+}
+__global__ void csr_copy_kernel(const int64_t* __restrict__ rowptr, unsigned long long* __restrict__ cursor, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) cursor[i] = (unsigned long long)rowptr[i];
+}
+__global__ void csr_fill_kernel(const int64_t* __restrict__ keys, int64_t E, int64_t n,
+                                unsigned long long* __restrict__ cursor, int32_t* __restrict__ perm) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < E) {
+    int64_t k = keys[e];
+    if (k >= 0 && k < n) {
+      unsigned long long pos = atomicAdd(&cursor[k], 1ull);
+      perm[pos] = (int32_t)e;
+    }
+  }
+}
+// restore ascending edge order inside each row (makes float summation order reproducible)
+__global__ void csr_sort_rows_kernel(const int64_t* __restrict__ rowptr, int32_t* __restrict__ perm, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t s = rowptr[i], e = rowptr[i + 1];
+  if (e - s < 2 || e - s > 1024) return;
+  for (int64_t a = s + 1; a < e; ++a) {
+    int32_t v = perm[a];
+    int64_t b = a - 1;
+    while (b >= s && perm[b] > v) {
+      perm[b + 1] = perm[b];
+      --b;
+    }
+    perm[b + 1] = v;
+  }
+}
+
+// ------------------------------------------------------------------ aggregation
+// tpn threads per node, each owning float4 channel groups c = 4*(lane + it*tpn)
+template <bool VEC4>
+__global__ void __launch_bounds__(256) graph_aggregate_fwd_kernel(const float* __restrict__ x,
+                                                                  const int64_t* __restrict__ src,
+                                                                  const float* __restrict__ w,
+                                                                  const int64_t* __restrict__ rowptr,
+                                                                  const int32_t* __restrict__ perm, int64_t n,
+                                                                  int64_t C, int aggr, int tpn,
+                                                                  float* __restrict__ out,
+                                                                  int32_t* __restrict__ arg_edge) {
+  const int npb = 256 / tpn;
+  const int64_t node = (int64_t)blockIdx.x * npb + threadIdx.x / tpn;
+  const int lane = threadIdx.x % tpn;
+  if (node >= n) return;
+  const int64_t pb = rowptr[node], pe = rowptr[node + 1];
+  constexpr int W = VEC4 ? 4 : 1;
+  for (int64_t c = (int64_t)lane * W; c < C; c += (int64_t)tpn * W) {
+    float acc[W];
+    int arg[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) { acc[j] = (aggr == PCC_POOL_MAX) ? -INFINITY : 0.f; arg[j] = -1; }
+    for (int64_t p = pb; p < pe; ++p) {
+      const int e = __ldg(perm + p);
+      const int64_t s = __ldg(src + e);
+      const float we = w ? __ldg(w + e) : 1.f;
+      float v[W];
+      if (VEC4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(x + s * C + c));
+        v[0] = t.x; v[1 % W] = t.y; v[2 % W] = t.z; v[3 % W] = t.w;
+      } else {
+        v[0] = __ldg(x + s * C + c);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        float m = v[j] * we;
+        if (aggr == PCC_POOL_MAX) {
+          if (m > acc[j] || arg[j] < 0) { acc[j] = m; arg[j] = e; }
+        } else {
+          acc[j] += m;
+        }
+      }
+    }
+    const float inv = (aggr == PCC_POOL_MEAN && pe > pb) ? 1.f / (float)(pe - pb) : 1.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      float r = acc[j];
+      if (aggr == PCC_POOL_MAX) {
+        if (arg[j] < 0) r = 0.f;
+        arg_edge[node * C + c + j] = arg[j];
+      } else {
+        r *= inv;
+      }
+      out[node * C + c + j] = r;
+    }
+  }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) graph_aggregate_bwd_kernel(const float* __restrict__ g,
+                                                                  const int64_t* __restrict__ dst,
+                                                                  const float* __restrict__ w,
+                                                                  const int64_t* __restrict__ rowptr_src,
+                                                                  const int32_t* __restrict__ perm_src,
+                                                                  const int64_t* __restrict__ rowptr_dst,
+                                                                  const int32_t* __restrict__ arg_edge, int64_t n,
+                                                                  int64_t C, int aggr, int tpn,
+                                                                  float* __restrict__ dx) {
+  const int npb = 256 / tpn;
+  const int64_t node = (int64_t)blockIdx.x * npb + threadIdx.x / tpn;
+  const int lane = threadIdx.x % tpn;
+  if (node >= n) return;
+  const int64_t pb = rowptr_src[node], pe = rowptr_src[node + 1];
+  constexpr int W = VEC4 ? 4 : 1;
+  for (int64_t c = (int64_t)lane * W; c < C; c += (int64_t)tpn * W) {
+    float acc[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[j] = 0.f;
+    for (int64_t p = pb; p < pe; ++p) {
+      const int e = __ldg(perm_src + p);
+      const int64_t t = __ldg(dst + e);
+      float we = w ? __ldg(w + e) : 1.f;
+      if (aggr == PCC_POOL_MEAN) we /= (float)(rowptr_dst[t + 1] - rowptr_dst[t]);
+      float v[W];
+      if (VEC4) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(g + t * C + c));
+        v[0] = q.x; v[1 % W] = q.y; v[2 % W] = q.z; v[3 % W] = q.w;
+      } else {
+        v[0] = __ldg(g + t * C + c);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        if (aggr == PCC_POOL_MAX) {
+          if (__ldg(arg_edge + t * C + c + j) == e) acc[j] += v[j] * we;
+        } else {
+          acc[j] += v[j] * we;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) dx[node * C + c + j] = acc[j];
+  }
+}
+
+static inline int threads_per_node(int64_t C, bool vec4) {
+  int64_t groups = vec4 ? C / 4 : C;
+  int t = 1;
+  while (t < 32 && t < groups) t <<= 1;
+  return t;
+}
+
+// ------------------------------------------------------------------ kNN
+// One warp serves QW query points of (normally) one cloud.  Every lane evaluates one
+// candidate per step for all QW queries; each query's running top-k lives distributed
+// across the warp (lane i holds the i-th best (d2, id)), insertion by shuffle.
+__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+template <int QW>
+__global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ pos, int64_t pos_stride,
+                                                  const int64_t* __restrict__ offsets, int64_t n, int64_t B, int k,
+                                                  int64_t* __restrict__ nbr, float* __restrict__ d2o) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t q0 = warp * QW;
+  if (q0 >= n) return;
+  float qx[QW], qy[QW], qz[QW];
+  int64_t cs[QW], ce[QW];
+  float ld[QW];   // this lane's list entry per query
+  int li[QW];
+  int64_t lo_all = n, hi_all = 0;
+#pragma unroll
+  for (int q = 0; q < QW; ++q) {
+    const int64_t r = q0 + q;
+    ld[q] = INFINITY;
+    li[q] = 0x7fffffff;
+    cs[q] = 0; ce[q] = 0;
+    qx[q] = qy[q] = qz[q] = 0.f;
+    if (r < n) {
+      qx[q] = __ldg(pos + r * pos_stride);
+      qy[q] = __ldg(pos + r * pos_stride + 1);
+      qz[q] = __ldg(pos + r * pos_stride + 2);
+      int64_t lo = 0, hi = B;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid + 1] <= r) lo = mid + 1; else hi = mid;
+      }
+      if (lo < B) { cs[q] = offsets[lo]; ce[q] = offsets[lo + 1]; }
+      lo_all = cs[q] < lo_all ? cs[q] : lo_all;
+      hi_all = ce[q] > hi_all ? ce[q] : hi_all;
+    }
+  }
+  for (int64_t j0 = lo_all; j0 < hi_all; j0 += 32) {
+    const int64_t j = j0 + lane;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (j < hi_all) {
+      px = __ldg(pos + j * pos_stride);
+      py = __ldg(pos + j * pos_stride + 1);
+      pz = __ldg(pos + j * pos_stride + 2);
+    }
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+      const float dx = px - qx[q], dy = py - qy[q], dz = pz - qz[q];
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float thr_d = __shfl_sync(0xffffffffu, ld[q], k - 1);
+      const int thr_i = __shfl_sync(0xffffffffu, li[q], k - 1);
+      bool pass = (j >= cs[q]) && (j < ce[q]) && (j != q0 + q) && lex_less(d, (int)j, thr_d, thr_i);
+      unsigned ballot = __ballot_sync(0xffffffffu, pass);
+      while (ballot) {
+        const int L = __ffs(ballot) - 1;
+        ballot &= ballot - 1;
+        const float cd = __shfl_sync(0xffffffffu, d, L);
+        const int ci = __shfl_sync(0xffffffffu, (int)j, L);
+        const float ud = __shfl_up_sync(0xffffffffu, ld[q], 1);
+        const int ui = __shfl_up_sync(0xffffffffu, li[q], 1);
+        if (lex_less(cd, ci, ld[q], li[q])) {  // my entry is worse than the candidate: shift or insert
+          if (lane > 0 && lex_less(cd, ci, ud, ui)) { ld[q] = ud; li[q] = ui; }
+          else { ld[q] = cd; li[q] = ci; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < QW; ++q) {
+    const int64_t r = q0 + q;
+    if (r < n && lane < k) {
+      const bool valid = li[q] != 0x7fffffff;
+      nbr[r * k + lane] = valid ? (int64_t)li[q] : -1;
+      d2o[r * k + lane] = valid ? ld[q] : INFINITY;
+    }
+  }
+}
+
+__global__ void knn_edges_kernel(const int64_t* __restrict__ nbr, int64_t total, int k, int64_t* __restrict__ ei) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < total) {
+    ei[i] = nbr[i];
+    ei[total + i] = i / k;
+  }
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" int64_t pcc_csr_workspace_bytes(int64_t n, int64_t E) {
+  (void)E;
+  return (n + cdiv(n + 1, 1024) + 8) * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t* rowptr, int32_t* perm, void* ws,
+                             int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(E < (int64_t)0x7fffffff, "edge count exceeds int32 range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* scan_ws = (int64_t*)ws;
+  unsigned long long* cursor = (unsigned long long*)(scan_ws + cdiv(n + 1, 1024) + 4);
+  csr_zero_kernel<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(rowptr, n + 1);
+  if (E > 0) csr_count_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, (unsigned long long*)rowptr);
+  exclusive_scan_i64(rowptr, n + 1, scan_ws, st);
+  if (E > 0 && n > 0) {
+    csr_copy_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr, cursor, n);
+    csr_fill_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, cursor, perm);
+    csr_sort_rows_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(rowptr, perm, n);
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_graph_aggregate_fwd(const float* x, const int64_t* src, const float* w, const int64_t* rowptr,
+                                       const int32_t* perm, int64_t n, int64_t C, int aggr, float* out,
+                                       int32_t* arg_edge, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(aggr == PCC_POOL_ADD || aggr == PCC_POOL_MEAN || aggr == PCC_POOL_MAX, "aggr must be add/mean/max");
+  PCC_REQUIRE(aggr != PCC_POOL_MAX || arg_edge != nullptr, "arg_edge buffer required for max aggregation");
+  if (n == 0 || C == 0) return 0;
+  const bool vec4 = (C % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  const int tpn = threads_per_node(C, vec4);
+  const unsigned grid = (unsigned)cdiv(n, 256 / tpn);
+  if (vec4)
+    graph_aggregate_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
+                                                                             out, arg_edge);
+  else
+    graph_aggregate_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
+                                                                              out, arg_edge);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_graph_aggregate_bwd(const float* g, const int64_t* dst, const float* w, const int64_t* rowptr_src,
+                                       const int32_t* perm_src, const int64_t* rowptr_dst, const int32_t* arg_edge,
+                                       int64_t n, int64_t C, int aggr, float* dx, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(aggr == PCC_POOL_ADD || aggr == PCC_POOL_MEAN || aggr == PCC_POOL_MAX, "aggr must be add/mean/max");
+  PCC_REQUIRE(aggr != PCC_POOL_MAX || arg_edge != nullptr, "arg_edge buffer required for max aggregation");
+  PCC_REQUIRE(aggr != PCC_POOL_MEAN || rowptr_dst != nullptr, "rowptr_dst required for mean aggregation");
+  if (n == 0 || C == 0) return 0;
+  const bool vec4 = (C % 4 == 0) && (((uintptr_t)g & 15) == 0);
+  const int tpn = threads_per_node(C, vec4);
+  const unsigned grid = (unsigned)cdiv(n, 256 / tpn);
+  if (vec4)
+    graph_aggregate_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
+                                                                             rowptr_dst, arg_edge, n, C, aggr, tpn, dx);
+  else
+    graph_aggregate_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
+                                                                              rowptr_dst, arg_edge, n, C, aggr, tpn, dx);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offsets, int64_t n, int64_t B, int k,
+                       int64_t* nbr, float* d2, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(k >= 1 && k <= 32, "k must be in [1,32]");
+  PCC_REQUIRE(n < (int64_t)0x7fffffff, "point count exceeds int32 range");
+  if (n == 0) return 0;
+  constexpr int QW = 4;
+  const int64_t warps = cdiv(n, QW);
+  knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge_index, int device, void* stream) {
+  PCC_ENTER(device);
+  const int64_t total = n * k;
+  if (total == 0) return 0;
+  knn_edges_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(nbr, total, k, edge_index);
+  return check_launch(__func__);
+}

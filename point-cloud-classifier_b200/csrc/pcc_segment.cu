@@ -1,0 +1,191 @@
+// Segment bookkeeping and ragged pooling.
+//   reference: /root/reference/models/deep_sets.py:91-106 (bincount/split/pool loop),
+//   PyG global_mean_pool called at /root/reference/models/graph_net.py:92,96.
+// HBM-bound kernels: coalesced 128 B row slabs, one pass over x.
+#include "pcc_common.cuh"
+#include "pcc_scan.cuh"
+
+namespace pcc {
+
+// ------------------------------------------------------------------ histogram of idx
+__global__ void zero_i64_kernel(int64_t* p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+__global__ void histogram_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t B,
+                                 unsigned long long* __restrict__ counts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t v = (i < n) ? idx[i] : -1;
+  bool valid = (v >= 0 && v < B);
+  // warp-aggregate: sorted idx makes most warps uniform
+  unsigned mask = __match_any_sync(0xffffffffu, valid ? v : -1 - (int64_t)(threadIdx.x & 31));
+  int leader = __ffs(mask) - 1;
+  if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&counts[v], (unsigned long long)__popc(mask));
+}
+
+__global__ void index_max_kernel(const int64_t* __restrict__ idx, int64_t n, long long* __restrict__ out) {
+  long long m = LLONG_MIN;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    long long v = idx[i];
+    m = v > m ? v : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void set_i64_kernel(long long* p, long long v) { *p = v; }
+
+// ------------------------------------------------------------------ pooling forward
+// block = 32 columns x 8 row lanes; grid = (B, ceil(H/32))
+__global__ void __launch_bounds__(256) segment_pool_fwd_kernel(const float* __restrict__ x,
+                                                               const int64_t* __restrict__ offsets, int64_t H,
+                                                               int pooling, float* __restrict__ pooled,
+                                                               int32_t* __restrict__ argmax) {
+  const int b = blockIdx.x;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.y * 32 + cx;
+  const int64_t s = offsets[b], e = offsets[b + 1];
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  float acc = (pooling == PCC_POOL_MAX) ? -INFINITY : 0.f;
+  int arg = 0x7fffffff;
+  if (c < H) {
+    if (pooling == PCC_POOL_MAX) {
+      for (int64_t r = s + ry; r < e; r += 8) {
+        float v = __ldg(x + r * H + c);
+        if (v > acc || arg == 0x7fffffff) { acc = v; arg = (int)r; }
+      }
+    } else {
+      for (int64_t r = s + ry; r < e; r += 8) acc += __ldg(x + r * H + c);
+    }
+  }
+  sv[ry][cx] = acc;
+  si[ry][cx] = arg;
+  __syncthreads();
+  if (ry == 0 && c < H) {
+    if (pooling == PCC_POOL_MAX) {
+      float best = sv[0][cx];
+      int bi = si[0][cx];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        float v = sv[j][cx];
+        int i = si[j][cx];
+        if (i != 0x7fffffff && (bi == 0x7fffffff || v > best || (v == best && i < bi))) { best = v; bi = i; }
+      }
+      if (bi == 0x7fffffff) { best = 0.f; bi = -1; }  // empty segment
+      pooled[(int64_t)b * H + c] = best;
+      argmax[(int64_t)b * H + c] = bi;
+    } else {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += sv[j][cx];
+      const float n = (float)(e - s);
+      if (pooling == PCC_POOL_SUM) t = (e > s) ? t / sqrtf(n) : 0.f;
+      else if (pooling == PCC_POOL_MEAN) t = (e > s) ? t / n : 0.f;
+      pooled[(int64_t)b * H + c] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pooling backward
+// block handles 32 rows; set id per row by binary search over offsets.
+__global__ void __launch_bounds__(256) segment_pool_bwd_kernel(const float* __restrict__ dpooled,
+                                                               const int64_t* __restrict__ offsets,
+                                                               const int32_t* __restrict__ argmax, int64_t n,
+                                                               int64_t B, int64_t H, int pooling,
+                                                               float* __restrict__ dx) {
+  __shared__ int s_set[32];
+  __shared__ float s_scale[32];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  if (threadIdx.x < 32) {
+    int64_t r = r0 + threadIdx.x;
+    int set = -1;
+    float scale = 0.f;
+    if (r < n) {
+      int64_t lo = 0, hi = B;  // find b with offsets[b] <= r < offsets[b+1]
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid + 1] <= r) lo = mid + 1; else hi = mid;
+      }
+      if (lo < B && offsets[lo] <= r) {
+        set = (int)lo;
+        float cnt = (float)(offsets[lo + 1] - offsets[lo]);
+        scale = pooling == PCC_POOL_SUM ? 1.f / sqrtf(cnt) : pooling == PCC_POOL_MEAN ? 1.f / cnt : 1.f;
+      }
+    }
+    s_set[threadIdx.x] = set;
+    s_scale[threadIdx.x] = scale;
+  }
+  __syncthreads();
+  const int64_t total = 32 * H;
+  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) {
+    int lr = (int)(t / H);
+    int64_t c = t - (int64_t)lr * H;
+    int64_t r = r0 + lr;
+    if (r >= n) break;
+    int set = s_set[lr];
+    float g = 0.f;
+    if (set >= 0) {
+      float dp = __ldg(dpooled + (int64_t)set * H + c);
+      if (pooling == PCC_POOL_MAX) g = (__ldg(argmax + (int64_t)set * H + c) == (int)r) ? dp : 0.f;
+      else g = dp * s_scale[lr];
+    }
+    dx[r * H + c] = g;
+  }
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int64_t* offsets, int device,
+                                   void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(n >= 0 && B >= 0, "negative size");
+  PCC_REQUIRE(B + 1 <= (int64_t)PCC_SCAN_SINGLE_MAX, "too many segments for the single-block scan");
+  cudaStream_t st = (cudaStream_t)stream;
+  zero_i64_kernel<<<(unsigned)cdiv(B + 1, 256), 256, 0, st>>>(offsets, B + 1);
+  if (n > 0)
+    histogram_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(idx, n, B, (unsigned long long*)offsets);
+  exclusive_scan_single_block_kernel<<<1, 1024, 0, st>>>(offsets, B + 1);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_index_max(const int64_t* idx, int64_t n, int64_t* out_max, int device, void* stream) {
+  PCC_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  set_i64_kernel<<<1, 1, 0, st>>>((long long*)out_max, -1);
+  if (n > 0) {
+    int blocks = (int)(cdiv(n, 256) < 592 ? cdiv(n, 256) : 592);
+    index_max_kernel<<<blocks, 256, 0, st>>>(idx, n, (long long*)out_max);
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_segment_pool_fwd(const float* x, const int64_t* offsets, int64_t n, int64_t B, int64_t H,
+                                    int pooling, float* pooled, int32_t* argmax, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(pooling >= PCC_POOL_SUM && pooling <= PCC_POOL_ADD, "bad pooling id");
+  PCC_REQUIRE(pooling != PCC_POOL_MAX || argmax != nullptr, "argmax buffer required for max pooling");
+  PCC_REQUIRE(n < (int64_t)0x7fffffff, "row count exceeds int32 argmax range");
+  if (B == 0 || H == 0) return 0;
+  dim3 grid((unsigned)B, (unsigned)cdiv(H, 32));
+  segment_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, offsets, H, pooling, pooled, argmax);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets, const int32_t* argmax, int64_t n,
+                                    int64_t B, int64_t H, int pooling, float* dx, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(pooling >= PCC_POOL_SUM && pooling <= PCC_POOL_ADD, "bad pooling id");
+  PCC_REQUIRE(pooling != PCC_POOL_MAX || argmax != nullptr, "argmax buffer required for max pooling");
+  if (n == 0 || H == 0) return 0;
+  segment_pool_bwd_kernel<<<(unsigned)cdiv(n, 32), 256, 0, (cudaStream_t)stream>>>(dpooled, offsets, argmax, n, B, H,
+                                                                                     pooling, dx);
+  return check_launch(__func__);
+}

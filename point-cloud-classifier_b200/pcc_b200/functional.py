@@ -1,0 +1,317 @@
+"""torch.autograd.Function wrappers around the libpcc.so entry points.
+
+Each Function corresponds to one reference call site (cited per class); PyTorch is used
+only to own device memory and to chain the backward calls.  Backward runs on the
+autograd worker thread, so every call passes device + current stream explicitly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT, POOL, call, ptr
+
+
+def _ctx(*tensors):
+    dev = L.require_cuda(*tensors)
+    return dev, L.stream_ptr(dev)
+
+
+# ------------------------------------------------------------------ segment bookkeeping
+def index_max(idx: torch.Tensor) -> int:
+    """max(idx) — one device->host read (the reference syncs here too: counts.tolist(),
+    /root/reference/models/deep_sets.py:92)."""
+    idx = L.i64c(idx)
+    dev, st = _ctx(idx)
+    out = torch.empty(1, dtype=torch.int64, device=idx.device)
+    call("pcc_index_max", ptr(idx), idx.numel(), ptr(out), dev, st)
+    return int(out.item())
+
+
+def segment_offsets(idx: torch.Tensor, num_sets: int) -> torch.Tensor:
+    """offsets[B+1] of the contiguous split by bincount(idx) (deep_sets.py:91-92)."""
+    idx = L.i64c(idx)
+    dev, st = _ctx(idx)
+    off = torch.empty(num_sets + 1, dtype=torch.int64, device=idx.device)
+    call("pcc_segment_offsets", ptr(idx), idx.numel(), num_sets, ptr(off), dev, st)
+    return off
+
+
+class SegmentPoolFn(torch.autograd.Function):
+    """deep_sets.py:94-106 (sum/sqrt(n) | mean | max) and PyG global_mean_pool
+    (graph_net.py:92,96)."""
+
+    @staticmethod
+    def forward(ctx, x, offsets, pooling: str):
+        x = L.f32c(x)
+        dev, st = _ctx(x, offsets)
+        n, H = x.shape
+        B = offsets.numel() - 1
+        pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, H), dtype=torch.int32, device=x.device) if pooling == "max" else None
+        call("pcc_segment_pool_fwd", ptr(x), ptr(offsets), n, B, H, POOL[pooling], ptr(pooled), ptr(arg), dev, st)
+        if arg is not None:
+            ctx.save_for_backward(offsets, arg)
+        else:
+            ctx.save_for_backward(offsets)
+        ctx.meta = (n, B, H, pooling)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        n, B, H, pooling = ctx.meta
+        saved = ctx.saved_tensors
+        offsets, arg = saved[0], (saved[1] if len(saved) > 1 else None)
+        dpooled = L.f32c(dpooled)
+        dev, st = _ctx(dpooled)
+        dx = torch.empty((n, H), dtype=torch.float32, device=dpooled.device)
+        call("pcc_segment_pool_bwd", ptr(dpooled), ptr(offsets), ptr(arg), n, B, H, POOL[pooling], ptr(dx), dev, st)
+        return dx, None, None
+
+
+def segment_pool(x, offsets, pooling: str, return_argmax: bool = False):
+    if return_argmax:
+        x = L.f32c(x)
+        dev, st = _ctx(x, offsets)
+        n, H = x.shape
+        B = offsets.numel() - 1
+        pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, H), dtype=torch.int32, device=x.device)
+        call("pcc_segment_pool_fwd", ptr(x), ptr(offsets), n, B, H, POOL["max"], ptr(pooled), ptr(arg), dev, st)
+        return pooled, arg
+    return SegmentPoolFn.apply(x, offsets, pooling)
+
+
+# ------------------------------------------------------------------ dense layers (fp32 SIMT)
+class LinearActFn(torch.autograd.Function):
+    """y = residual? + act(x W^T + b + pre_add?): nn.Linear + activation (+ ResidualBlock
+    add), deep_sets.py:48-53,64-68,156-160; graph_net.py lin_rel/lin_root/fc1/fc2."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pre_add, residual, act: str):
+        x, w = L.f32c(x), L.f32c(w)
+        b = L.f32c(b) if b is not None else None
+        pre_add = L.f32c(pre_add) if pre_add is not None else None
+        residual = L.f32c(residual) if residual is not None else None
+        dev, st = _ctx(x, w, b, pre_add, residual)
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        need_z = act != "none"
+        z = torch.empty_like(y) if need_z else None
+        call("pcc_linear_fwd", ptr(x), ptr(w), ptr(b), ptr(pre_add), ptr(residual), ptr(y), ptr(z), M, N, K, ACT[act],
+             0, dev, st)
+        ctx.save_for_backward(x, w, z)
+        ctx.meta = (M, N, K, act, b is not None, pre_add is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z = ctx.saved_tensors
+        M, N, K, act, has_b, has_pre, has_res = ctx.meta
+        dy = L.f32c(dy)
+        dev, st = _ctx(dy)
+        if act != "none":
+            dz = torch.empty_like(dy)
+            call("pcc_act_bwd", ptr(dy), ptr(z), ptr(dz), dy.numel(), ACT[act], dev, st)
+        else:
+            dz = dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            call("pcc_linear_bwd_data", ptr(dz), ptr(w), None, ptr(dx), M, N, K, dev, st)
+        if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
+            dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+            db = torch.empty((N,), dtype=torch.float32, device=dy.device) if has_b else None
+            call("pcc_linear_bwd_weight", ptr(dz), ptr(x), ptr(dw), ptr(db), M, N, K, 0, dev, st)
+        dpre = dz if (has_pre and ctx.needs_input_grad[3]) else None
+        dres = dy if (has_res and ctx.needs_input_grad[4]) else None
+        return dx, dw, db, dpre, dres, None
+
+
+def linear_act(x, w, b=None, residual=None, act: str = "none", pre_add=None):
+    return LinearActFn.apply(x, w, b, pre_add, residual, act)
+
+
+class LayerNormActFn(torch.autograd.Function):
+    """y = residual? + act(LayerNorm(z)): deep_sets.py:50-53,65-68,153-160."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, residual, act: str, eps: float):
+        z, gamma, beta = L.f32c(z), L.f32c(gamma), L.f32c(beta)
+        residual = L.f32c(residual) if residual is not None else None
+        dev, st = _ctx(z, gamma, beta, residual)
+        M, H = z.shape
+        y = torch.empty_like(z)
+        mean = torch.empty((M,), dtype=torch.float32, device=z.device)
+        rstd = torch.empty((M,), dtype=torch.float32, device=z.device)
+        call("pcc_layernorm_fwd", ptr(z), ptr(gamma), ptr(beta), ptr(residual), ptr(y), ptr(mean), ptr(rstd), M, H,
+             ACT[act], float(eps), dev, st)
+        ctx.save_for_backward(z, gamma, beta, mean, rstd)
+        ctx.meta = (M, H, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, gamma, beta, mean, rstd = ctx.saved_tensors
+        M, H, act, has_res = ctx.meta
+        dy = L.f32c(dy)
+        dev, st = _ctx(dy)
+        dz = torch.empty_like(z)
+        dgamma = torch.zeros((H,), dtype=torch.float32, device=dy.device)
+        dbeta = torch.zeros((H,), dtype=torch.float32, device=dy.device)
+        call("pcc_layernorm_bwd", ptr(dy), ptr(z), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), ptr(dz), ptr(dgamma),
+             ptr(dbeta), M, H, ACT[act], dev, st)
+        return dz, dgamma, dbeta, (dy if has_res else None), None, None
+
+
+def layernorm_act(z, gamma, beta, residual=None, act: str = "none", eps: float = 1e-5):
+    return LayerNormActFn.apply(z, gamma, beta, residual, act, eps)
+
+
+class BatchNormTrainFn(torch.autograd.Function):
+    """nn.BatchNorm1d in training mode over rows (graph_net.py:76,84,89,100); updates the
+    running statistics in place like torch does."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum: float, eps: float):
+        x, gamma, beta = L.f32c(x), L.f32c(gamma), L.f32c(beta)
+        dev, st = _ctx(x, gamma, beta, running_mean, running_var)
+        n, Cc = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty((Cc,), dtype=torch.float32, device=x.device)
+        invstd = torch.empty((Cc,), dtype=torch.float32, device=x.device)
+        call("pcc_batchnorm_fwd_train", ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(invstd),
+             ptr(running_mean), ptr(running_var), n, Cc, float(momentum), float(eps), dev, st)
+        ctx.save_for_backward(x, gamma, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, invstd = ctx.saved_tensors
+        dy = L.f32c(dy)
+        dev, st = _ctx(dy)
+        n, Cc = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty((Cc,), dtype=torch.float32, device=dy.device)
+        dbeta = torch.empty((Cc,), dtype=torch.float32, device=dy.device)
+        call("pcc_batchnorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(invstd), ptr(dx), ptr(dgamma),
+             ptr(dbeta), n, Cc, dev, st)
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+class BatchNormEvalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps: float):
+        x = L.f32c(x)
+        dev, st = _ctx(x, gamma, beta, running_mean, running_var)
+        n, Cc = x.shape
+        y = torch.empty_like(x)
+        call("pcc_batchnorm_fwd_eval", ptr(x), ptr(L.f32c(gamma)), ptr(L.f32c(beta)), ptr(running_mean),
+             ptr(running_var), ptr(y), n, Cc, float(eps), dev, st)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        raise RuntimeError("BatchNorm eval-mode backward is not part of the hot path")
+
+
+def batchnorm(x, bn: torch.nn.BatchNorm1d):
+    if bn.training:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                      bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+    return BatchNormEvalFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+
+# ------------------------------------------------------------------ graph stage
+class GraphCSR:
+    """CSR views (by target and, lazily, by source) of one batched edge list
+    (layout of /root/reference/utils/data.py:1228-1261)."""
+
+    def __init__(self, edges: torch.Tensor, n: int):
+        edges = L.i64c(edges)
+        self.src = edges[0].contiguous()
+        self.dst = edges[1].contiguous()
+        self.n = n
+        self.E = edges.shape[1]
+        self.by_dst = self._build(self.dst)
+        self._by_src = None
+
+    def _build(self, keys) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev, st = _ctx(keys)
+        rowptr = torch.empty(self.n + 1, dtype=torch.int64, device=keys.device)
+        perm = torch.empty(max(self.E, 1), dtype=torch.int32, device=keys.device)
+        ws_bytes = call("pcc_csr_workspace_bytes", self.n, self.E)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+        call("pcc_csr_build", ptr(keys), self.E, self.n, ptr(rowptr), ptr(perm), ptr(ws), dev, st)
+        return rowptr, perm
+
+    @property
+    def by_src(self):
+        if self._by_src is None:
+            self._by_src = self._build(self.src)
+        return self._by_src
+
+
+class GraphAggregateFn(torch.autograd.Function):
+    """agg_i = aggr_{e: dst(e)=i} w_e * x[src(e)] — the propagate step of PyG GraphConv
+    (graph_net.py:73,82)."""
+
+    @staticmethod
+    def forward(ctx, x, w, csr: GraphCSR, aggr: str):
+        x = L.f32c(x)
+        w = L.f32c(w) if w is not None else None
+        dev, st = _ctx(x, w)
+        n, Cc = x.shape
+        rowptr, perm = csr.by_dst
+        out = torch.empty_like(x)
+        arg = torch.empty((n, Cc), dtype=torch.int32, device=x.device) if aggr == "max" else None
+        call("pcc_graph_aggregate_fwd", ptr(x), ptr(csr.src), ptr(w), ptr(rowptr), ptr(perm), n, Cc, POOL[aggr],
+             ptr(out), ptr(arg), dev, st)
+        ctx.csr, ctx.aggr, ctx.w, ctx.arg = csr, aggr, w, arg
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        g = L.f32c(g)
+        dev, st = _ctx(g)
+        csr = ctx.csr
+        n, Cc = g.shape
+        rowptr_s, perm_s = csr.by_src
+        dx = torch.empty_like(g)
+        call("pcc_graph_aggregate_bwd", ptr(g), ptr(csr.dst), ptr(ctx.w), ptr(rowptr_s), ptr(perm_s),
+             ptr(csr.by_dst[0]), ptr(ctx.arg), n, Cc, POOL[ctx.aggr], ptr(dx), dev, st)
+        return dx, None, None, None
+
+
+def graph_aggregate(x, w, csr: GraphCSR, aggr: str):
+    return GraphAggregateFn.apply(x, w, csr, aggr)
+
+
+# ------------------------------------------------------------------ kNN
+def knn(pos: torch.Tensor, offsets: torch.Tensor, k: int):
+    """pos[n,>=3] fp32 view with unit inner stride (e.g. features[:, 1:4]) -> (nbr[n,k] i64, d2[n,k] f32)."""
+    if pos.dtype != torch.float32 or pos.stride(1) != 1:
+        pos = pos.float().contiguous()
+    dev, st = _ctx(pos, offsets)
+    n = pos.shape[0]
+    B = offsets.numel() - 1
+    nbr = torch.empty((n, k), dtype=torch.int64, device=pos.device)
+    d2 = torch.empty((n, k), dtype=torch.float32, device=pos.device)
+    call("pcc_knn", ptr(pos), pos.stride(0), ptr(offsets), n, B, int(k), ptr(nbr), ptr(d2), dev, st)
+    return nbr, d2
+
+
+def knn_edges(nbr: torch.Tensor) -> torch.Tensor:
+    dev, st = _ctx(nbr)
+    n, k = nbr.shape
+    ei = torch.empty((2, n * k), dtype=torch.int64, device=nbr.device)
+    call("pcc_knn_edges", ptr(nbr), n, k, ptr(ei), dev, st)
+    return ei

@@ -1,0 +1,111 @@
+"""Host side of the fused tcgen05 phi+pool path (pcc_deepsets_phi_pool_fwd / _bwd).
+
+Replaces /root/reference/models/deep_sets.py:89-106 and its autograd with two kernel
+launches; per-point activations never reach HBM (the backward recomputes them per tile).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT, POOL, PhiDesc, call, ptr
+
+
+def _build_desc(plan: List[dict], act: str, pooling: str, tensors=None) -> PhiDesc:
+    d = PhiDesc()
+    d.n_layers = len(plan)
+    d.input_dim = plan[0]["lin"].in_features
+    d.hidden = plan[0]["lin"].out_features
+    d.act = ACT[act]
+    d.pooling = POOL[pooling]
+    mask = 0
+    for i, Lr in enumerate(plan):
+        if Lr["res"]:
+            mask |= 1 << i
+    d.residual_mask = mask
+    if tensors is not None:
+        for i, (w, b) in enumerate(tensors):
+            d.w[i] = w.data_ptr()
+            d.b[i] = b.data_ptr()
+    return d
+
+
+def phi_supported(plan: List[dict], act: str, pooling: str) -> bool:
+    """Static shape/feature check (no device pointers needed)."""
+    if len(plan) < 2 or len(plan) > L.MAX_PHI_LAYERS or act not in ("relu", "gelu", "silu"):
+        return False
+    H = plan[0]["lin"].out_features
+    for i, Lr in enumerate(plan):
+        lin = Lr["lin"]
+        if Lr["ln"] is not None or lin.bias is None or lin.out_features != H:
+            return False
+        if i > 0 and lin.in_features != H:
+            return False
+        if i == 0 and Lr["res"]:
+            return False
+        if (i == len(plan) - 1) == Lr["act"]:  # hidden layers activate, the final Linear does not
+            return False
+    d = _build_desc(plan, act, pooling)
+    lib = L.load()
+    return lib.pcc_phi_fused_supported(C.byref(d)) == 0
+
+
+class FusedPhiPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offsets, meta, *params):
+        plan_len, act, pooling, res_mask = meta
+        x = L.f32c(x)
+        dev = L.require_cuda(x, offsets, *params)
+        st = L.stream_ptr(dev)
+        ws_ = [L.f32c(p) for p in params]
+        tensors = [(ws_[2 * i], ws_[2 * i + 1]) for i in range(plan_len)]
+        d = PhiDesc()
+        d.n_layers, d.input_dim, d.hidden = plan_len, tensors[0][0].shape[1], tensors[0][0].shape[0]
+        d.act, d.pooling, d.residual_mask = ACT[act], POOL[pooling], res_mask
+        for i, (w, b) in enumerate(tensors):
+            d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
+        n, B, H = x.shape[0], offsets.numel() - 1, d.hidden
+        ws_bytes = call("pcc_phi_fused_workspace_bytes", C.byref(d), n, B)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+        pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, H), dtype=torch.int32, device=x.device) if pooling == "max" else None
+        call("pcc_deepsets_phi_pool_fwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(pooled), ptr(arg), ptr(ws), dev, st)
+        ctx.save_for_backward(x, offsets, arg, *ws_)
+        ctx.meta = meta
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        plan_len, act, pooling, res_mask = ctx.meta
+        x, offsets, arg, *ws_ = ctx.saved_tensors
+        dpooled = L.f32c(dpooled)
+        dev = L.require_cuda(dpooled)
+        st = L.stream_ptr(dev)
+        tensors = [(ws_[2 * i], ws_[2 * i + 1]) for i in range(plan_len)]
+        d = PhiDesc()
+        d.n_layers, d.input_dim, d.hidden = plan_len, tensors[0][0].shape[1], tensors[0][0].shape[0]
+        d.act, d.pooling, d.residual_mask = ACT[act], POOL[pooling], res_mask
+        for i, (w, b) in enumerate(tensors):
+            d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
+        n, B = x.shape[0], offsets.numel() - 1
+        grads = [torch.empty_like(t) for t in ws_]
+        dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])
+        db = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i + 1].data_ptr() for i in range(plan_len)])
+        ws_bytes = call("pcc_phi_fused_workspace_bytes", C.byref(d), n, B)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+        call("pcc_deepsets_phi_pool_bwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(dpooled), ptr(arg),
+             C.cast(dw, C.c_void_p), C.cast(db, C.c_void_p), ptr(ws), dev, st)
+        return (None, None, None, *grads)
+
+
+def phi_pool(x, offsets, plan: List[dict], act: str, pooling: str):
+    params = []
+    mask = 0
+    for i, Lr in enumerate(plan):
+        params += [Lr["lin"].weight, Lr["lin"].bias]
+        if Lr["res"]:
+            mask |= 1 << i
+    return FusedPhiPoolFn.apply(x, offsets, (len(plan), act, pooling, mask), *params)

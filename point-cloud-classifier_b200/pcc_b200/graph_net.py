@@ -1,0 +1,125 @@
+"""B200-native GraphNet — drop-in for /root/reference/models/graph_net.py.
+
+Same constructor kwargs (graph_net.py:10-22) and `forward(x, membership, edges,
+weights=None)` (:65); same `state_dict` layout (`conv{1,2}.lin_rel.{weight,bias}`,
+`conv{1,2}.lin_root.weight`, `bn{1,2,3}.*`, `fc1.*`, `fc2.*`).  `GraphConv` below is a
+parameter container with PyG's parameter names; the arithmetic (neighbour aggregation,
+dense layers, BatchNorm1d, segmented mean pool) runs in libpcc.so.  No CPU fallback and
+no torch_geometric dependency.
+
+Out of scope: `use_gat=True` (GATConv) and `sag_pool=True`
+(SAGPooling) raise NotImplementedError instead of silently computing something else.
+BatchNorm statistics are per process (per replica under data parallelism), as with
+torch DDP's default.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as PF
+
+
+class GraphConv(nn.Module):
+    """Parameter container with torch_geometric.nn.GraphConv's names:
+    out_i = lin_rel(aggr_j w_ji x_j) + lin_root(x_i); lin_rel has the bias."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggr: str = "add"):
+        super().__init__()
+        if aggr not in ("add", "mean", "max"):
+            raise ValueError("aggr must be 'add', 'mean' or 'max'")
+        self.in_channels, self.out_channels, self.aggr = in_channels, out_channels, aggr
+        self.lin_rel = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_root = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, csr: PF.GraphCSR, weights, act: str):
+        """act( lin_rel(agg) + lin_root(x) ) with the activation of graph_net.py:75,83 fused in."""
+        agg = PF.graph_aggregate(x, weights, csr, self.aggr)
+        root = PF.linear_act(x, self.lin_root.weight, None, None, "none")
+        return PF.linear_act(agg, self.lin_rel.weight, self.lin_rel.bias, None, act, pre_add=root)
+
+
+class GraphNet(nn.Module):
+
+    def __init__(self,
+                 input_dim,
+                 hidden_dim,
+                 output_dim,
+                 activation,
+                 use_gat=False,
+                 gat_heads=4,
+                 sag_pool=False,
+                 pool_ratio=0.5,
+                 local_pooling="add",
+                 global_pooling="mean",
+                 deepchem_style=False):
+        super().__init__()
+        if use_gat:
+            raise NotImplementedError("use_gat=True (GATConv, graph_net.py:47-48) is outside the B200 hot path")
+        if sag_pool:
+            raise NotImplementedError("sag_pool=True (SAGPooling, graph_net.py:57-58) is outside the B200 hot path")
+        # the reference selects self.global_pooling here (:26-31) but forward never uses it
+        # (:92,:96 hard-code global_mean_pool); kept for attribute compatibility.
+        self.global_pooling = global_pooling
+        self.deepchem_style = deepchem_style
+        self.local_pooling = local_pooling
+        self.sag_pool = sag_pool
+        self.use_gat = use_gat
+
+        if activation == "tanh":
+            self.activation = nn.Tanh()
+        elif activation == "relu":
+            self.activation = nn.ReLU()
+        elif activation == "gelu":
+            self.activation = nn.GELU()
+        self._act_name = activation
+
+        self.conv1 = GraphConv(input_dim, hidden_dim, aggr=self.local_pooling)
+        self.conv2 = GraphConv(hidden_dim, hidden_dim, aggr=self.local_pooling)
+        self.bn1 = nn.BatchNorm1d(hidden_dim)
+        self.bn2 = nn.BatchNorm1d(hidden_dim)
+        self.fc1 = nn.Linear(hidden_dim, 256)
+        self.bn3 = nn.BatchNorm1d(256)
+        self.fc2 = nn.Linear(256, output_dim)
+
+    def forward(self, x, membership, edges, weights=None, num_graphs: Optional[int] = None):
+        if not x.is_cuda:
+            raise RuntimeError("pcc_b200.GraphNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)")
+        if not hasattr(self, "activation"):
+            raise AttributeError("'GraphNet' object has no attribute 'activation'")
+        act = self._act_name
+        n = x.shape[0]
+        csr = PF.GraphCSR(edges, n)
+        if num_graphs is None:
+            num_graphs = PF.index_max(membership) + 1
+        offsets = PF.segment_offsets(membership, num_graphs)
+
+        h = self.conv1(x, csr, weights, act)
+        h = PF.batchnorm(h, self.bn1)
+        h = self.conv2(h, csr, weights, act)
+        h = PF.batchnorm(h, self.bn2)
+        if self.deepchem_style:
+            h = PF.linear_act(h, self.fc1.weight, self.fc1.bias, None, act)
+            h = PF.batchnorm(h, self.bn3)
+            h = PF.segment_pool(h, offsets, "mean")
+        else:
+            h = PF.segment_pool(h, offsets, "mean")
+            h = PF.linear_act(h, self.fc1.weight, self.fc1.bias, None, act)
+            h = PF.batchnorm(h, self.bn3)
+        return PF.linear_act(h, self.fc2.weight, self.fc2.bias, None, "none")
+
+
+def knn_graph(features: torch.Tensor, membership: torch.Tensor, k: int = 20, pos_cols=(1, 4),
+              num_graphs: Optional[int] = None):
+    """kNN edge list in GraphConv's convention (row 0 = neighbour, row 1 = centre) over the
+    position columns of the node features (cols 1:4, cf. utils/data.py:808-813, 837).
+    Every cloud must have more than k points (otherwise use functional.knn and filter)."""
+    if num_graphs is None:
+        num_graphs = PF.index_max(membership) + 1
+    offsets = PF.segment_offsets(membership, num_graphs)
+    pos = features[:, pos_cols[0]:pos_cols[1]]
+    nbr, d2 = PF.knn(pos, offsets, k)
+    return PF.knn_edges(nbr), d2

@@ -1,0 +1,39 @@
+"""Shared loaders for the parity tests (test infrastructure)."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases(prefix="deepsets_"):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+    out = {"cfg": cfg, "sd": sd, "grads": grads, "x": torch.from_numpy(z["x"]), "idx": torch.from_numpy(z["idx"]),
+           "y": torch.from_numpy(z["y"]), "logits": torch.from_numpy(z["logits"]), "loss": float(z["loss"])}
+    if "argmax" in z.files:
+        out["argmax"] = torch.from_numpy(z["argmax"])
+    return out
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| / max |b| — scale-aware error for gradient tensors."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def ragged_batch(sizes, d, seed, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    n = sum(sizes)
+    x = torch.randn(n, d, generator=g)
+    idx = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    return x.to(device), idx.to(device)

@@ -1,0 +1,120 @@
+"""GPU parity for the graph neighbour stage: kNN vs oracle/knn_oracle.py (bit-exact
+indices and distances), CSR, GraphConv aggregation and the full GraphNet train step vs
+oracle/graphnet_oracle.py (PyG semantics restated; parity unpinned — see its header)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import graphnet_oracle as GO
+from oracle import knn_oracle as KO
+
+import pcc_b200
+from pcc_b200 import functional as PF
+
+pytestmark = pytest.mark.gpu
+
+
+def _clouds(sizes, seed, F=4):
+    g = torch.Generator().manual_seed(seed)
+    n = sum(sizes)
+    feats = torch.randn(n, F, generator=g)
+    feats[:, 0] = torch.rand(n, generator=g)
+    memb = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return feats, memb, off
+
+
+@pytest.mark.parametrize("sizes,k", [([64, 100, 33], 20), ([1024, 1024], 20), ([21, 22, 500], 20), ([5, 3, 1, 40], 4),
+                                     ([300], 32), ([10, 15], 20)])
+def test_knn_bit_exact(sizes, k):
+    feats, memb, off = _clouds(sizes, seed=7)
+    ref_nbr, ref_d2 = KO.knn_neighbours(feats[:, 1:4].numpy(), off, k)
+    nbr, d2 = PF.knn(feats.cuda()[:, 1:4], torch.from_numpy(off).cuda(), k)
+    assert np.array_equal(nbr.cpu().numpy(), ref_nbr)
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)  # identical fp32 bits (no FMA contraction)
+
+
+def test_knn_graph_edge_convention():
+    feats, memb, off = _clouds([50, 70], seed=8)
+    ei, _ = pcc_b200.knn_graph(feats.cuda(), memb.cuda(), k=20)
+    ref = KO.knn_edges(KO.knn_neighbours(feats[:, 1:4].numpy(), off, 20)[0])
+    assert np.array_equal(ei.cpu().numpy(), ref)
+    assert ei.shape == (2, 120 * 20)
+    assert bool((ei[0] != ei[1]).all())  # no self loops
+
+
+def test_csr_build_sorted_rows():
+    g = torch.Generator().manual_seed(1)
+    n, E = 500, 7000
+    edges = torch.randint(0, n, (2, E), generator=g)
+    csr = PF.GraphCSR(edges.cuda(), n)
+    rowptr, perm = (t.cpu() for t in csr.by_dst)
+    counts = torch.bincount(edges[1], minlength=n)
+    assert torch.equal(rowptr[1:] - rowptr[:-1], counts)
+    for i in (0, 17, 499):
+        seg = perm[rowptr[i]:rowptr[i + 1]].long()
+        assert torch.equal(seg, torch.nonzero(edges[1] == i).flatten())  # ascending edge ids
+
+
+@pytest.mark.parametrize("aggr", ["add", "mean", "max"])
+@pytest.mark.parametrize("C,use_w", [(4, False), (128, True), (1, True), (6, False)])
+def test_graph_aggregate_fwd_bwd(aggr, C, use_w):
+    g = torch.Generator().manual_seed(2)
+    n, E = 300, 4000
+    edges = torch.randint(0, n, (2, E), generator=g)
+    edges[1, edges[1] == 5] = 6  # node 5 has no incoming edge -> aggregates to 0
+    x = torch.randn(n, C, generator=g)
+    w = torch.rand(E, generator=g) if use_w else None
+    xr = x.clone().requires_grad_(True)
+    ref = GO.graph_aggregate(xr, edges, w, aggr)
+    go = torch.randn(n, C, generator=g)
+    ref.backward(go)
+    xc = x.cuda().requires_grad_(True)
+    out = PF.graph_aggregate(xc, w.cuda() if use_w else None, PF.GraphCSR(edges.cuda(), n), aggr)
+    out.backward(go.cuda())
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-5)
+    assert rel_err(xc.grad, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("act,aggr,deepchem,use_w,hidden,F", [
+    ("tanh", "add", True, False, 128, 4),   # configs/graph_net.yaml
+    ("relu", "mean", False, True, 64, 4),
+    ("gelu", "max", True, True, 64, 1),
+    ("tanh", "add", False, False, 256, 4),
+])
+def test_graphnet_train_step_matches_oracle(act, aggr, deepchem, use_w, hidden, F):
+    cfg = dict(input_dim=F, hidden_dim=hidden, output_dim=1, activation=act, use_gat=False, gat_heads=4,
+               sag_pool=False, pool_ratio=0.5, local_pooling=aggr, global_pooling="mean", deepchem_style=deepchem)
+    sizes = [60, 45, 80, 33]
+    feats, memb, off = _clouds(sizes, seed=21, F=max(F, 4))
+    nbr, _ = KO.knn_neighbours(feats[:, 1:4].numpy(), off, 8)
+    edges = torch.from_numpy(KO.knn_edges(nbr))
+    x = feats[:, :F].contiguous()
+    gen = torch.Generator().manual_seed(22)
+    w = torch.rand(edges.shape[1], generator=gen) if use_w else None
+    y = (torch.rand(len(sizes), 1, generator=gen) > 0.5).float()
+    sd = GO.init_state_dict(cfg, seed=23)
+    ref_logits, ref_loss, ref_grads, ref_stats = GO.graphnet_train_step(sd, cfg, x, memb, edges, w, y)
+
+    m = pcc_b200.GraphNet(**cfg).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    args = [x.cuda(), memb.cuda(), edges.cuda()] + ([w.cuda()] if use_w else [])
+    logits = m(*args)
+    loss = torch.nn.BCEWithLogitsLoss()(logits, y.cuda())
+    loss.backward()
+    torch.testing.assert_close(logits.detach().cpu(), ref_logits, rtol=1e-4, atol=1e-5)
+    for k, ref in ref_grads.items():
+        got = dict(m.named_parameters())[k].grad
+        assert got is not None and rel_err(got, ref) < 2e-4, (k, rel_err(got, ref))
+    new_sd = m.state_dict()
+    for k, v in ref_stats.items():
+        torch.testing.assert_close(new_sd[k].cpu(), v, rtol=1e-4, atol=1e-6)
+    # eval mode uses the running statistics
+    m.eval()
+    with torch.no_grad():
+        ev = m(*args)
+    sd_eval = {k: v.cpu() for k, v in m.state_dict().items()}
+    ref_ev = GO.graphnet_forward(sd_eval, cfg, x, memb, edges, w, training=False)
+    torch.testing.assert_close(ev.cpu(), ref_ev, rtol=1e-4, atol=1e-5)
