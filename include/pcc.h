@@ -159,6 +159,11 @@ int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, int device, void* stream);
 
+/* ---- diagnostics: one-CTA tcgen05 GEMM on integer data, out[128,64] fp32.
+ *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
+ *      (wgrad).  Expected values: tests/test_fused_gpu.py. */
+int pcc_selftest_umma(int mode, float* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

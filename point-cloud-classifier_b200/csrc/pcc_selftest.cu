@@ -1,0 +1,90 @@
+// Diagnostics: one-CTA tcgen05 GEMMs on exactly representable integer data, covering the
+// three operand descriptor conventions the fused kernels rely on (see pcc_tc.cuh).
+//   mode 0: D[i][j] = sum_k A[i][k] * B[j][k]      A, B K-major blobs          (forward)
+//   mode 1: D[i][j] = sum_k A[i][k] * W[k][j]      B = MN-major view of W blob (dgrad)
+//   mode 2: D[i][j] = sum_p G[p][i] * Hh[p][j]     both MN-major views         (wgrad)
+#include "pcc_common.cuh"
+#include "pcc_tc.cuh"
+
+namespace pcc {
+using namespace tc;
+
+__device__ __host__ inline float st_a(int i, int k) { return (float)((i * 3 + k * 5) % 7 - 3); }
+__device__ __host__ inline float st_b(int j, int k) { return (float)((j * 2 + k) % 5 - 2); }
+
+// blob [C/8][128][8]: element (row, col)
+__device__ inline void blob_store(__nv_bfloat16* blob, int row, int col, float v) {
+  blob[((col >> 3) * 128 + row) * 8 + (col & 7)] = __float2bfloat16(v);
+}
+
+__global__ void __launch_bounds__(128, 1) selftest_umma_kernel(int mode, float* out) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  __nv_bfloat16* blobA = reinterpret_cast<__nv_bfloat16*>(dyn_smem);
+  __nv_bfloat16* blobB = blobA + 128 * 128;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int N = 64;
+  // mode 0: A[128 x 64] rows=i cols=k ; B[64(rows j, padded to 128 rows) x 64]
+  // mode 1: A[128 x 128] rows=i cols=k ; W blob rows=k(128) cols=j(64)
+  // mode 2: G blob rows=p(128) cols=i(128) ; Hh blob rows=p(128) cols=j(64)
+  for (int e = t; e < 128 * 128; e += 128) {
+    const int row = e / 128, col = e % 128;
+    float a = 0.f, b = 0.f;
+    if (mode == 0) { a = col < 64 ? st_a(row, col) : 0.f; b = (col < 64 && row < N) ? st_b(row, col) : 0.f; }
+    if (mode == 1) { a = st_a(row, col); b = col < N ? st_b(col, row) : 0.f; }   // W[k=row][j=col] = st_b(j,k)
+    if (mode == 2) { a = st_a(col, row); b = col < N ? st_b(col, row) : 0.f; }   // G[p][i] = st_a(i,p); Hh[p][j] = st_b(j,p)
+    blob_store(blobA, row, col, a);
+    blob_store(blobB, row, col, b);
+  }
+  if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (t == 0) {
+    const uint32_t a0 = smem_u32(blobA), b0 = smem_u32(blobB);
+    if (mode == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem, make_smem_desc(a0 + ks * 2 * 2048, 2048, 128), make_smem_desc(b0 + ks * 2 * 2048, 2048, 128),
+                  idesc, ks > 0);
+    } else if (mode == 1) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 1);
+      for (int ks = 0; ks < 8; ++ks)  // K step = 16 rows of the W blob = 256 B
+        umma_bf16(tmem, make_smem_desc(a0 + ks * 2 * 2048, 2048, 128), make_smem_desc(b0 + ks * 256, 128, 2048), idesc,
+                  ks > 0);
+    } else {
+      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16(tmem, make_smem_desc(a0 + ks * 256, 128, 2048), make_smem_desc(b0 + ks * 256, 128, 2048), idesc,
+                  ks > 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  uint32_t v[32];
+  for (int c = 0; c < N / 32; ++c) {
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j) out[t * N + c * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" int pcc_selftest_umma(int mode, float* out, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0..2");
+  const int smem = 2 * 128 * 128 * 2;
+  PCC_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, out);
+  return check_launch(__func__);
+}

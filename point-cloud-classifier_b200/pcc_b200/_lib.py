@@ -49,6 +49,7 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_selftest_umma": [_i32, _vp, _i32, _vp],
     "pcc_phi_fused_supported": [C.POINTER(PhiDesc)],
     "pcc_phi_fused_workspace_bytes": [C.POINTER(PhiDesc), _i64, _i64],
     "pcc_deepsets_phi_pool_fwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp],
