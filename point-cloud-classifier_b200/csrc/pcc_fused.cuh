@@ -1,0 +1,108 @@
+// Shared definitions of the fused tcgen05 DeepSets kernels (forward, backward chain, wgrad).
+#pragma once
+#include "pcc_common.cuh"
+#include "pcc_tc.cuh"
+
+namespace pcc {
+using namespace tc;
+
+constexpr int kMaxLayers = 6;
+constexpr int kTileM = 128;
+constexpr int kRing = 8;        // weight slabs in flight
+constexpr int kThreads = 192;   // 4 epilogue warps + producer warp + MMA warp
+constexpr int kK0 = 16;         // layer-0 K padded to one UMMA K step
+
+struct PhiParams {
+  const float* x;
+  const int64_t* offsets;
+  int64_t n, B, num_tiles;
+  int d, L, pooling, res_mask;
+  const uint8_t* wpack;          // packed bf16 weight blobs, all layers
+  uint32_t w_off[kMaxLayers];    // byte offset of layer l inside wpack
+  const float* bias[kMaxLayers];
+  void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
+};
+
+// ------------------------------------------------------------------ weight packing
+// W_l fp32 [H, K_l] (nn.Linear layout) -> blob [Kp/8][H][8] bf16, Kp = 16 for layer 0
+struct PackParams {
+  const float* w[kMaxLayers];
+  uint8_t* wpack;
+  uint32_t w_off[kMaxLayers];
+  uint32_t wt_off[kMaxLayers];  // transposed images (layers >= 1), used when gridDim.z == 2
+  int d, H, L;
+};
+// blockIdx.z == 0: blob of W_l   (rows = out features, K index = in features)   -> forward / recompute
+// blockIdx.z == 1: blob of W_l^T (rows = in features,  K index = out features)  -> dgrad, layers >= 1
+static __global__ void pack_weights_kernel(PackParams p) {
+  const int l = blockIdx.y;
+  if (l >= p.L) return;
+  const bool tr = blockIdx.z == 1;
+  if (tr && l == 0) return;
+  const int K = (l == 0) ? p.d : p.H;   // in features of W_l
+  const int Kp = (l == 0) ? kK0 : p.H;
+  const int total = (Kp / 8) * p.H;     // one thread per 16-byte chunk
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.wpack + (tr ? p.wt_off[l] : p.w_off[l]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kc = i / p.H, row = i % p.H;
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k0 = kc * 8 + 2 * j;
+      float a, b;
+      if (!tr) {
+        a = (k0 < K) ? __ldg(p.w[l] + (int64_t)row * K + k0) : 0.f;
+        b = (k0 + 1 < K) ? __ldg(p.w[l] + (int64_t)row * K + k0 + 1) : 0.f;
+      } else {  // element (row = in, k = out) = W[out][in]
+        a = __ldg(p.w[l] + (int64_t)k0 * K + row);
+        b = __ldg(p.w[l] + (int64_t)(k0 + 1) * K + row);
+      }
+      pk[j] = pack_bf16x2(a, b);
+    }
+    *reinterpret_cast<uint4*>(dst + (int64_t)i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+static __global__ void zero_u64_kernel(unsigned long long* p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0ull;
+}
+
+// ------------------------------------------------------------------ helpers
+template <int ACT>
+__device__ __forceinline__ float act_t(float z) {
+  if (ACT == PCC_ACT_RELU) return fmaxf(z, 0.f);
+  if (ACT == PCC_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+  if (ACT == PCC_ACT_SILU) return z / (1.f + __expf(-z));
+  return z;
+}
+
+__device__ __forceinline__ uint32_t float_ordered(float v) {
+  uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_float(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  return __uint_as_float(b);
+}
+
+
+template <int ACT>
+__device__ __forceinline__ float act_grad_t(float z) {
+  if (ACT == PCC_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (ACT == PCC_ACT_GELU) {
+    const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * z * z);
+    return cdf + z * pdf;
+  }
+  if (ACT == PCC_ACT_SILU) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+  }
+  return 1.f;
+}
+
+int check_phi_desc(const pcc_phi_desc* d, const char* where);
+int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n);
+
+}  // namespace pcc

@@ -13,80 +13,9 @@
 //   mbarrier ring with cp.async.bulk (TMA engine).
 // Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 bulk-copy
 // producer, warp 5 TMEM allocator + MMA issuer (one elected thread).
-#include "pcc_common.cuh"
-#include "pcc_tc.cuh"
+#include "pcc_fused.cuh"
 
 namespace pcc {
-using namespace tc;
-
-constexpr int kMaxLayers = 6;
-constexpr int kTileM = 128;
-constexpr int kRing = 8;        // weight slabs in flight
-constexpr int kThreads = 192;   // 4 epilogue warps + producer warp + MMA warp
-constexpr int kK0 = 16;         // layer-0 K padded to one UMMA K step
-
-struct PhiParams {
-  const float* x;
-  const int64_t* offsets;
-  int64_t n, B, num_tiles;
-  int d, L, pooling, res_mask;
-  const uint8_t* wpack;          // packed bf16 weight blobs, all layers
-  uint32_t w_off[kMaxLayers];    // byte offset of layer l inside wpack
-  const float* bias[kMaxLayers];
-  void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
-};
-
-// ------------------------------------------------------------------ weight packing
-// W_l fp32 [H, K_l] (nn.Linear layout) -> blob [Kp/8][H][8] bf16, Kp = 16 for layer 0
-struct PackParams {
-  const float* w[kMaxLayers];
-  uint8_t* wpack;
-  uint32_t w_off[kMaxLayers];
-  int d, H, L;
-};
-__global__ void pack_weights_kernel(PackParams p) {
-  const int l = blockIdx.y;
-  if (l >= p.L) return;
-  const int K = (l == 0) ? p.d : p.H;
-  const int Kp = (l == 0) ? kK0 : p.H;
-  const int total = (Kp / 8) * p.H;  // one thread per 16-byte chunk
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.wpack + p.w_off[l]);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int kc = i / p.H, row = i % p.H;
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k0 = kc * 8 + 2 * j;
-      float a = (k0 < K) ? __ldg(p.w[l] + (int64_t)row * K + k0) : 0.f;
-      float b = (k0 + 1 < K) ? __ldg(p.w[l] + (int64_t)row * K + k0 + 1) : 0.f;
-      pk[j] = pack_bf16x2(a, b);
-    }
-    *reinterpret_cast<uint4*>(dst + (int64_t)i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
-}
-
-__global__ void zero_u64_kernel(unsigned long long* p, int64_t n) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0ull;
-}
-
-// ------------------------------------------------------------------ helpers
-template <int ACT>
-__device__ __forceinline__ float act_t(float z) {
-  if (ACT == PCC_ACT_RELU) return fmaxf(z, 0.f);
-  if (ACT == PCC_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
-  if (ACT == PCC_ACT_SILU) return z / (1.f + __expf(-z));
-  return z;
-}
-
-__device__ __forceinline__ uint32_t float_ordered(float v) {
-  uint32_t b = __float_as_uint(v);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float ordered_float(uint32_t o) {
-  uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-  return __uint_as_float(b);
-}
 
 struct SmemLayout {
   uint32_t bufA, bufX, ring, bias, bars, total;
@@ -390,9 +319,11 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t B) {
   return w;
 }
 
-static int check_desc(const pcc_phi_desc* d, const char* where) {
+int check_phi_desc(const pcc_phi_desc* d, const char* where) {
   if (!d) return fail(where, "null descriptor");
-  if (d->n_layers < 2 || d->n_layers > kMaxLayers) return fail(where, "fused path needs 2..6 phi layers");
+  // the backward chain keeps z of the last hidden layer in TMEM and recomputes only z_0, which
+  // covers phi = Linear(d,H) [+ one H x H hidden layer] + final Linear(H,H)
+  if (d->n_layers < 2 || d->n_layers > 3) return fail(where, "fused path needs 1 or 2 hidden phi layers (+ final Linear)");
   if (d->input_dim < 1 || d->input_dim > kK0) return fail(where, "fused path needs input_dim <= 16");
   if (d->hidden != 128 && d->hidden != 256) return fail(where, "fused path needs hidden width 128 or 256");
   if (d->act != PCC_ACT_RELU && d->act != PCC_ACT_GELU && d->act != PCC_ACT_SILU)
@@ -422,19 +353,19 @@ static int launch_fwd(const PhiParams& p, cudaStream_t st) {
 
 using namespace pcc;
 
-extern "C" int pcc_phi_fused_supported(const pcc_phi_desc* d) { return check_desc(d, __func__); }
+extern "C" int pcc_phi_fused_supported(const pcc_phi_desc* d) { return check_phi_desc(d, __func__); }
 
 extern "C" int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B) {
-  (void)n;
-  if (check_desc(d, __func__) != 0) return -1;
-  return ws_layout(d, B).total;
+  if (check_phi_desc(d, __func__) != 0) return -1;
+  const int64_t fwd = ws_layout(d, B).total, bwd = phi_bwd_workspace_bytes(d, n);
+  return fwd > bwd ? fwd : bwd;  // one query serves both directions
 }
 
 extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n,
                                          int64_t B, float* pooled, int32_t* argmax, void* ws, int device,
                                          void* stream) {
   PCC_ENTER(device);
-  if (check_desc(d, __func__) != 0) return -1;
+  if (check_phi_desc(d, __func__) != 0) return -1;
   PCC_REQUIRE(d->pooling != PCC_POOL_MAX || argmax != nullptr, "argmax buffer required for max pooling");
   PCC_REQUIRE(n < (int64_t)0x7fffffff, "row count exceeds int32 argmax range");
   cudaStream_t st = (cudaStream_t)stream;
@@ -472,10 +403,3 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   return check_launch(__func__);
 }
 
-extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n,
-                                         int64_t B, const float* dpooled, const int32_t* argmax, float* const* dw,
-                                         float* const* db, void* ws, int device, void* stream) {
-  (void)d; (void)x; (void)offsets; (void)n; (void)B; (void)dpooled; (void)argmax; (void)dw; (void)db; (void)ws;
-  (void)device; (void)stream;
-  return fail(__func__, "fused backward not built yet");
-}

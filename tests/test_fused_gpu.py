@@ -48,9 +48,10 @@ CASES = [
     ("relu", "max", False, 256, 2, 3, [1024, 1024, 1024]),
     ("relu", "max", False, 128, 2, 3, [100, 128, 129, 1, 300, 33]),
     ("gelu", "mean", True, 256, 2, 6, [33, 1, 200, 128, 129, 64, 7, 500]),
-    ("silu", "sum", True, 128, 3, 4, [31, 32, 33, 127, 128, 129, 1, 300]),
+    ("silu", "sum", True, 128, 2, 4, [31, 32, 33, 127, 128, 129, 1, 300]),
     ("relu", "sum", False, 256, 1, 3, [256, 100, 156]),
-    ("gelu", "max", True, 128, 4, 16, [700, 5, 250]),
+    ("gelu", "max", True, 128, 2, 16, [700, 5, 250]),
+    ("silu", "mean", False, 128, 1, 1, [64, 64]),
 ]
 
 
@@ -119,3 +120,37 @@ def test_fused_large_config2_properties():
         pooled = FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
         ref = m._mlp(m._phi_plan, x).view(B, N, -1).max(dim=1)[0]   # fp32 CUDA path
     assert rel_err(pooled, ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("act,pool,res,H,depth,d,sizes", CASES)
+def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
+    """forward + BCEWithLogitsLoss + backward through the fused kernels vs the fp32 oracle."""
+    cfg = _cfg(act, pool, res, H, depth, d)
+    sd = O.init_state_dict(cfg, seed=51)
+    x, idx = ragged_batch(sizes, d, seed=52)
+    y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(53)) > 0.5).float()
+    ref_logits, ref_loss, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    logits = m(x.cuda(), idx.cuda())
+    assert m.last_path == "fused-bf16"
+    loss = torch.nn.BCEWithLogitsLoss()(logits, y.cuda())
+    loss.backward()
+    assert rel_err(logits, ref_logits) < BF16_TOL
+    worst = 0.0
+    for k, ref in ref_grads.items():
+        got = dict(m.named_parameters())[k].grad
+        assert got is not None, k
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        assert e < BF16_TOL, (k, e)
+    print(f"fused train {act}/{pool}/res={res}/H={H}/depth={depth}: logits {rel_err(logits, ref_logits):.2e} worst grad {worst:.2e}")
+
+
+def test_deeper_phi_falls_back_to_fp32_path():
+    cfg = _cfg("relu", "max", False, 128, 3, 3)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    assert not m.fused_supported()
+    x, idx = ragged_batch([50, 60], 3, seed=1)
+    m(x.cuda(), idx.cuda()).sum().backward()
+    assert m.last_path == "fp32"
