@@ -159,6 +159,15 @@ int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, int device, void* stream);
 
+/* ---- accounting / measurement helpers used by bench.py.
+ *      pcc_launch_count: kernels launched by this library since the last reset.
+ *      pcc_prof_*: CUDA-event brackets around the three fused kernels, recorded on the launching
+ *      stream (slot 0 = phi+pool forward, 1 = backward chain, 2 = wgrad).  Not for use under CUDA
+ *      graph capture. */
+int64_t pcc_launch_count(int reset);
+int pcc_prof_enable(int on);
+int pcc_prof_read(int slot, double* ms_total, int64_t* count);
+
 /* ---- diagnostics: one-CTA tcgen05 GEMM on integer data, out[128,64] fp32.
  *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
  *      (wgrad).  Expected values: tests/test_fused_gpu.py. */

@@ -99,23 +99,25 @@ def segment_pool(phi_x: torch.Tensor, offsets: torch.Tensor, pooling: str
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """deep_sets.py:96-106.  Returns (pooled[B,H], argmax[B,H] global row ids or None)."""
     B = offsets.numel() - 1
-    H = phi_x.shape[1]
-    pooled = phi_x.new_empty((B, H))
-    arg = torch.empty((B, H), dtype=torch.int64) if pooling == "max" else None
-    for b in range(B):
-        s, e = int(offsets[b]), int(offsets[b + 1])
-        chunk = phi_x[s:e]
-        n = e - s
+    if pooling not in POOLS:
+        raise ValueError("pooling must be 'mean', 'sum', or 'max'")
+    counts = (offsets[1:] - offsets[:-1]).tolist()
+    chunks = torch.split(phi_x, counts, dim=0)
+    pooled_list, arg_list = [], []
+    start = 0
+    for chunk in chunks:
+        n = chunk.size(0)
         if pooling == "sum":
-            pooled[b] = chunk.sum(dim=0) / torch.sqrt(torch.tensor(n, dtype=chunk.dtype))
+            pooled_list.append(chunk.sum(dim=0) / torch.sqrt(torch.tensor(n, dtype=chunk.dtype)))
         elif pooling == "mean":
-            pooled[b] = chunk.mean(dim=0)
-        elif pooling == "max":
-            v, i = chunk.max(dim=0)  # first occurrence on ties
-            pooled[b] = v
-            arg[b] = i + s
+            pooled_list.append(chunk.mean(dim=0))
         else:
-            raise ValueError("pooling must be 'mean', 'sum', or 'max'")
+            v, i = chunk.max(dim=0)  # first occurrence on ties
+            pooled_list.append(v)
+            arg_list.append(i + start)
+        start += n
+    pooled = torch.stack(pooled_list)
+    arg = torch.stack(arg_list) if pooling == "max" else None
     return pooled, arg
 
 

@@ -11,6 +11,20 @@
 namespace pcc {
 
 void set_error(const std::string& msg);
+void note_launch(int kernels);  // launch accounting (pcc_launch_count)
+
+// CUDA-event bracket around one of the big fused kernels (pcc_prof_*); no-op unless enabled.
+// Not usable while the stream is being captured into a CUDA graph.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(int slot, cudaStream_t st);
+  ~ProfScope();
+};
+
+// kernel launch with accounting: PCC_K(kernel<...>)<<<grid, block, smem, stream>>>(args)
+#define PCC_K(...) (pcc::note_launch(1), (__VA_ARGS__))
 
 struct DeviceGuard {
   int prev = -1;

@@ -133,13 +133,13 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   p.atomic = split > 1 ? 1 : 0;
   if (cfg == 0) {
     dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
-    sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
   } else if (cfg == 1) {
     dim3 grid((unsigned)cdiv(p.N, 64), (unsigned)cdiv(p.M, 64), (unsigned)split);
-    sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
-    sgemm_kernel<32, 32, 32, 4, 4, A_T, B_T><<<grid, 64, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_kernel<32, 32, 32, 4, 4, A_T, B_T><<<grid, 64, 0, st>>>(p);
   }
   return 0;
 }
@@ -370,8 +370,8 @@ extern "C" int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw,
   PCC_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) {
-    zero_f32_kernel<<<(unsigned)cdiv(N * K, 256), 256, 0, st>>>(dw, N * K);
-    if (db) zero_f32_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(db, N);
+    PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N * K, 256), 256, 0, st>>>(dw, N * K);
+    if (db) PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(db, N);
   }
   if (M > 0) {
     GemmArgs p{};  // dw[N,K] = dy^T[N,M] * x[M,K]  (reduction over M)
@@ -380,7 +380,7 @@ extern "C" int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw,
     launch_gemm<true, false>(p, 2, st);
     if (db) {
       dim3 grid((unsigned)cdiv(N, 256), (unsigned)cdiv(M, 128));
-      colsum_kernel<<<grid, 256, 0, st>>>(dy, M, N, db);
+      PCC_K(colsum_kernel)<<<grid, 256, 0, st>>>(dy, M, N, db);
     }
   }
   return check_launch(__func__);
@@ -390,7 +390,7 @@ extern "C" int pcc_act_bwd(const float* dy, const float* z, float* dz, int64_t c
                            void* stream) {
   PCC_ENTER(device);
   if (count == 0) return 0;
-  act_bwd_kernel<<<ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, count, act);
+  PCC_K(act_bwd_kernel)<<<ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, count, act);
   return check_launch(__func__);
 }
 
@@ -399,7 +399,7 @@ extern "C" int pcc_layernorm_fwd(const float* z, const float* gamma, const float
                                  int device, void* stream) {
   PCC_ENTER(device);
   if (M == 0) return 0;
-  layernorm_fwd_kernel<<<(unsigned)cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, residual, y, mean,
+  PCC_K(layernorm_fwd_kernel)<<<(unsigned)cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, residual, y, mean,
                                                                                  rstd, M, H, act, eps);
   return check_launch(__func__);
 }
@@ -411,7 +411,7 @@ extern "C" int pcc_layernorm_bwd(const float* dy, const float* z, const float* g
   if (M == 0) return 0;
   PCC_REQUIRE(H <= 4096, "LayerNorm width > 4096 unsupported");
   const int rows_per_block = 64;
-  layernorm_bwd_kernel<<<(unsigned)cdiv(M, rows_per_block), 256, 2 * H * sizeof(float), (cudaStream_t)stream>>>(
+  PCC_K(layernorm_bwd_kernel)<<<(unsigned)cdiv(M, rows_per_block), 256, 2 * H * sizeof(float), (cudaStream_t)stream>>>(
       dy, z, gamma, beta, mean, rstd, dz, dgamma, dbeta, M, H, act, rows_per_block);
   return check_launch(__func__);
 }
@@ -425,14 +425,14 @@ extern "C" int pcc_batchnorm_fwd_train(const float* x, const float* gamma, const
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned cb = (unsigned)cdiv(C, 256);
   dim3 grid(cb, (unsigned)cdiv(n, 256));
-  zero_f32_kernel<<<cb, 256, 0, st>>>(save_mean, C);
-  zero_f32_kernel<<<cb, 256, 0, st>>>(save_invstd, C);
-  bn_colsum_kernel<<<grid, 256, 0, st>>>(x, n, C, nullptr, save_mean);
-  bn_mean_finalize_kernel<<<cb, 256, 0, st>>>(save_mean, C, 1.f / (float)n);
-  bn_colsum_kernel<<<grid, 256, 0, st>>>(x, n, C, save_mean, save_invstd);  // holds ssq until finalize
-  bn_var_finalize_kernel<<<cb, 256, 0, st>>>(save_mean, save_invstd, save_invstd, running_mean, running_var, C, n,
+  PCC_K(zero_f32_kernel)<<<cb, 256, 0, st>>>(save_mean, C);
+  PCC_K(zero_f32_kernel)<<<cb, 256, 0, st>>>(save_invstd, C);
+  PCC_K(bn_colsum_kernel)<<<grid, 256, 0, st>>>(x, n, C, nullptr, save_mean);
+  PCC_K(bn_mean_finalize_kernel)<<<cb, 256, 0, st>>>(save_mean, C, 1.f / (float)n);
+  PCC_K(bn_colsum_kernel)<<<grid, 256, 0, st>>>(x, n, C, save_mean, save_invstd);  // holds ssq until finalize
+  PCC_K(bn_var_finalize_kernel)<<<cb, 256, 0, st>>>(save_mean, save_invstd, save_invstd, running_mean, running_var, C, n,
                                              momentum, eps);
-  bn_apply_kernel<<<ew_blocks(n * C), 256, 0, st>>>(x, gamma, beta, save_mean, save_invstd, y, n * C, C, eps, 0);
+  PCC_K(bn_apply_kernel)<<<ew_blocks(n * C), 256, 0, st>>>(x, gamma, beta, save_mean, save_invstd, y, n * C, C, eps, 0);
   return check_launch(__func__);
 }
 
@@ -441,7 +441,7 @@ extern "C" int pcc_batchnorm_fwd_eval(const float* x, const float* gamma, const 
                                       int64_t C, float eps, int device, void* stream) {
   PCC_ENTER(device);
   if (n == 0) return 0;
-  bn_apply_kernel<<<ew_blocks(n * C), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, running_mean, running_var, y,
+  PCC_K(bn_apply_kernel)<<<ew_blocks(n * C), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, running_mean, running_var, y,
                                                                         n * C, C, eps, 1);
   return check_launch(__func__);
 }
@@ -453,11 +453,11 @@ extern "C" int pcc_batchnorm_bwd(const float* dy, const float* x, const float* g
   PCC_REQUIRE(n > 0, "BatchNorm1d backward needs at least one row");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned cb = (unsigned)cdiv(C, 256);
-  zero_f32_kernel<<<cb, 256, 0, st>>>(dgamma, C);
-  zero_f32_kernel<<<cb, 256, 0, st>>>(dbeta, C);
+  PCC_K(zero_f32_kernel)<<<cb, 256, 0, st>>>(dgamma, C);
+  PCC_K(zero_f32_kernel)<<<cb, 256, 0, st>>>(dbeta, C);
   dim3 grid(cb, (unsigned)cdiv(n, 256));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, x, save_mean, save_invstd, n, C, dgamma, dbeta);
-  bn_bwd_apply_kernel<<<ew_blocks(n * C), 256, 0, st>>>(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, n * C,
+  PCC_K(bn_bwd_reduce_kernel)<<<grid, 256, 0, st>>>(dy, x, save_mean, save_invstd, n, C, dgamma, dbeta);
+  PCC_K(bn_bwd_apply_kernel)<<<ew_blocks(n * C), 256, 0, st>>>(dy, x, gamma, save_mean, save_invstd, dgamma, dbeta, dx, n * C,
                                                         C, 1.f / (float)n);
   return check_launch(__func__);
 }

@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         }
         mbar_arrive(&empty[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
-        if (l >= 1) {  // the input blob slot is only read by the tensor core
+        if (l >= 1) {  // the input blob slot is only read by the tensor core; wait for THIS use of the slot
+          // to be filled before releasing it, otherwise the arrival could land in the previous phase
+          mbar_wait(&full[stage], phase);
           mbar_arrive(&empty[stage]);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
         }
@@ -544,7 +546,10 @@ static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
   auto kern = phi_bwd_chain_kernel<H, ACT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
-  kern<<<grid, kThreads, lay.total, st>>>(p);
+  {
+    ProfScope prof(1, st);
+    PCC_K(kern)<<<grid, kThreads, lay.total, st>>>(p);
+  }
   return 0;
 }
 template <int H>
@@ -553,7 +558,10 @@ static int launch_wgrad(const BwdParams& p, int grid, cudaStream_t st) {
   auto kern = phi_wgrad_kernel<H>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
-  kern<<<grid, kThreads, smem_bytes, st>>>(p);
+  {
+    ProfScope prof(2, st);
+    PCC_K(kern)<<<grid, kThreads, smem_bytes, st>>>(p);
+  }
   return 0;
 }
 
@@ -577,8 +585,8 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (tiles == 0) {
     for (int l = 0; l < L; ++l) {
       const int64_t cnt = (int64_t)H * (l == 0 ? d->input_dim : H);
-      zero_f32_kernel_b<<<(unsigned)cdiv(cnt, 256), 256, 0, st>>>(dw[l], cnt);
-      zero_f32_kernel_b<<<(unsigned)cdiv(H, 256), 256, 0, st>>>(db[l], H);
+      PCC_K(zero_f32_kernel_b)<<<(unsigned)cdiv(cnt, 256), 256, 0, st>>>(dw[l], cnt);
+      PCC_K(zero_f32_kernel_b)<<<(unsigned)cdiv(H, 256), 256, 0, st>>>(db[l], H);
     }
     return check_launch(__func__);
   }
@@ -586,7 +594,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   PackParams pk{};
   for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = wl.w_off[l]; pk.wt_off[l] = wl.wt_off[l]; }
   pk.wpack = wsb; pk.d = d->input_dim; pk.H = H; pk.L = L;
-  pack_weights_kernel<<<dim3(32, L, 2), 256, 0, st>>>(pk);
+  PCC_K(pack_weights_kernel)<<<dim3(32, L, 2), 256, 0, st>>>(pk);
 
   BwdParams p{};
   p.x = x; p.offsets = offsets; p.n = n; p.B = B; p.num_tiles = tiles;
@@ -613,7 +621,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   for (int l = 0; l < L; ++l) {
     const int K = (l == 0) ? d->input_dim : H, Kp = (l == 0) ? kK0 : H;
-    wgrad_reduce_kernel<<<(unsigned)cdiv((int64_t)H * K + H, 256), 256, 0, st>>>(p.part_w[l], p.part_b[l], wl.grid, H,
+    PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv((int64_t)H * K + H, 256), 256, 0, st>>>(p.part_w[l], p.part_b[l], wl.grid, H,
                                                                                 Kp, K, dw[l], db[l]);
   }
   return check_launch(__func__);

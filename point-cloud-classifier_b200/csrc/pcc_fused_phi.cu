@@ -345,7 +345,10 @@ static int launch_fwd(const PhiParams& p, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
-  kern<<<grid, kThreads, lay.total, st>>>(p);
+  {
+    ProfScope prof(0, st);
+    PCC_K(kern)<<<grid, kThreads, lay.total, st>>>(p);
+  }
   return 0;
 }
 
@@ -376,8 +379,8 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   PackParams pk{};
   for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = wl.w_off[l]; }
   pk.wpack = wsb; pk.d = d->input_dim; pk.H = H; pk.L = L;
-  pack_weights_kernel<<<dim3(32, L), 256, 0, st>>>(pk);
-  if (B * H > 0) zero_u64_kernel<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>((unsigned long long*)(wsb + wl.pool_off), B * H);
+  PCC_K(pack_weights_kernel)<<<dim3(32, L), 256, 0, st>>>(pk);
+  if (B * H > 0) PCC_K(zero_u64_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>((unsigned long long*)(wsb + wl.pool_off), B * H);
 
   PhiParams p{};
   p.x = x; p.offsets = offsets; p.n = n; p.B = B; p.num_tiles = cdiv(n, kTileM);
@@ -398,7 +401,7 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
     if (rc != 0) return rc;
   }
   if (B * H > 0)
-    pool_finalize_kernel<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>(wsb + wl.pool_off, offsets, d->b[L - 1], B, H,
+    PCC_K(pool_finalize_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>(wsb + wl.pool_off, offsets, d->b[L - 1], B, H,
                                                                      d->pooling, pooled, argmax);
   return check_launch(__func__);
 }

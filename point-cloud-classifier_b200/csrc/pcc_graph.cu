@@ -273,13 +273,13 @@ extern "C" int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t*
   cudaStream_t st = (cudaStream_t)stream;
   int64_t* scan_ws = (int64_t*)ws;
   unsigned long long* cursor = (unsigned long long*)(scan_ws + cdiv(n + 1, 1024) + 4);
-  csr_zero_kernel<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(rowptr, n + 1);
-  if (E > 0) csr_count_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, (unsigned long long*)rowptr);
+  PCC_K(csr_zero_kernel)<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(rowptr, n + 1);
+  if (E > 0) PCC_K(csr_count_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, (unsigned long long*)rowptr);
   exclusive_scan_i64(rowptr, n + 1, scan_ws, st);
   if (E > 0 && n > 0) {
-    csr_copy_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr, cursor, n);
-    csr_fill_kernel<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, cursor, perm);
-    csr_sort_rows_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(rowptr, perm, n);
+    PCC_K(csr_copy_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr, cursor, n);
+    PCC_K(csr_fill_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, cursor, perm);
+    PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(rowptr, perm, n);
   }
   return check_launch(__func__);
 }
@@ -295,10 +295,10 @@ extern "C" int pcc_graph_aggregate_fwd(const float* x, const int64_t* src, const
   const int tpn = threads_per_node(C, vec4);
   const unsigned grid = (unsigned)cdiv(n, 256 / tpn);
   if (vec4)
-    graph_aggregate_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
+    pcc::note_launch(1), graph_aggregate_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
                                                                              out, arg_edge);
   else
-    graph_aggregate_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
+    pcc::note_launch(1), graph_aggregate_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, src, w, rowptr, perm, n, C, aggr, tpn,
                                                                               out, arg_edge);
   return check_launch(__func__);
 }
@@ -315,10 +315,10 @@ extern "C" int pcc_graph_aggregate_bwd(const float* g, const int64_t* dst, const
   const int tpn = threads_per_node(C, vec4);
   const unsigned grid = (unsigned)cdiv(n, 256 / tpn);
   if (vec4)
-    graph_aggregate_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
+    pcc::note_launch(1), graph_aggregate_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
                                                                              rowptr_dst, arg_edge, n, C, aggr, tpn, dx);
   else
-    graph_aggregate_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
+    pcc::note_launch(1), graph_aggregate_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, dst, w, rowptr_src, perm_src,
                                                                               rowptr_dst, arg_edge, n, C, aggr, tpn, dx);
   return check_launch(__func__);
 }
@@ -331,7 +331,7 @@ extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offs
   if (n == 0) return 0;
   constexpr int QW = 4;
   const int64_t warps = cdiv(n, QW);
-  knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  pcc::note_launch(1), knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
   return check_launch(__func__);
 }
 
@@ -339,6 +339,6 @@ extern "C" int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge
   PCC_ENTER(device);
   const int64_t total = n * k;
   if (total == 0) return 0;
-  knn_edges_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(nbr, total, k, edge_index);
+  PCC_K(knn_edges_kernel)<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(nbr, total, k, edge_index);
   return check_launch(__func__);
 }

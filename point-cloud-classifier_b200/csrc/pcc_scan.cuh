@@ -68,13 +68,13 @@ static __global__ void __launch_bounds__(1024) scan_add_kernel(int64_t* data, in
 // in-place exclusive scan of data[count]; ws must hold cdiv(count,1024) int64
 inline void exclusive_scan_i64(int64_t* data, int64_t count, int64_t* ws, cudaStream_t st) {
   if (count <= 4096) {
-    exclusive_scan_single_block_kernel<<<1, 1024, 0, st>>>(data, count);
+    PCC_K(exclusive_scan_single_block_kernel)<<<1, 1024, 0, st>>>(data, count);
     return;
   }
   int64_t chunks = cdiv(count, 1024);
-  scan_chunks_kernel<<<(unsigned)chunks, 1024, 0, st>>>(data, count, ws);
-  exclusive_scan_single_block_kernel<<<1, 1024, 0, st>>>(ws, chunks);
-  scan_add_kernel<<<(unsigned)chunks, 1024, 0, st>>>(data, count, ws);
+  PCC_K(scan_chunks_kernel)<<<(unsigned)chunks, 1024, 0, st>>>(data, count, ws);
+  PCC_K(exclusive_scan_single_block_kernel)<<<1, 1024, 0, st>>>(ws, chunks);
+  PCC_K(scan_add_kernel)<<<(unsigned)chunks, 1024, 0, st>>>(data, count, ws);
 }
 
 }  // namespace pcc

@@ -149,20 +149,20 @@ extern "C" int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int
   PCC_REQUIRE(n >= 0 && B >= 0, "negative size");
   PCC_REQUIRE(B + 1 <= (int64_t)PCC_SCAN_SINGLE_MAX, "too many segments for the single-block scan");
   cudaStream_t st = (cudaStream_t)stream;
-  zero_i64_kernel<<<(unsigned)cdiv(B + 1, 256), 256, 0, st>>>(offsets, B + 1);
+  PCC_K(zero_i64_kernel)<<<(unsigned)cdiv(B + 1, 256), 256, 0, st>>>(offsets, B + 1);
   if (n > 0)
-    histogram_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(idx, n, B, (unsigned long long*)offsets);
-  exclusive_scan_single_block_kernel<<<1, 1024, 0, st>>>(offsets, B + 1);
+    PCC_K(histogram_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(idx, n, B, (unsigned long long*)offsets);
+  PCC_K(exclusive_scan_single_block_kernel)<<<1, 1024, 0, st>>>(offsets, B + 1);
   return check_launch(__func__);
 }
 
 extern "C" int pcc_index_max(const int64_t* idx, int64_t n, int64_t* out_max, int device, void* stream) {
   PCC_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
-  set_i64_kernel<<<1, 1, 0, st>>>((long long*)out_max, -1);
+  PCC_K(set_i64_kernel)<<<1, 1, 0, st>>>((long long*)out_max, -1);
   if (n > 0) {
     int blocks = (int)(cdiv(n, 256) < 592 ? cdiv(n, 256) : 592);
-    index_max_kernel<<<blocks, 256, 0, st>>>(idx, n, (long long*)out_max);
+    PCC_K(index_max_kernel)<<<blocks, 256, 0, st>>>(idx, n, (long long*)out_max);
   }
   return check_launch(__func__);
 }
@@ -175,7 +175,7 @@ extern "C" int pcc_segment_pool_fwd(const float* x, const int64_t* offsets, int6
   PCC_REQUIRE(n < (int64_t)0x7fffffff, "row count exceeds int32 argmax range");
   if (B == 0 || H == 0) return 0;
   dim3 grid((unsigned)B, (unsigned)cdiv(H, 32));
-  segment_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, offsets, H, pooling, pooled, argmax);
+  PCC_K(segment_pool_fwd_kernel)<<<grid, 256, 0, (cudaStream_t)stream>>>(x, offsets, H, pooling, pooled, argmax);
   return check_launch(__func__);
 }
 
@@ -185,7 +185,7 @@ extern "C" int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets
   PCC_REQUIRE(pooling >= PCC_POOL_SUM && pooling <= PCC_POOL_ADD, "bad pooling id");
   PCC_REQUIRE(pooling != PCC_POOL_MAX || argmax != nullptr, "argmax buffer required for max pooling");
   if (n == 0 || H == 0) return 0;
-  segment_pool_bwd_kernel<<<(unsigned)cdiv(n, 32), 256, 0, (cudaStream_t)stream>>>(dpooled, offsets, argmax, n, B, H,
+  PCC_K(segment_pool_bwd_kernel)<<<(unsigned)cdiv(n, 32), 256, 0, (cudaStream_t)stream>>>(dpooled, offsets, argmax, n, B, H,
                                                                                      pooling, dx);
   return check_launch(__func__);
 }

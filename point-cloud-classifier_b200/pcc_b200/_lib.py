@@ -49,13 +49,16 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_launch_count": [_i32],
+    "pcc_prof_enable": [_i32],
+    "pcc_prof_read": [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "pcc_selftest_umma": [_i32, _vp, _i32, _vp],
     "pcc_phi_fused_supported": [C.POINTER(PhiDesc)],
     "pcc_phi_fused_workspace_bytes": [C.POINTER(PhiDesc), _i64, _i64],
     "pcc_deepsets_phi_pool_fwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp],
     "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
-_RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64}
+_RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64}
 EXPORTS = tuple(_SIGS) + ("pcc_last_error",)
 
 _lib = None

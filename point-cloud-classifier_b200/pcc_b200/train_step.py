@@ -1,0 +1,88 @@
+"""CUDA-graph captured training step for the drop-in modules.
+
+The reference trains with an eager python loop (/root/reference/models/wrapper.py:51-74:
+forward, BCEWithLogitsLoss, zero_grad, backward, optimizer.step, loss.item()).  On a B200
+the fused kernels finish a step in a few hundred microseconds, so python / launch
+overhead would dominate.  `GraphedTrainStep` captures forward + loss + backward
+(+ gradient all-reduce + optimizer) of a fixed-shape batch once and replays it; new
+batches are copied into static device buffers (from pinned host memory when given host
+tensors).  Shapes are static per instance; build one instance per batch shape (sweep.py
+instantiates many shapes in one process).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GraphedTrainStep:
+    def __init__(self, model: torch.nn.Module, example_inputs: Sequence[torch.Tensor], example_target: torch.Tensor,
+                 loss_fn: Optional[Callable] = None, forward_kwargs: Optional[dict] = None,
+                 optimizer: Optional[torch.optim.Optimizer] = None, allreduce: bool = False, warmup: int = 3,
+                 use_graph: bool = True):
+        self.model, self.optimizer = model, optimizer
+        self.loss_fn = loss_fn or torch.nn.BCEWithLogitsLoss()  # wrapper.py:38
+        self.kw = dict(forward_kwargs or {})
+        self.allreduce = allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.allreduce else 1
+        self.static_in = [t.clone() for t in example_inputs]
+        self.static_y = example_target.clone()
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = None
+        self.graph = None
+        self.loss = None
+        self.logits = None
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if use_graph:
+            for p in self.params:
+                p.grad = None
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            torch.cuda.synchronize()
+
+    # one training step on the static buffers
+    def _step_body(self):
+        for p in self.params:
+            p.grad = None
+        self.logits = self.model(*self.static_in, **self.kw)
+        self.loss = self.loss_fn(self.logits, self.static_y)
+        self.loss.backward()
+        if self.allreduce:
+            # one flat fp32 bucket, averaged (loss is a mean over the local batch)
+            grads = [p.grad for p in self.params]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.mul_(1.0 / self.world)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        if self.optimizer is not None:
+            self.optimizer.step()
+
+    def load(self, inputs: Sequence[torch.Tensor], target: torch.Tensor):
+        """copy a batch (host pinned or device tensors) into the static buffers"""
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.static_y.copy_(target, non_blocking=True)
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        return self.loss
+
+    def step(self, inputs: Sequence[torch.Tensor], target: torch.Tensor) -> torch.Tensor:
+        self.load(inputs, target)
+        return self.run()

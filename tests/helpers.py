@@ -37,3 +37,10 @@ def ragged_batch(sizes, d, seed, device="cpu"):
     x = torch.randn(n, d, generator=g)
     idx = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
     return x.to(device), idx.to(device)
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a-b||_F / ||b||_F — robust to the isolated flips (argmax / relu mask) that a change of
+    operand precision causes."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))

@@ -1,11 +1,16 @@
 """GPU: the fused tcgen05 / TMEM phi+pool path (bf16 operands, fp32 accumulate).
 
 Stated bf16 tolerance (north_star "or a stated bf16 tolerance"): operands are rounded to
-bf16 (8-bit mantissa) before every tensor-core contraction, so pooled features, logits
-and gradients are compared against the fp32 oracle with
-    max|got - ref| <= BF16_TOL * max|ref|,   BF16_TOL = 3e-2
-(measured errors are printed; typical 3e-3..1e-2).  Pool argmax rows must agree with the
-fp32 oracle wherever the oracle's top-2 gap exceeds the same tolerance.
+bf16 (8-bit mantissa) before every tensor-core contraction.  Forward values (pooled
+features, logits) are compared against the fp32 oracle with
+    max|got - ref| <= BF16_TOL * max|ref|,   BF16_TOL = 3e-2      (measured: 1e-3..4e-3)
+and parameter gradients with the relative Frobenius error
+    ||got - ref||_F <= BF16_GRAD_TOL * ||ref||_F,   BF16_GRAD_TOL = 2e-2   (measured: 2e-3..8e-3)
+(max-norm is not meaningful for gradients across precisions: one flipped relu mask or argmax
+row moves a single entry by O(1)).  Max pooling: a precision change can move an argmax between
+near-tied rows, so (a) argmax rows must lie in their set and be maximal in fp32 within
+BF16_TOL, with > 97 % identical to the fp32 oracle's, and (b) gradients are checked against
+an fp32 oracle evaluated with the SAME argmax rows the kernel selected.
 """
 import ctypes as C
 
@@ -13,7 +18,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ragged_batch, rel_err
+from helpers import ragged_batch, rel_err, rel_l2
 from oracle import deepsets_oracle as O
 
 import pcc_b200
@@ -21,6 +26,7 @@ from pcc_b200 import _lib, functional as PF, fused as FZ
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 3e-2
+BF16_GRAD_TOL = 2e-2
 
 
 def _st_a(i, k):
@@ -104,7 +110,7 @@ def test_fused_argmax_consistent_with_fp32_oracle():
     assert float(gap) < BF16_TOL                            # picked rows are (near-)maximal in fp32 too
     agree = (arg == aux["argmax"]).float().mean()
     print(f"argmax agreement with fp32 oracle: {float(agree):.3f}")
-    assert float(agree) > 0.7
+    assert float(agree) > 0.97
 
 
 def test_fused_large_config2_properties():
@@ -122,6 +128,32 @@ def test_fused_large_config2_properties():
     assert rel_err(pooled, ref) < BF16_TOL
 
 
+def _fused_argmax(m, x, off, act):
+    """argmax rows the fused forward selects (deterministic: packed atomicMax is order independent)."""
+    dsc = FZ._build_desc(m._phi_plan, act, "max", [(L["lin"].weight, L["lin"].bias) for L in m._phi_plan])
+    n, B, H = x.shape[0], off.numel() - 1, dsc.hidden
+    ws = torch.empty(_lib.call("pcc_phi_fused_workspace_bytes", C.byref(dsc), n, B), dtype=torch.uint8, device="cuda")
+    pooled = torch.empty(B, H, device="cuda")
+    arg = torch.empty(B, H, dtype=torch.int32, device="cuda")
+    _lib.call("pcc_deepsets_phi_pool_fwd", C.byref(dsc), _lib.ptr(x), _lib.ptr(off), n, B, _lib.ptr(pooled),
+              _lib.ptr(arg), _lib.ptr(ws), 0, _lib.stream_ptr(0))
+    return arg.cpu().long()
+
+
+def _oracle_step_with_argmax(sd, cfg, x, idx, y, arg):
+    """fp32 oracle train step with max pooling pinned to given argmax rows."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    phi = O.layer_plan("phi", cfg["input_dim"], list(cfg["phi_layers"]), cfg["phi_layers"][-1], False,
+                       cfg["residual_block"])
+    rho = O.layer_plan("rho", phi[-1]["out"], list(cfg["rho_layers"]), cfg["output_dim"], False, False)
+    phi_x = O.mlp_forward(leaves, phi, cfg["activation"], x)
+    pooled = phi_x[arg, torch.arange(phi_x.shape[1]).expand(arg.shape[0], -1)]
+    logits = O.mlp_forward(leaves, rho, cfg["activation"], pooled)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    return logits.detach(), {k: v.grad for k, v in leaves.items()}
+
+
 @pytest.mark.parametrize("act,pool,res,H,depth,d,sizes", CASES)
 def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
     """forward + BCEWithLogitsLoss + backward through the fused kernels vs the fp32 oracle."""
@@ -129,9 +161,14 @@ def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
     sd = O.init_state_dict(cfg, seed=51)
     x, idx = ragged_batch(sizes, d, seed=52)
     y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(53)) > 0.5).float()
-    ref_logits, ref_loss, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
     m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
     m.load_state_dict(sd)
+    if pool == "max":
+        off = PF.segment_offsets(idx.cuda(), len(sizes))
+        arg = _fused_argmax(m, x.cuda(), off, act)
+        ref_logits, ref_grads = _oracle_step_with_argmax(sd, cfg, x, idx, y, arg)
+    else:
+        ref_logits, _, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
     logits = m(x.cuda(), idx.cuda())
     assert m.last_path == "fused-bf16"
     loss = torch.nn.BCEWithLogitsLoss()(logits, y.cuda())
@@ -141,10 +178,28 @@ def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
     for k, ref in ref_grads.items():
         got = dict(m.named_parameters())[k].grad
         assert got is not None, k
-        e = rel_err(got, ref)
+        e = rel_l2(got, ref)
         worst = max(worst, e)
-        assert e < BF16_TOL, (k, e)
-    print(f"fused train {act}/{pool}/res={res}/H={H}/depth={depth}: logits {rel_err(logits, ref_logits):.2e} worst grad {worst:.2e}")
+        assert e < BF16_GRAD_TOL, (k, e)
+    print(f"fused train {act}/{pool}/res={res}/H={H}/depth={depth}: logits {rel_err(logits, ref_logits):.2e} "
+          f"worst grad rel-L2 {worst:.2e}")
+
+
+def test_fused_multi_tile_per_cta_backward():
+    """more tiles than SMs (several tiles per persistent CTA) through fwd + bwd, H=256"""
+    cfg = _cfg("relu", "mean", False, 256, 2, 3)
+    sd = O.init_state_dict(cfg, seed=61)
+    sizes = [1024] * 40
+    x, idx = ragged_batch(sizes, 3, seed=62)
+    y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(63)) > 0.5).float()
+    ref_logits, _, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    logits = m(x.cuda(), idx.cuda())
+    torch.nn.BCEWithLogitsLoss()(logits, y.cuda()).backward()
+    assert rel_err(logits, ref_logits) < BF16_TOL
+    for k, ref in ref_grads.items():
+        assert rel_l2(dict(m.named_parameters())[k].grad, ref) < BF16_GRAD_TOL, k
 
 
 def test_deeper_phi_falls_back_to_fp32_path():
