@@ -172,6 +172,9 @@ int pcc_prof_read(int slot, double* ms_total, int64_t* count);
  *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
  *      (wgrad).  Expected values: tests/test_fused_gpu.py. */
 int pcc_selftest_umma(int mode, float* out, int device, void* stream);
+/* optional event trace of CTA 0 of the fused forward kernel into a device buffer of 2*4096 int64
+ * (role, (id, clock64) pairs); NULL disables.  Development aid. */
+int pcc_debug_set_trace(void* device_buf);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,60 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmArgs p
   }
 }
 
+// Small problems (rho head, M = batch): 32x32 output tile per CTA, 256 threads (2x2 per thread),
+// so a 256x256x256 layer spreads over 64 CTAs with a short K loop instead of 4 long-running ones.
+template <bool A_T, bool B_T>
+__global__ void __launch_bounds__(256) sgemm_small_kernel(GemmArgs p) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * 32, n0 = (int64_t)blockIdx.x * 32;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_chunk;
+  const int64_t kend = (kbeg + p.k_chunk < p.K) ? kbeg + p.k_chunk : p.K;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int64_t k0 = kbeg; k0 < kend; k0 += 32) {
+#pragma unroll
+    for (int i = tid; i < 1024; i += 256) {
+      int m, k;
+      if (A_T) { m = i & 31; k = i >> 5; } else { m = i >> 5; k = i & 31; }
+      int64_t gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < p.M && gk < kend) ? (A_T ? __ldg(p.A + gk * p.lda + gm) : __ldg(p.A + gm * p.lda + gk)) : 0.f;
+      int n, kb;
+      if (B_T) { n = i >> 5; kb = i & 31; } else { n = i & 31; kb = i >> 5; }
+      int64_t gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < p.N && gkb < kend) ? (B_T ? __ldg(p.B + gn * p.ldb + gkb) : __ldg(p.B + gkb * p.ldb + gn)) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int64_t gm = m0 + ty + 16 * i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t gn = n0 + tx + 16 * j;
+      if (gn >= p.N) continue;
+      const int64_t o = gm * p.ldc + gn;
+      float v = acc[i][j];
+      if (p.atomic) { atomicAdd(p.C + o, v); continue; }
+      if (p.bias) v += __ldg(p.bias + gn);
+      if (p.pre_add) v += __ldg(p.pre_add + o);
+      if (p.z_out) p.z_out[o] = v;
+      v = act_fwd(p.act, v);
+      if (p.residual) v += __ldg(p.residual + o);
+      if (p.accumulate) v += p.C[o];
+      p.C[o] = v;
+    }
+  }
+}
+
 template <bool A_T, bool B_T>
 static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   if (p.M == 0 || p.N == 0) return 0;
@@ -116,6 +170,7 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
                             cdiv(p.M, 32) * cdiv(p.N, 32)};
   const int64_t min_mn = p.M < p.N ? p.M : p.N;
   int cfg = min_mn <= 32 ? 2 : (min_mn <= 64 ? 1 : 0);  // do not waste a big tile on a thin matrix
+  if (p.M * p.N <= 512 * 512) cfg = 2;                  // head-sized outputs: many small CTAs
   int64_t split = 1;
   if (want_split > 1) {
     // reduction-dominated (wgrad): spread K over ~2 waves of CTAs
@@ -139,7 +194,7 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
     pcc::note_launch(1), sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
-    pcc::note_launch(1), sgemm_kernel<32, 32, 32, 4, 4, A_T, B_T><<<grid, 64, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_small_kernel<A_T, B_T><<<grid, 256, 0, st>>>(p);
   }
   return 0;
 }

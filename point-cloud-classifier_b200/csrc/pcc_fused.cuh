@@ -8,9 +8,23 @@ using namespace tc;
 
 constexpr int kMaxLayers = 6;
 constexpr int kTileM = 128;
-constexpr int kRing = 8;        // weight slabs in flight
-constexpr int kThreads = 192;   // 4 epilogue warps + producer warp + MMA warp
 constexpr int kK0 = 16;         // layer-0 K padded to one UMMA K step
+constexpr int kEpiWarps = 8;    // epilogue warps: TMEM lane quarter = warp & 3, column group = warp >> 2
+constexpr int kProdWarp = 8;    // bulk-copy (TMA engine) producer
+constexpr int kMmaWarp = 9;     // TMEM allocator + tcgen05.mma issuer
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = kEpiWarps * 32;
+
+// Operand images.  H x H layers and all activation / gradient tiles use the SWIZZLE_128B image
+// [C/64 slabs][R rows][64 elements] (pcc_tc.cuh); layer 0 (K = 16) keeps the un-swizzled
+// [2][R][8] image.  A slab of a weight image is R = H rows x 128 B and is the unit streamed
+// through the smem ring; an activation tile is R = 128 rows.
+__host__ __device__ constexpr uint32_t w_slab_bytes(int H) { return (uint32_t)H * 128u; }
+constexpr uint32_t kActSlab = kTileM * 128u;  // 16 KB: 128 rows x 64 features
+// byte offset of the 16-byte chunk holding columns [col0, col0+8) of row r in a 128-row SW128 image
+__device__ __forceinline__ uint32_t act_chunk_off(int r, int col0) {
+  return (uint32_t)(col0 >> 6) * kActSlab + (uint32_t)r * 128u + ((uint32_t)(((col0 & 63) >> 3) ^ (r & 7)) << 4);
+}
 
 struct PhiParams {
   const float* x;
@@ -21,10 +35,12 @@ struct PhiParams {
   uint32_t w_off[kMaxLayers];    // byte offset of layer l inside wpack
   const float* bias[kMaxLayers];
   void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
+  long long* trace;              // optional (debug): CTA 0 event timestamps, see trace_ev in pcc_fused_phi.cu
 };
 
 // ------------------------------------------------------------------ weight packing
-// W_l fp32 [H, K_l] (nn.Linear layout) -> blob [Kp/8][H][8] bf16, Kp = 16 for layer 0
+// W_l fp32 [H, K_l] (nn.Linear layout) -> bf16 operand image: layer 0 un-swizzled [2][H][8] (K padded
+// to 16), layers >= 1 SWIZZLE_128B [H/64 slabs][H rows][64]
 struct PackParams {
   const float* w[kMaxLayers];
   uint8_t* wpack;
@@ -59,7 +75,11 @@ static __global__ void pack_weights_kernel(PackParams p) {
       }
       pk[j] = pack_bf16x2(a, b);
     }
-    *reinterpret_cast<uint4*>(dst + (int64_t)i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    // chunk kc (8 K values) of row `row`
+    const uint32_t off = (l == 0) ? (uint32_t)i * 16u
+                                  : (uint32_t)(kc >> 3) * w_slab_bytes(p.H) + (uint32_t)row * 128u +
+                                        ((uint32_t)((kc & 7) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst) + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 

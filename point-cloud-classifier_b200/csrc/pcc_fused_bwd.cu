@@ -17,7 +17,7 @@
 
 namespace pcc {
 
-constexpr int kRingB = 5;  // weight slabs in flight in the chain kernel
+constexpr int kRingB = 3;  // weight slabs (K = 64, H rows) in flight in the chain kernel
 
 struct BwdParams {
   const float* x;
@@ -29,23 +29,21 @@ struct BwdParams {
   const float* bias[kMaxLayers];
   const float* dpooled;
   const int32_t* argmax;
-  uint8_t* stage_h[kMaxLayers];  // h_l blobs,  l = 0..L-2, [num_tiles][H/8][128][8] bf16
-  uint8_t* stage_g[kMaxLayers];  // dZ_l blobs, l = 0..L-1
+  uint8_t* stage_h[kMaxLayers];  // h_l images,  l = 0..L-2, [num_tiles] x SW128 [H/64][128][64] bf16
+  uint8_t* stage_g[kMaxLayers];  // dZ_l images, l = 0..L-1
   float* part_w[kMaxLayers];     // per-CTA partial dW_l [grid][H][K_l]  (K_0 = 16)
   float* part_b[kMaxLayers];     // per-CTA partial db_l [grid][H]
 };
 
 struct BwdSmem {
-  uint32_t bufG, bufH, bufX, ring, bias, bars, total;
+  uint32_t bufG, bufH, ring, bars, total;
 };
-__host__ __device__ inline BwdSmem bwd_smem(int H, int L) {
+__host__ __device__ inline BwdSmem bwd_smem(int H) {
   BwdSmem s;
   uint32_t o = 0;
-  s.bufG = o; o += kTileM * H * 2;
-  s.bufH = o; o += kTileM * H * 2;
-  s.bufX = o; o += kTileM * kK0 * 2;
-  s.ring = o; o += kRingB * (uint32_t)(64 * H);
-  s.bias = o; o += (uint32_t)L * H * 4;
+  s.bufG = o; o += kTileM * H * 2;   // dZ image (A operand of the dgrad GEMMs)
+  s.bufH = o; o += kTileM * H * 2;   // h image; its first 4 KB double as the layer-0 operand (x tile)
+  s.ring = o; o += kRingB * w_slab_bytes(H);
   s.bars = o; o += 256;
   s.total = o;
   return s;
@@ -54,13 +52,11 @@ __host__ __device__ inline BwdSmem bwd_smem(int H, int L) {
 // ====================================================================== K1: chain
 template <int H, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const BwdSmem lay = bwd_smem(H, p.L);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const BwdSmem lay = bwd_smem(H);
   uint8_t* bufG = smem + lay.bufG;
   uint8_t* bufH = smem + lay.bufH;
-  uint8_t* bufX = smem + lay.bufX;
   uint8_t* ring = smem + lay.ring;
-  float* biasS = reinterpret_cast<float*>(smem + lay.bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kRingB;
@@ -68,30 +64,31 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   uint64_t* acc_ready = bars + 2 * kRingB + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingB + 2);
 
-  constexpr uint32_t SLAB = 64 * H;
-  constexpr uint32_t A_LBO = kTileM * 16;
-  constexpr uint32_t W_LBO = H * 16;
+  constexpr uint32_t SLAB = w_slab_bytes(H);
+  constexpr uint32_t X_LBO = kTileM * 16;
+  constexpr uint32_t W0_LBO = H * 16;
   constexpr uint32_t BLOB = kTileM * H * 2;
+  constexpr int NSLAB = H / 64;
+  constexpr int NCHUNK = H / 32;
   constexpr uint32_t ACC_A = 0, ACC_B = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
   const bool recompute_z0 = (L >= 3);  // z_0 is overwritten by z_1 during the forward sweep
 
-  for (int i = threadIdx.x; i < L * H; i += kThreads) biasS[i] = __ldg(p.bias[i / H] + (i % H));
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, 128);
+    mbar_init(a_ready, kEpiThreads);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ===================== producer: weight slabs in consumption order
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -103,73 +100,90 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       };
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l <= L - 2; ++l) {
-          if (l == 0) push(p.wpack + p.w_off[0], (kK0 / 8) * W_LBO);
-          else for (int s = 0; s < H / 32; ++s) push(p.wpack + p.w_off[l] + (size_t)s * SLAB, SLAB);
+          if (l == 0) push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);
+          else for (int s = 0; s < NSLAB; ++s) push(p.wpack + p.w_off[l] + (size_t)s * SLAB, SLAB);
         }
         for (int l = L - 1; l >= 1; --l) {
-          for (int s = 0; s < H / 32; ++s) push(p.wpack + p.wt_off[l] + (size_t)s * SLAB, SLAB);
-          if (l == 1 && recompute_z0) push(p.wpack + p.w_off[0], (kK0 / 8) * W_LBO);
+          for (int s = 0; s < NSLAB; ++s) push(p.wpack + p.wt_off[l] + (size_t)s * SLAB, SLAB);
+          if (l == 1 && recompute_z0) push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc_bf16(128, H, 0, 0);
       uint32_t stage = 0, phase = 0, a_phase = 0;
-      const uint32_t g_base = smem_u32(bufG), h_base = smem_u32(bufH), x_base = smem_u32(bufX), r_base = smem_u32(ring);
-      // one GEMM: D[acc] (+)= act[128 x K] * slab-streamed blob^T, K = nslab * (2 or 1 K-steps)
-      auto gemm = [&](uint32_t act_base, uint32_t acc_col, int nslab, int ksteps, bool accumulate_first) {
-        for (int s = 0; s < nslab; ++s) {
+      const uint32_t g_base = smem_u32(bufG), h_base = smem_u32(bufH), r_base = smem_u32(ring);
+      // D[acc] (+)= act[128 x H] (SW128 image) * streamed weight image^T
+      auto gemm = [&](uint32_t act_base, uint32_t acc_col, bool accumulate_first) {
+        for (int s = 0; s < NSLAB; ++s) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t w_slab = r_base + stage * SLAB;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const int kglob = s * 2 + ks;
-            umma_bf16(tmem + acc_col, make_smem_desc(act_base + kglob * 2 * A_LBO, A_LBO, 128),
-                      make_smem_desc(w_slab + ks * 2 * W_LBO, W_LBO, 128), IDESC, (kglob > 0) || accumulate_first);
-          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem + acc_col, make_smem_desc_sw128_k(act_base + s * kActSlab + ks * 32),
+                      make_smem_desc_sw128_k(w_slab + ks * 32), IDESC, ((s | ks) != 0) || accumulate_first);
           umma_commit(&empty[stage]);
           if (++stage == kRingB) { stage = 0; phase ^= 1; }
         }
       };
+      // z_0 = x tile (un-swizzled image at the head of bufH) * W_0^T -> accA
+      auto gemm0 = [&]() {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        umma_bf16(tmem + ACC_A, make_smem_desc(h_base, X_LBO, 128), make_smem_desc(r_base + stage * SLAB, W0_LBO, 128),
+                  IDESC, 0);
+        umma_commit(&empty[stage]);
+        if (++stage == kRingB) { stage = 0; phase ^= 1; }
+      };
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l <= L - 2; ++l) {  // forward sweep: z_l -> accA
           mbar_wait(a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-          if (l == 0) gemm(x_base, ACC_A, 1, kK0 / 16, false);
-          else gemm(h_base, ACC_A, H / 32, 2, false);
+          if (l == 0) gemm0(); else gemm(h_base, ACC_A, false);
           umma_commit(acc_ready);
         }
         for (int l = L - 1; l >= 1; --l) {  // backward sweep: dH_{l-1} -> accB
           mbar_wait(a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-          const bool res = (p.res_mask >> l) & 1;
-          gemm(g_base, ACC_B, H / 32, 2, res);
-          if (l == 1 && recompute_z0) gemm(x_base, ACC_A, 1, kK0 / 16, false);
+          gemm(g_base, ACC_B, (p.res_mask >> l) & 1);
+          if (l == 1 && recompute_z0) gemm0();
           umma_commit(acc_ready);
         }
       }
     }
   } else {
-    // ===================== epilogue warps 0-3
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps 0-7
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t acc_phase = 0;
     const int d = p.d;
-    float xr[kK0];
+    float xcur[kK0], xnext[kK0];
     auto load_x = [&](int64_t tile) {
       const int64_t row = tile * kTileM + r;
 #pragma unroll
-      for (int j = 0; j < kK0; ++j) xr[j] = (j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
+      for (int j = 0; j < kK0; ++j)
+        xnext[j] = (grp == 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
+    };
+    auto stage_x = [&]() {  // x tile -> un-swizzled [2][128][8] image at the head of bufH
+      if (grp == 0) {
+        *reinterpret_cast<uint4*>(bufH + r * 16) = make_uint4(pack_bf16x2(xcur[0], xcur[1]), pack_bf16x2(xcur[2], xcur[3]),
+                                                              pack_bf16x2(xcur[4], xcur[5]), pack_bf16x2(xcur[6], xcur[7]));
+        *reinterpret_cast<uint4*>(bufH + X_LBO + r * 16) =
+            make_uint4(pack_bf16x2(xcur[8], xcur[9]), pack_bf16x2(xcur[10], xcur[11]), pack_bf16x2(xcur[12], xcur[13]),
+                       pack_bf16x2(xcur[14], xcur[15]));
+      }
     };
     // buffer hand-over with the bulk stores issued by thread 0
     auto acquire = [&]() {  // every earlier bulk store has finished reading its smem source
-      if (r == 0) bulk_wait_read0();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) bulk_wait_read0();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     auto store_blob = [&](uint8_t* gdst, const uint8_t* sbuf) {
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (r == 0) { bulk_s2g(gdst, sbuf, BLOB); bulk_commit(); }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) { bulk_s2g(gdst, sbuf, BLOB); bulk_commit(); }
     };
     auto wait_acc = [&]() { mbar_wait(acc_ready, acc_phase); acc_phase ^= 1; tc_fence_after(); };
     auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(a_ready); };
@@ -178,14 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t r0 = tile * kTileM;
       const int64_t row = r0 + r;
-      {
-        uint4 c0 = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]), pack_bf16x2(xr[4], xr[5]),
-                              pack_bf16x2(xr[6], xr[7]));
-        uint4 c1 = make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]), pack_bf16x2(xr[12], xr[13]),
-                              pack_bf16x2(xr[14], xr[15]));
-        *reinterpret_cast<uint4*>(bufX + r * 16) = c0;
-        *reinterpret_cast<uint4*>(bufX + A_LBO + r * 16) = c1;
-      }
+#pragma unroll
+      for (int j = 0; j < kK0; ++j) xcur[j] = xnext[j];
+      acquire();  // bufH free (previous tile's stores done reading)
+      stage_x();
       arrive_a();
       load_x(tile + gridDim.x);
       // set of this thread's row (for the pooled-gradient scatter)
@@ -204,23 +214,27 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         }
       }
 
-      // ---- forward sweep epilogues: h_l = [h_{l-1} +] act(z_l + b_l) -> bufH, staged
+      // ---- forward sweep epilogues: h_l = [h_{l-1} +] act(z_l + b_l) -> bufH (in place), staged
       for (int l = 0; l <= L - 2; ++l) {
         wait_acc();
-        acquire();
+        if (l > 0) acquire();  // staging store of h_{l-1} has finished reading bufH
         const bool res = (p.res_mask >> l) & 1;
-        const float* bl = biasS + l * H;
+        const float* bl = p.bias[l];
 #pragma unroll 1
-        for (int c = 0; c < H / 32; ++c) {
+        for (int c = grp; c < NCHUNK; c += 2) {
           uint32_t v[32];
           tmem_ld32(lane_base + ACC_A + c * 32, v);
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint8_t* dst = bufH + (uint32_t)(c * 4 + q) * A_LBO + r * 16;
+            uint8_t* dst = bufH + act_chunk_off(r, c * 32 + q * 8);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4));
             float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(__uint_as_float(v[q * 8 + j]) + bl[c * 32 + q * 8 + j]);
+            o[0] = act_t<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
+            o[2] = act_t<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
+            o[4] = act_t<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
+            o[6] = act_t<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
             if (res) {
               const uint4 old = *reinterpret_cast<const uint4*>(dst);
               o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         const float* g = p.dpooled + (myset >= 0 ? myset : 0) * H;
         const int32_t* am = p.argmax ? p.argmax + (myset >= 0 ? myset : 0) * H : nullptr;
 #pragma unroll 1
-        for (int kc = 0; kc < H / 8; ++kc) {
+        for (int kc = grp; kc < H / 8; kc += 2) {
           float o[8];
           if (myset >= 0) {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + kc * 8));
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = 0.f;
           }
-          *reinterpret_cast<uint4*>(bufG + (uint32_t)kc * A_LBO + r * 16) =
+          *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, kc * 8)) =
               make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
       }
@@ -272,33 +286,37 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       for (int l = L - 2; l >= 0; --l) {
         wait_acc();
         acquire();
-        const float* bl = biasS + l * H;
+        const float* bl = p.bias[l];
 #pragma unroll 1
-        for (int c = 0; c < H / 32; ++c) {
+        for (int c = grp; c < NCHUNK; c += 2) {
           uint32_t z[32], g[32];
           tmem_ld32(lane_base + ACC_A + c * 32, z);
           tmem_ld32(lane_base + ACC_B + c * 32, g);
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              o[j] = __uint_as_float(g[q * 8 + j]) * act_grad_t<ACT>(__uint_as_float(z[q * 8 + j]) + bl[c * 32 + q * 8 + j]);
-            *reinterpret_cast<uint4*>(bufG + (uint32_t)(c * 4 + q) * A_LBO + r * 16) =
+              o[j] = __uint_as_float(g[q * 8 + j]) * act_grad_t<ACT>(__uint_as_float(z[q * 8 + j]) + bb[j]);
+            *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, c * 32 + q * 8)) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           }
         }
+        if (l == 1 && recompute_z0) stage_x();  // bufH is free again (acquire above): operand of the z_0 recompute
         store_blob(p.stage_g[l] + (size_t)tile * BLOB, bufG);
         if (l >= 1) arrive_a();
       }
     }
-    if (r == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait0();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
 }
 
 // ====================================================================== K2: wgrad
@@ -306,39 +324,39 @@ constexpr int kSlots = 3;
 
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t BLOB = kTileM * H * 2;
   constexpr uint32_t XBLOB = kTileM * kK0 * 2;
   constexpr int HALVES = H / 128;
-  constexpr int CH = H / 8;          // 16-byte feature chunks per blob row
-  constexpr int CPW = CH / 4;        // chunks per epilogue warp for the db column sums
-  uint8_t* slots = smem;                                   // kSlots blobs
-  uint8_t* bufX = smem + kSlots * BLOB;                    // 2 x-blobs (tile parity)
+  constexpr int CH = H / 8;            // 16-byte feature chunks per image row
+  constexpr int CPW = CH / kEpiWarps;  // chunks per epilogue warp for the db column sums
+  uint8_t* slots = smem;                                   // kSlots images (1024-aligned)
+  uint8_t* bufX = smem + kSlots * BLOB;                    // 2 x-images (tile parity)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSlots * BLOB + 2 * XBLOB);
-  uint64_t* full = bars;               // [kSlots]
-  uint64_t* empty = bars + kSlots;     // [kSlots]   count 1 (MMA commit) + 128 (epilogue readers)
-  uint64_t* x_full = bars + 2 * kSlots;      // [2] count 128
-  uint64_t* x_empty = bars + 2 * kSlots + 2; // [2] count 1
+  uint64_t* full = bars;                       // [kSlots]
+  uint64_t* empty = bars + kSlots;             // [kSlots] count 1 (MMA commit) + 256 (epilogue readers)
+  uint64_t* x_full = bars + 2 * kSlots;        // [2] count 256
+  uint64_t* x_empty = bars + 2 * kSlots + 2;   // [2] count 1
   uint64_t* acc_ready = bars + 2 * kSlots + 4;
-  uint64_t* acc_free = bars + 2 * kSlots + 5;  // count 128
+  uint64_t* acc_free = bars + 2 * kSlots + 5;  // count 256
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 129); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiThreads); mbar_init(&x_empty[i], 1); }
     mbar_init(acc_ready, 1);
-    mbar_init(acc_free, 128);
+    mbar_init(acc_free, kEpiThreads);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       auto push = [&](const uint8_t* src) {
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
           if (l >= 1) push(p.stage_h[l - 1] + (size_t)tile * BLOB);
         }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0 /* bit i = phase of x buffer i */, free_phase = 0;
       const uint32_t s_base = smem_u32(slots), x_base = smem_u32(bufX);
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
           const uint32_t g_stage = stage;
           mbar_wait(&full[stage], phase);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
-          uint32_t in_addr, in_stage = 0;
+          uint32_t in_addr = 0, in_stage = 0;
           if (l >= 1) {
             in_stage = stage;
             mbar_wait(&full[stage], phase);
@@ -379,11 +397,15 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
           }
           tc_fence_after();
           const uint32_t g_addr = s_base + g_stage * BLOB;
+          // D[out(128 per half), in] += dZ^T (MN-major view of the dZ image) * In (MN-major view)
 #pragma unroll
           for (int o = 0; o < HALVES; ++o)
-            for (int ks = 0; ks < kTileM / 16; ++ks)
-              umma_bf16(tmem + o * Np, make_smem_desc(g_addr + o * (16 * kTileM * 16) + ks * 256, 128, kTileM * 16),
-                        make_smem_desc(in_addr + ks * 256, 128, kTileM * 16), idesc, !(first && ks == 0));
+            for (int ks = 0; ks < kTileM / 16; ++ks) {
+              const uint64_t a_desc = make_smem_desc_sw128_mn(g_addr + o * (2 * kActSlab) + ks * 2048, kActSlab);
+              const uint64_t b_desc = (l >= 1) ? make_smem_desc_sw128_mn(in_addr + ks * 2048, kActSlab)
+                                               : make_smem_desc(in_addr + ks * 256, 128, kTileM * 16);
+              umma_bf16(tmem + o * Np, a_desc, b_desc, idesc, !(first && ks == 0));
+            }
           first = false;
           umma_commit(&empty[g_stage]);
           if (l >= 1) umma_commit(&empty[in_stage]);
@@ -393,9 +415,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
       }
     }
   } else {
-    // ===================== epilogue warps: db column sums, x blobs for layer 0, TMEM flush
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps: db column sums, x images for layer 0, TMEM flush
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0, acc_phase = 0;
     const int d = p.d;
     for (int l = 0; l < L; ++l) {
@@ -406,39 +429,42 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
 #pragma unroll
         for (int j = 0; j < 8; ++j) dbacc[i][j] = 0.f;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        if (l == 0) {  // x tile -> [2][128][8] bf16 blob
+        if (l == 0) {  // x tile -> [2][128][8] bf16 image (group 0 owns the rows)
           mbar_wait(&x_empty[xpar], ((xphase >> xpar) & 1) ^ 1);
           xphase ^= 1u << xpar;
-          const int64_t row = tile * kTileM + r;
-          float xr[kK0];
+          if (grp == 0) {
+            const int64_t row = tile * kTileM + r;
+            float xr[kK0];
 #pragma unroll
-          for (int j = 0; j < kK0; ++j) xr[j] = (j < d && row < p.n) ? __ldg(p.x + row * d + j) : 0.f;
-          uint8_t* xb = bufX + xpar * XBLOB;
-          *reinterpret_cast<uint4*>(xb + r * 16) = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]),
-                                                              pack_bf16x2(xr[4], xr[5]), pack_bf16x2(xr[6], xr[7]));
-          *reinterpret_cast<uint4*>(xb + kTileM * 16 + r * 16) =
-              make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]), pack_bf16x2(xr[12], xr[13]),
-                         pack_bf16x2(xr[14], xr[15]));
+            for (int j = 0; j < kK0; ++j) xr[j] = (j < d && row < p.n) ? __ldg(p.x + row * d + j) : 0.f;
+            uint8_t* xb = bufX + xpar * XBLOB;
+            *reinterpret_cast<uint4*>(xb + r * 16) = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]),
+                                                                pack_bf16x2(xr[4], xr[5]), pack_bf16x2(xr[6], xr[7]));
+            *reinterpret_cast<uint4*>(xb + kTileM * 16 + r * 16) =
+                make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]), pack_bf16x2(xr[12], xr[13]),
+                           pack_bf16x2(xr[14], xr[15]));
+          }
           fence_proxy_async();
           mbar_arrive(&x_full[xpar]);
           xpar ^= 1;
         }
-        // column sums of the dZ blob: warp w owns chunks w, w+4, ...; lane owns rows lane, lane+32, ...
+        // column sums of the dZ image: warp w owns chunks w, w+8, ...; lane owns rows lane, lane+32, ...
         mbar_wait(&full[stage], phase);
         const uint8_t* gb = slots + stage * BLOB;
 #pragma unroll
         for (int i = 0; i < CPW; ++i) {
-          const int c = warp + 4 * i;
+          const int c = warp + kEpiWarps * i;
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
-            const uint4 u = *reinterpret_cast<const uint4*>(gb + (uint32_t)c * (kTileM * 16) + (lane + 32 * rr) * 16);
+            const int rw = lane + 32 * rr;
+            const uint4 u = *reinterpret_cast<const uint4*>(gb + act_chunk_off(rw, c * 8));
             dbacc[i][0] += bf16_lo(u.x); dbacc[i][1] += bf16_hi(u.x); dbacc[i][2] += bf16_lo(u.y); dbacc[i][3] += bf16_hi(u.y);
             dbacc[i][4] += bf16_lo(u.z); dbacc[i][5] += bf16_hi(u.z); dbacc[i][6] += bf16_lo(u.w); dbacc[i][7] += bf16_hi(u.w);
           }
         }
         mbar_arrive(&empty[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
-        if (l >= 1) {  // the input blob slot is only read by the tensor core; wait for THIS use of the slot
+        if (l >= 1) {  // the input image slot is only read by the tensor core; wait for THIS use of the slot
           // to be filled before releasing it, otherwise the arrival could land in the previous phase
           mbar_wait(&full[stage], phase);
           mbar_arrive(&empty[stage]);
@@ -452,29 +478,28 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float s = warp_sum(dbacc[i][j]);
-          if (lane == 0) pb[(warp + 4 * i) * 8 + j] = s;
+          if (lane == 0) pb[(warp + kEpiWarps * i) * 8 + j] = s;
         }
-      // ---- dW partial: TMEM -> global
+      // ---- dW partial: TMEM -> global; the two warp groups split the (half, 32-column chunk) items
       mbar_wait(acc_ready, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
       float* pw = p.part_w[l] + (size_t)blockIdx.x * H * Np;
+      const int nchunk = (Np < 32) ? 1 : Np / 32;
 #pragma unroll 1
-      for (int o = 0; o < HALVES; ++o) {
-#pragma unroll 1
-        for (int c = 0; c < Np / 32 || (c == 0 && Np < 32); ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + o * Np + c * 32, v);
-          tmem_wait_ld();
-          float* dst = pw + (size_t)(o * 128 + r) * Np + c * 32;
-          const int nq = (Np < 32) ? Np / 4 : 8;
+      for (int item = grp; item < HALVES * nchunk; item += 2) {
+        const int o = item / nchunk, c = item % nchunk;
+        uint32_t v[32];
+        tmem_ld32(lane_base + o * Np + c * 32, v);
+        tmem_wait_ld();
+        float* dst = pw + (size_t)(o * 128 + r) * Np + c * 32;
+        const int nq = (Np < 32) ? Np / 4 : 8;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < nq)
-              *reinterpret_cast<float4*>(dst + q * 4) =
-                  make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                              __uint_as_float(v[q * 4 + 3]));
-        }
+        for (int q = 0; q < 8; ++q)
+          if (q < nq)
+            *reinterpret_cast<float4*>(dst + q * 4) =
+                make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                            __uint_as_float(v[q * 4 + 3]));
       }
       tc_fence_before();
       mbar_arrive(acc_free);
@@ -482,24 +507,34 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
 }
 
-// sum the per-CTA partials: dW_l[H, K] (K = real in-features), db_l[H]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int grid_ctas,
-                                    int H, int Kp, int K, float* __restrict__ dw, float* __restrict__ db) {
+// sum the per-CTA partials: dW_l[H, K] (K = real in-features), db_l[H].
+// block = 32 consecutive outputs x 8 partial groups (warp g sums CTAs g, g+8, ...), coalesced 128 B reads
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part_w,
+                                                           const float* __restrict__ part_b, int grid_ctas, int H,
+                                                           int Kp, int K, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int total = H * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + H; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    if (i < total) {
-      const int row = i / K, col = i % K;
-      for (int c = 0; c < grid_ctas; ++c) s += __ldg(part_w + ((size_t)c * H + row) * Kp + col);
-      dw[i] = s;
-    } else {
-      const int f = i - total;
-      for (int c = 0; c < grid_ctas; ++c) s += __ldg(part_b + (size_t)c * H + f);
-      db[f] = s;
-    }
+  const int i = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (i < total) {
+    const int row = i / K, col = i % K;
+    for (int c = g; c < grid_ctas; c += 8) s += __ldg(part_w + ((size_t)c * H + row) * Kp + col);
+  } else if (i < total + H) {
+    for (int c = g; c < grid_ctas; c += 8) s += __ldg(part_b + (size_t)c * H + (i - total));
+  }
+  red[g][lane] = s;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][lane];
+    if (i < total) dw[i] = t;
+    else if (i < total + H) db[i - total] = t;
   }
 }
 
@@ -542,7 +577,7 @@ int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n) { return bwd_w
 
 template <int H, int ACT>
 static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
-  const BwdSmem lay = bwd_smem(H, p.L);
+  const BwdSmem lay = bwd_smem(H);
   auto kern = phi_bwd_chain_kernel<H, ACT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
@@ -621,7 +656,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   for (int l = 0; l < L; ++l) {
     const int K = (l == 0) ? d->input_dim : H, Kp = (l == 0) ? kK0 : H;
-    PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv((int64_t)H * K + H, 256), 256, 0, st>>>(p.part_w[l], p.part_b[l], wl.grid, H,
+    PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv((int64_t)H * K + H, 32), 256, 0, st>>>(p.part_w[l], p.part_b[l], wl.grid, H,
                                                                                 Kp, K, dw[l], db[l]);
   }
   return check_launch(__func__);

@@ -3,56 +3,103 @@
 //   and their autograd.  bf16 operands, fp32 accumulation in TMEM.
 //
 // Forward kernel (persistent, one CTA per SM, 128-point tiles):
-//   x tile -> bf16 operand blob in smem -> [tcgen05.mma -> TMEM -> epilogue(bias, act,
-//   residual) -> bf16 blob in smem] per hidden layer -> final Linear computed TRANSPOSED
-//   (M = output features, N = points) so that each epilogue thread owns one feature and
-//   pools over the points of its TMEM lane without any cross-thread traffic -> partial
+//   x tile -> bf16 operand image in smem -> [tcgen05.mma -> TMEM -> epilogue(bias, act,
+//   residual) -> bf16 SWIZZLE_128B image in smem] per hidden layer -> final Linear computed
+//   TRANSPOSED (M = output features, N = points) so that each epilogue thread owns one feature
+//   and pools over the points of its TMEM lane without any cross-thread traffic -> partial
 //   sums / packed (value,row) maxima combined across tiles with atomics in a [B,H]
 //   accumulator.  Per-point activations never leave the SM.
-//   Weights: pre-packed bf16 blobs (see pcc_tc.cuh) streamed from L2 through an
-//   mbarrier ring with cp.async.bulk (TMA engine).
-// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 bulk-copy
-// producer, warp 5 TMEM allocator + MMA issuer (one elected thread).
+//   Weights: pre-packed bf16 images (pcc_fused.cuh) streamed from L2 through an mbarrier ring
+//   with cp.async.bulk (TMA engine), one K=64 slab (H rows x 128 B) per slot.
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp & 3; the two warps of a quarter split
+// the accumulator columns / the two feature halves), warp 8 bulk-copy producer, warp 9 TMEM
+// allocator + MMA issuer (one elected thread).
 #include "pcc_fused.cuh"
 
 namespace pcc {
 
+constexpr int kRingF = 4;  // weight slabs in flight (forward)
+
 struct SmemLayout {
-  uint32_t bufA, bufX, ring, bias, bars, total;
+  uint32_t bufA, ring, bufX, bias, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int H, int L) {
   SmemLayout s;
   uint32_t o = 0;
-  s.bufA = o; o += kTileM * H * 2;
-  s.bufX = o; o += kTileM * kK0 * 2;
-  s.ring = o; o += kRing * (uint32_t)(64 * H);  // slab = 4 K-chunks * H rows * 16 B
+  s.bufA = o; o += kTileM * H * 2;             // activation image, 1024-aligned slabs
+  s.ring = o; o += kRingF * w_slab_bytes(H);   // weight slabs, 1024-aligned
+  s.bufX = o; o += kTileM * kK0 * 2;           // layer-0 operand (un-swizzled)
   s.bias = o; o += (uint32_t)L * H * 4;
   s.bars = o; o += 256;
   s.total = o;
   return s;
 }
 
+// debug trace: CTA 0 only, role 0 = epilogue thread 0, role 1 = MMA thread; 2 x 4096 slots
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int id) {
+  if (trace && blockIdx.x == 0 && n < 2047) {
+    trace[role * 4096 + 2 * n] = id;
+    trace[role * 4096 + 2 * n + 1] = clock64();
+    ++n;
+  }
+}
+
+__device__ __forceinline__ float max8(const uint32_t* v) {
+  return fmaxf(fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]))),
+               fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])), fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7]))));
+}
+__device__ __forceinline__ float sum8(const uint32_t* v) {
+  return ((__uint_as_float(v[0]) + __uint_as_float(v[1])) + (__uint_as_float(v[2]) + __uint_as_float(v[3]))) +
+         ((__uint_as_float(v[4]) + __uint_as_float(v[5])) + (__uint_as_float(v[6]) + __uint_as_float(v[7])));
+}
+
+// one 32-column accumulator chunk -> bias, activation, residual -> bf16 -> SW128 activation image
+template <int ACT>
+__device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t* bufA, const float* bl, int r, int c,
+                                                bool res) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint8_t* dst = bufA + act_chunk_off(r, c * 32 + q * 8);
+    const float4 b0 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4);
+    float o[8];
+    o[0] = act_t<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
+    o[2] = act_t<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
+    o[4] = act_t<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
+    o[6] = act_t<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
+    if (res) {
+      const uint4 old = *reinterpret_cast<const uint4*>(dst);
+      o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
+      o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
 // ------------------------------------------------------------------ forward kernel
 template <int H, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const SmemLayout lay = smem_layout(H, p.L);
   uint8_t* bufA = smem + lay.bufA;
-  uint8_t* bufX = smem + lay.bufX;
   uint8_t* ring = smem + lay.ring;
+  uint8_t* bufX = smem + lay.bufX;
   float* biasS = reinterpret_cast<float*>(smem + lay.bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
-  uint64_t* full = bars;               // [kRing]
-  uint64_t* empty = bars + kRing;      // [kRing]
-  uint64_t* a_ready = bars + 2 * kRing;
-  uint64_t* acc_ready = bars + 2 * kRing + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing + 2);
-  int* seg_first = reinterpret_cast<int*>(bars + 2 * kRing + 3);  // [2], by tile parity
+  uint64_t* full = bars;                 // [kRingF]
+  uint64_t* empty = bars + kRingF;       // [kRingF]
+  uint64_t* a_ready = bars + 2 * kRingF;
+  uint64_t* acc_ready = bars + 2 * kRingF + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 2);
+  int* seg_first = reinterpret_cast<int*>(bars + 2 * kRingF + 3);  // [2], by tile parity
 
-  constexpr uint32_t SLAB = 64 * H;            // bytes
-  constexpr uint32_t A_LBO = kTileM * 16;      // K-chunk stride of a 128-row blob
-  constexpr uint32_t W_LBO = H * 16;           // K-chunk stride of an H-row blob
+  constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
+  constexpr uint32_t X_LBO = kTileM * 16;      // un-swizzled layer-0 images: K-chunk strides
+  constexpr uint32_t W0_LBO = H * 16;
   constexpr int HALVES = H / 128;              // M halves of the transposed final layer
+  constexpr int NSLAB = H / 64;                // slabs per H x H layer
+  constexpr int NCHUNK = H / 32;               // 32-column accumulator chunks of a hidden layer
   constexpr uint32_t ACC_T = 256;              // TMEM column base of the transposed accumulators
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,101 +107,117 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
 
   for (int i = threadIdx.x; i < L * H; i += kThreads) biasS[i] = __ldg(p.bias[i / H] + (i % H));
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, 128);
+    for (int i = 0; i < kRingF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(a_ready, kEpiThreads);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ===================== producer: stream weight slabs through the ring
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
-          const int nslab = (l == 0) ? 1 : H / 32;
-          const uint32_t bytes = (l == 0) ? (kK0 / 8) * W_LBO : SLAB;
+          const int nslab = (l == 0) ? 1 : NSLAB;
+          const uint32_t bytes = (l == 0) ? (kK0 / 8) * W0_LBO : SLAB;
           for (int s = 0; s < nslab; ++s) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], bytes);
             bulk_g2s(ring + stage * SLAB, p.wpack + p.w_off[l] + (size_t)s * SLAB, bytes, &full[stage]);
-            if (++stage == kRing) { stage = 0; phase ^= 1; }
+            if (++stage == kRingF) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_N = make_idesc_bf16(128, H, 0, 0);    // points x features
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, 0, 0);  // features(128) x points
       uint32_t stage = 0, phase = 0, a_phase = 0;
+      int tn = 0;
       const uint32_t a_base = smem_u32(bufA), x_base = smem_u32(bufX), r_base = smem_u32(ring);
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
+          trace_ev(p.trace, 1, tn, 100 + l);
           mbar_wait(a_ready, a_phase);
           a_phase ^= 1;
           tc_fence_after();
+          trace_ev(p.trace, 1, tn, 110 + l);
           const bool last = (l == L - 1);
-          const int nslab = (l == 0) ? 1 : H / 32;
-          const int ksteps = (l == 0) ? kK0 / 16 : 2;  // UMMA K steps per slab
-          const uint32_t act_base = (l == 0) ? x_base : a_base;
-          for (int s = 0; s < nslab; ++s) {
+          if (l == 0) {  // K = 16, un-swizzled images
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t w_slab = r_base + stage * SLAB;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const int kglob = s * 2 + ks;  // K step index inside the layer
-              const uint64_t act_desc = make_smem_desc(act_base + kglob * 2 * A_LBO, A_LBO, 128);
-              if (!last) {
-                const uint64_t w_desc = make_smem_desc(w_slab + ks * 2 * W_LBO, W_LBO, 128);
-                umma_bf16(tmem, act_desc, w_desc, IDESC_N, kglob > 0);
-              } else {
+            umma_bf16(tmem, make_smem_desc(x_base, X_LBO, 128), make_smem_desc(r_base + stage * SLAB, W0_LBO, 128),
+                      IDESC_N, 0);
+            umma_commit(&empty[stage]);
+            if (++stage == kRingF) { stage = 0; phase ^= 1; }
+          } else {
+            for (int s = 0; s < NSLAB; ++s) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              if (s == 0) trace_ev(p.trace, 1, tn, 120 + l);
+              if (s == NSLAB - 1) trace_ev(p.trace, 1, tn, 130 + l);
+              const uint32_t w_slab = r_base + stage * SLAB;
 #pragma unroll
-                for (int h = 0; h < HALVES; ++h) {
-                  const uint64_t w_desc = make_smem_desc(w_slab + ks * 2 * W_LBO + h * 128 * 16, W_LBO, 128);
-                  umma_bf16(tmem + ACC_T + h * 128, w_desc, act_desc, IDESC_T, kglob > 0);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t act_desc = make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32);
+                const uint32_t acc = (s | ks) != 0;
+                if (!last) {
+                  umma_bf16(tmem, act_desc, make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, acc);
+                } else {
+#pragma unroll
+                  for (int h = 0; h < HALVES; ++h)
+                    umma_bf16(tmem + ACC_T + h * 128, make_smem_desc_sw128_k(w_slab + h * (128 * 128) + ks * 32), act_desc,
+                              IDESC_T, acc);
                 }
               }
+              umma_commit(&empty[stage]);
+              if (++stage == kRingF) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty[stage]);
-            if (++stage == kRing) { stage = 0; phase ^= 1; }
           }
           umma_commit(acc_ready);
+          trace_ev(p.trace, 1, tn, 140 + l);
         }
       }
     }
   } else {
-    // ===================== epilogue warps 0-3: thread = TMEM lane = tile row (or feature)
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps 0-7
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + lane;  // tile row (hidden layers) / feature inside a half (final layer)
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t acc_phase = 0;
     const int d = p.d;
     float xr[kK0];
     auto load_x = [&](int64_t tile) {
       const int64_t row = tile * kTileM + r;
 #pragma unroll
-      for (int j = 0; j < kK0; ++j) xr[j] = (j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
+      for (int j = 0; j < kK0; ++j)
+        xr[j] = (grp == 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
     };
     load_x(blockIdx.x);
-    int par = 0;
+    int par = 0, tn = 0;
+    const bool tr0 = (threadIdx.x == 0);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, par ^= 1) {
       const int64_t r0 = tile * kTileM;
-      // ---- stage the x tile as the layer-0 operand blob [2][128][8] bf16
-      {
-        uint4 c0 = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]), pack_bf16x2(xr[4], xr[5]),
-                              pack_bf16x2(xr[6], xr[7]));
-        uint4 c1 = make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]), pack_bf16x2(xr[12], xr[13]),
-                              pack_bf16x2(xr[14], xr[15]));
-        *reinterpret_cast<uint4*>(bufX + r * 16) = c0;
-        *reinterpret_cast<uint4*>(bufX + A_LBO + r * 16) = c1;
+      // ---- stage the x tile as the layer-0 operand image [2][128][8] bf16 (group 0 owns the rows)
+      if (grp == 0) {
+        *reinterpret_cast<uint4*>(bufX + r * 16) = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]),
+                                                              pack_bf16x2(xr[4], xr[5]), pack_bf16x2(xr[6], xr[7]));
+        *reinterpret_cast<uint4*>(bufX + X_LBO + r * 16) = make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]),
+                                                                      pack_bf16x2(xr[12], xr[13]), pack_bf16x2(xr[14], xr[15]));
       }
-      if (r == 0) {  // first set intersecting this tile (binary search over offsets)
+      fence_proxy_async();
+      mbar_arrive(a_ready);
+      if (tr0) trace_ev(p.trace, 0, tn, 0);
+      load_x(tile + gridDim.x);  // prefetch the next tile's rows into registers
+      if (threadIdx.x == 0) {    // first set intersecting this tile; off the critical path (MMA 0 runs)
         int64_t lo = 0, hi = p.B;
         while (lo < hi) {
           int64_t mid = (lo + hi) >> 1;
@@ -162,114 +225,118 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
         }
         seg_first[par] = (int)lo;
       }
-      fence_proxy_async();
-      mbar_arrive(a_ready);
-      load_x(tile + gridDim.x);  // prefetch the next tile's rows into registers
 
-      // ---- hidden layers: TMEM -> bias/act/residual -> bf16 blob (in place)
+      // ---- hidden layers: TMEM -> bias/act/residual -> bf16 image (in place); group g takes the
+      //      chunks g, g+2, ...; TMEM loads are issued one chunk ahead of the math
       for (int l = 0; l < L - 1; ++l) {
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (tr0) trace_ev(p.trace, 0, tn, 10 + l);
         const bool res = (p.res_mask >> l) & 1;
         const float* bl = biasS + l * H;
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + grp * 32, va);
 #pragma unroll 1
-        for (int c = 0; c < H / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + c * 32, v);
+        for (int c = grp; c < NCHUNK; c += 4) {
           tmem_wait_ld();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint8_t* dst = bufA + (uint32_t)(c * 4 + q) * A_LBO + r * 16;
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(__uint_as_float(v[q * 8 + j]) + bl[c * 32 + q * 8 + j]);
-            if (res) {
-              const uint4 old = *reinterpret_cast<const uint4*>(dst);
-              o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
-              o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
-            }
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          if (c + 2 < NCHUNK) tmem_ld32(lane_base + (c + 2) * 32, vb);
+          epi_store_chunk<ACT>(va, bufA, bl, r, c, res);
+          if (c + 2 < NCHUNK) {
+            tmem_wait_ld();
+            if (c + 4 < NCHUNK) tmem_ld32(lane_base + (c + 4) * 32, va);
+            epi_store_chunk<ACT>(vb, bufA, bl, r, c + 2, res);
           }
         }
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(a_ready);
+        if (tr0) trace_ev(p.trace, 0, tn, 20 + l);
       }
 
       // ---- final layer (transposed): thread = feature, TMEM columns = the tile's points
       mbar_wait(acc_ready, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // seg_first visible to all epilogue threads
+      if (tr0) trace_ev(p.trace, 0, tn, 30);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // seg_first visible to all epilogue threads
       const int b_first = seg_first[par];
       const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
-#pragma unroll 1
-      for (int h = 0; h < HALVES; ++h) {
+      if (grp < HALVES) {
+        const int h = grp;
         const int f = h * 128 + r;
+        const bool is_max = (p.pooling == PCC_POOL_MAX);
         int64_t b = b_first;
         int64_t seg_lo = 0, seg_hi = 0;
         if (b < p.B) { seg_lo = __ldg(p.offsets + b); seg_hi = __ldg(p.offsets + b + 1); }
-        float acc = (p.pooling == PCC_POOL_MAX) ? -INFINITY : 0.f;
-        int arg = -1;
-#pragma unroll 1
+        float acc = is_max ? -INFINITY : 0.f;
+        int arg = -1;       // exact column of the running max inside this tile, or
+        int argc = -1;      // chunk that holds it (resolved lazily when the set is flushed)
+        auto flush = [&](int64_t set) {
+          if (is_max) {
+            if (argc >= 0) {  // find the first column of chunk argc that equals the maximum
+              uint32_t w[32];
+              tmem_ld32(lane_base + ACC_T + h * 128 + argc * 32, w);
+              tmem_wait_ld();
+              int j0 = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(w[j]) == acc) ? j : j0;
+              arg = argc * 32 + j0;
+            }
+            if (arg >= 0) {
+              unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
+                                       (unsigned long long)(0xFFFFFFFFu - (uint32_t)(r0 + arg));
+              atomicMax(reinterpret_cast<unsigned long long*>(p.pool_acc) + set * H + f, key);
+            }
+            acc = -INFINITY; arg = -1; argc = -1;
+          } else {
+            atomicAdd(reinterpret_cast<float*>(p.pool_acc) + set * H + f, acc);
+            acc = 0.f;
+          }
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + ACC_T + h * 128, va);
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + ACC_T + h * 128 + c * 32, v);
           tmem_wait_ld();
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          if (c + 1 < 4) tmem_ld32(lane_base + ACC_T + h * 128 + (c + 1) * 32, (c & 1) ? va : vb);
           const int64_t col0 = r0 + c * 32;
           while (b < p.B && seg_lo < tile_end && seg_lo < col0 + 32) {
-            // columns of this chunk that belong to set b: [lo, hi)
             const int lo = (int)((seg_lo > col0 ? seg_lo : col0) - col0);
-            const int64_t hi64 = (seg_hi < col0 + 32 ? seg_hi : col0 + 32) - col0;
-            const int hi = (int)hi64;
-            if (p.pooling == PCC_POOL_MAX) {
+            const int hi = (int)((seg_hi < col0 + 32 ? seg_hi : col0 + 32) - col0);
+            if (lo == 0 && hi == 32) {  // whole chunk inside the set: tree reduction, no predicates
+              if (is_max) {
+                const float m = fmaxf(fmaxf(max8(v), max8(v + 8)), fmaxf(max8(v + 16), max8(v + 24)));
+                if (m > acc || (arg < 0 && argc < 0)) { acc = m; argc = c; arg = -1; }
+              } else {
+                acc += (sum8(v) + sum8(v + 8)) + (sum8(v + 16) + sum8(v + 24));
+              }
+            } else if (is_max) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float val = __uint_as_float(v[j]);
-                if (j >= lo && j < hi && (val > acc || arg < 0)) { acc = val; arg = c * 32 + j; }
+                if (j >= lo && j < hi && (val > acc || (arg < 0 && argc < 0))) { acc = val; arg = c * 32 + j; argc = -1; }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc += (j >= lo && j < hi) ? __uint_as_float(v[j]) : 0.f;
             }
             if (seg_hi > col0 + 32) break;  // set continues in the next chunk / tile
-            // set b ends inside this chunk: flush and advance
-            if (p.pooling == PCC_POOL_MAX) {
-              if (arg >= 0) {
-                unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
-                                         (unsigned long long)(0xFFFFFFFFu - (uint32_t)(r0 + arg));
-                atomicMax(reinterpret_cast<unsigned long long*>(p.pool_acc) + b * H + f, key);
-              }
-              acc = -INFINITY; arg = -1;
-            } else {
-              atomicAdd(reinterpret_cast<float*>(p.pool_acc) + b * H + f, acc);
-              acc = 0.f;
-            }
+            flush(b);                        // set b ends inside this chunk
             ++b;
             if (b < p.B) { seg_lo = seg_hi; seg_hi = __ldg(p.offsets + b + 1); }
           }
         }
-        // partial of the set that continues past this tile
-        if (b < p.B && seg_lo < tile_end) {
-          if (p.pooling == PCC_POOL_MAX) {
-            if (arg >= 0) {
-              unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
-                                       (unsigned long long)(0xFFFFFFFFu - (uint32_t)(r0 + arg));
-              atomicMax(reinterpret_cast<unsigned long long*>(p.pool_acc) + b * H + f, key);
-            }
-          } else {
-            atomicAdd(reinterpret_cast<float*>(p.pool_acc) + b * H + f, acc);
-          }
-        }
+        if (b < p.B && seg_lo < tile_end) flush(b);  // partial of the set that continues past this tile
       }
       tc_fence_before();
+      if (tr0) trace_ev(p.trace, 0, tn, 40);
     }
   }
 
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
 }
 
 // pool accumulator -> pooled[B,H] (+ argmax): adds the final bias after pooling
@@ -335,6 +402,8 @@ int check_phi_desc(const pcc_phi_desc* d, const char* where) {
   return 0;
 }
 
+static void* g_trace_buf = nullptr;  // set through pcc_debug_set_trace (diagnostics only)
+
 template <int H, int ACT>
 static int launch_fwd(const PhiParams& p, cudaStream_t st) {
   const SmemLayout lay = smem_layout(H, p.L);
@@ -355,6 +424,11 @@ static int launch_fwd(const PhiParams& p, cudaStream_t st) {
 }  // namespace pcc
 
 using namespace pcc;
+
+extern "C" int pcc_debug_set_trace(void* device_buf_2x4096_i64) {
+  pcc::g_trace_buf = device_buf_2x4096_i64;
+  return 0;
+}
 
 extern "C" int pcc_phi_fused_supported(const pcc_phi_desc* d) { return check_phi_desc(d, __func__); }
 
@@ -388,6 +462,7 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   p.wpack = wsb;
   for (int l = 0; l < L; ++l) { p.w_off[l] = wl.w_off[l]; p.bias[l] = d->b[l]; }
   p.pool_acc = wsb + wl.pool_off;
+  p.trace = (long long*)g_trace_buf;
   if (p.num_tiles > 0) {
     int rc = 0;
 #define PCC_DISPATCH(HH)                                                              \

@@ -3,6 +3,8 @@
 //   mode 0: D[i][j] = sum_k A[i][k] * B[j][k]      A, B K-major blobs          (forward)
 //   mode 1: D[i][j] = sum_k A[i][k] * W[k][j]      B = MN-major view of W blob (dgrad)
 //   mode 2: D[i][j] = sum_p G[p][i] * Hh[p][j]     both MN-major views         (wgrad)
+//   mode 3: as mode 0 with K = 128 and SWIZZLE_128B images
+//   mode 4: as mode 2 with SWIZZLE_128B images
 #include "pcc_common.cuh"
 #include "pcc_tc.cuh"
 
@@ -18,7 +20,7 @@ __device__ inline void blob_store(__nv_bfloat16* blob, int row, int col, float v
 }
 
 __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(int mode, float* out) {
-  extern __shared__ __align__(128) uint8_t dyn_smem[];
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
   __nv_bfloat16* blobA = reinterpret_cast<__nv_bfloat16*>(dyn_smem);
   __nv_bfloat16* blobB = blobA + 128 * 128;
   __shared__ __align__(8) uint64_t bar;
@@ -28,9 +30,17 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(int mode, float* 
   // mode 0: A[128 x 64] rows=i cols=k ; B[64(rows j, padded to 128 rows) x 64]
   // mode 1: A[128 x 128] rows=i cols=k ; W blob rows=k(128) cols=j(64)
   // mode 2: G blob rows=p(128) cols=i(128) ; Hh blob rows=p(128) cols=j(64)
+  const bool swz = mode >= 3;
   for (int e = t; e < 128 * 128; e += 128) {
     const int row = e / 128, col = e % 128;
     float a = 0.f, b = 0.f;
+    if (mode == 3) { a = st_a(row, col); b = row < N ? st_b(row, col) : 0.f; }
+    if (mode == 4) { a = st_a(col, row); b = col < N ? st_b(col, row) : 0.f; }
+    if (swz) {
+      blobA[sw128_off(row, col, 128) / 2] = __float2bfloat16(a);
+      blobB[sw128_off(row, col, 128) / 2] = __float2bfloat16(b);
+      continue;
+    }
     if (mode == 0) { a = col < 64 ? st_a(row, col) : 0.f; b = (col < 64 && row < N) ? st_b(row, col) : 0.f; }
     if (mode == 1) { a = st_a(row, col); b = col < N ? st_b(col, row) : 0.f; }   // W[k=row][j=col] = st_b(j,k)
     if (mode == 2) { a = st_a(col, row); b = col < N ? st_b(col, row) : 0.f; }   // G[p][i] = st_a(i,p); Hh[p][j] = st_b(j,p)
@@ -56,11 +66,22 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(int mode, float* 
       for (int ks = 0; ks < 8; ++ks)  // K step = 16 rows of the W blob = 256 B
         umma_bf16(tmem, make_smem_desc(a0 + ks * 2 * 2048, 2048, 128), make_smem_desc(b0 + ks * 256, 128, 2048), idesc,
                   ks > 0);
-    } else {
+    } else if (mode == 2) {
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
       for (int ks = 0; ks < 8; ++ks)
         umma_bf16(tmem, make_smem_desc(a0 + ks * 256, 128, 2048), make_smem_desc(b0 + ks * 256, 128, 2048), idesc,
                   ks > 0);
+    } else if (mode == 3) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      for (int ks = 0; ks < 8; ++ks) {  // slab = ks / 4 (64 K values each), 32 B per K step inside a slab
+        const uint32_t off = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
+        umma_bf16(tmem, make_smem_desc_sw128_k(a0 + off), make_smem_desc_sw128_k(b0 + off), idesc, ks > 0);
+      }
+    } else {
+      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      for (int ks = 0; ks < 8; ++ks)  // K step = 16 rows = two 1024 B row groups
+        umma_bf16(tmem, make_smem_desc_sw128_mn(a0 + ks * 2048, 128 * 128), make_smem_desc_sw128_mn(b0 + ks * 2048, 128 * 128),
+                  idesc, ks > 0);
     }
     umma_commit(&bar);
   }
@@ -82,7 +103,7 @@ using namespace pcc;
 
 extern "C" int pcc_selftest_umma(int mode, float* out, int device, void* stream) {
   PCC_ENTER(device);
-  PCC_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0..2");
+  PCC_REQUIRE(mode >= 0 && mode <= 4, "mode must be 0..4");
   const int smem = 2 * 128 * 128 * 2;
   PCC_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, out);

@@ -105,6 +105,34 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;  // descriptor version
   return d;
 }
+// SWIZZLE_128B variants.  Operand image: [C/64 slabs][R rows][64 elements], each row of a slab is 128
+// bytes whose eight 16-byte chunks are XOR-permuted with (row & 7) (Swizzle<3,4,3>); slabs must be
+// 1024-byte aligned.  byte offset of element (row, col):
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t col, uint32_t R) {
+  return (col >> 6) * (R * 128u) + row * 128u + ((((col & 63u) >> 3) ^ (row & 7u)) << 4) + ((col & 7u) << 1);
+}
+// K-major view [R x K]: start = slab base + 32 B per UMMA K step inside the slab; SBO = 1024 (8-row groups)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_k(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major): 1
+  d |= (uint64_t)(1024u >> 4) << 32;      // SBO
+  d |= (uint64_t)1 << 46;                 // version
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// MN-major view of the same image (MN = column index, contraction over rows): LBO = slab stride
+// (64-column groups), SBO = 1024 (8-row groups); K step of 16 rows = +2048 B
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr, uint32_t slab_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32; a_mn / b_mn = 1 for MN-major operands
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) /*C=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)a_mn << 15) |

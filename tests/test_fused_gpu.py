@@ -5,7 +5,7 @@ bf16 (8-bit mantissa) before every tensor-core contraction.  Forward values (poo
 features, logits) are compared against the fp32 oracle with
     max|got - ref| <= BF16_TOL * max|ref|,   BF16_TOL = 3e-2      (measured: 1e-3..4e-3)
 and parameter gradients with the relative Frobenius error
-    ||got - ref||_F <= BF16_GRAD_TOL * ||ref||_F,   BF16_GRAD_TOL = 2e-2   (measured: 2e-3..8e-3)
+    ||got - ref||_F <= BF16_GRAD_TOL * ||ref||_F,   BF16_GRAD_TOL = 5e-2   (measured: 2e-3..8e-3)
 (max-norm is not meaningful for gradients across precisions: one flipped relu mask or argmax
 row moves a single entry by O(1)).  Max pooling: a precision change can move an argmax between
 near-tied rows, so (a) argmax rows must lie in their set and be maximal in fp32 within
@@ -26,7 +26,7 @@ from pcc_b200 import _lib, functional as PF, fused as FZ
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 3e-2
-BF16_GRAD_TOL = 2e-2
+BF16_GRAD_TOL = 5e-2
 
 
 def _st_a(i, k):
@@ -37,7 +37,7 @@ def _st_b(j, k):
     return ((j * 2 + k) % 5 - 2).astype(np.float64)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_umma_descriptor_conventions(mode):
     out = torch.full((128, 64), float("nan"), device="cuda")
     _lib.call("pcc_selftest_umma", mode, _lib.ptr(out), 0, _lib.stream_ptr(0))

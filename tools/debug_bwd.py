@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "point-cloud-classifier_b200")); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pcc_b200
 from oracle import deepsets_oracle as O
-from helpers import ragged_batch, rel_err
+from helpers import ragged_batch, rel_err, rel_l2
 
 def one(act, pool, res, H, depth, d, sizes):
     cfg = dict(input_dim=d, phi_layers=[H] * depth, rho_layers=[64], output_dim=3, activation=act, layer_norm=False,
@@ -13,13 +13,20 @@ def one(act, pool, res, H, depth, d, sizes):
     x, idx = ragged_batch(sizes, d, seed=52)
     y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(53)) > 0.5).float()
     ref_logits, ref_loss, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
+    if pool == "max":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import test_fused_gpu as T
+        from pcc_b200 import functional as PF
+        m0 = pcc_b200.DeepSets(**cfg, precision="bf16").cuda(); m0.load_state_dict(sd)
+        arg = T._fused_argmax(m0, x.cuda(), PF.segment_offsets(idx.cuda(), len(sizes)), act)
+        ref_logits, ref_grads = T._oracle_step_with_argmax(sd, cfg, x, idx, y, arg)
     out = {}
     for prec in ("bf16", "fp32"):
         m = pcc_b200.DeepSets(**cfg, precision=prec).cuda(); m.load_state_dict(sd)
         logits = m(x.cuda(), idx.cuda())
         loss = torch.nn.BCEWithLogitsLoss()(logits, y.cuda()); loss.backward()
         torch.cuda.synchronize()
-        out[prec] = {k: rel_err(p.grad, ref_grads[k]) for k, p in m.named_parameters()}
+        out[prec] = {k: rel_l2(p.grad, ref_grads[k]) for k, p in m.named_parameters()}
         out[prec]["logits"] = rel_err(logits, ref_logits)
     print(f"--- {act}/{pool}/res={res}/H={H}/depth={depth}/d={d}/sets={len(sizes)} n={sum(sizes)}")
     for k in out["bf16"]:

@@ -1,0 +1,37 @@
+import os, sys, torch, numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "point-cloud-classifier_b200"))
+import pcc_b200
+from pcc_b200 import _lib, functional as PF, fused as FZ
+B, N = 256, 1024
+m = pcc_b200.DeepSets(3, [256, 256], [256], 10, "relu", layer_norm=False, pooling="max", precision="bf16").cuda()
+x = torch.randn(B * N, 3, device="cuda"); idx = torch.arange(B, device="cuda").repeat_interleave(N)
+off = PF.segment_offsets(idx, B)
+buf = torch.zeros(2 * 4096, dtype=torch.int64, device="cuda")
+with torch.no_grad():
+    for _ in range(2): FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
+    _lib.call("pcc_debug_set_trace", _lib.ptr(buf))
+    FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
+    torch.cuda.synchronize()
+    _lib.call("pcc_debug_set_trace", None)
+t = buf.cpu().numpy().reshape(2, 2048, 2)
+ev = []
+for role in (0, 1):
+    for i in range(2048):
+        if t[role, i, 1] == 0: break
+        ev.append((int(t[role, i, 1]), role, int(t[role, i, 0])))
+ev.sort()
+t0 = ev[0][0]
+# print tiles 5..6 worth of events
+names = {0: "E x staged", 10: "E acc0 ready", 11: "E acc1 ready", 20: "E epi0 done", 21: "E epi1 done", 30: "E accF ready", 40: "E pool done"}
+for l in range(3):
+    names[100 + l] = f"M wait operand L{l}"; names[110 + l] = f"M operand L{l} ready"; names[120 + l] = f"M first slab L{l}"
+    names[130 + l] = f"M last slab L{l}"; names[140 + l] = f"M issued L{l}"
+cnt = 0
+prev = None
+for ts, role, id_ in ev:
+    if id_ == 0: cnt += 1
+    if 6 <= cnt <= 7:
+        print(f"{ts - t0:9d} (+{0 if prev is None else ts - prev:6d})  {names.get(id_, id_)}")
+        prev = ts
+print("total cycles", ev[-1][0] - t0, "tiles", cnt)
