@@ -36,7 +36,42 @@ struct PhiParams {
   const float* bias[kMaxLayers];
   void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
   long long* trace;              // optional (debug): CTA 0 event timestamps, see trace_ev in pcc_fused_phi.cu
+  const int32_t* tile_first;     // [num_tiles] first set intersecting each 128-row tile (seg_prep_kernel)
 };
+
+// Segment lookups hoisted out of the persistent kernels (a dependent binary search on the epilogue's
+// critical path costs ~2k cycles per tile): tile_first[t] = first set b with offsets[b+1] > 128 t;
+// row_set[r] = set of row r (-1 past the last set), row_scale[r] = pooled-gradient scale of that set.
+static __global__ void seg_prep_kernel(const int64_t* __restrict__ offsets, int64_t n, int64_t B, int64_t num_tiles,
+                                       int pooling, int32_t* __restrict__ tile_first, int32_t* __restrict__ row_set,
+                                       float* __restrict__ row_scale) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tile_first && i < num_tiles) {
+    const int64_t r0 = i * kTileM;
+    int64_t lo = 0, hi = B;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid + 1) <= r0) lo = mid + 1; else hi = mid;
+    }
+    tile_first[i] = (int32_t)lo;
+  }
+  if (row_set && i < n) {
+    int64_t lo = 0, hi = B;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid + 1) <= i) lo = mid + 1; else hi = mid;
+    }
+    int32_t set = -1;
+    float scale = 0.f;
+    if (lo < B && __ldg(offsets + lo) <= i) {
+      set = (int32_t)lo;
+      const float cnt = (float)(__ldg(offsets + lo + 1) - __ldg(offsets + lo));
+      scale = pooling == PCC_POOL_SUM ? rsqrtf(cnt) : (pooling == PCC_POOL_MEAN ? 1.f / cnt : 1.f);
+    }
+    row_set[i] = set;
+    row_scale[i] = scale;
+  }
+}
 
 // ------------------------------------------------------------------ weight packing
 // W_l fp32 [H, K_l] (nn.Linear layout) -> bf16 operand image: layer 0 un-swizzled [2][H][8] (K padded

@@ -33,6 +33,8 @@ struct BwdParams {
   uint8_t* stage_g[kMaxLayers];  // dZ_l images, l = 0..L-1
   float* part_w[kMaxLayers];     // per-CTA partial dW_l [grid][H][K_l]  (K_0 = 16)
   float* part_b[kMaxLayers];     // per-CTA partial db_l [grid][H]
+  const int32_t* row_set;        // [n] set of each row (-1: none), seg_prep_kernel
+  const float* row_scale;        // [n] pooled-gradient scale of the row's set
 };
 
 struct BwdSmem {
@@ -198,21 +200,9 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       stage_x();
       arrive_a();
       load_x(tile + gridDim.x);
-      // set of this thread's row (for the pooled-gradient scatter)
-      int64_t myset = -1;
-      float scale = 0.f;
-      if (row < p.n) {
-        int64_t lo = 0, hi = p.B;
-        while (lo < hi) {
-          int64_t mid = (lo + hi) >> 1;
-          if (__ldg(p.offsets + mid + 1) <= row) lo = mid + 1; else hi = mid;
-        }
-        if (lo < p.B && __ldg(p.offsets + lo) <= row) {
-          myset = lo;
-          const float cnt = (float)(__ldg(p.offsets + lo + 1) - __ldg(p.offsets + lo));
-          scale = p.pooling == PCC_POOL_SUM ? rsqrtf(cnt) : (p.pooling == PCC_POOL_MEAN ? 1.f / cnt : 1.f);
-        }
-      }
+      // set of this thread's row (for the pooled-gradient scatter), precomputed
+      const int64_t myset = (row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
+      const float scale = (row < p.n) ? __ldg(p.row_scale + row) : 0.f;
 
       // ---- forward sweep epilogues: h_l = [h_{l-1} +] act(z_l + b_l) -> bufH (in place), staged
       for (int l = 0; l <= L - 2; ++l) {
@@ -547,6 +537,7 @@ __global__ void zero_f32_kernel_b(float* p, int64_t n) {
 struct BwdWs {
   uint32_t w_off[kMaxLayers], wt_off[kMaxLayers];
   int64_t stage_h[kMaxLayers], stage_g[kMaxLayers], part_w[kMaxLayers], part_b[kMaxLayers];
+  int64_t row_set, row_scale;
   int64_t total;
   int grid;
 };
@@ -569,6 +560,8 @@ static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms) {
     w.part_w[l] = take((int64_t)kGridCap * H * ((l == 0) ? kK0 : H) * 4);
     w.part_b[l] = take((int64_t)kGridCap * H * 4);
   }
+  w.row_set = take(n * 4);
+  w.row_scale = take(n * 4);
   w.total = o;
   return w;
 }
@@ -642,6 +635,10 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
     p.part_w[l] = (float*)(wsb + wl.part_w[l]);
     p.part_b[l] = (float*)(wsb + wl.part_b[l]);
   }
+  p.row_set = (const int32_t*)(wsb + wl.row_set);
+  p.row_scale = (const float*)(wsb + wl.row_scale);
+  PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(offsets, n, B, tiles, d->pooling, nullptr,
+                                                                (int32_t*)(wsb + wl.row_set), (float*)(wsb + wl.row_scale));
   int rc = 0;
 #define PCC_DISPATCH(HH)                                                                 \
   switch (d->act) {                                                                      \

@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
   uint64_t* a_ready = bars + 2 * kRingF;
   uint64_t* acc_ready = bars + 2 * kRingF + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 2);
-  int* seg_first = reinterpret_cast<int*>(bars + 2 * kRingF + 3);  // [2], by tile parity
 
   constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
   constexpr uint32_t X_LBO = kTileM * 16;      // un-swizzled layer-0 images: K-chunk strides
@@ -217,14 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
       mbar_arrive(a_ready);
       if (tr0) trace_ev(p.trace, 0, tn, 0);
       load_x(tile + gridDim.x);  // prefetch the next tile's rows into registers
-      if (threadIdx.x == 0) {    // first set intersecting this tile; off the critical path (MMA 0 runs)
-        int64_t lo = 0, hi = p.B;
-        while (lo < hi) {
-          int64_t mid = (lo + hi) >> 1;
-          if (__ldg(p.offsets + mid + 1) <= r0) lo = mid + 1; else hi = mid;
-        }
-        seg_first[par] = (int)lo;
-      }
+      const int b_first = __ldg(p.tile_first + tile);  // first set intersecting this tile (precomputed)
 
       // ---- hidden layers: TMEM -> bias/act/residual -> bf16 image (in place); group g takes the
       //      chunks g, g+2, ...; TMEM loads are issued one chunk ahead of the math
@@ -259,8 +251,6 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
       acc_phase ^= 1;
       tc_fence_after();
       if (tr0) trace_ev(p.trace, 0, tn, 30);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // seg_first visible to all epilogue threads
-      const int b_first = seg_first[par];
       const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
       if (grp < HALVES) {
         const int h = grp;
@@ -274,14 +264,21 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
         int argc = -1;      // chunk that holds it (resolved lazily when the set is flushed)
         auto flush = [&](int64_t set) {
           if (is_max) {
-            if (argc >= 0) {  // find the first column of chunk argc that equals the maximum
-              uint32_t w[32];
-              tmem_ld32(lane_base + ACC_T + h * 128 + argc * 32, w);
-              tmem_wait_ld();
-              int j0 = 31;
+            // resolve chunk-level argmax to a column: tcgen05.ld is warp-collective with a uniform
+            // address, and lanes (features) may point at different chunks, so visit each needed chunk
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              if (__any_sync(0xffffffffu, argc == cc)) {
+                uint32_t w[32];
+                tmem_ld32(lane_base + ACC_T + h * 128 + cc * 32, w);
+                tmem_wait_ld();
+                if (argc == cc) {
+                  int j0 = 31;
 #pragma unroll
-              for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(w[j]) == acc) ? j : j0;
-              arg = argc * 32 + j0;
+                  for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(w[j]) == acc) ? j : j0;
+                  arg = cc * 32 + j0;
+                }
+              }
             }
             if (arg >= 0) {
               unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
@@ -369,9 +366,9 @@ __global__ void pool_finalize_kernel(const void* __restrict__ pool_acc, const in
 // ------------------------------------------------------------------ host side
 struct WsLayout {
   uint32_t w_off[kMaxLayers];
-  int64_t wpack_bytes, pool_off, total;
+  int64_t wpack_bytes, pool_off, tile_first_off, total;
 };
-static WsLayout ws_layout(const pcc_phi_desc* d, int64_t B) {
+static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
   WsLayout w{};
   int64_t o = 0;
   for (int l = 0; l < d->n_layers; ++l) {
@@ -382,6 +379,9 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t B) {
   o = (o + 255) / 256 * 256;
   w.pool_off = o;
   o += B * d->hidden * 8;
+  o = (o + 255) / 256 * 256;
+  w.tile_first_off = o;
+  o += cdiv(n, kTileM) * 4;
   w.total = (o + 255) / 256 * 256;
   return w;
 }
@@ -434,7 +434,7 @@ extern "C" int pcc_phi_fused_supported(const pcc_phi_desc* d) { return check_phi
 
 extern "C" int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B) {
   if (check_phi_desc(d, __func__) != 0) return -1;
-  const int64_t fwd = ws_layout(d, B).total, bwd = phi_bwd_workspace_bytes(d, n);
+  const int64_t fwd = ws_layout(d, n, B).total, bwd = phi_bwd_workspace_bytes(d, n);
   return fwd > bwd ? fwd : bwd;  // one query serves both directions
 }
 
@@ -447,7 +447,7 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   PCC_REQUIRE(n < (int64_t)0x7fffffff, "row count exceeds int32 argmax range");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = d->hidden, L = d->n_layers;
-  const WsLayout wl = ws_layout(d, B);
+  const WsLayout wl = ws_layout(d, n, B);
   uint8_t* wsb = (uint8_t*)ws;
 
   PackParams pk{};
@@ -463,6 +463,10 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   for (int l = 0; l < L; ++l) { p.w_off[l] = wl.w_off[l]; p.bias[l] = d->b[l]; }
   p.pool_acc = wsb + wl.pool_off;
   p.trace = (long long*)g_trace_buf;
+  p.tile_first = (const int32_t*)(wsb + wl.tile_first_off);
+  if (p.num_tiles > 0)
+    PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(p.num_tiles, 256), 256, 0, st>>>(offsets, n, B, p.num_tiles, d->pooling,
+                                                                            (int32_t*)(wsb + wl.tile_first_off), nullptr, nullptr);
   if (p.num_tiles > 0) {
     int rc = 0;
 #define PCC_DISPATCH(HH)                                                              \
