@@ -260,32 +260,15 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
         int64_t seg_lo = 0, seg_hi = 0;
         if (b < p.B) { seg_lo = __ldg(p.offsets + b); seg_hi = __ldg(p.offsets + b + 1); }
         float acc = is_max ? -INFINITY : 0.f;
-        int arg = -1;       // exact column of the running max inside this tile, or
-        int argc = -1;      // chunk that holds it (resolved lazily when the set is flushed)
+        int arg = -1;       // column of the running max inside this tile (first occurrence)
         auto flush = [&](int64_t set) {
           if (is_max) {
-            // resolve chunk-level argmax to a column: tcgen05.ld is warp-collective with a uniform
-            // address, and lanes (features) may point at different chunks, so visit each needed chunk
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-              if (__any_sync(0xffffffffu, argc == cc)) {
-                uint32_t w[32];
-                tmem_ld32(lane_base + ACC_T + h * 128 + cc * 32, w);
-                tmem_wait_ld();
-                if (argc == cc) {
-                  int j0 = 31;
-#pragma unroll
-                  for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(w[j]) == acc) ? j : j0;
-                  arg = cc * 32 + j0;
-                }
-              }
-            }
             if (arg >= 0) {
               unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
                                        (unsigned long long)(0xFFFFFFFFu - (uint32_t)(r0 + arg));
               atomicMax(reinterpret_cast<unsigned long long*>(p.pool_acc) + set * H + f, key);
             }
-            acc = -INFINITY; arg = -1; argc = -1;
+            acc = -INFINITY; arg = -1;
           } else {
             atomicAdd(reinterpret_cast<float*>(p.pool_acc) + set * H + f, acc);
             acc = 0.f;
@@ -305,7 +288,13 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
             if (lo == 0 && hi == 32) {  // whole chunk inside the set: tree reduction, no predicates
               if (is_max) {
                 const float m = fmaxf(fmaxf(max8(v), max8(v + 8)), fmaxf(max8(v + 16), max8(v + 24)));
-                if (m > acc || (arg < 0 && argc < 0)) { acc = m; argc = c; arg = -1; }
+                if (m > acc || arg < 0) {  // the chunk improves the maximum: locate its first occurrence
+                  int j0 = 31;
+#pragma unroll
+                  for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(v[j]) == m) ? j : j0;
+                  acc = m;
+                  arg = c * 32 + j0;
+                }
               } else {
                 acc += (sum8(v) + sum8(v + 8)) + (sum8(v + 16) + sum8(v + 24));
               }
@@ -313,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float val = __uint_as_float(v[j]);
-                if (j >= lo && j < hi && (val > acc || (arg < 0 && argc < 0))) { acc = val; arg = c * 32 + j; argc = -1; }
+                if (j >= lo && j < hi && (val > acc || arg < 0)) { acc = val; arg = c * 32 + j; }
               }
             } else {
 #pragma unroll
