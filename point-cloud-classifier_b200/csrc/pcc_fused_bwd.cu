@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, kEpiThreads);
+    mbar_init(a_ready, kEpiWarps);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       if (threadIdx.x == 0) { bulk_s2g(gdst, sbuf, BLOB); bulk_commit(); }
     };
     auto wait_acc = [&]() { mbar_wait(acc_ready, acc_phase); acc_phase ^= 1; tc_fence_after(); };
-    auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(a_ready); };
+    auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(a_ready); };
 
     load_x(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiThreads); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiThreads); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiWarps); mbar_init(&x_empty[i], 1); }
     mbar_init(acc_ready, 1);
-    mbar_init(acc_free, kEpiThreads);
+    mbar_init(acc_free, kEpiWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
                            pack_bf16x2(xr[14], xr[15]));
           }
           fence_proxy_async();
-          mbar_arrive(&x_full[xpar]);
+          mbar_arrive_warp(&x_full[xpar]);
           xpar ^= 1;
         }
         // column sums of the dZ image: warp w owns chunks w, w+8, ...; lane owns rows lane, lane+32, ...
@@ -452,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
             dbacc[i][4] += bf16_lo(u.z); dbacc[i][5] += bf16_hi(u.z); dbacc[i][6] += bf16_lo(u.w); dbacc[i][7] += bf16_hi(u.w);
           }
         }
-        mbar_arrive(&empty[stage]);
+        mbar_arrive_warp(&empty[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
         if (l >= 1) {  // the input image slot is only read by the tensor core; wait for THIS use of the slot
           // to be filled before releasing it, otherwise the arrival could land in the previous phase
           mbar_wait(&full[stage], phase);
-          mbar_arrive(&empty[stage]);
+          mbar_arrive_warp(&empty[stage]);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
         }
       }
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
                             __uint_as_float(v[q * 4 + 3]));
       }
       tc_fence_before();
-      mbar_arrive(acc_free);
+      mbar_arrive_warp(acc_free);
     }
   }
   tc_fence_before();

@@ -89,9 +89,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   uint64_t* full = bars;                 // [kRingF]
   uint64_t* empty = bars + kRingF;       // [kRingF]
-  uint64_t* a_ready = bars + 2 * kRingF;
-  uint64_t* acc_ready = bars + 2 * kRingF + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 2);
+  uint64_t* x_ready = bars + 2 * kRingF;           // layer-0 operand staged (count: all epilogue threads)
+  uint64_t* acc_ready = bars + 2 * kRingF + 1;      // one MMA phase (layer of a tile) complete
+  uint64_t* slab_ready = bars + 2 * kRingF + 2;     // [4] 64-column slab of the activation image written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 6);
 
   constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
   constexpr uint32_t X_LBO = kTileM * 16;      // un-swizzled layer-0 images: K-chunk strides
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
   constexpr int HALVES = H / 128;              // M halves of the transposed final layer
   constexpr int NSLAB = H / 64;                // slabs per H x H layer
   constexpr int NCHUNK = H / 32;               // 32-column accumulator chunks of a hidden layer
-  constexpr uint32_t ACC_T = 256;              // TMEM column base of the transposed accumulators
+  // TMEM: two 256-column accumulators used alternately by successive MMA phases, so the MMA of
+  // layer l+1 can start on the first activation slabs while the epilogue still drains layer l
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
@@ -107,8 +109,9 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
   for (int i = threadIdx.x; i < L * H; i += kThreads) biasS[i] = __ldg(p.bias[i / H] + (i % H));
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, kEpiThreads);
+    mbar_init(x_ready, kEpiWarps);
     mbar_init(acc_ready, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], kEpiWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -139,27 +142,28 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
     if (lane == 0) {
       constexpr uint32_t IDESC_N = make_idesc_bf16(128, H, 0, 0);    // points x features
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, 0, 0);  // features(128) x points
-      uint32_t stage = 0, phase = 0, a_phase = 0;
+      uint32_t stage = 0, phase = 0, x_phase = 0, sl_phase = 0, ph = 0;
       int tn = 0;
       const uint32_t a_base = smem_u32(bufA), x_base = smem_u32(bufX), r_base = smem_u32(ring);
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < L; ++l) {
-          trace_ev(p.trace, 1, tn, 100 + l);
-          mbar_wait(a_ready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
-          trace_ev(p.trace, 1, tn, 110 + l);
+        for (int l = 0; l < L; ++l, ++ph) {
+          const uint32_t acc_col = tmem + (ph & 1) * 256;
           const bool last = (l == L - 1);
+          trace_ev(p.trace, 1, tn, 100 + l);
           if (l == 0) {  // K = 16, un-swizzled images
+            mbar_wait(x_ready, x_phase);
+            x_phase ^= 1;
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            umma_bf16(tmem, make_smem_desc(x_base, X_LBO, 128), make_smem_desc(r_base + stage * SLAB, W0_LBO, 128),
+            trace_ev(p.trace, 1, tn, 110 + l);
+            umma_bf16(acc_col, make_smem_desc(x_base, X_LBO, 128), make_smem_desc(r_base + stage * SLAB, W0_LBO, 128),
                       IDESC_N, 0);
             umma_commit(&empty[stage]);
             if (++stage == kRingF) { stage = 0; phase ^= 1; }
           } else {
             for (int s = 0; s < NSLAB; ++s) {
-              mbar_wait(&full[stage], phase);
+              mbar_wait(&slab_ready[s], sl_phase);  // activation slab s written by the epilogue
+              mbar_wait(&full[stage], phase);        // weight slab s landed
               tc_fence_after();
               if (s == 0) trace_ev(p.trace, 1, tn, 120 + l);
               if (s == NSLAB - 1) trace_ev(p.trace, 1, tn, 130 + l);
@@ -169,17 +173,18 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
                 const uint64_t act_desc = make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32);
                 const uint32_t acc = (s | ks) != 0;
                 if (!last) {
-                  umma_bf16(tmem, act_desc, make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, acc);
+                  umma_bf16(acc_col, act_desc, make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, acc);
                 } else {
 #pragma unroll
                   for (int h = 0; h < HALVES; ++h)
-                    umma_bf16(tmem + ACC_T + h * 128, make_smem_desc_sw128_k(w_slab + h * (128 * 128) + ks * 32), act_desc,
+                    umma_bf16(acc_col + h * 128, make_smem_desc_sw128_k(w_slab + h * (128 * 128) + ks * 32), act_desc,
                               IDESC_T, acc);
                 }
               }
               umma_commit(&empty[stage]);
               if (++stage == kRingF) { stage = 0; phase ^= 1; }
             }
+            sl_phase ^= 1;
           }
           umma_commit(acc_ready);
           trace_ev(p.trace, 1, tn, 140 + l);
@@ -200,12 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
       for (int j = 0; j < kK0; ++j)
         xr[j] = (grp == 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
     };
-    load_x(blockIdx.x);
-    int par = 0, tn = 0;
-    const bool tr0 = (threadIdx.x == 0);
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, par ^= 1) {
-      const int64_t r0 = tile * kTileM;
-      // ---- stage the x tile as the layer-0 operand image [2][128][8] bf16 (group 0 owns the rows)
+    auto stage_x = [&]() {  // registers -> un-swizzled [2][128][8] layer-0 operand image (group 0 owns the rows)
       if (grp == 0) {
         *reinterpret_cast<uint4*>(bufX + r * 16) = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]),
                                                               pack_bf16x2(xr[4], xr[5]), pack_bf16x2(xr[6], xr[7]));
@@ -213,37 +213,57 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
                                                                       pack_bf16x2(xr[12], xr[13]), pack_bf16x2(xr[14], xr[15]));
       }
       fence_proxy_async();
-      mbar_arrive(a_ready);
+      mbar_arrive_warp(x_ready);
+    };
+    load_x(blockIdx.x);
+    int tn = 0;
+    uint32_t ph = 0;
+    const bool tr0 = (threadIdx.x == 0);
+    if (blockIdx.x < p.num_tiles) {
+      stage_x();
+      load_x(blockIdx.x + gridDim.x);
+    }
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t r0 = tile * kTileM;
       if (tr0) trace_ev(p.trace, 0, tn, 0);
-      load_x(tile + gridDim.x);  // prefetch the next tile's rows into registers
       const int b_first = __ldg(p.tile_first + tile);  // first set intersecting this tile (precomputed)
 
       // ---- hidden layers: TMEM -> bias/act/residual -> bf16 image (in place); group g takes the
-      //      chunks g, g+2, ...; TMEM loads are issued one chunk ahead of the math
-      for (int l = 0; l < L - 1; ++l) {
+      //      chunks g, g+2, ...; TMEM loads run one chunk ahead of the math; every finished 64-column
+      //      slab is handed to the MMA warp at once so the next layer's MMAs overlap this epilogue
+      for (int l = 0; l < L - 1; ++l, ++ph) {
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         if (tr0) trace_ev(p.trace, 0, tn, 10 + l);
         const bool res = (p.res_mask >> l) & 1;
         const float* bl = biasS + l * H;
+        const uint32_t acc_base = lane_base + (ph & 1) * 256;
         uint32_t va[32], vb[32];
-        tmem_ld32(lane_base + grp * 32, va);
+        tmem_ld32(acc_base + grp * 32, va);
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 4) {
           tmem_wait_ld();
-          if (c + 2 < NCHUNK) tmem_ld32(lane_base + (c + 2) * 32, vb);
+          if (c + 2 < NCHUNK) tmem_ld32(acc_base + (c + 2) * 32, vb);
           epi_store_chunk<ACT>(va, bufA, bl, r, c, res);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive_warp(&slab_ready[c >> 1]);
           if (c + 2 < NCHUNK) {
             tmem_wait_ld();
-            if (c + 4 < NCHUNK) tmem_ld32(lane_base + (c + 4) * 32, va);
+            if (c + 4 < NCHUNK) tmem_ld32(acc_base + (c + 4) * 32, va);
             epi_store_chunk<ACT>(vb, bufA, bl, r, c + 2, res);
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive_warp(&slab_ready[(c + 2) >> 1]);
           }
         }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(a_ready);
         if (tr0) trace_ev(p.trace, 0, tn, 20 + l);
+      }
+      // ---- the next tile's layer-0 operand can be staged already (its MMA uses the other accumulator)
+      if (tile + gridDim.x < p.num_tiles) {
+        stage_x();
+        load_x(tile + 2 * (int64_t)gridDim.x);
       }
 
       // ---- final layer (transposed): thread = feature, TMEM columns = the tile's points
@@ -251,6 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
       acc_phase ^= 1;
       tc_fence_after();
       if (tr0) trace_ev(p.trace, 0, tn, 30);
+      const uint32_t accT = lane_base + (ph & 1) * 256;
+      ++ph;
       const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
       if (grp < HALVES) {
         const int h = grp;
@@ -275,12 +297,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
           }
         };
         uint32_t va[32], vb[32];
-        tmem_ld32(lane_base + ACC_T + h * 128, va);
+        tmem_ld32(accT + h * 128, va);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tmem_wait_ld();
           uint32_t (&v)[32] = (c & 1) ? vb : va;
-          if (c + 1 < 4) tmem_ld32(lane_base + ACC_T + h * 128 + (c + 1) * 32, (c & 1) ? va : vb);
+          if (c + 1 < 4) tmem_ld32(accT + h * 128 + (c + 1) * 32, (c & 1) ? va : vb);
           const int64_t col0 = r0 + c * 32;
           while (b < p.B && seg_lo < tile_end && seg_lo < col0 + 32) {
             const int lo = (int)((seg_lo > col0 ? seg_lo : col0) - col0);

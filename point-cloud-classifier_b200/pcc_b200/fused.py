@@ -90,7 +90,21 @@ class FusedPhiPoolFn(torch.autograd.Function):
         d.act, d.pooling, d.residual_mask = ACT[act], POOL[pooling], res_mask
         for i, (w, b) in enumerate(tensors):
             d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
-        n, B = x.shape[0], offsets.numel() - 1
+        n, B, H = x.shape[0], offsets.numel() - 1, d.hidden
+        if pooling == "max" and B * H < n:
+            # Max pooling sends gradient only to the argmax rows (autograd of deep_sets.py:104): every
+            # other row of dphi is exactly zero and contributes nothing to any dW / db.  Run the backward
+            # on the B*H "virtual" rows (b, f) -> x[argmax[b, f]] instead of all n rows: set b owns the H
+            # virtual rows b*H .. b*H+H-1 and feature f's argmax is virtual row b*H+f, so the same kernels
+            # produce the identical sums with n/(B*H) times less work.
+            flat = arg.reshape(-1).clamp_min(0).long()
+            x = x.index_select(0, flat)
+            key = (B, H, x.device)
+            if _VIRT.get("key") != key:
+                _VIRT["key"] = key
+                _VIRT["offsets"] = torch.arange(B + 1, device=x.device, dtype=torch.int64) * H
+                _VIRT["arg"] = torch.arange(B * H, device=x.device, dtype=torch.int32).view(B, H)
+            offsets, arg, n = _VIRT["offsets"], _VIRT["arg"], B * H
         grads = [torch.empty_like(t) for t in ws_]
         dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])
         db = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i + 1].data_ptr() for i in range(plan_len)])
@@ -99,6 +113,9 @@ class FusedPhiPoolFn(torch.autograd.Function):
         call("pcc_deepsets_phi_pool_bwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(dpooled), ptr(arg),
              C.cast(dw, C.c_void_p), C.cast(db, C.c_void_p), ptr(ws), dev, st)
         return (None, None, None, *grads)
+
+
+_VIRT = {}  # cached index tensors of the virtual-row backward (static per (B, H, device))
 
 
 def phi_pool(x, offsets, plan: List[dict], act: str, pooling: str):
