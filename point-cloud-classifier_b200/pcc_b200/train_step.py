@@ -16,6 +16,8 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from .distributed import allreduce_gradients
+
 
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, example_inputs: Sequence[torch.Tensor], example_target: torch.Tensor,
@@ -59,14 +61,7 @@ class GraphedTrainStep:
         self.loss.backward()
         if self.allreduce:
             # one flat fp32 bucket, averaged (loss is a mean over the local batch)
-            grads = [p.grad for p in self.params]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            flat.mul_(1.0 / self.world)
-            off = 0
-            for g in grads:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+            allreduce_gradients(self.params, self.world)
         if self.optimizer is not None:
             self.optimizer.step()
 
