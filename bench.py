@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -158,8 +158,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback. Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    def log(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        log(f"process group up: world {world}")
     _lib.call("pcc_check_device", local)
 
     torch.manual_seed(0)
@@ -180,6 +184,7 @@ def run_ours(args):
         gs = build(False)
         graphed = False
     assert model.last_path == ("fused-bf16" if args.precision == "bf16" else "fp32")
+    log(f"train step built (cuda graph: {graphed})")
 
     def barrier():
         if world > 1:
@@ -215,7 +220,9 @@ def run_ours(args):
         loss = gs.step(b[:2], b[2])
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the user reads the loss (wrapper.py:73)
+    log(f"device-resident timing done: {ms_dev:.3f} ms/step")
     ms_e2e = timed(e2e_step, args.steps, W)
+    log(f"e2e timing done: {ms_e2e:.3f} ms/step")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel durations (CUDA events inside the library, eager launches of the same step)

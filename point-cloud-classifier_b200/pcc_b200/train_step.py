@@ -16,7 +16,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from .distributed import allreduce_gradients
+from .distributed import flatten_grads, unflatten_into_grads
 
 
 class GraphedTrainStep:
@@ -42,6 +42,7 @@ class GraphedTrainStep:
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self._step_body()
+                self._post()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if use_graph:
@@ -60,10 +61,19 @@ class GraphedTrainStep:
         self.loss = self.loss_fn(self.logits, self.static_y)
         self.loss.backward()
         if self.allreduce:
-            # one flat fp32 bucket, averaged (loss is a mean over the local batch)
-            allreduce_gradients(self.params, self.world)
-        if self.optimizer is not None:
+            # gradients gathered into one flat fp32 bucket inside the captured region; the collective itself
+            # runs right after the replay (NCCL launches are kept out of the CUDA graph)
+            self.flat = flatten_grads(self.params)
+        elif self.optimizer is not None:
             self.optimizer.step()
+
+    def _post(self):
+        if self.allreduce:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / self.world)   # loss is a mean over the local batch
+            unflatten_into_grads(self.flat, self.params)
+            if self.optimizer is not None:
+                self.optimizer.step()
 
     def load(self, inputs: Sequence[torch.Tensor], target: torch.Tensor):
         """copy a batch (host pinned or device tensors) into the static buffers"""
@@ -76,6 +86,7 @@ class GraphedTrainStep:
             self.graph.replay()
         else:
             self._step_body()
+        self._post()
         return self.loss
 
     def step(self, inputs: Sequence[torch.Tensor], target: torch.Tensor) -> torch.Tensor:
