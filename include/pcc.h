@@ -159,6 +159,16 @@ int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, int device, void* stream);
 
+/* ---- loss and row gather.
+ *      pcc_bce_logits: nn.BCEWithLogitsLoss(reduction="mean") forward AND its gradient in one pass
+ *      (/root/reference/models/wrapper.py:38,64-67): loss[1], dlogits[count] = (sigmoid(z) - y) / count.
+ *      pcc_gather_rows: out[i,:] = x[clamp(idx[i]),:] for rows of d floats (argmax-row backward of max
+ *      pooling). */
+int pcc_bce_logits(const float* logits, const float* target, int64_t count, float* loss, float* dlogits, int device,
+                   void* stream);
+int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count, int d, int64_t n, float* out, int device,
+                    void* stream);
+
 /* ---- accounting / measurement helpers used by bench.py.
  *      pcc_launch_count: kernels launched by this library since the last reset.
  *      pcc_prof_*: CUDA-event brackets around the three fused kernels, recorded on the launching

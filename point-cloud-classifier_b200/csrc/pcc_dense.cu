@@ -120,19 +120,32 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(GemmArgs p) {
   const int64_t kbeg = (int64_t)blockIdx.z * p.k_chunk;
   const int64_t kend = (kbeg + p.k_chunk < p.K) ? kbeg + p.k_chunk : p.K;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int64_t k0 = kbeg; k0 < kend; k0 += 32) {
+  // global -> registers one K tile ahead of the math (the K loop is short: latency, not bandwidth, bound)
+  float ra[4], rb[4];
+  auto fetch = [&](int64_t k0) {
 #pragma unroll
-    for (int i = tid; i < 1024; i += 256) {
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j;
       int m, k;
       if (A_T) { m = i & 31; k = i >> 5; } else { m = i >> 5; k = i & 31; }
-      int64_t gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < p.M && gk < kend) ? (A_T ? __ldg(p.A + gk * p.lda + gm) : __ldg(p.A + gm * p.lda + gk)) : 0.f;
+      const int64_t gm = m0 + m, gk = k0 + k;
+      ra[j] = (gm < p.M && gk < kend) ? (A_T ? __ldg(p.A + gk * p.lda + gm) : __ldg(p.A + gm * p.lda + gk)) : 0.f;
       int n, kb;
       if (B_T) { n = i >> 5; kb = i & 31; } else { n = i & 31; kb = i >> 5; }
-      int64_t gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < p.N && gkb < kend) ? (B_T ? __ldg(p.B + gn * p.ldb + gkb) : __ldg(p.B + gkb * p.ldb + gn)) : 0.f;
+      const int64_t gn = n0 + n, gkb = k0 + kb;
+      rb[j] = (gn < p.N && gkb < kend) ? (B_T ? __ldg(p.B + gn * p.ldb + gkb) : __ldg(p.B + gkb * p.ldb + gn)) : 0.f;
+    }
+  };
+  fetch(kbeg);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += 32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j;
+      if (A_T) As[i >> 5][i & 31] = ra[j]; else As[i & 31][i >> 5] = ra[j];
+      if (B_T) Bs[i & 31][i >> 5] = rb[j]; else Bs[i >> 5][i & 31] = rb[j];
     }
     __syncthreads();
+    if (k0 + 32 < kend) fetch(k0 + 32);
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
@@ -205,15 +218,24 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
   if (i < n) p[i] = 0.f;
 }
 
-// column sums of dy[M,N] -> db[N] (atomic accumulate); block: 256 threads, 128-row slab
+// column sums of dy[M,N] -> db[N] (atomic accumulate): block = 32 columns x 8 row lanes over a 256-row slab
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int64_t M, int64_t N,
                                                      float* __restrict__ db) {
-  const int64_t r0 = (int64_t)blockIdx.y * 128;
-  const int64_t r1 = r0 + 128 < M ? r0 + 128 : M;
-  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < N; c += (int64_t)gridDim.x * 256) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += __ldg(dy + r * N + c);
-    atomicAdd(db + c, s);
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * 256;
+  const int64_t r1 = r0 + 256 < M ? r0 + 256 : M;
+  float s = 0.f;
+  if (c < N)
+    for (int64_t r = r0 + ry; r < r1; r += 8) s += __ldg(dy + r * N + c);
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cx];
+    atomicAdd(db + c, t);
   }
 }
 
@@ -434,7 +456,7 @@ extern "C" int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw,
     p.act = PCC_ACT_NONE; p.accumulate = 1;
     launch_gemm<true, false>(p, 2, st);
     if (db) {
-      dim3 grid((unsigned)cdiv(N, 256), (unsigned)cdiv(M, 128));
+      dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, 256));
       PCC_K(colsum_kernel)<<<grid, 256, 0, st>>>(dy, M, N, db);
     }
   }

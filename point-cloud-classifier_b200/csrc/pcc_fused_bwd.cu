@@ -500,31 +500,58 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
 }
 
-// sum the per-CTA partials: dW_l[H, K] (K = real in-features), db_l[H].
-// block = 32 consecutive outputs x 8 partial groups (warp g sums CTAs g, g+8, ...), coalesced 128 B reads
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part_w,
-                                                           const float* __restrict__ part_b, int grid_ctas, int H,
-                                                           int Kp, int K, float* __restrict__ dw,
-                                                           float* __restrict__ db) {
-  __shared__ float red[8][33];
+// sum the per-CTA partials of ALL layers in one launch: dW_l[H, K] (K = real in-features), db_l[H].
+// One thread owns 4 consecutive outputs of a row (float4 loads over the padded row), 8 thread groups of
+// a block split the CTA range and combine through shared memory.
+struct ReduceParams {
+  const float* part_w[kMaxLayers];
+  const float* part_b[kMaxLayers];
+  float* dw[kMaxLayers];
+  float* db[kMaxLayers];
+  int Kp[kMaxLayers], K[kMaxLayers];
+  int vec_begin[kMaxLayers + 1];  // first float4 work item of each layer
+  int L, H, grid_ctas;
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p) {
+  __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int total = H * K;
-  const int i = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (i < total) {
-    const int row = i / K, col = i % K;
-    for (int c = g; c < grid_ctas; c += 8) s += __ldg(part_w + ((size_t)c * H + row) * Kp + col);
-  } else if (i < total + H) {
-    for (int c = g; c < grid_ctas; c += 8) s += __ldg(part_b + (size_t)c * H + (i - total));
+  const int item = blockIdx.x * 32 + lane;  // float4 work item over [layers][H][(Kp + 4) / 4]  (last vec = bias)
+  int l = 0;
+  while (l + 1 < p.L && item >= p.vec_begin[l + 1]) ++l;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int local = item - p.vec_begin[l];
+  const int vec_per_row = p.Kp[l] / 4 + 1;
+  const int row = local / vec_per_row, v = local % vec_per_row;
+  const bool valid = item < p.vec_begin[p.L] && row < p.H;
+  const bool is_bias = (v == vec_per_row - 1);
+  if (valid) {
+    if (!is_bias) {
+      const float* src = p.part_w[l] + (size_t)row * p.Kp[l] + v * 4;
+      const size_t stride = (size_t)p.H * p.Kp[l];
+      for (int c = g; c < p.grid_ctas; c += 8) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + c * stride));
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+    } else {
+      for (int c = g; c < p.grid_ctas; c += 8) s.x += __ldg(p.part_b[l] + (size_t)c * p.H + row);
+    }
   }
   red[g][lane] = s;
   __syncthreads();
-  if (g == 0) {
-    float t = 0.f;
+  if (g == 0 && valid) {
+    float4 t = red[0][lane];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t += red[j][lane];
-    if (i < total) dw[i] = t;
-    else if (i < total + H) db[i - total] = t;
+    for (int j = 1; j < 8; ++j) { t.x += red[j][lane].x; t.y += red[j][lane].y; t.z += red[j][lane].z; t.w += red[j][lane].w; }
+    if (is_bias) {
+      p.db[l][row] = t.x;
+    } else {
+      const int K = p.K[l], k0 = v * 4;
+      float* dst = p.dw[l] + (size_t)row * K + k0;
+      if (k0 + 0 < K) dst[0] = t.x;
+      if (k0 + 1 < K) dst[1] = t.y;
+      if (k0 + 2 < K) dst[2] = t.z;
+      if (k0 + 3 < K) dst[3] = t.w;
+    }
   }
 }
 
@@ -651,10 +678,17 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
   if (rc != 0) return rc;
+  ReduceParams rp{};
+  rp.L = L; rp.H = H; rp.grid_ctas = wl.grid;
+  int items = 0;
   for (int l = 0; l < L; ++l) {
-    const int K = (l == 0) ? d->input_dim : H, Kp = (l == 0) ? kK0 : H;
-    PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv((int64_t)H * K + H, 32), 256, 0, st>>>(p.part_w[l], p.part_b[l], wl.grid, H,
-                                                                                Kp, K, dw[l], db[l]);
+    rp.part_w[l] = p.part_w[l]; rp.part_b[l] = p.part_b[l]; rp.dw[l] = dw[l]; rp.db[l] = db[l];
+    rp.K[l] = (l == 0) ? d->input_dim : H;
+    rp.Kp[l] = (l == 0) ? kK0 : H;
+    rp.vec_begin[l] = items;
+    items += H * (rp.Kp[l] / 4 + 1);
   }
+  rp.vec_begin[L] = items;
+  PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv(items, 32), 256, 0, st>>>(rp);
   return check_launch(__func__);
 }

@@ -139,9 +139,65 @@ __global__ void __launch_bounds__(256) segment_pool_bwd_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------ fused loss + row gather
+// BCEWithLogitsLoss(reduction=mean) forward and its gradient in one pass (wrapper.py:38,64-67):
+// loss = mean(max(z,0) - z*y + log1p(exp(-|z|))), dlogits = (sigmoid(z) - y) / count
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                                         int64_t count, float* __restrict__ loss,
+                                                         float* __restrict__ dz) {
+  __shared__ float red[8];
+  const float inv = 1.f / (float)count;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float zi = z[i], yi = y[i];
+    s += fmaxf(zi, 0.f) - zi * yi + log1pf(expf(-fabsf(zi)));
+    dz[i] = (1.f / (1.f + expf(-zi)) - yi) * inv;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int j = 0; j < 8; ++j) t += red[j];
+    atomicAdd(loss, t * inv);
+  }
+}
+
+// out[i, :] = x[clamp(idx[i], 0, n-1), :]  (rows of d floats)
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t count, int d,
+                                   int64_t n, float* __restrict__ out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= count * d) return;
+  const int64_t i = t / d;
+  const int j = (int)(t - i * d);
+  int64_t r = idx[i];
+  r = r < 0 ? 0 : (r >= n ? n - 1 : r);
+  out[t] = __ldg(x + r * d + j);
+}
+
 }  // namespace pcc
 
 using namespace pcc;
+
+extern "C" int pcc_bce_logits(const float* logits, const float* target, int64_t count, float* loss, float* dlogits,
+                              int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(count > 0, "empty logits");
+  cudaStream_t st = (cudaStream_t)stream;
+  PCC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  const int blocks = (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
+  PCC_K(bce_logits_kernel)<<<blocks, 256, 0, st>>>(logits, target, count, loss, dlogits);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count, int d, int64_t n, float* out,
+                               int device, void* stream) {
+  PCC_ENTER(device);
+  if (count == 0 || d == 0) return 0;
+  PCC_REQUIRE(n > 0, "gather from an empty tensor");
+  PCC_K(gather_rows_kernel)<<<(unsigned)cdiv(count * d, 256), 256, 0, (cudaStream_t)stream>>>(x, idx, count, d, n, out);
+  return check_launch(__func__);
+}
 
 extern "C" int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int64_t* offsets, int device,
                                    void* stream) {

@@ -49,6 +49,8 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
+    "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp],
     "pcc_launch_count": [_i32],
     "pcc_prof_enable": [_i32],
     "pcc_prof_read": [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],

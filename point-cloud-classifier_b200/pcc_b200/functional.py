@@ -315,3 +315,44 @@ def knn_edges(nbr: torch.Tensor) -> torch.Tensor:
     ei = torch.empty((2, n * k), dtype=torch.int64, device=nbr.device)
     call("pcc_knn_edges", ptr(nbr), n, k, ptr(ei), dev, st)
     return ei
+
+
+# ------------------------------------------------------------------ fused loss, row gather
+class BCEWithLogitsFn(torch.autograd.Function):
+    """nn.BCEWithLogitsLoss(reduction='mean') (wrapper.py:38) with its gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        logits, target = L.f32c(logits), L.f32c(target)
+        dev, st = _ctx(logits, target)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        call("pcc_bce_logits", ptr(logits), ptr(target), logits.numel(), ptr(loss), ptr(dlogits), dev, st)
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None
+
+
+def bce_with_logits(logits, target):
+    return BCEWithLogitsFn.apply(logits, target)
+
+
+class BCEWithLogitsLoss(torch.nn.Module):
+    """drop-in for nn.BCEWithLogitsLoss() (mean reduction) running one fused kernel"""
+
+    def forward(self, logits, target):
+        return bce_with_logits(logits, target)
+
+
+def gather_rows(x: torch.Tensor, idx_i32: torch.Tensor) -> torch.Tensor:
+    """out[i] = x[clamp(idx[i])] for int32 row ids (used by the argmax-row backward of max pooling)"""
+    x = L.f32c(x)
+    dev, st = _ctx(x, idx_i32)
+    flat = idx_i32.reshape(-1)
+    out = torch.empty((flat.numel(), x.shape[1]), dtype=torch.float32, device=x.device)
+    call("pcc_gather_rows", ptr(x), ptr(flat), flat.numel(), x.shape[1], x.shape[0], ptr(out), dev, st)
+    return out

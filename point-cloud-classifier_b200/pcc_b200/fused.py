@@ -97,8 +97,8 @@ class FusedPhiPoolFn(torch.autograd.Function):
             # on the B*H "virtual" rows (b, f) -> x[argmax[b, f]] instead of all n rows: set b owns the H
             # virtual rows b*H .. b*H+H-1 and feature f's argmax is virtual row b*H+f, so the same kernels
             # produce the identical sums with n/(B*H) times less work.
-            flat = arg.reshape(-1).clamp_min(0).long()
-            x = x.index_select(0, flat)
+            from .functional import gather_rows
+            x = gather_rows(x, arg)
             key = (B, H, x.device)
             if _VIRT.get("key") != key:
                 _VIRT["key"] = key

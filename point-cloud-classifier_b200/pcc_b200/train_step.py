@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from .distributed import flatten_grads, unflatten_into_grads
+from .functional import BCEWithLogitsLoss
 
 
 class GraphedTrainStep:
@@ -25,7 +26,7 @@ class GraphedTrainStep:
                  optimizer: Optional[torch.optim.Optimizer] = None, allreduce: bool = False, warmup: int = 3,
                  use_graph: bool = True):
         self.model, self.optimizer = model, optimizer
-        self.loss_fn = loss_fn or torch.nn.BCEWithLogitsLoss()  # wrapper.py:38
+        self.loss_fn = loss_fn or BCEWithLogitsLoss()  # wrapper.py:38, fused forward + gradient kernel
         self.kw = dict(forward_kwargs or {})
         self.allreduce = allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.allreduce else 1

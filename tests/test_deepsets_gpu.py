@@ -112,3 +112,19 @@ def test_large_equal_sets_properties():
     lo = (torch.arange(B, device="cuda") * N).view(B, 1)
     assert bool(((arg >= lo) & (arg < lo + N)).all())
     assert torch.equal(phi_x[arg.long(), torch.arange(256, device="cuda").expand(B, -1)], pooled)
+
+
+def test_fused_bce_loss_and_gather():
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(256, 10, generator=g) * 3).cuda().requires_grad_(True)
+    y = (torch.rand(256, 10, generator=g) > 0.5).float().cuda()
+    loss = PF.bce_with_logits(z, y)
+    (loss * 2.0).backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    ref = torch.nn.BCEWithLogitsLoss()(z2, y)
+    (ref * 2.0).backward()
+    torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(z.grad, z2.grad, rtol=1e-5, atol=1e-8)
+    x = torch.randn(1000, 3, generator=g).cuda()
+    idx = torch.randint(-1, 1000, (777,), generator=g).int().cuda()
+    assert torch.equal(PF.gather_rows(x, idx), x[idx.long().clamp_min(0)])

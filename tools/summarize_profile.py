@@ -1,0 +1,54 @@
+"""Turn gpurun_out/launches_*.csv + a .ncu-rep into the text summaries committed under profiles/."""
+import csv, subprocess, sys, collections
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]; ci = {h: i for i, h in enumerate(hdr)}
+    data = rows[1:]
+    names = [r[ci['Kernel Name']] for r in data]
+    idxs = [i for i, n in enumerate(names) if 'phi_pool_fwd' in n]
+    # last full step: from the segment-offset kernels preceding the last forward kernel to the end
+    start = idxs[-1]
+    while start > 0 and 'wgrad_reduce' not in names[start - 1]:
+        start -= 1
+    step = data[start:]
+    tot = sum(float(r[ci['Metric Value']]) for r in step)
+    with open(out, 'w') as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none: launches of ONE eager train step\n")
+        f.write(f"# (cold-cache, serialised: compare shares, not absolutes).  total {tot/1e3:.1f} us, {len(step)} launches\n")
+        f.write("#   ns      share  kernel\n")
+        for r in step:
+            t = float(r[ci['Metric Value']])
+            f.write(f"{t:9.0f}  {100*t/tot:5.1f}%  {r[ci['Kernel Name']][:110]}\n")
+        agg = collections.defaultdict(float)
+        for r in step:
+            agg[r[ci['Kernel Name']].split('(')[0][:60]] += float(r[ci['Metric Value']])
+        f.write("\n# aggregated by kernel\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            f.write(f"{v:9.0f}  {100*v/tot:5.1f}%  {k}\n")
+    print(open(out).read())
+
+def full(rep, out):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ['Kernel Name', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+            'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+            'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+            'launch__registers_per_thread', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+            'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum',
+            'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
+            'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active']
+    idx = [i for i, h in enumerate(hdr) if h in want]
+    with open(out, 'w') as f:
+        f.write("# ncu --set full --clock-control none, one launch of each fused kernel (B=256, N=1024, H=256, relu+max)\n")
+        for r in rows[2:]:
+            f.write("=====\n")
+            for i in idx:
+                f.write(f"{hdr[i]:80s} {units[i]:14s} {r[i][:70]}\n")
+    print(open(out).read())
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    launches(f"gpurun_out/launches_{tag}.csv", f"profiles/launches_{tag}.txt")
+    full(f"gpurun_out/prof_{tag}.ncu-rep", f"profiles/ncu_full_{tag}.txt")
