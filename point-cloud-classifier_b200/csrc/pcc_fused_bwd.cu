@@ -312,6 +312,34 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 // ====================================================================== K2: wgrad
 constexpr int kSlots = 3;
 
+// Work split of the wgrad kernel.  Each CTA runs two jobs: (0) ONE of the H x H layers (layers 1..L-1
+// are dealt round-robin over the CTAs) on every members-th tile, (1) layer 0 (K = 16) on every grid-th
+// tile.  A CTA therefore flushes one big partial instead of one per layer, and the partial count per
+// big layer is grid / (L-1).
+struct WgradJob {
+  int layer;
+  int64_t first, stride;
+  int slot;  // index of this CTA's partial inside the layer's partial array
+};
+__host__ __device__ inline int wgrad_members(int grid, int L, int layer) {  // CTAs that work on `layer`
+  if (layer == 0) return grid;
+  const int nbig = L - 1;
+  return (grid - (layer - 1) + nbig - 1) / nbig;
+}
+__device__ inline WgradJob wgrad_job(int j, int cta, int grid, int L) {
+  WgradJob w;
+  if (j == 0) {
+    const int nbig = L - 1;
+    w.layer = 1 + cta % nbig;
+    w.first = cta / nbig;
+    w.stride = wgrad_members(grid, L, w.layer);
+    w.slot = cta / nbig;
+  } else {
+    w.layer = 0; w.first = cta; w.stride = grid; w.slot = cta;
+  }
+  return w;
+}
+
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -355,22 +383,27 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         bulk_g2s(slots + stage * BLOB, src, BLOB, &full[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
       };
-      for (int l = 0; l < L; ++l)
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int j = 0; j < 2; ++j) {
+        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+        const int l = jb.layer;
+        for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
           push(p.stage_g[l] + (size_t)tile * BLOB);
           if (l >= 1) push(p.stage_h[l - 1] + (size_t)tile * BLOB);
         }
+      }
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0 /* bit i = phase of x buffer i */, free_phase = 0;
       const uint32_t s_base = smem_u32(slots), x_base = smem_u32(bufX);
-      for (int l = 0; l < L; ++l) {
+      for (int j = 0; j < 2; ++j) {
+        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+        const int l = jb.layer;
         const int Np = (l == 0) ? kK0 : H;
         const uint32_t idesc = make_idesc_bf16(128, Np, 1, 1);
-        if (l > 0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
+        if (j > 0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
         bool first = true;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
           const uint32_t g_stage = stage;
           mbar_wait(&full[stage], phase);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
@@ -411,14 +444,16 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0, acc_phase = 0;
     const int d = p.d;
-    for (int l = 0; l < L; ++l) {
+    for (int j = 0; j < 2; ++j) {
+      const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+      const int l = jb.layer;
       const int Np = (l == 0) ? kK0 : H;
       float dbacc[CPW][8];
 #pragma unroll
       for (int i = 0; i < CPW; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dbacc[i][j] = 0.f;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
         if (l == 0) {  // x tile -> [2][128][8] bf16 image (group 0 owns the rows)
           mbar_wait(&x_empty[xpar], ((xphase >> xpar) & 1) ^ 1);
           xphase ^= 1u << xpar;
@@ -462,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         }
       }
       // ---- db partial: reduce over lanes, lane 0 writes
-      float* pb = p.part_b[l] + (size_t)blockIdx.x * H;
+      float* pb = p.part_b[l] + (size_t)jb.slot * H;
 #pragma unroll
       for (int i = 0; i < CPW; ++i)
 #pragma unroll
@@ -474,22 +509,21 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
       mbar_wait(acc_ready, acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      float* pw = p.part_w[l] + (size_t)blockIdx.x * H * Np;
+      // partial layout: [k (Np)][row (H)] — thread = row, so every store of a warp is one coalesced 128 B line
+      float* pw = p.part_w[l] + (size_t)jb.slot * H * Np;
       const int nchunk = (Np < 32) ? 1 : Np / 32;
+      const int ncol = (Np < 32) ? Np : 32;
 #pragma unroll 1
       for (int item = grp; item < HALVES * nchunk; item += 2) {
         const int o = item / nchunk, c = item % nchunk;
         uint32_t v[32];
         tmem_ld32(lane_base + o * Np + c * 32, v);
         tmem_wait_ld();
-        float* dst = pw + (size_t)(o * 128 + r) * Np + c * 32;
-        const int nq = (Np < 32) ? Np / 4 : 8;
+        float* dst = pw + (size_t)(c * 32) * H + (o * 128 + r);
+        const bool has_tiles = jb.first < p.num_tiles;  // a CTA without tiles for this job contributes zeros
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < nq)
-            *reinterpret_cast<float4*>(dst + q * 4) =
-                make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                            __uint_as_float(v[q * 4 + 3]));
+        for (int q = 0; q < 32; ++q)
+          if (q < ncol) dst[(size_t)q * H] = has_tiles ? __uint_as_float(v[q]) : 0.f;
       }
       tc_fence_before();
       mbar_arrive_warp(acc_free);
@@ -501,39 +535,35 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
 }
 
 // sum the per-CTA partials of ALL layers in one launch: dW_l[H, K] (K = real in-features), db_l[H].
-// One thread owns 4 consecutive outputs of a row (float4 loads over the padded row), 8 thread groups of
-// a block split the CTA range and combine through shared memory.
+// Partials are stored [k][row]; one thread owns 4 consecutive rows of one k (float4 loads), the 8 thread
+// groups of a block split the partial range and combine through shared memory.
 struct ReduceParams {
   const float* part_w[kMaxLayers];
   const float* part_b[kMaxLayers];
   float* dw[kMaxLayers];
   float* db[kMaxLayers];
-  int Kp[kMaxLayers], K[kMaxLayers];
-  int vec_begin[kMaxLayers + 1];  // first float4 work item of each layer
-  int L, H, grid_ctas;
+  int Kp[kMaxLayers], K[kMaxLayers], np[kMaxLayers];
+  int vec_begin[kMaxLayers + 1];  // first float4 work item of each layer: (Kp + 1) * H / 4 items (last k = bias)
+  int L, H;
 };
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p) {
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int item = blockIdx.x * 32 + lane;  // float4 work item over [layers][H][(Kp + 4) / 4]  (last vec = bias)
+  const int item = blockIdx.x * 32 + lane;
   int l = 0;
   while (l + 1 < p.L && item >= p.vec_begin[l + 1]) ++l;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   const int local = item - p.vec_begin[l];
-  const int vec_per_row = p.Kp[l] / 4 + 1;
-  const int row = local / vec_per_row, v = local % vec_per_row;
-  const bool valid = item < p.vec_begin[p.L] && row < p.H;
-  const bool is_bias = (v == vec_per_row - 1);
+  const int vec_per_k = p.H / 4;
+  const int k = local / vec_per_k, row4 = (local % vec_per_k) * 4;
+  const bool valid = item < p.vec_begin[p.L];
+  const bool is_bias = valid && (k == p.Kp[l]);
   if (valid) {
-    if (!is_bias) {
-      const float* src = p.part_w[l] + (size_t)row * p.Kp[l] + v * 4;
-      const size_t stride = (size_t)p.H * p.Kp[l];
-      for (int c = g; c < p.grid_ctas; c += 8) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(src + c * stride));
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-      }
-    } else {
-      for (int c = g; c < p.grid_ctas; c += 8) s.x += __ldg(p.part_b[l] + (size_t)c * p.H + row);
+    const float* src = is_bias ? p.part_b[l] + row4 : p.part_w[l] + (size_t)k * p.H + row4;
+    const size_t stride = is_bias ? (size_t)p.H : (size_t)p.H * p.Kp[l];
+    for (int c = g; c < p.np[l]; c += 8) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + c * stride));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     }
   }
   red[g][lane] = s;
@@ -543,14 +573,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p)
 #pragma unroll
     for (int j = 1; j < 8; ++j) { t.x += red[j][lane].x; t.y += red[j][lane].y; t.z += red[j][lane].z; t.w += red[j][lane].w; }
     if (is_bias) {
-      p.db[l][row] = t.x;
-    } else {
-      const int K = p.K[l], k0 = v * 4;
-      float* dst = p.dw[l] + (size_t)row * K + k0;
-      if (k0 + 0 < K) dst[0] = t.x;
-      if (k0 + 1 < K) dst[1] = t.y;
-      if (k0 + 2 < K) dst[2] = t.z;
-      if (k0 + 3 < K) dst[3] = t.w;
+      *reinterpret_cast<float4*>(p.db[l] + row4) = t;
+    } else if (k < p.K[l]) {
+      float* dst = p.dw[l] + (size_t)row4 * p.K[l] + k;
+      dst[0] = t.x; dst[(size_t)p.K[l]] = t.y; dst[2 * (size_t)p.K[l]] = t.z; dst[3 * (size_t)p.K[l]] = t.w;
     }
   }
 }
@@ -575,6 +601,7 @@ static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms) {
   const int64_t tiles = cdiv(n, kTileM);
   if (sms > kGridCap) sms = kGridCap;
   w.grid = (int)(tiles < sms ? tiles : sms);
+  if (w.grid < L - 1) w.grid = L - 1;  // the wgrad kernel deals the H x H layers round-robin over the CTAs
   if (w.grid < 1) w.grid = 1;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t at = o; o = (o + bytes + 255) / 256 * 256; return at; };
@@ -679,14 +706,15 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
   if (rc != 0) return rc;
   ReduceParams rp{};
-  rp.L = L; rp.H = H; rp.grid_ctas = wl.grid;
+  rp.L = L; rp.H = H;
   int items = 0;
   for (int l = 0; l < L; ++l) {
     rp.part_w[l] = p.part_w[l]; rp.part_b[l] = p.part_b[l]; rp.dw[l] = dw[l]; rp.db[l] = db[l];
     rp.K[l] = (l == 0) ? d->input_dim : H;
     rp.Kp[l] = (l == 0) ? kK0 : H;
+    rp.np[l] = wgrad_members(wl.grid, L, l);
     rp.vec_begin[l] = items;
-    items += H * (rp.Kp[l] / 4 + 1);
+    items += (rp.Kp[l] + 1) * (H / 4);
   }
   rp.vec_begin[L] = items;
   PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv(items, 32), 256, 0, st>>>(rp);
