@@ -38,33 +38,46 @@ struct BwdParams {
 };
 
 struct BwdSmem {
-  uint32_t bufG, bufH, ring, bars, total;
+  uint32_t bufG, bufH, ring, bias, bars, total;
 };
-__host__ __device__ inline BwdSmem bwd_smem(int H) {
+__host__ __device__ inline BwdSmem bwd_smem(int H, int L) {
   BwdSmem s;
   uint32_t o = 0;
   s.bufG = o; o += kTileM * H * 2;   // dZ image (A operand of the dgrad GEMMs)
   s.bufH = o; o += kTileM * H * 2;   // h image; its first 4 KB double as the layer-0 operand (x tile)
   s.ring = o; o += kRingB * w_slab_bytes(H);
-  s.bars = o; o += 256;
+  s.bias = o; o += (uint32_t)(L - 1) * H * 4;  // biases of the hidden layers 0..L-2
+  s.bars = o; o += 128;
   s.total = o;
   return s;
 }
 
 // ====================================================================== K1: chain
+// Per 128-row tile (lh = L-2 is the last hidden layer; L is 2 or 3):
+//   E: x tile -> bufH head                                   | M: z_0 = x W_0^T            -> accA
+//   E: dZ_{L-1} from the pooled gradient -> bufG (staged)     | M: dH_lh = dZ_{L-1} W_{L-1} -> accB
+//   L = 3 only:  E: h_0 = act(z_0 + b_0) -> bufH (staged)     | M: z_1 = h_0 W_1^T          -> accA
+//   E: ONE pass over (accA, accB): h_lh -> bufH and dZ_lh = dH_lh * act'(z_lh) -> bufG (both staged)
+//   L = 3 only:  E: x tile -> bufH head again                 | M: dH_0 = dZ_1 W_1 (+ dH_1 for a ResidualBlock:
+//                                                                  the MMA accumulates onto accB), z_0 -> accA
+//                E: dZ_0 = dH_0 * act'(z_0) -> bufG (staged)
+// so the dgrad of the final layer runs under the h_0 epilogue and z of the last hidden layer is read
+// from TMEM once for both of its uses.
 template <int H, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const BwdSmem lay = bwd_smem(H);
+  const BwdSmem lay = bwd_smem(H, p.L);
   uint8_t* bufG = smem + lay.bufG;
   uint8_t* bufH = smem + lay.bufH;
   uint8_t* ring = smem + lay.ring;
+  float* biasS = reinterpret_cast<float*>(smem + lay.bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kRingB;
-  uint64_t* a_ready = bars + 2 * kRingB;
-  uint64_t* acc_ready = bars + 2 * kRingB + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingB + 2);
+  uint64_t* a_ready = bars + 2 * kRingB;      // an operand image is ready (epilogue warps -> MMA thread)
+  uint64_t* accA_ready = bars + 2 * kRingB + 1;  // z in accA complete
+  uint64_t* accB_ready = bars + 2 * kRingB + 2;  // dH in accB complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingB + 3);
 
   constexpr uint32_t SLAB = w_slab_bytes(H);
   constexpr uint32_t X_LBO = kTileM * 16;
@@ -76,12 +89,14 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
-  const bool recompute_z0 = (L >= 3);  // z_0 is overwritten by z_1 during the forward sweep
+  const int lh = L - 2;
 
+  for (int i = threadIdx.x; i < (L - 1) * H; i += kThreads) biasS[i] = __ldg(p.bias[i / H] + (i % H));
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(a_ready, kEpiWarps);
-    mbar_init(acc_ready, 1);
+    mbar_init(accA_ready, 1);
+    mbar_init(accB_ready, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -100,14 +115,14 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         bulk_g2s(ring + stage * SLAB, src, bytes, &full[stage]);
         if (++stage == kRingB) { stage = 0; phase ^= 1; }
       };
+      auto push_layer = [&](uint32_t off) { for (int s = 0; s < NSLAB; ++s) push(p.wpack + off + (size_t)s * SLAB, SLAB); };
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l <= L - 2; ++l) {
-          if (l == 0) push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);
-          else for (int s = 0; s < NSLAB; ++s) push(p.wpack + p.w_off[l] + (size_t)s * SLAB, SLAB);
-        }
-        for (int l = L - 1; l >= 1; --l) {
-          for (int s = 0; s < NSLAB; ++s) push(p.wpack + p.wt_off[l] + (size_t)s * SLAB, SLAB);
-          if (l == 1 && recompute_z0) push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);
+        push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);        // z_0
+        push_layer(p.wt_off[L - 1]);                            // dgrad of the final layer
+        if (L == 3) {
+          push_layer(p.w_off[1]);                               // z_1
+          push_layer(p.wt_off[1]);                              // dgrad of layer 1
+          push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);      // z_0 again
         }
       }
     }
@@ -117,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       constexpr uint32_t IDESC = make_idesc_bf16(128, H, 0, 0);
       uint32_t stage = 0, phase = 0, a_phase = 0;
       const uint32_t g_base = smem_u32(bufG), h_base = smem_u32(bufH), r_base = smem_u32(ring);
+      auto wait_a = [&]() { mbar_wait(a_ready, a_phase); a_phase ^= 1; tc_fence_after(); };
       // D[acc] (+)= act[128 x H] (SW128 image) * streamed weight image^T
       auto gemm = [&](uint32_t act_base, uint32_t acc_col, bool accumulate_first) {
         for (int s = 0; s < NSLAB; ++s) {
@@ -141,16 +157,21 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         if (++stage == kRingB) { stage = 0; phase ^= 1; }
       };
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l <= L - 2; ++l) {  // forward sweep: z_l -> accA
-          mbar_wait(a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-          if (l == 0) gemm0(); else gemm(h_base, ACC_A, false);
-          umma_commit(acc_ready);
-        }
-        for (int l = L - 1; l >= 1; --l) {  // backward sweep: dH_{l-1} -> accB
-          mbar_wait(a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-          gemm(g_base, ACC_B, (p.res_mask >> l) & 1);
-          if (l == 1 && recompute_z0) gemm0();
-          umma_commit(acc_ready);
+        wait_a();                                   // x tile staged
+        gemm0();
+        umma_commit(accA_ready);
+        wait_a();                                   // dZ of the final layer built
+        gemm(g_base, ACC_B, false);                 // dH_lh
+        umma_commit(accB_ready);
+        if (L == 3) {
+          wait_a();                                 // h_0 image written
+          gemm(h_base, ACC_A, false);               // z_1
+          umma_commit(accA_ready);
+          wait_a();                                 // dZ_1 image written, x tile staged again
+          gemm(g_base, ACC_B, (p.res_mask >> 1) & 1);  // dH_0 (+ dH_1)
+          umma_commit(accB_ready);
+          gemm0();                                  // z_0 again
+          umma_commit(accA_ready);
         }
       }
     }
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     const int quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t acc_phase = 0;
+    uint32_t phA = 0, phB = 0;
     const int d = p.d;
     float xcur[kK0], xnext[kK0];
     auto load_x = [&](int64_t tile) {
@@ -187,8 +208,37 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) { bulk_s2g(gdst, sbuf, BLOB); bulk_commit(); }
     };
-    auto wait_acc = [&]() { mbar_wait(acc_ready, acc_phase); acc_phase ^= 1; tc_fence_after(); };
+    auto wait_A = [&]() { mbar_wait(accA_ready, phA); phA ^= 1; tc_fence_after(); };
+    auto wait_B = [&]() { mbar_wait(accB_ready, phB); phB ^= 1; tc_fence_after(); };
     auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(a_ready); };
+    // h = [old +] act(z + b) for one 8-column group
+    auto h_chunk8 = [&](const uint32_t* z, const float* bl, uint8_t* dst, bool res) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bl);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
+      float o[8];
+      o[0] = act_t<ACT>(__uint_as_float(z[0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(z[1]) + b0.y);
+      o[2] = act_t<ACT>(__uint_as_float(z[2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(z[3]) + b0.w);
+      o[4] = act_t<ACT>(__uint_as_float(z[4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(z[5]) + b1.y);
+      o[6] = act_t<ACT>(__uint_as_float(z[6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(z[7]) + b1.w);
+      if (res) {
+        const uint4 old = *reinterpret_cast<const uint4*>(dst);
+        o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
+        o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    };
+    // dZ = dH * act'(z + b) for one 8-column group
+    auto dz_chunk8 = [&](const uint32_t* z, const uint32_t* g, const float* bl, uint8_t* dst) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bl);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(g[j]) * act_grad_t<ACT>(__uint_as_float(z[j]) + bb[j]);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    };
 
     load_x(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -196,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       const int64_t row = r0 + r;
 #pragma unroll
       for (int j = 0; j < kK0; ++j) xcur[j] = xnext[j];
-      acquire();  // bufH free (previous tile's stores done reading)
+      acquire();  // previous tile's staging stores have finished reading bufH / bufG
       stage_x();
       arrive_a();
       load_x(tile + gridDim.x);
@@ -204,42 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       const int64_t myset = (row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
       const float scale = (row < p.n) ? __ldg(p.row_scale + row) : 0.f;
 
-      // ---- forward sweep epilogues: h_l = [h_{l-1} +] act(z_l + b_l) -> bufH (in place), staged
-      for (int l = 0; l <= L - 2; ++l) {
-        wait_acc();
-        if (l > 0) acquire();  // staging store of h_{l-1} has finished reading bufH
-        const bool res = (p.res_mask >> l) & 1;
-        const float* bl = p.bias[l];
-#pragma unroll 1
-        for (int c = grp; c < NCHUNK; c += 2) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + ACC_A + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint8_t* dst = bufH + act_chunk_off(r, c * 32 + q * 8);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4));
-            float o[8];
-            o[0] = act_t<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
-            o[2] = act_t<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
-            o[4] = act_t<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
-            o[6] = act_t<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
-            if (res) {
-              const uint4 old = *reinterpret_cast<const uint4*>(dst);
-              o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
-              o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
-            }
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          }
-        }
-        store_blob(p.stage_h[l] + (size_t)tile * BLOB, bufH);
-        if (l < L - 2) arrive_a();
-      }
-
       // ---- dZ of the final Linear from the pooled gradient (autograd of deep_sets.py:96-106)
-      acquire();
       {
         const float* g = p.dpooled + (myset >= 0 ? myset : 0) * H;
         const int32_t* am = p.argmax ? p.argmax + (myset >= 0 ? myset : 0) * H : nullptr;
@@ -272,11 +287,37 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       store_blob(p.stage_g[L - 1] + (size_t)tile * BLOB, bufG);
       arrive_a();
 
-      // ---- backward sweep epilogues: dZ_l = dH_l * act'(z_l + b_l) -> bufG, staged
-      for (int l = L - 2; l >= 0; --l) {
-        wait_acc();
-        acquire();
-        const float* bl = p.bias[l];
+      // ---- L = 3: h_0 = act(z_0 + b_0) -> bufH (over the x tile), staged; TMEM loads one chunk ahead
+      if (L == 3) {
+        wait_A();
+        const float* bl = biasS;
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + ACC_A + grp * 32, va);
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 4) {
+          tmem_wait_ld();
+          if (c + 2 < NCHUNK) tmem_ld32(lane_base + ACC_A + (c + 2) * 32, vb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h_chunk8(va + q * 8, bl + c * 32 + q * 8, bufH + act_chunk_off(r, c * 32 + q * 8), false);
+          if (c + 2 < NCHUNK) {
+            tmem_wait_ld();
+            if (c + 4 < NCHUNK) tmem_ld32(lane_base + ACC_A + (c + 4) * 32, va);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              h_chunk8(vb + q * 8, bl + (c + 2) * 32 + q * 8, bufH + act_chunk_off(r, (c + 2) * 32 + q * 8), false);
+          }
+        }
+        store_blob(p.stage_h[0] + (size_t)tile * BLOB, bufH);
+        arrive_a();
+      }
+
+      // ---- one pass over z_lh (accA) and dH_lh (accB): h_lh -> bufH, dZ_lh -> bufG, both staged
+      wait_B();
+      wait_A();
+      acquire();  // staging stores of h_0 (bufH) and dZ_{L-1} (bufG) have finished reading
+      {
+        const bool res = (p.res_mask >> lh) & 1;
+        const float* bl = biasS + lh * H;
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 2) {
           uint32_t z[32], g[32];
@@ -285,20 +326,35 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = __uint_as_float(g[q * 8 + j]) * act_grad_t<ACT>(__uint_as_float(z[q * 8 + j]) + bb[j]);
-            *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, c * 32 + q * 8)) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
+            h_chunk8(z + q * 8, bl + c * 32 + q * 8, bufH + off, res);
+            dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + off);
           }
         }
-        if (l == 1 && recompute_z0) stage_x();  // bufH is free again (acquire above): operand of the z_0 recompute
-        store_blob(p.stage_g[l] + (size_t)tile * BLOB, bufG);
-        if (l >= 1) arrive_a();
+      }
+      store_blob(p.stage_h[lh] + (size_t)tile * BLOB, bufH);
+      store_blob(p.stage_g[lh] + (size_t)tile * BLOB, bufG);
+
+      if (L == 3) {
+        acquire();   // h_1 staged out of bufH: its head can take the x tile again
+        stage_x();
+        arrive_a();
+        // ---- dZ_0 = dH_0 * act'(z_0 + b_0) -> bufG, staged
+        wait_B();
+        wait_A();
+        acquire();
+        const float* bl = biasS;
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 2) {
+          uint32_t z[32], g[32];
+          tmem_ld32(lane_base + ACC_A + c * 32, z);
+          tmem_ld32(lane_base + ACC_B + c * 32, g);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + act_chunk_off(r, c * 32 + q * 8));
+        }
+        store_blob(p.stage_g[0] + (size_t)tile * BLOB, bufG);
       }
     }
     if (threadIdx.x == 0) bulk_wait0();
@@ -624,7 +680,7 @@ int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n) { return bwd_w
 
 template <int H, int ACT>
 static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
-  const BwdSmem lay = bwd_smem(H);
+  const BwdSmem lay = bwd_smem(H, p.L);
   auto kern = phi_bwd_chain_kernel<H, ACT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
