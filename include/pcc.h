@@ -150,14 +150,18 @@ typedef struct {
 /* 0 when the fused path supports the descriptor; <0 with a reason otherwise */
 int pcc_phi_fused_supported(const pcc_phi_desc* d);
 int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B);
-/* x[n,d] fp32, offsets[B+1] -> pooled[B,H] (+ argmax[B,H] for MAX).  ws: workspace. */
+/* bytes of the packed bf16 weight images (forward + transposed) the forward writes and the backward reads */
+int64_t pcc_phi_packed_bytes(const pcc_phi_desc* d);
+/* x[n,d] fp32, offsets[B+1] -> pooled[B,H] (+ argmax[B,H] for MAX).  ws: workspace; wpack: caller buffer of
+ * pcc_phi_packed_bytes() that RECEIVES the packed weight images (keep it for the backward of the same step). */
 int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
-                              float* pooled, int32_t* argmax, void* ws, int device, void* stream);
+                              float* pooled, int32_t* argmax, void* ws, void* wpack, int device, void* stream);
 /* dpooled[B,H] -> dw[l] / db[l] (fp32, OVERWRITTEN) for every phi layer; recomputes the
- * forward per tile.  dw/db arrays follow d->w / d->b order. */
+ * forward per tile.  dw/db arrays follow d->w / d->b order.  wpack: the images written by the forward of
+ * the same parameters. */
 int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
-                              void* ws, int device, void* stream);
+                              void* ws, const void* wpack, int device, void* stream);
 
 /* ---- loss and row gather.
  *      pcc_bce_logits: nn.BCEWithLogitsLoss(reduction="mean") forward AND its gradient in one pass

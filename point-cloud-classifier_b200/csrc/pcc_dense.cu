@@ -176,9 +176,30 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(GemmArgs p) {
   }
 }
 
+// tile configuration (0 = 128x128, 1 = 64x64, 2 = 32x32 small kernel) and split-K factor of a problem
+static void plan_gemm(const GemmArgs& p, int64_t want_split, int* cfg_out, int64_t* split_out, int64_t* k_chunk_out);
+
 template <bool A_T, bool B_T>
 static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   if (p.M == 0 || p.N == 0) return 0;
+  int cfg;
+  int64_t split;
+  plan_gemm(p, want_split, &cfg, &split, &p.k_chunk);
+  p.atomic = split > 1 ? 1 : 0;
+  if (cfg == 0) {
+    dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
+    pcc::note_launch(1), sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
+  } else if (cfg == 1) {
+    dim3 grid((unsigned)cdiv(p.N, 64), (unsigned)cdiv(p.M, 64), (unsigned)split);
+    pcc::note_launch(1), sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
+    pcc::note_launch(1), sgemm_small_kernel<A_T, B_T><<<grid, 256, 0, st>>>(p);
+  }
+  return 0;
+}
+
+static void plan_gemm(const GemmArgs& p, int64_t want_split, int* cfg_out, int64_t* split_out, int64_t* k_chunk_out) {
   const int64_t tiles[3] = {cdiv(p.M, 128) * cdiv(p.N, 128), cdiv(p.M, 64) * cdiv(p.N, 64),
                             cdiv(p.M, 32) * cdiv(p.N, 32)};
   const int64_t min_mn = p.M < p.N ? p.M : p.N;
@@ -194,22 +215,11 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   } else {
     while (cfg < 2 && tiles[cfg] < 120) ++cfg;
   }
-  p.k_chunk = cdiv(cdiv(p.K, split), 32) * 32;
-  if (p.k_chunk == 0) p.k_chunk = 32;
-  split = cdiv(p.K, p.k_chunk);
+  int64_t k_chunk = cdiv(cdiv(p.K, split), 32) * 32;
+  if (k_chunk == 0) k_chunk = 32;
+  split = cdiv(p.K, k_chunk);
   if (split < 1) split = 1;
-  p.atomic = split > 1 ? 1 : 0;
-  if (cfg == 0) {
-    dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
-    pcc::note_launch(1), sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
-  } else if (cfg == 1) {
-    dim3 grid((unsigned)cdiv(p.N, 64), (unsigned)cdiv(p.M, 64), (unsigned)split);
-    pcc::note_launch(1), sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
-  } else {
-    dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
-    pcc::note_launch(1), sgemm_small_kernel<A_T, B_T><<<grid, 256, 0, st>>>(p);
-  }
-  return 0;
+  *cfg_out = cfg; *split_out = split; *k_chunk_out = k_chunk;
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -220,7 +230,7 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
 
 // column sums of dy[M,N] -> db[N] (atomic accumulate): block = 32 columns x 8 row lanes over a 256-row slab
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int64_t M, int64_t N,
-                                                     float* __restrict__ db) {
+                                                     float* __restrict__ db, int direct) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + cx;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][cx];
-    atomicAdd(db + c, t);
+    if (direct) db[c] = t; else atomicAdd(db + c, t);
   }
 }
 
@@ -446,18 +456,22 @@ extern "C" int pcc_linear_bwd_weight(const float* dy, const float* x, float* dw,
                                      int64_t K, int accumulate, int device, void* stream) {
   PCC_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (!accumulate) {
-    PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N * K, 256), 256, 0, st>>>(dw, N * K);
-    if (db) PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(db, N);
-  }
+  GemmArgs p{};  // dw[N,K] = dy^T[N,M] * x[M,K]  (reduction over M)
+  p.A = dy; p.B = x; p.C = dw; p.M = N; p.N = K; p.K = M; p.lda = N; p.ldb = K; p.ldc = K;
+  p.act = PCC_ACT_NONE;
+  int cfg;
+  int64_t split, k_chunk;
+  plan_gemm(p, 2, &cfg, &split, &k_chunk);
+  const bool single_slab = cdiv(M, 256) <= 1;
+  // zero only what will be accumulated into with atomics (split-K partials / multi-slab column sums)
+  if (!accumulate && (split > 1 || M == 0)) PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N * K, 256), 256, 0, st>>>(dw, N * K);
+  if (!accumulate && db && (!single_slab || M == 0)) PCC_K(zero_f32_kernel)<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(db, N);
   if (M > 0) {
-    GemmArgs p{};  // dw[N,K] = dy^T[N,M] * x[M,K]  (reduction over M)
-    p.A = dy; p.B = x; p.C = dw; p.M = N; p.N = K; p.K = M; p.lda = N; p.ldb = K; p.ldc = K;
-    p.act = PCC_ACT_NONE; p.accumulate = 1;
+    p.accumulate = accumulate;  // split == 1: plain store (or += when accumulating); split > 1: atomics
     launch_gemm<true, false>(p, 2, st);
     if (db) {
       dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, 256));
-      PCC_K(colsum_kernel)<<<grid, 256, 0, st>>>(dy, M, N, db);
+      PCC_K(colsum_kernel)<<<grid, 256, 0, st>>>(dy, M, N, db, (single_slab && !accumulate) ? 1 : 0);
     }
   }
   return check_launch(__func__);

@@ -118,6 +118,21 @@ static __global__ void pack_weights_kernel(PackParams p) {
   }
 }
 
+// byte offsets of the weight images inside the packed buffer (same for forward and backward)
+struct PackLayout {
+  uint32_t w_off[kMaxLayers], wt_off[kMaxLayers];
+  int64_t total;
+};
+inline PackLayout pack_layout(int L, int H) {
+  PackLayout w{};
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = (o + bytes + 1023) / 1024 * 1024; return at; };
+  for (int l = 0; l < L; ++l) w.w_off[l] = (uint32_t)take((int64_t)((l == 0) ? kK0 : H) * H * 2);
+  for (int l = 1; l < L; ++l) w.wt_off[l] = (uint32_t)take((int64_t)H * H * 2);
+  w.total = o;
+  return w;
+}
+
 static __global__ void zero_u64_kernel(unsigned long long* p, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0ull;

@@ -644,7 +644,6 @@ __global__ void zero_f32_kernel_b(float* p, int64_t n) {
 
 // ------------------------------------------------------------------ host side
 struct BwdWs {
-  uint32_t w_off[kMaxLayers], wt_off[kMaxLayers];
   int64_t stage_h[kMaxLayers], stage_g[kMaxLayers], part_w[kMaxLayers], part_b[kMaxLayers];
   int64_t row_set, row_scale;
   int64_t total;
@@ -661,8 +660,6 @@ static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms) {
   if (w.grid < 1) w.grid = 1;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t at = o; o = (o + bytes + 255) / 256 * 256; return at; };
-  for (int l = 0; l < L; ++l) w.w_off[l] = (uint32_t)take((int64_t)((l == 0) ? kK0 : H) * H * 2);
-  for (int l = 1; l < L; ++l) w.wt_off[l] = (uint32_t)take((int64_t)H * H * 2);
   const int64_t blob = (int64_t)kTileM * H * 2;
   for (int l = 0; l <= L - 2; ++l) w.stage_h[l] = take(tiles * blob);
   for (int l = 0; l < L; ++l) w.stage_g[l] = take(tiles * blob);
@@ -709,7 +706,7 @@ using namespace pcc;
 
 extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n,
                                          int64_t B, const float* dpooled, const int32_t* argmax, float* const* dw,
-                                         float* const* db, void* ws, int device, void* stream) {
+                                         float* const* db, void* ws, const void* wpack, int device, void* stream) {
   PCC_ENTER(device);
   if (check_phi_desc(d, __func__) != 0) return -1;
   PCC_REQUIRE(d->pooling != PCC_POOL_MAX || argmax != nullptr, "argmax required for max pooling");
@@ -729,17 +726,15 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
     return check_launch(__func__);
   }
 
-  PackParams pk{};
-  for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = wl.w_off[l]; pk.wt_off[l] = wl.wt_off[l]; }
-  pk.wpack = wsb; pk.d = d->input_dim; pk.H = H; pk.L = L;
-  PCC_K(pack_weights_kernel)<<<dim3(32, L, 2), 256, 0, st>>>(pk);
+  PCC_REQUIRE(wpack != nullptr, "packed weight images of the forward pass required");
+  const PackLayout pl = pack_layout(L, H);
 
   BwdParams p{};
   p.x = x; p.offsets = offsets; p.n = n; p.B = B; p.num_tiles = tiles;
   p.d = d->input_dim; p.L = L; p.pooling = d->pooling; p.res_mask = d->residual_mask;
-  p.wpack = wsb; p.dpooled = dpooled; p.argmax = argmax;
+  p.wpack = (const uint8_t*)wpack; p.dpooled = dpooled; p.argmax = argmax;
   for (int l = 0; l < L; ++l) {
-    p.w_off[l] = wl.w_off[l]; p.wt_off[l] = wl.wt_off[l]; p.bias[l] = d->b[l];
+    p.w_off[l] = pl.w_off[l]; p.wt_off[l] = pl.wt_off[l]; p.bias[l] = d->b[l];
     p.stage_g[l] = wsb + wl.stage_g[l];
     if (l <= L - 2) p.stage_h[l] = wsb + wl.stage_h[l];
     p.part_w[l] = (float*)(wsb + wl.part_w[l]);

@@ -376,18 +376,11 @@ __global__ void pool_finalize_kernel(const void* __restrict__ pool_acc, const in
 
 // ------------------------------------------------------------------ host side
 struct WsLayout {
-  uint32_t w_off[kMaxLayers];
-  int64_t wpack_bytes, pool_off, tile_first_off, total;
+  int64_t pool_off, tile_first_off, total;
 };
 static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
   WsLayout w{};
   int64_t o = 0;
-  for (int l = 0; l < d->n_layers; ++l) {
-    w.w_off[l] = (uint32_t)o;
-    o += (int64_t)((l == 0) ? kK0 : d->hidden) * d->hidden * 2;
-  }
-  w.wpack_bytes = o;
-  o = (o + 255) / 256 * 256;
   w.pool_off = o;
   o += B * d->hidden * 8;
   o = (o + 255) / 256 * 256;
@@ -395,6 +388,56 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
   o += cdiv(n, kTileM) * 4;
   w.total = (o + 255) / 256 * 256;
   return w;
+}
+
+// ONE launch for everything the forward kernel needs prepared: blockIdx.y < 2L packs weight image
+// (layer y>>1, transposed if y&1); y == 2L zeroes the pool accumulator; y == 2L+1 computes tile_first
+__global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t pool_count, const int64_t* offsets,
+                                int64_t B, int64_t num_tiles, int32_t* tile_first) {
+  const int y = blockIdx.y;
+  if (y < 2 * pk.L) {
+    const int l = y >> 1;
+    const bool tr = y & 1;
+    if (tr && l == 0) return;
+    const int K = (l == 0) ? pk.d : pk.H;
+    const int Kp = (l == 0) ? kK0 : pk.H;
+    const int total = (Kp / 8) * pk.H;
+    uint8_t* dst = pk.wpack + (tr ? pk.wt_off[l] : pk.w_off[l]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int kc = i / pk.H, row = i % pk.H;
+      uint32_t q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k0 = kc * 8 + 2 * j;
+        float a, b;
+        if (!tr) {
+          a = (k0 < K) ? __ldg(pk.w[l] + (int64_t)row * K + k0) : 0.f;
+          b = (k0 + 1 < K) ? __ldg(pk.w[l] + (int64_t)row * K + k0 + 1) : 0.f;
+        } else {
+          a = __ldg(pk.w[l] + (int64_t)k0 * K + row);
+          b = __ldg(pk.w[l] + (int64_t)(k0 + 1) * K + row);
+        }
+        q[j] = pack_bf16x2(a, b);
+      }
+      const uint32_t off = (l == 0) ? (uint32_t)i * 16u
+                                    : (uint32_t)(kc >> 3) * w_slab_bytes(pk.H) + (uint32_t)row * 128u +
+                                          ((uint32_t)((kc & 7) ^ (row & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst + off) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+  } else if (y == 2 * pk.L) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pool_count; i += (int64_t)gridDim.x * blockDim.x)
+      pool[i] = 0ull;
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < num_tiles; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r0 = i * kTileM;
+      int64_t lo = 0, hi = B;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid + 1) <= r0) lo = mid + 1; else hi = mid;
+      }
+      tile_first[i] = (int32_t)lo;
+    }
+  }
 }
 
 int check_phi_desc(const pcc_phi_desc* d, const char* where) {
@@ -449,8 +492,13 @@ extern "C" int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t 
   return fwd > bwd ? fwd : bwd;  // one query serves both directions
 }
 
+extern "C" int64_t pcc_phi_packed_bytes(const pcc_phi_desc* d) {
+  if (check_phi_desc(d, __func__) != 0) return -1;
+  return pack_layout(d->n_layers, d->hidden).total;
+}
+
 extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n,
-                                         int64_t B, float* pooled, int32_t* argmax, void* ws, int device,
+                                         int64_t B, float* pooled, int32_t* argmax, void* ws, void* wpack, int device,
                                          void* stream) {
   PCC_ENTER(device);
   if (check_phi_desc(d, __func__) != 0) return -1;
@@ -461,23 +509,22 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   const WsLayout wl = ws_layout(d, n, B);
   uint8_t* wsb = (uint8_t*)ws;
 
+  PCC_REQUIRE(wpack != nullptr, "packed-weight buffer required (pcc_phi_packed_bytes)");
+  const PackLayout pl = pack_layout(L, H);
   PackParams pk{};
-  for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = wl.w_off[l]; }
-  pk.wpack = wsb; pk.d = d->input_dim; pk.H = H; pk.L = L;
-  PCC_K(pack_weights_kernel)<<<dim3(32, L), 256, 0, st>>>(pk);
-  if (B * H > 0) PCC_K(zero_u64_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>((unsigned long long*)(wsb + wl.pool_off), B * H);
+  for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = pl.w_off[l]; pk.wt_off[l] = pl.wt_off[l]; }
+  pk.wpack = (uint8_t*)wpack; pk.d = d->input_dim; pk.H = H; pk.L = L;
 
   PhiParams p{};
   p.x = x; p.offsets = offsets; p.n = n; p.B = B; p.num_tiles = cdiv(n, kTileM);
   p.d = d->input_dim; p.L = L; p.pooling = d->pooling; p.res_mask = d->residual_mask;
-  p.wpack = wsb;
-  for (int l = 0; l < L; ++l) { p.w_off[l] = wl.w_off[l]; p.bias[l] = d->b[l]; }
+  p.wpack = (const uint8_t*)wpack;
+  for (int l = 0; l < L; ++l) { p.w_off[l] = pl.w_off[l]; p.bias[l] = d->b[l]; }
   p.pool_acc = wsb + wl.pool_off;
   p.trace = (long long*)g_trace_buf;
   p.tile_first = (const int32_t*)(wsb + wl.tile_first_off);
-  if (p.num_tiles > 0)
-    PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(p.num_tiles, 256), 256, 0, st>>>(offsets, n, B, p.num_tiles, d->pooling,
-                                                                            (int32_t*)(wsb + wl.tile_first_off), nullptr, nullptr);
+  PCC_K(fwd_prep_kernel)<<<dim3(32, 2 * L + 2), 256, 0, st>>>(pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
+                                                             p.num_tiles, (int32_t*)(wsb + wl.tile_first_off));
   if (p.num_tiles > 0) {
     int rc = 0;
 #define PCC_DISPATCH(HH)                                                              \

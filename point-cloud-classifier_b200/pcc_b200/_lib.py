@@ -58,10 +58,12 @@ _SIGS = {
     "pcc_selftest_umma": [_i32, _vp, _i32, _vp],
     "pcc_phi_fused_supported": [C.POINTER(PhiDesc)],
     "pcc_phi_fused_workspace_bytes": [C.POINTER(PhiDesc), _i64, _i64],
-    "pcc_deepsets_phi_pool_fwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp],
-    "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "pcc_phi_packed_bytes": [C.POINTER(PhiDesc)],
+    "pcc_deepsets_phi_pool_fwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
+    "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
-_RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64}
+_RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64,
+             "pcc_phi_packed_bytes": _i64}
 EXPORTS = tuple(_SIGS) + ("pcc_last_error",)
 
 _lib = None

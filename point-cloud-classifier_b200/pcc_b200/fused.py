@@ -72,15 +72,17 @@ class FusedPhiPoolFn(torch.autograd.Function):
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
         pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
         arg = torch.empty((B, H), dtype=torch.int32, device=x.device) if pooling == "max" else None
-        call("pcc_deepsets_phi_pool_fwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(pooled), ptr(arg), ptr(ws), dev, st)
-        ctx.save_for_backward(x, offsets, arg, *ws_)
+        wpack = torch.empty(call("pcc_phi_packed_bytes", C.byref(d)), dtype=torch.uint8, device=x.device)
+        call("pcc_deepsets_phi_pool_fwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(pooled), ptr(arg), ptr(ws), ptr(wpack),
+             dev, st)
+        ctx.save_for_backward(x, offsets, arg, wpack, *ws_)
         ctx.meta = meta
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
         plan_len, act, pooling, res_mask = ctx.meta
-        x, offsets, arg, *ws_ = ctx.saved_tensors
+        x, offsets, arg, wpack, *ws_ = ctx.saved_tensors
         dpooled = L.f32c(dpooled)
         dev = L.require_cuda(dpooled)
         st = L.stream_ptr(dev)
@@ -111,7 +113,7 @@ class FusedPhiPoolFn(torch.autograd.Function):
         ws_bytes = call("pcc_phi_fused_workspace_bytes", C.byref(d), n, B)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
         call("pcc_deepsets_phi_pool_bwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(dpooled), ptr(arg),
-             C.cast(dw, C.c_void_p), C.cast(db, C.c_void_p), ptr(ws), dev, st)
+             C.cast(dw, C.c_void_p), C.cast(db, C.c_void_p), ptr(ws), ptr(wpack), dev, st)
         return (None, None, None, *grads)
 
 

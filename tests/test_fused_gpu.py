@@ -98,8 +98,9 @@ def test_fused_argmax_consistent_with_fp32_oracle():
     pooled = torch.empty(B, H, device="cuda")
     arg = torch.empty(B, H, dtype=torch.int32, device="cuda")
     xc = x.cuda()
+    wpack = torch.empty(_lib.call("pcc_phi_packed_bytes", C.byref(dsc)), dtype=torch.uint8, device="cuda")
     _lib.call("pcc_deepsets_phi_pool_fwd", C.byref(dsc), _lib.ptr(xc), _lib.ptr(off), n, B, _lib.ptr(pooled),
-              _lib.ptr(arg), _lib.ptr(ws), 0, _lib.stream_ptr(0))
+              _lib.ptr(arg), _lib.ptr(ws), _lib.ptr(wpack), 0, _lib.stream_ptr(0))
     arg = arg.cpu().long()
     offs = aux["offsets"]
     lo, hi = offs[:-1].view(B, 1), offs[1:].view(B, 1)
@@ -135,8 +136,9 @@ def _fused_argmax(m, x, off, act):
     ws = torch.empty(_lib.call("pcc_phi_fused_workspace_bytes", C.byref(dsc), n, B), dtype=torch.uint8, device="cuda")
     pooled = torch.empty(B, H, device="cuda")
     arg = torch.empty(B, H, dtype=torch.int32, device="cuda")
+    wpack = torch.empty(_lib.call("pcc_phi_packed_bytes", C.byref(dsc)), dtype=torch.uint8, device="cuda")
     _lib.call("pcc_deepsets_phi_pool_fwd", C.byref(dsc), _lib.ptr(x), _lib.ptr(off), n, B, _lib.ptr(pooled),
-              _lib.ptr(arg), _lib.ptr(ws), 0, _lib.stream_ptr(0))
+              _lib.ptr(arg), _lib.ptr(ws), _lib.ptr(wpack), 0, _lib.stream_ptr(0))
     return arg.cpu().long()
 
 
