@@ -26,6 +26,11 @@ class PhiDesc(C.Structure):
                 ("w", _vp * MAX_PHI_LAYERS), ("b", _vp * MAX_PHI_LAYERS)]
 
 
+class HeadDesc(C.Structure):
+    """mirror of pcc_head_desc (include/pcc.h)"""
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * 5), ("act", C.c_int32), ("w", _vp * 4), ("b", _vp * 4)]
+
+
 # name -> argtypes (every entry returns int unless listed in _RESTYPES)
 _SIGS = {
     "pcc_version": [],
@@ -49,6 +54,9 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_mlp_head_supported": [C.POINTER(HeadDesc)],
+    "pcc_mlp_head_fwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _i64, _i32, _vp],
+    "pcc_mlp_head_bwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
     "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp],
     "pcc_launch_count": [_i32],

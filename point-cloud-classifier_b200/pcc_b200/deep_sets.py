@@ -149,7 +149,20 @@ class DeepSets(nn.Module):
             phi_x = self._mlp(self._phi_plan, x)
             pooled = PF.segment_pool(phi_x, offsets, self.pooling)
             self.last_path = "fp32"
-        return self._mlp(self._rho_plan, pooled)
+        return self._rho(pooled)
+
+    def _rho(self, pooled):
+        """set encoder head: one fused launch per direction when the stack has no LayerNorm and fits the
+        head kernel (widths <= 1024, multiples of 4); otherwise layer by layer."""
+        plan = self._rho_plan
+        dims = [plan[0]["lin"].in_features] + [Lr["lin"].out_features for Lr in plan]
+        plain = all(Lr["ln"] is None and not Lr["res"] and Lr["lin"].bias is not None for Lr in plan)
+        if plain and PF.head_supported(dims, self._act_name) and pooled.shape[0] <= 65536:
+            params = []
+            for Lr in plan:
+                params += [Lr["lin"].weight, Lr["lin"].bias]
+            return PF.mlp_head(pooled, self._act_name, params)
+        return self._mlp(plan, pooled)
 
     def forward(self, *args, **kwargs):
         """(x[sum N_i, input_dim] f32, idx[sum N_i] i64) -> logits[B, output_dim].

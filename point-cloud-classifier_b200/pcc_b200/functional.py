@@ -356,3 +356,59 @@ def gather_rows(x: torch.Tensor, idx_i32: torch.Tensor) -> torch.Tensor:
     out = torch.empty((flat.numel(), x.shape[1]), dtype=torch.float32, device=x.device)
     call("pcc_gather_rows", ptr(x), ptr(flat), flat.numel(), x.shape[1], x.shape[0], ptr(out), dev, st)
     return out
+
+
+# ------------------------------------------------------------------ fused rho head
+def _head_desc(ws, act: str) -> "L.HeadDesc":
+    d = L.HeadDesc()
+    d.n_layers = len(ws) // 2
+    d.dims[0] = ws[0].shape[1]
+    for i in range(d.n_layers):
+        d.dims[i + 1] = ws[2 * i].shape[0]
+        d.w[i], d.b[i] = ws[2 * i].data_ptr(), ws[2 * i + 1].data_ptr()
+    d.act = ACT[act]
+    return d
+
+
+def head_supported(dims, act: str) -> bool:
+    """static check: 1..4 layers, widths <= 1024, every layer input width a multiple of 4"""
+    if len(dims) < 2 or len(dims) > 5 or act not in ("relu", "gelu", "silu", "tanh"):
+        return False
+    return all(1 <= v <= 1024 for v in dims) and all(v % 4 == 0 for v in dims[:-1])
+
+
+class MLPHeadFn(torch.autograd.Function):
+    """rho(pooled) of deep_sets.py:112 (Linear/act stack without LayerNorm) in one launch per direction."""
+
+    @staticmethod
+    def forward(ctx, x, act: str, *params):
+        x = L.f32c(x)
+        ws = [L.f32c(p) for p in params]
+        dev, st = _ctx(x, *ws)
+        d = _head_desc(ws, act)
+        M = x.shape[0]
+        zwidth = sum(ws[2 * i].shape[0] for i in range(d.n_layers - 1))
+        y = torch.empty((M, ws[-2].shape[0]), dtype=torch.float32, device=x.device)
+        zsave = torch.empty((M, max(zwidth, 1)), dtype=torch.float32, device=x.device)
+        call("pcc_mlp_head_fwd", C.byref(d), ptr(x), ptr(y), ptr(zsave), M, dev, st)
+        ctx.save_for_backward(x, zsave, *ws)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, zsave, *ws = ctx.saved_tensors
+        dy = L.f32c(dy)
+        dev, st = _ctx(dy)
+        d = _head_desc(ws, ctx.act)
+        grads = [torch.empty_like(t) for t in ws]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = (C.c_void_p * 4)(*[grads[2 * i].data_ptr() for i in range(d.n_layers)])
+        db = (C.c_void_p * 4)(*[grads[2 * i + 1].data_ptr() for i in range(d.n_layers)])
+        call("pcc_mlp_head_bwd", C.byref(d), ptr(x), ptr(zsave), ptr(dy), ptr(dx), C.cast(dw, C.c_void_p),
+             C.cast(db, C.c_void_p), x.shape[0], dev, st)
+        return (dx, None, *grads)
+
+
+def mlp_head(x, act: str, params):
+    return MLPHeadFn.apply(x, act, *params)

@@ -128,3 +128,33 @@ def test_fused_bce_loss_and_gather():
     x = torch.randn(1000, 3, generator=g).cuda()
     idx = torch.randint(-1, 1000, (777,), generator=g).int().cuda()
     assert torch.equal(PF.gather_rows(x, idx), x[idx.long().clamp_min(0)])
+
+
+@pytest.mark.parametrize("dims,act,M", [([256, 256, 10], "relu", 256), ([128, 64, 32, 1], "gelu", 37),
+                                        ([256, 1], "silu", 5), ([1024, 512, 128, 256, 3], "tanh", 70)])
+def test_fused_head_matches_torch(dims, act, M):
+    g = torch.Generator().manual_seed(9)
+    ws, ps = [], []
+    for i in range(len(dims) - 1):
+        w = (torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).cuda().requires_grad_(True)
+        b = (torch.randn(dims[i + 1], generator=g) * 0.1).cuda().requires_grad_(True)
+        ws += [w, b]
+    x = torch.randn(M, dims[0], generator=g).cuda().requires_grad_(True)
+    go = torch.randn(M, dims[-1], generator=g).cuda()
+    assert PF.head_supported(dims, act)
+    y = PF.mlp_head(x, act, ws)
+    y.backward(go)
+    got = [x.grad.clone()] + [t.grad.clone() for t in ws]
+    x.grad = None
+    for t in ws:
+        t.grad = None
+    fn = {"relu": torch.relu, "gelu": torch.nn.functional.gelu, "silu": torch.nn.functional.silu, "tanh": torch.tanh}[act]
+    h = x
+    for i in range(len(dims) - 1):
+        h = torch.nn.functional.linear(h, ws[2 * i], ws[2 * i + 1])
+        if i < len(dims) - 2:
+            h = fn(h)
+    h.backward(go)
+    torch.testing.assert_close(y, h, rtol=1e-4, atol=1e-5)
+    for a, b in zip(got, [x.grad] + [t.grad for t in ws]):
+        assert rel_err(a, b) < 1e-4
