@@ -239,6 +239,28 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     };
+    // both at once (the activation and its derivative share their transcendental)
+    auto hdz_chunk8 = [&](const uint32_t* z, const uint32_t* g, const float* bl, uint8_t* hdst, uint8_t* gdst, bool res) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bl);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float da;
+        act_and_grad_t<ACT>(__uint_as_float(z[j]) + bb[j], o[j], da);
+        q[j] = __uint_as_float(g[j]) * da;
+      }
+      if (res) {
+        const uint4 old = *reinterpret_cast<const uint4*>(hdst);
+        o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
+        o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+      }
+      *reinterpret_cast<uint4*>(hdst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      *reinterpret_cast<uint4*>(gdst) = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]),
+                                                   pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
+    };
 
     load_x(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -327,8 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
-            h_chunk8(z + q * 8, bl + c * 32 + q * 8, bufH + off, res);
-            dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + off);
+            hdz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufH + off, bufG + off, res);
           }
         }
       }
