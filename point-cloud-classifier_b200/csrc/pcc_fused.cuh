@@ -197,6 +197,7 @@ __device__ __forceinline__ float act_grad_t(float z) {
 }
 
 int check_phi_desc(const pcc_phi_desc* d, const char* where);
+void* debug_trace_buffer();  // device buffer set through pcc_debug_set_trace, or null
 int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n);
 
 }  // namespace pcc

@@ -35,7 +35,16 @@ struct BwdParams {
   float* part_b[kMaxLayers];     // per-CTA partial db_l [grid][H]
   const int32_t* row_set;        // [n] set of each row (-1: none), seg_prep_kernel
   const float* row_scale;        // [n] pooled-gradient scale of the row's set
+  long long* trace;              // optional (debug) event trace of CTA 0
 };
+
+__device__ __forceinline__ void trace_b(long long* trace, int role, int& n, int id) {
+  if (trace && blockIdx.x == 0 && n < 2047) {
+    trace[role * 4096 + 2 * n] = id;
+    trace[role * 4096 + 2 * n + 1] = clock64();
+    ++n;
+  }
+}
 
 struct BwdSmem {
   uint32_t bufG, bufH, ring, bias, bars, total;
@@ -167,9 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           wait_a();                                 // h_0 image written
           gemm(h_base, ACC_A, false);               // z_1
           umma_commit(accA_ready);
-          wait_a();                                 // dZ_1 image written, x tile staged again
+          wait_a();                                 // dZ_1 image written
           gemm(g_base, ACC_B, (p.res_mask >> 1) & 1);  // dH_0 (+ dH_1)
           umma_commit(accB_ready);
+          wait_a();                                 // x tile staged again
           gemm0();                                  // z_0 again
           umma_commit(accA_ready);
         }
@@ -263,55 +273,79 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     };
 
     load_x(blockIdx.x);
+    int tn = 0;
+    const bool tr0 = threadIdx.x == 0;
+#define TRE(id) do { if (tr0) trace_b(p.trace, 0, tn, id); } while (0)
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t r0 = tile * kTileM;
       const int64_t row = r0 + r;
 #pragma unroll
       for (int j = 0; j < kK0; ++j) xcur[j] = xnext[j];
-      acquire();  // previous tile's staging stores have finished reading bufH / bufG
-      stage_x();
+      TRE(0);
+      stage_x();  // bufH is free: its last staging store (h_lh) was waited for before dZ_0 / at the previous tile
       arrive_a();
+      TRE(2);
       load_x(tile + gridDim.x);
       // set of this thread's row (for the pooled-gradient scatter), precomputed
       const int64_t myset = (row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
       const float scale = (row < p.n) ? __ldg(p.row_scale + row) : 0.f;
 
       // ---- dZ of the final Linear from the pooled gradient (autograd of deep_sets.py:96-106)
+      acquire();  // the previous tile's dZ_0 store has finished reading bufG
+      TRE(1);
       {
-        const float* g = p.dpooled + (myset >= 0 ? myset : 0) * H;
-        const int32_t* am = p.argmax ? p.argmax + (myset >= 0 ? myset : 0) * H : nullptr;
-#pragma unroll 1
-        for (int kc = grp; kc < H / 8; kc += 2) {
-          float o[8];
-          if (myset >= 0) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + kc * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + kc * 8 + 4));
-            o[0] = g0.x; o[1] = g0.y; o[2] = g0.z; o[3] = g0.w; o[4] = g1.x; o[5] = g1.y; o[6] = g1.z; o[7] = g1.w;
-            if (p.pooling == PCC_POOL_MAX) {
-              const int4 a0 = __ldg(reinterpret_cast<const int4*>(am + kc * 8));
-              const int4 a1 = __ldg(reinterpret_cast<const int4*>(am + kc * 8 + 4));
-              const int rr = (int)row;
-              o[0] = a0.x == rr ? o[0] : 0.f; o[1] = a0.y == rr ? o[1] : 0.f; o[2] = a0.z == rr ? o[2] : 0.f;
-              o[3] = a0.w == rr ? o[3] : 0.f; o[4] = a1.x == rr ? o[4] : 0.f; o[5] = a1.y == rr ? o[5] : 0.f;
-              o[6] = a1.z == rr ? o[6] : 0.f; o[7] = a1.w == rr ? o[7] : 0.f;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] *= scale;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        // the pooled-gradient rows of the sets that intersect this tile are staged one set at a time in a
+        // scratch area of bufH (free until the h_0 epilogue) and broadcast from shared memory; a thread
+        // writes its row when its own set is staged.  (Per-thread global loads here were latency bound:
+        // 6.6k cycles per tile.)
+        float* gS = reinterpret_cast<float*>(bufH + 16384);
+        int* aS = reinterpret_cast<int*>(bufH + 16384 + H * 4);
+        const int64_t last_row = (r0 + kTileM - 1 < p.n - 1) ? r0 + kTileM - 1 : p.n - 1;
+        const int64_t b_lo = __ldg(p.row_set + r0), b_hi = __ldg(p.row_set + last_row);
+        const bool is_max = (p.pooling == PCC_POOL_MAX);
+        if (myset < 0) {  // rows past the last set carry no gradient
+          for (int kc = grp; kc < H / 8; kc += 2)
+            *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, kc * 8)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int64_t b = (b_lo < 0 ? 0 : b_lo); b <= b_hi; ++b) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // previous set's scratch fully consumed
+          for (int i = threadIdx.x; i < H; i += kEpiThreads) {
+            gS[i] = __ldg(p.dpooled + b * H + i);
+            if (is_max) aS[i] = __ldg(p.argmax + b * H + i);
           }
-          *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, kc * 8)) =
-              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (myset == b) {
+            const int rr = (int)row;
+#pragma unroll 2
+            for (int kc = grp; kc < H / 8; kc += 2) {
+              const float4 g0 = *reinterpret_cast<const float4*>(gS + kc * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(gS + kc * 8 + 4);
+              float o[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              if (is_max) {
+                const int4 a0 = *reinterpret_cast<const int4*>(aS + kc * 8);
+                const int4 a1 = *reinterpret_cast<const int4*>(aS + kc * 8 + 4);
+                o[0] = a0.x == rr ? o[0] : 0.f; o[1] = a0.y == rr ? o[1] : 0.f; o[2] = a0.z == rr ? o[2] : 0.f;
+                o[3] = a0.w == rr ? o[3] : 0.f; o[4] = a1.x == rr ? o[4] : 0.f; o[5] = a1.y == rr ? o[5] : 0.f;
+                o[6] = a1.z == rr ? o[6] : 0.f; o[7] = a1.w == rr ? o[7] : 0.f;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] *= scale;
+              }
+              *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, kc * 8)) =
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+          }
         }
       }
+      TRE(3);
       store_blob(p.stage_g[L - 1] + (size_t)tile * BLOB, bufG);
       arrive_a();
+      TRE(4);
 
       // ---- L = 3: h_0 = act(z_0 + b_0) -> bufH (over the x tile), staged; TMEM loads one chunk ahead
       if (L == 3) {
         wait_A();
+        TRE(5);
         const float* bl = biasS;
         uint32_t va[32], vb[32];
         tmem_ld32(lane_base + ACC_A + grp * 32, va);
@@ -329,14 +363,19 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
               h_chunk8(vb + q * 8, bl + (c + 2) * 32 + q * 8, bufH + act_chunk_off(r, (c + 2) * 32 + q * 8), false);
           }
         }
+        TRE(6);
         store_blob(p.stage_h[0] + (size_t)tile * BLOB, bufH);
         arrive_a();
+        TRE(7);
       }
 
       // ---- one pass over z_lh (accA) and dH_lh (accB): h_lh -> bufH, dZ_lh -> bufG, both staged
       wait_B();
+      TRE(8);
       wait_A();
+      TRE(9);
       acquire();  // staging stores of h_0 (bufH) and dZ_{L-1} (bufG) have finished reading
+      TRE(10);
       {
         const bool res = (p.res_mask >> lh) & 1;
         const float* bl = biasS + lh * H;
@@ -353,17 +392,26 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           }
         }
       }
+      TRE(11);
       store_blob(p.stage_h[lh] + (size_t)tile * BLOB, bufH);
       store_blob(p.stage_g[lh] + (size_t)tile * BLOB, bufG);
+      TRE(12);
 
       if (L == 3) {
-        acquire();   // h_1 staged out of bufH: its head can take the x tile again
+        arrive_a();  // dZ_1 image complete: the dgrad of layer 1 can start while the staging stores drain
+        // h_1 (the older of the two stores) staged out of bufH: its head can take the x tile again; the
+        // dZ_1 store may still be reading bufG
+        if (threadIdx.x == 0) bulk_wait_read1();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        TRE(13);
         stage_x();
         arrive_a();
         // ---- dZ_0 = dH_0 * act'(z_0 + b_0) -> bufG, staged
         wait_B();
         wait_A();
+        TRE(14);
         acquire();
+        TRE(15);
         const float* bl = biasS;
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 2) {
@@ -375,9 +423,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           for (int q = 0; q < 4; ++q)
             dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + act_chunk_off(r, c * 32 + q * 8));
         }
+        TRE(16);
         store_blob(p.stage_g[0] + (size_t)tile * BLOB, bufG);
+        TRE(17);
       }
     }
+#undef TRE
     if (threadIdx.x == 0) bulk_wait0();
   }
 
@@ -761,6 +812,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
     p.part_w[l] = (float*)(wsb + wl.part_w[l]);
     p.part_b[l] = (float*)(wsb + wl.part_b[l]);
   }
+  p.trace = (long long*)debug_trace_buffer();
   p.row_set = (const int32_t*)(wsb + wl.row_set);
   p.row_scale = (const float*)(wsb + wl.row_scale);
   PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(offsets, n, B, tiles, d->pooling, nullptr,

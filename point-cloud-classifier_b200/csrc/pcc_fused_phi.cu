@@ -457,6 +457,7 @@ int check_phi_desc(const pcc_phi_desc* d, const char* where) {
 }
 
 static void* g_trace_buf = nullptr;  // set through pcc_debug_set_trace (diagnostics only)
+void* debug_trace_buffer() { return g_trace_buf; }
 
 template <int H, int ACT>
 static int launch_fwd(const PhiParams& p, cudaStream_t st) {
