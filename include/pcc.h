@@ -163,21 +163,25 @@ int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, const void* wpack, int device, void* stream);
 
-/* ---- fused set-encoder head: rho = [Linear + act] x (n_layers-1) + Linear over M = batch rows
- *      (deep_sets.py:112 with the stack of :59-72, no LayerNorm).  One launch forward, one backward.
- *      zsave[M, sum of hidden widths] keeps the pre-activations for the backward.  dw / db are OVERWRITTEN. */
+/* ---- set-encoder head: rho = [Linear + act] x (n_layers-1) + Linear over M = batch rows
+ *      (deep_sets.py:112 with the stack of :59-72, no LayerNorm).  One launch per layer and direction
+ *      (32x32 output tiles over the whole chip; activation, act' and the bias gradient are folded into the
+ *      operand loads), no atomics: results are bitwise reproducible.
+ *      zsave[M, sum of hidden widths] keeps the pre-activations for the backward.  dw / db are OVERWRITTEN.
+ *      ws (backward): pcc_mlp_head_workspace_bytes(d, M) bytes of scratch, may be null for n_layers == 1. */
 typedef struct {
   int32_t n_layers;   /* hidden layers + final Linear, 1..4 */
-  int32_t dims[5];    /* dims[0] = input width, dims[l+1] = output width of layer l; <= 1024, inputs % 4 == 0 */
+  int32_t dims[5];    /* dims[0] = input width, dims[l+1] = output width of layer l; <= 1024 */
   int32_t act;        /* PCC_ACT_RELU / GELU / SILU / TANH (hidden layers) */
   const float* w[4];  /* fp32 [out, in], nn.Linear layout */
   const float* b[4];
 } pcc_head_desc;
 int pcc_mlp_head_supported(const pcc_head_desc* d);
+int64_t pcc_mlp_head_workspace_bytes(const pcc_head_desc* d, int64_t M);
 int pcc_mlp_head_fwd(const pcc_head_desc* d, const float* x, float* y, float* zsave, int64_t M, int device,
                      void* stream);
 int pcc_mlp_head_bwd(const pcc_head_desc* d, const float* x, const float* zsave, const float* dy, float* dx,
-                     float* const* dw, float* const* db, int64_t M, int device, void* stream);
+                     float* const* dw, float* const* db, void* ws, int64_t M, int device, void* stream);
 
 /* ---- loss and row gather.
  *      pcc_bce_logits: nn.BCEWithLogitsLoss(reduction="mean") forward AND its gradient in one pass

@@ -1,219 +1,245 @@
-// Fused rho head (set encoder): [Linear + act] x (0..3) + Linear, M = batch rows.
+// rho head (set encoder): [Linear + act] x (0..3) + Linear, M = batch rows.
 //   reference: /root/reference/models/deep_sets.py:112 (self.rho(pooled)) with the layer stack of :59-72
 //   (no LayerNorm variant) and its autograd.
-// The head is tiny (0.07 GFLOP per train step at the yaml shape) and pure launch latency when run layer by
-// layer (13 launches); here the whole forward is one launch and the whole backward another.  Each CTA owns 8
-// rows through ALL layers (rows are independent), activations live in shared memory, weights stream from L2
-// with 128-bit loads (one warp per output unit in the forward, one thread per input column in the dgrad),
-// weight gradients are combined across CTAs with vector atomics (red.global.add.v4.f32).
+// The head is tiny (0.07 GFLOP per train step at the yaml shape), so what matters is the LENGTH of the
+// dependent chain, not throughput.  An earlier version ran one CTA per 4 rows through all layers in a
+// single launch: every CTA streamed every weight matrix through a latency-bound loop and the weight
+// gradients needed ~1M vector atomics (16 us forward, 30 us backward, warm).  Here every layer is ONE
+// launch of 32x32 output tiles spread over the whole chip (a 256x256x256 layer = 64 CTAs, K loop of 4
+// tiles), with all elementwise work folded into the operand loads:
+//   forward  layer l : z_l = f(in) W_l^T + b_l          f = act for l > 0 (input is the saved z_{l-1})
+//   backward layer l : dz_l = g_l * act'(z_l) built on load (g_L-1 = dy), and in the SAME launch
+//                        dW_l = dz_l^T in_l , db_l = colsum(dz_l)      (tiles over [N_l, K_l])
+//                        g_{l-1} = dz_l W_l                            (tiles over [M,   K_l])
+// No atomics, no zero-fill launches, bitwise deterministic.
 #include "pcc_common.cuh"
 
 namespace pcc {
 
-constexpr int kHeadRows = 4;   // rows per CTA (64 CTAs at B = 256)
-constexpr int kHeadUnits = 4;  // output units a warp processes together (independent weight-load streams)
 constexpr int kHeadMaxDim = 1024;
 constexpr int kHeadMaxLayers = 4;
+constexpr int kHT = 32;    // output tile edge
+constexpr int kHK = 64;    // contraction tile
+constexpr int kHThreads = 256;
 
-struct HeadParams {
-  int L;                        // layers incl. the final Linear
-  int dims[kHeadMaxLayers + 1]; // dims[0] = input width, dims[l+1] = output width of layer l
-  int zoff[kHeadMaxLayers];     // column offset of hidden layer l inside zsave
-  int zwidth;                   // sum of hidden widths
+// operand element (i, kk): i = output index of the tile problem, kk = contraction index
+struct HeadOperand {
+  const float* p;
+  const float* q;     // act' argument (mode 2)
+  int64_t si, sk;     // element strides of p along i / kk (one of them is 1)
+  int64_t qi, qk;
+  int mode;           // 0: p   1: act(p)   2: p * act'(q)
+};
+// C[i][j] = sum_kk A(i,kk) B(j,kk) (+ bias[j]);  colsum[i] = sum_kk A(i,kk)
+struct HeadTileProb {
+  HeadOperand A, B;
+  int I, J, KK;
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  float* colsum;
+  int tiles_j, tiles;
+};
+struct HeadTileParams {
+  HeadTileProb prob[2];
   int act;
-  const float* w[kHeadMaxLayers];
-  const float* b[kHeadMaxLayers];
-  float* dw[kHeadMaxLayers];
-  float* db[kHeadMaxLayers];
-  const float* x;               // [M, dims[0]]
-  float* y;                     // [M, dims[L]]
-  float* zsave;                 // [M, zwidth] pre-activations of the hidden layers
-  const float* dy;              // [M, dims[L]]
-  float* dx;                    // [M, dims[0]] or null
-  int64_t M;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+// The raw loads of a K tile are issued as one unconditional batch (memory-level parallelism: the loop is
+// latency bound); the elementwise transforms run afterwards, with the mode tests hoisted out of the loops.
+// Math: 256 threads = 4 k-groups x 64 threads; a group covers the whole 32x32 tile with 4x4 register
+// micro-tiles (two LDS.128 per 16 FMA) over a quarter of every K tile; the four partial tiles are summed
+// through shared memory at the end (fixed order).  Operand staging is bank-conflict free both ways: rows
+// of 36 floats, lanes laid out 8 (kk) x 4 (i) when the operand is contiguous along kk.
+template <int ACT>
+__global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTileParams hp) {
+  constexpr int S = kHT + 4;
+  __shared__ __align__(16) float smem_f[2 * kHK * S];
+  float (*As)[S] = reinterpret_cast<float (*)[S]>(smem_f);
+  float (*Bs)[S] = reinterpret_cast<float (*)[S]>(smem_f + kHK * S);
+  int t = blockIdx.x;
+  const bool second = t >= hp.prob[0].tiles;
+  if (second) t -= hp.prob[0].tiles;
+  const HeadTileProb& pr = second ? hp.prob[1] : hp.prob[0];
+  const int I = pr.I, J = pr.J, KK = pr.KK;
+  const int i0 = (t / pr.tiles_j) * kHT, j0 = (t % pr.tiles_j) * kHT;
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6, tyq = (tid & 63) >> 3, txq = tid & 7;  // group: rows 4 tyq.., columns 4 txq..
+  const float* __restrict__ ap = pr.A.p;
+  const float* __restrict__ aq = pr.A.q;
+  const float* __restrict__ bp = pr.B.p;
+  const int64_t a_si = pr.A.si, a_sk = pr.A.sk, a_qi = pr.A.qi, a_qk = pr.A.qk, b_si = pr.B.si, b_sk = pr.B.sk;
+  const int a_mode = pr.A.mode, b_mode = pr.B.mode;
+  const bool a_kc = a_sk == 1, b_kc = b_sk == 1;  // contiguous along kk -> lanes run along kk
+  constexpr int PER = kHT * kHK / kHThreads;       // 8 elements per thread per operand
+  // element e (0..7) of this thread inside a 32 (i) x 64 (kk) operand tile: contiguous-along-kk operands use
+  // lanes 8 (kk) x 4 (i): i = ((tid >> 3) & 3) + 4 e, kk = ((tid >> 5) << 3 | (tid & 7)); the others use lanes
+  // along i: i = tid & 31, kk = (tid >> 5) + 8 e.  Global and shared addresses are base + e * step.
+  const int ai_f = a_kc ? ((tid >> 3) & 3) : (tid & 31), ai_s = a_kc ? 4 : 0;
+  const int ak_f = a_kc ? (((tid >> 5) << 3) | (tid & 7)) : (tid >> 5), ak_s = a_kc ? 0 : 8;
+  const int bi_f = b_kc ? ((tid >> 3) & 3) : (tid & 31), bi_s = b_kc ? 4 : 0;
+  const int bk_f = b_kc ? (((tid >> 5) << 3) | (tid & 7)) : (tid >> 5), bk_s = b_kc ? 0 : 8;
+  const int64_t a_step_e = ai_s * a_si + ak_s * a_sk, a_step_t = kHK * a_sk;
+  const int64_t q_step_e = ai_s * a_qi + ak_s * a_qk, q_step_t = kHK * a_qk;
+  const int64_t b_step_e = bi_s * b_si + bk_s * b_sk, b_step_t = kHK * b_sk;
+  float* const a_sts = &As[ak_f][ai_f];
+  float* const b_sts = &Bs[bk_f][bi_f];
+  const int a_sstep = ak_s * S + ai_s, b_sstep = bk_s * S + bi_s;
 
-__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams p) {
-  extern __shared__ __align__(16) float hs[];
-  float* bufA = hs;                              // [8][maxdim]
-  float* bufB = hs + kHeadRows * kHeadMaxDim;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * kHeadRows;
-  const int nrow = (int)((p.M - r0) < kHeadRows ? (p.M - r0) : kHeadRows);
-  const int K0 = p.dims[0];
-  for (int i = threadIdx.x; i < kHeadRows * K0; i += 256) {
-    const int r = i / K0, k = i % K0;
-    bufA[r * kHeadMaxDim + k] = (r < nrow) ? __ldg(p.x + (r0 + r) * K0 + k) : 0.f;
+  // All loads of a 256-wide K range (4 staging tiles) are in flight at once: a dependent global round trip
+  // costs more than the math of a whole tile, so the K loop must not serialise them.
+  constexpr int NT = 4;
+  float ra[NT][PER], rq[NT][PER], rb[NT][PER];
+  auto fetch = [&](int kbase) {
+    const float* pa = ap + (i0 + ai_f) * a_si + (kbase + ak_f) * a_sk;
+    const float* pb = bp + (j0 + bi_f) * b_si + (kbase + bk_f) * b_sk;
+    const float* pq = aq + (i0 + ai_f) * a_qi + (kbase + ak_f) * a_qk;
+    if (i0 + kHT <= I && j0 + kHT <= J && kbase + NT * kHK <= KK) {  // interior: no predicates
+#pragma unroll
+      for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          ra[tl][e] = __ldg(pa + tl * a_step_t + e * a_step_e);
+          rb[tl][e] = __ldg(pb + tl * b_step_t + e * b_step_e);
+        }
+      if (a_mode == 2) {
+#pragma unroll
+        for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+          for (int e = 0; e < PER; ++e) rq[tl][e] = __ldg(pq + tl * q_step_t + e * q_step_e);
+      }
+    } else {
+#pragma unroll
+      for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          const bool oka = (i0 + ai_f + e * ai_s < I) && (kbase + tl * kHK + ak_f + e * ak_s < KK);
+          const bool okb = (j0 + bi_f + e * bi_s < J) && (kbase + tl * kHK + bk_f + e * bk_s < KK);
+          ra[tl][e] = oka ? __ldg(pa + tl * a_step_t + e * a_step_e) : 0.f;
+          rb[tl][e] = okb ? __ldg(pb + tl * b_step_t + e * b_step_e) : 0.f;
+          rq[tl][e] = (oka && a_mode == 2) ? __ldg(pq + tl * q_step_t + e * q_step_e) : 0.f;
+        }
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float csum = 0.f;
+  const bool want_colsum = pr.colsum != nullptr && j0 == 0;
+
+  for (int kbase = 0; kbase < KK; kbase += NT * kHK) {
+    fetch(kbase);
+#pragma unroll
+    for (int tl = 0; tl < NT; ++tl) {
+      if (kbase + tl * kHK >= KK) break;
+      if (a_mode == 1) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) ra[tl][e] = act_fwd(ACT, ra[tl][e]);
+      } else if (a_mode == 2) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) ra[tl][e] *= act_grad(ACT, rq[tl][e]);
+      }
+      if (b_mode == 1) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) rb[tl][e] = act_fwd(ACT, rb[tl][e]);
+      }
+      if (tl > 0 || kbase > 0) __syncthreads();  // the previous tile has been consumed
+#pragma unroll
+      for (int e = 0; e < PER; ++e) {
+        a_sts[e * a_sstep] = ra[tl][e];
+        b_sts[e * b_sstep] = rb[tl][e];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kHK / 4; ++kk) {
+        const int k = grp * (kHK / 4) + kk;
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][tyq * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][txq * 4]);
+        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+        acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+        acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+        acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+        acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+      }
+      if (want_colsum && tid < kHT) {
+#pragma unroll 16
+        for (int k = 0; k < kHK; ++k) csum += As[k][tid];
+      }
+    }
   }
   __syncthreads();
-  float* in = bufA;
-  float* out = bufB;
-  for (int l = 0; l < p.L; ++l) {
-    const int K = p.dims[l], N = p.dims[l + 1];
-    const bool hidden = l < p.L - 1;
-    for (int u0 = warp * kHeadUnits; u0 < N; u0 += 8 * kHeadUnits) {
-      float acc[kHeadUnits][kHeadRows];
+
+  // ---- sum the four k-group partials (reusing the staging memory: 4 x 32 x 33 floats) and store
+  float (*red)[kHT][kHT + 1] = reinterpret_cast<float (*)[kHT][kHT + 1]>(smem_f);
 #pragma unroll
-      for (int j = 0; j < kHeadUnits; ++j)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int r = 0; r < kHeadRows; ++r) acc[j][r] = 0.f;
-      for (int k0 = lane * 4; k0 < K; k0 += 128) {
-        float4 wv[kHeadUnits];
+    for (int b = 0; b < 4; ++b) red[grp][tyq * 4 + a][txq * 4 + b] = acc[a][b];
+  __syncthreads();
+  {
+    const int li = tid >> 3, lj = (tid & 7) * 4;
+    const int i = i0 + li;
+    if (i < I) {
 #pragma unroll
-        for (int j = 0; j < kHeadUnits; ++j)
-          wv[j] = (u0 + j < N) ? __ldg(reinterpret_cast<const float4*>(p.w[l] + (int64_t)(u0 + j) * K + k0))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < kHeadRows; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(in + r * kHeadMaxDim + k0);
-#pragma unroll
-          for (int j = 0; j < kHeadUnits; ++j)
-            acc[j][r] = fmaf(a.x, wv[j].x, fmaf(a.y, wv[j].y, fmaf(a.z, wv[j].z, fmaf(a.w, wv[j].w, acc[j][r]))));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kHeadUnits; ++j)
-#pragma unroll
-        for (int r = 0; r < kHeadRows; ++r) acc[j][r] = warp_sum(acc[j][r]);
-      // lane (j * kHeadRows + r) finishes unit u0 + j of row r
-      if (lane < kHeadUnits * kHeadRows) {
-        const int j = lane / kHeadRows, r = lane % kHeadRows;
-        const int u = u0 + j;
-        float z = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < kHeadUnits; ++jj)
-#pragma unroll
-          for (int rr = 0; rr < kHeadRows; ++rr) z = (jj == j && rr == r) ? acc[jj][rr] : z;
-        if (u < N) {
-          z += __ldg(p.b[l] + u);
-          if (hidden) {
-            if (r < nrow) p.zsave[(r0 + r) * p.zwidth + p.zoff[l] + u] = z;
-            out[r * kHeadMaxDim + u] = act_fwd(p.act, z);
-          } else if (r < nrow) {
-            p.y[(r0 + r) * N + u] = z;
-          }
-        }
+      for (int b = 0; b < 4; ++b) {
+        const int j = j0 + lj + b;
+        if (j >= J) continue;
+        float v = (red[0][li][lj + b] + red[1][li][lj + b]) + (red[2][li][lj + b] + red[3][li][lj + b]);
+        if (pr.bias) v += __ldg(pr.bias + j);
+        pr.C[(int64_t)i * pr.ldc + j] = v;
       }
     }
-    __syncthreads();
-    float* t = in; in = out; out = t;
   }
+  if (want_colsum && tid < kHT && i0 + tid < I) pr.colsum[i0 + tid] = csum;
 }
 
-// backward: dy -> (dz_l, dW_l, db_l) for l = L-1 .. 0, dx
-__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadParams p) {
-  extern __shared__ __align__(16) float hs[];
-  float* ain = hs;                                   // [8][maxdim] input activations of the current layer
-  float* dcur = hs + kHeadRows * kHeadMaxDim;        // [8][maxdim] gradient w.r.t. the current layer's output / dz
-  float* dprev = hs + 2 * kHeadRows * kHeadMaxDim;   // [8][maxdim] gradient w.r.t. its input
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * kHeadRows;
-  const int nrow = (int)((p.M - r0) < kHeadRows ? (p.M - r0) : kHeadRows);
-  const int NO = p.dims[p.L];
-  for (int i = threadIdx.x; i < kHeadRows * NO; i += 256) {
-    const int r = i / NO, u = i % NO;
-    dcur[r * kHeadMaxDim + u] = (r < nrow) ? __ldg(p.dy + (r0 + r) * NO + u) : 0.f;
+static void launch_head_tiles(const HeadTileParams& hp, int tiles, cudaStream_t st) {
+  if (tiles <= 0) return;
+  auto kern = head_tile_kernel<PCC_ACT_TANH>;
+  switch (hp.act) {
+    case PCC_ACT_RELU: kern = head_tile_kernel<PCC_ACT_RELU>; break;
+    case PCC_ACT_GELU: kern = head_tile_kernel<PCC_ACT_GELU>; break;
+    case PCC_ACT_SILU: kern = head_tile_kernel<PCC_ACT_SILU>; break;
+    default: break;
   }
-  for (int l = p.L - 1; l >= 0; --l) {
-    const int K = p.dims[l], N = p.dims[l + 1];
-    // input activations of layer l: x (l == 0) or act(z_{l-1}); dz_l = dcur * act'(z_l) for hidden layers
-    for (int i = threadIdx.x; i < kHeadRows * K; i += 256) {
-      const int r = i / K, k = i % K;
-      float v = 0.f;
-      if (r < nrow) v = (l == 0) ? __ldg(p.x + (r0 + r) * K + k)
-                                 : act_fwd(p.act, __ldg(p.zsave + (r0 + r) * p.zwidth + p.zoff[l - 1] + k));
-      ain[r * kHeadMaxDim + k] = v;
-    }
-    if (l < p.L - 1) {
-      __syncthreads();  // dcur fully written by the previous dgrad
-      for (int i = threadIdx.x; i < kHeadRows * N; i += 256) {
-        const int r = i / N, u = i % N;
-        const float z = (r < nrow) ? __ldg(p.zsave + (r0 + r) * p.zwidth + p.zoff[l] + u) : 0.f;
-        dcur[r * kHeadMaxDim + u] *= act_grad(p.act, z);
-      }
-    }
-    __syncthreads();
-    // ---- db_l and dW_l: warp w owns units w, w+8, ...; lanes own 4 consecutive input columns
-    for (int u = warp; u < N; u += 8) {
-      float dz[kHeadRows];
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) { dz[r] = dcur[r * kHeadMaxDim + u]; s += dz[r]; }
-      if (lane == 0) atomicAdd(p.db[l] + u, s);
-      float* dwr = p.dw[l] + (int64_t)u * K;
-      for (int k0 = lane * 4; k0 < K; k0 += 128) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < kHeadRows; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(ain + r * kHeadMaxDim + k0);
-          g.x = fmaf(dz[r], a.x, g.x); g.y = fmaf(dz[r], a.y, g.y); g.z = fmaf(dz[r], a.z, g.z); g.w = fmaf(dz[r], a.w, g.w);
-        }
-        red_add_v4(dwr + k0, g.x, g.y, g.z, g.w);
-      }
-    }
-    // ---- dgrad: dprev[r, k] = sum_u dz[r, u] * W[u, k]   (thread per input column, coalesced over k)
-    if (l > 0 || p.dx) {
-      for (int k = threadIdx.x; k < K; k += 256) {
-        float acc[kHeadRows];
-#pragma unroll
-        for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
-#pragma unroll 8
-        for (int u = 0; u < N; ++u) {
-          const float wv = __ldg(p.w[l] + (int64_t)u * K + k);
-#pragma unroll
-          for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(dcur[r * kHeadMaxDim + u], wv, acc[r]);
-        }
-        if (l > 0) {
-#pragma unroll
-          for (int r = 0; r < kHeadRows; ++r) dprev[r * kHeadMaxDim + k] = acc[r];
-        } else {
-#pragma unroll
-          for (int r = 0; r < kHeadRows; ++r)
-            if (r < nrow) p.dx[(r0 + r) * K + k] = acc[r];
-        }
-      }
-    }
-    __syncthreads();
-    float* t = dcur; dcur = dprev; dprev = t;
-  }
-}
-
-__global__ void head_zero_kernel(HeadParams p) {
-  const int l = blockIdx.y;
-  if (l >= p.L) return;
-  const int64_t nw = (int64_t)p.dims[l] * p.dims[l + 1], nb = p.dims[l + 1];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nw + nb; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i < nw) p.dw[l][i] = 0.f; else p.db[l][i - nw] = 0.f;
-  }
+  PCC_K(kern)<<<tiles, kHThreads, 0, st>>>(hp);
 }
 
 static int check_head(const pcc_head_desc* d, const char* where) {
   if (!d) return fail(where, "null descriptor");
   if (d->n_layers < 1 || d->n_layers > kHeadMaxLayers) return fail(where, "head needs 1..4 layers");
-  for (int l = 0; l <= d->n_layers; ++l) {
+  for (int l = 0; l <= d->n_layers; ++l)
     if (d->dims[l] < 1 || d->dims[l] > kHeadMaxDim) return fail(where, "head widths must be in [1,1024]");
-    if (l < d->n_layers && d->dims[l] % 4 != 0) return fail(where, "head input widths must be multiples of 4");
-  }
   if (d->act != PCC_ACT_RELU && d->act != PCC_ACT_GELU && d->act != PCC_ACT_SILU && d->act != PCC_ACT_TANH)
     return fail(where, "head activation must be relu/gelu/silu/tanh");
   return 0;
 }
 
-static HeadParams make_params(const pcc_head_desc* d, int64_t M) {
-  HeadParams p{};
-  p.L = d->n_layers; p.act = d->act; p.M = M;
-  int off = 0;
-  for (int l = 0; l <= d->n_layers; ++l) p.dims[l] = d->dims[l];
-  for (int l = 0; l < d->n_layers; ++l) {
-    p.w[l] = d->w[l]; p.b[l] = d->b[l];
-    if (l < d->n_layers - 1) { p.zoff[l] = off; off += d->dims[l + 1]; }
+struct HeadGeom {
+  int zoff[kHeadMaxLayers];
+  int zwidth, maxhid;
+};
+static HeadGeom head_geom(const pcc_head_desc* d) {
+  HeadGeom g{};
+  int off = 0, mh = 1;
+  for (int l = 0; l < d->n_layers - 1; ++l) {
+    g.zoff[l] = off;
+    off += d->dims[l + 1];
+    if (d->dims[l + 1] > mh) mh = d->dims[l + 1];
   }
-  p.zwidth = off;
-  return p;
+  g.zwidth = off;
+  g.maxhid = mh;
+  return g;
+}
+
+static void set_tiles(HeadTileProb& p) {
+  p.tiles_j = (int)cdiv(p.J, kHT);
+  p.tiles = (int)cdiv(p.I, kHT) * p.tiles_j;
 }
 
 }  // namespace pcc
@@ -222,32 +248,74 @@ using namespace pcc;
 
 extern "C" int pcc_mlp_head_supported(const pcc_head_desc* d) { return check_head(d, __func__); }
 
+extern "C" int64_t pcc_mlp_head_workspace_bytes(const pcc_head_desc* d, int64_t M) {
+  if (check_head(d, __func__) != 0) return -1;
+  const HeadGeom g = head_geom(d);
+  return 2 * (M > 0 ? M : 1) * (int64_t)g.maxhid * (int64_t)sizeof(float);
+}
+
 extern "C" int pcc_mlp_head_fwd(const pcc_head_desc* d, const float* x, float* y, float* zsave, int64_t M, int device,
                                 void* stream) {
   PCC_ENTER(device);
   if (check_head(d, __func__) != 0) return -1;
+  PCC_REQUIRE(M < (int64_t)0x7fffffff, "row count exceeds int32");
   if (M == 0) return 0;
-  HeadParams p = make_params(d, M);
-  p.x = x; p.y = y; p.zsave = zsave;
-  const int smem = 2 * kHeadRows * kHeadMaxDim * (int)sizeof(float);
-  PCC_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  PCC_K(head_fwd_kernel)<<<(unsigned)cdiv(M, kHeadRows), 256, smem, (cudaStream_t)stream>>>(p);
+  const HeadGeom g = head_geom(d);
+  const int L = d->n_layers;
+  for (int l = 0; l < L; ++l) {
+    const int K = d->dims[l], N = d->dims[l + 1];
+    HeadTileParams hp{};
+    hp.act = d->act;
+    HeadTileProb& p = hp.prob[0];
+    if (l == 0) p.A = HeadOperand{x, nullptr, K, 1, 0, 0, 0};
+    else p.A = HeadOperand{zsave + g.zoff[l - 1], nullptr, g.zwidth, 1, 0, 0, 1};
+    p.B = HeadOperand{d->w[l], nullptr, K, 1, 0, 0, 0};
+    p.I = (int)M; p.J = N; p.KK = K;
+    if (l < L - 1) { p.C = zsave + g.zoff[l]; p.ldc = g.zwidth; } else { p.C = y; p.ldc = N; }
+    p.bias = d->b[l];
+    set_tiles(p);
+    launch_head_tiles(hp, p.tiles, (cudaStream_t)stream);
+  }
   return check_launch(__func__);
 }
 
 extern "C" int pcc_mlp_head_bwd(const pcc_head_desc* d, const float* x, const float* zsave, const float* dy, float* dx,
-                                float* const* dw, float* const* db, int64_t M, int device, void* stream) {
+                                float* const* dw, float* const* db, void* ws, int64_t M, int device, void* stream) {
   PCC_ENTER(device);
   if (check_head(d, __func__) != 0) return -1;
-  cudaStream_t st = (cudaStream_t)stream;
-  HeadParams p = make_params(d, M);
-  p.x = x; p.zsave = const_cast<float*>(zsave); p.dy = dy; p.dx = dx;
-  for (int l = 0; l < d->n_layers; ++l) { p.dw[l] = dw[l]; p.db[l] = db[l]; }
-  PCC_K(head_zero_kernel)<<<dim3(64, d->n_layers), 256, 0, st>>>(p);
-  if (M > 0) {
-    const int smem = 3 * kHeadRows * kHeadMaxDim * (int)sizeof(float);
-    PCC_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PCC_K(head_bwd_kernel)<<<(unsigned)cdiv(M, kHeadRows), 256, smem, st>>>(p);
+  PCC_REQUIRE(M < (int64_t)0x7fffffff, "row count exceeds int32");
+  const HeadGeom g = head_geom(d);
+  const int L = d->n_layers;
+  PCC_REQUIRE(L == 1 || ws != nullptr || M == 0, "workspace required (pcc_mlp_head_workspace_bytes)");
+  float* gbuf[2] = {(float*)ws, (float*)ws + (M > 0 ? M : 1) * (int64_t)g.maxhid};
+  for (int l = L - 1; l >= 0; --l) {
+    const int K = d->dims[l], N = d->dims[l + 1];
+    HeadTileParams hp{};
+    hp.act = d->act;
+    // dz_l(r, u): dy for the final layer, g_l * act'(z_l) for hidden layers
+    const float* gsrc = (l == L - 1) ? dy : gbuf[l & 1];
+    const int64_t gld = N;
+    const float* zq = (l == L - 1) ? nullptr : zsave + g.zoff[l];
+    const int dzmode = (l == L - 1) ? 0 : 2;
+    // ---- dW_l[u][k] = sum_r dz(r,u) in(r,k); db_l[u] = sum_r dz(r,u)
+    HeadTileProb& pw = hp.prob[0];
+    pw.A = HeadOperand{gsrc, zq, 1, gld, 1, g.zwidth, dzmode};
+    if (l == 0) pw.B = HeadOperand{x, nullptr, 1, K, 0, 0, 0};
+    else pw.B = HeadOperand{zsave + g.zoff[l - 1], nullptr, 1, g.zwidth, 0, 0, 1};
+    pw.I = N; pw.J = K; pw.KK = (int)M;
+    pw.C = dw[l]; pw.ldc = K; pw.bias = nullptr; pw.colsum = db[l];
+    set_tiles(pw);
+    // ---- g_{l-1}[r][k] = sum_u dz(r,u) W_l[u][k]
+    HeadTileProb& pd = hp.prob[1];
+    float* dst = (l == 0) ? dx : gbuf[(l - 1) & 1];
+    if (dst != nullptr && M > 0) {
+      pd.A = HeadOperand{gsrc, zq, gld, 1, g.zwidth, 1, dzmode};
+      pd.B = HeadOperand{d->w[l], nullptr, 1, K, 0, 0, 0};
+      pd.I = (int)M; pd.J = K; pd.KK = N;
+      pd.C = dst; pd.ldc = K;
+      set_tiles(pd);
+    }
+    launch_head_tiles(hp, pw.tiles + pd.tiles, (cudaStream_t)stream);
   }
   return check_launch(__func__);
 }

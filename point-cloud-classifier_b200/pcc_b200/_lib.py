@@ -56,7 +56,8 @@ _SIGS = {
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
     "pcc_mlp_head_supported": [C.POINTER(HeadDesc)],
     "pcc_mlp_head_fwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _i64, _i32, _vp],
-    "pcc_mlp_head_bwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "pcc_mlp_head_workspace_bytes": [C.POINTER(HeadDesc), _i64],
+    "pcc_mlp_head_bwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
     "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp],
     "pcc_launch_count": [_i32],
@@ -71,7 +72,7 @@ _SIGS = {
     "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
 _RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64,
-             "pcc_phi_packed_bytes": _i64}
+             "pcc_phi_packed_bytes": _i64, "pcc_mlp_head_workspace_bytes": _i64}
 EXPORTS = tuple(_SIGS) + ("pcc_last_error",)
 
 _lib = None

@@ -152,8 +152,8 @@ class DeepSets(nn.Module):
         return self._rho(pooled)
 
     def _rho(self, pooled):
-        """set encoder head: one fused launch per direction when the stack has no LayerNorm and fits the
-        head kernel (widths <= 1024, multiples of 4); otherwise layer by layer."""
+        """set encoder head: the tiled head kernels (one launch per layer and direction) when the stack has
+        no LayerNorm and fits them (widths <= 1024); otherwise layer by layer."""
         plan = self._rho_plan
         dims = [plan[0]["lin"].in_features] + [Lr["lin"].out_features for Lr in plan]
         plain = all(Lr["ln"] is None and not Lr["res"] and Lr["lin"].bias is not None for Lr in plan)

@@ -371,14 +371,15 @@ def _head_desc(ws, act: str) -> "L.HeadDesc":
 
 
 def head_supported(dims, act: str) -> bool:
-    """static check: 1..4 layers, widths <= 1024, every layer input width a multiple of 4"""
+    """static check: 1..4 layers, widths <= 1024"""
     if len(dims) < 2 or len(dims) > 5 or act not in ("relu", "gelu", "silu", "tanh"):
         return False
-    return all(1 <= v <= 1024 for v in dims) and all(v % 4 == 0 for v in dims[:-1])
+    return all(1 <= v <= 1024 for v in dims)
 
 
 class MLPHeadFn(torch.autograd.Function):
-    """rho(pooled) of deep_sets.py:112 (Linear/act stack without LayerNorm) in one launch per direction."""
+    """rho(pooled) of deep_sets.py:112 (Linear/act stack without LayerNorm): one tiled launch per layer and
+    direction, activation / act' / bias gradient folded into the operand loads (pcc_head.cu)."""
 
     @staticmethod
     def forward(ctx, x, act: str, *params):
@@ -405,8 +406,10 @@ class MLPHeadFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = (C.c_void_p * 4)(*[grads[2 * i].data_ptr() for i in range(d.n_layers)])
         db = (C.c_void_p * 4)(*[grads[2 * i + 1].data_ptr() for i in range(d.n_layers)])
+        ws_bytes = call("pcc_mlp_head_workspace_bytes", C.byref(d), x.shape[0])
+        scratch = torch.empty(max(int(ws_bytes), 4), dtype=torch.uint8, device=x.device)
         call("pcc_mlp_head_bwd", C.byref(d), ptr(x), ptr(zsave), ptr(dy), ptr(dx), C.cast(dw, C.c_void_p),
-             C.cast(db, C.c_void_p), x.shape[0], dev, st)
+             C.cast(db, C.c_void_p), ptr(scratch), x.shape[0], dev, st)
         return (dx, None, *grads)
 
 

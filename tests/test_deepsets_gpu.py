@@ -131,7 +131,8 @@ def test_fused_bce_loss_and_gather():
 
 
 @pytest.mark.parametrize("dims,act,M", [([256, 256, 10], "relu", 256), ([128, 64, 32, 1], "gelu", 37),
-                                        ([256, 1], "silu", 5), ([1024, 512, 128, 256, 3], "tanh", 70)])
+                                        ([256, 1], "silu", 5), ([1024, 512, 128, 256, 3], "tanh", 70),
+                                        ([10, 7, 3], "relu", 33), ([256, 256, 10], "gelu", 0)])
 def test_fused_head_matches_torch(dims, act, M):
     g = torch.Generator().manual_seed(9)
     ws, ps = [], []
