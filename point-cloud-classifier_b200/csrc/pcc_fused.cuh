@@ -32,6 +32,7 @@ struct PhiParams {
   int64_t n, B, num_tiles;
   int d, L, pooling, res_mask;
   const uint8_t* wpack;          // packed bf16 weight blobs, all layers
+  const float* w0tab;            // layer-0 table [H][4Q] fp32: {b_0, bf16-rounded W_0 row, 0 ...} (forward)
   uint32_t w_off[kMaxLayers];    // byte offset of layer l inside wpack
   const float* bias[kMaxLayers];
   void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
@@ -78,6 +79,9 @@ static __global__ void seg_prep_kernel(const int64_t* __restrict__ offsets, int6
 // to 16), layers >= 1 SWIZZLE_128B [H/64 slabs][H rows][64]
 struct PackParams {
   const float* w[kMaxLayers];
+  const float* b0;              // layer-0 bias (for the forward's fp32 layer-0 table)
+  uint32_t w0tab_off;           // byte offset of that table inside wpack
+  int q4;                       // float4 per table row: 4 q4 - 1 >= d
   uint8_t* wpack;
   uint32_t w_off[kMaxLayers];
   uint32_t wt_off[kMaxLayers];  // transposed images (layers >= 1), used when gridDim.z == 2
@@ -121,6 +125,7 @@ static __global__ void pack_weights_kernel(PackParams p) {
 // byte offsets of the weight images inside the packed buffer (same for forward and backward)
 struct PackLayout {
   uint32_t w_off[kMaxLayers], wt_off[kMaxLayers];
+  uint32_t w0tab_off;  // [H][16] fp32 (sized for the widest table, q4 = 4)
   int64_t total;
 };
 inline PackLayout pack_layout(int L, int H) {
@@ -129,6 +134,7 @@ inline PackLayout pack_layout(int L, int H) {
   auto take = [&](int64_t bytes) { int64_t at = o; o = (o + bytes + 1023) / 1024 * 1024; return at; };
   for (int l = 0; l < L; ++l) w.w_off[l] = (uint32_t)take((int64_t)((l == 0) ? kK0 : H) * H * 2);
   for (int l = 1; l < L; ++l) w.wt_off[l] = (uint32_t)take((int64_t)H * H * 2);
+  w.w0tab_off = (uint32_t)take((int64_t)H * 16 * 4);
   w.total = o;
   return w;
 }

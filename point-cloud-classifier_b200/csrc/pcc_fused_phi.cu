@@ -2,40 +2,47 @@
 //   reference: /root/reference/models/deep_sets.py:89 (phi), :91-106 (split + pool loop)
 //   and their autograd.  bf16 operands, fp32 accumulation in TMEM.
 //
-// Forward kernel (persistent, one CTA per SM, 128-point tiles):
-//   x tile -> bf16 operand image in smem -> [tcgen05.mma -> TMEM -> epilogue(bias, act,
-//   residual) -> bf16 SWIZZLE_128B image in smem] per hidden layer -> final Linear computed
-//   TRANSPOSED (M = output features, N = points) so that each epilogue thread owns one feature
-//   and pools over the points of its TMEM lane without any cross-thread traffic -> partial
-//   sums / packed (value,row) maxima combined across tiles with atomics in a [B,H]
-//   accumulator.  Per-point activations never leave the SM.
-//   Weights: pre-packed bf16 images (pcc_fused.cuh) streamed from L2 through an mbarrier ring
-//   with cp.async.bulk (TMA engine), one K=64 slab (H rows x 128 B) per slot.
-// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp & 3; the two warps of a quarter split
-// the accumulator columns / the two feature halves), warp 8 bulk-copy producer, warp 9 TMEM
-// allocator + MMA issuer (one elected thread).
+// Forward kernel (persistent, one CTA per SM, 128-point tiles), three concurrent roles per tile:
+//   hidden warps (0-7)  : layer 0 (K = input_dim <= 15) on the FP32 pipe straight from x into the bf16
+//                         SWIZZLE_128B activation image (no TMEM round trip: a TMEM read of a 128 x 256
+//                         fp32 accumulator costs as much as the MMA that produced it), then the epilogue
+//                         of the H x H hidden layer (TMEM -> bias/act/residual -> image, in place);
+//                         every finished 64-column slab is handed to the MMA warp at once
+//   MMA warp (17)       : hidden layer into accumulator A; final Linear computed TRANSPOSED
+//                         (M = output features, N = points) into accumulator B
+//   pool warps (8-15)   : thread = output feature, TMEM columns = the tile's points: in-lane masked
+//                         max / sum over the ragged sets, partials combined across tiles with atomics
+//                         in a [B,H] accumulator — overlapped with the NEXT tile's layers
+//   producer warp (16)  : weight slabs (H rows x 128 B) from L2 through an mbarrier ring with
+//                         cp.async.bulk (TMA engine).
+// Per-point activations never leave the SM.
 #include "pcc_fused.cuh"
 
 namespace pcc {
 
 constexpr int kRingF = 4;  // weight slabs in flight (forward)
+constexpr int kFwdHidWarps = 8, kFwdPoolWarps = 8;
+constexpr int kFwdProdWarp = 16, kFwdMmaWarp = 17;
+constexpr int kFwdThreads = 18 * 32;  // register cap 96: warps are allocated in groups of 4 (20 x 32 x 96 <= 64 K)
 
 struct SmemLayout {
-  uint32_t bufA, ring, bufX, bias, bars, total;
+  uint32_t bufA, ring, ones, bimg, w0, xs, bars, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int H, int L) {
+__host__ __device__ inline SmemLayout smem_layout(int H, int L, int Q) {
   SmemLayout s;
   uint32_t o = 0;
   s.bufA = o; o += kTileM * H * 2;             // activation image, 1024-aligned slabs
   s.ring = o; o += kRingF * w_slab_bytes(H);   // weight slabs, 1024-aligned
-  s.bufX = o; o += kTileM * kK0 * 2;           // layer-0 operand (un-swizzled)
-  s.bias = o; o += (uint32_t)L * H * 4;
+  s.ones = o; o += kTileM * kK0 * 2;           // un-swizzled [2][128][8] bf16 image: columns 0,1 = 1, rest 0
+  s.bimg = o; o += (uint32_t)H * kK0 * 2;      // un-swizzled [2][H][8] bf16 image: hidden-layer bias as (hi, lo, 0 ...)
+  s.w0 = o;   o += (uint32_t)H * 4 * Q * 4;    // layer-0 table (see fwd_prep_kernel)
+  s.xs = o;   o += 2u * kTileM * 4 * Q * 4;    // layer-0 inputs of two tiles: [128][4Q] fp32 = {-, x_0 .. x_{4Q-2}}
   s.bars = o; o += 256;
   s.total = o;
   return s;
 }
 
-// debug trace: CTA 0 only, role 0 = epilogue thread 0, role 1 = MMA thread; 2 x 4096 slots
+// debug trace: CTA 0 only, role 0 = hidden thread 0, role 1 = MMA thread, role 2 = pool thread 0; 3 x 4096 slots
 __device__ __forceinline__ void trace_ev(long long* trace, int role, int& n, int id) {
   if (trace && blockIdx.x == 0 && n < 2047) {
     trace[role * 4096 + 2 * n] = id;
@@ -52,21 +59,26 @@ __device__ __forceinline__ float sum8(const uint32_t* v) {
   return ((__uint_as_float(v[0]) + __uint_as_float(v[1])) + (__uint_as_float(v[2]) + __uint_as_float(v[3]))) +
          ((__uint_as_float(v[4]) + __uint_as_float(v[5])) + (__uint_as_float(v[6]) + __uint_as_float(v[7])));
 }
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// one 32-column accumulator chunk -> bias, activation, residual -> bf16 -> SW128 activation image
+// one 32-column accumulator chunk (bias already inside: it enters through an extra MMA K step) -> activation,
+// residual -> bf16 -> SW128 activation image
 template <int ACT>
-__device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t* bufA, const float* bl, int r, int c,
-                                                bool res) {
+__device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t* bufA, int r, int c, bool res) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint8_t* dst = bufA + act_chunk_off(r, c * 32 + q * 8);
-    const float4 b0 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(bl + c * 32 + q * 8 + 4);
+    if (ACT == PCC_ACT_RELU && !res) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(
+          pack_bf16x2_relu(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])),
+          pack_bf16x2_relu(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
+          pack_bf16x2_relu(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
+          pack_bf16x2_relu(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+      continue;
+    }
     float o[8];
-    o[0] = act_t<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
-    o[2] = act_t<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
-    o[4] = act_t<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
-    o[6] = act_t<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(__uint_as_float(v[q * 8 + j]));
     if (res) {
       const uint4 old = *reinterpret_cast<const uint4*>(dst);
       o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
@@ -78,209 +90,297 @@ __device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t
 }
 
 // ------------------------------------------------------------------ forward kernel
-template <int H, int ACT>
-__global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiParams p) {
+// L = 2 (phi = Linear, final Linear) or 3 (one H x H hidden layer / ResidualBlock in between).
+// TMEM: L = 3: hidden accumulator = columns [0,256), final accumulator = [256,512);
+//       L = 2: the final accumulator alternates between the two halves from tile to tile.
+template <int H, int ACT, int Q>
+__global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout lay = smem_layout(H, p.L);
+  const SmemLayout lay = smem_layout(H, p.L, Q);
   uint8_t* bufA = smem + lay.bufA;
   uint8_t* ring = smem + lay.ring;
-  uint8_t* bufX = smem + lay.bufX;
-  float* biasS = reinterpret_cast<float*>(smem + lay.bias);
+  const ulonglong2* w0S = reinterpret_cast<const ulonglong2*>(smem + lay.w0);
+  float* xS = reinterpret_cast<float*>(smem + lay.xs);
+  __nv_bfloat16* onesS = reinterpret_cast<__nv_bfloat16*>(smem + lay.ones);
+  __nv_bfloat16* bimgS = reinterpret_cast<__nv_bfloat16*>(smem + lay.bimg);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
-  uint64_t* full = bars;                 // [kRingF]
-  uint64_t* empty = bars + kRingF;       // [kRingF]
-  uint64_t* x_ready = bars + 2 * kRingF;           // layer-0 operand staged (count: all epilogue threads)
-  uint64_t* acc_ready = bars + 2 * kRingF + 1;      // one MMA phase (layer of a tile) complete
-  uint64_t* slab_ready = bars + 2 * kRingF + 2;     // [4] 64-column slab of the activation image written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 6);
+  uint64_t* full = bars;                        // [kRingF]
+  uint64_t* empty = bars + kRingF;              // [kRingF]
+  uint64_t* slab_ready = bars + 2 * kRingF;     // [4] 64-column slab of the activation image written
+  uint64_t* acc_h = bars + 2 * kRingF + 4;      // hidden-layer accumulator complete
+  uint64_t* acc_f = bars + 2 * kRingF + 5;      // [2] final accumulator (slot) complete
+  uint64_t* pool_done = bars + 2 * kRingF + 7;  // [2] final accumulator (slot) drained by the pool warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 9);
 
   constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
-  constexpr uint32_t X_LBO = kTileM * 16;      // un-swizzled layer-0 images: K-chunk strides
-  constexpr uint32_t W0_LBO = H * 16;
   constexpr int HALVES = H / 128;              // M halves of the transposed final layer
   constexpr int NSLAB = H / 64;                // slabs per H x H layer
-  constexpr int NCHUNK = H / 32;               // 32-column accumulator chunks of a hidden layer
-  // TMEM: two 256-column accumulators used alternately by successive MMA phases, so the MMA of
-  // layer l+1 can start on the first activation slabs while the epilogue still drains layer l
+  constexpr int NCHUNK = H / 32;               // 32-column chunks of a hidden layer
+  constexpr int XW = 4 * Q;                    // padded layer-0 row: {-, x_0 .. x_{4Q-2}}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
 
-  for (int i = threadIdx.x; i < L * H; i += kThreads) biasS[i] = __ldg(p.bias[i / H] + (i % H));
+  // constant operands of the bias K step of the hidden layer: A = [128 x 16] with ones in columns 0, 1;
+  // B = [H x 16] with (bf16 hi, bf16 lo) of b_1 in columns 0, 1 (hi + lo carries ~16 mantissa bits)
+  for (int i = threadIdx.x; i < kTileM * kK0; i += kFwdThreads) {  // image [2][128][8]: i = (kc, row, k8)
+    const int kc = i / (kTileM * 8), k8 = i % 8;
+    onesS[i] = __float2bfloat16_rn((kc == 0 && k8 < 2) ? 1.f : 0.f);
+  }
+  for (int i = threadIdx.x; i < H * kK0; i += kFwdThreads) {       // image [2][H][8]
+    const int kc = i / (H * 8), row = (i / 8) % H, k8 = i % 8;
+    float v = 0.f;
+    if (L == 3 && kc == 0 && k8 < 2) {
+      const float b = __ldg(p.bias[1] + row);
+      const float hi = bf16_round(b);
+      v = (k8 == 0) ? hi : (b - hi);
+    }
+    bimgS[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = threadIdx.x; i < H * 4 * Q; i += kFwdThreads) reinterpret_cast<float*>(smem + lay.w0)[i] = __ldg(p.w0tab + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(x_ready, kEpiWarps);
-    mbar_init(acc_ready, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], kFwdHidWarps);
+    mbar_init(acc_h, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_f[i], 1); mbar_init(&pool_done[i], 4 * HALVES); }
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  if (warp == kFwdMmaWarp) tmem_alloc<512>(tmem_slot);
+  fence_proxy_async();  // the two constant images are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kProdWarp) {
-    // ===================== producer: stream weight slabs through the ring
+  if (warp == kFwdProdWarp) {
+    // ===================== producer: stream the weight slabs of layers 1 .. L-1 through the ring
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < L; ++l) {
-          const int nslab = (l == 0) ? 1 : NSLAB;
-          const uint32_t bytes = (l == 0) ? (kK0 / 8) * W0_LBO : SLAB;
-          for (int s = 0; s < nslab; ++s) {
+        for (int l = 1; l < L; ++l) {
+          for (int s = 0; s < NSLAB; ++s) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            bulk_g2s(ring + stage * SLAB, p.wpack + p.w_off[l] + (size_t)s * SLAB, bytes, &full[stage]);
+            mbar_arrive_expect_tx(&full[stage], SLAB);
+            bulk_g2s(ring + stage * SLAB, p.wpack + p.w_off[l] + (size_t)s * SLAB, SLAB, &full[stage]);
             if (++stage == kRingF) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kFwdMmaWarp) {
     // ===================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_N = make_idesc_bf16(128, H, 0, 0);    // points x features
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, 0, 0);  // features(128) x points
-      uint32_t stage = 0, phase = 0, x_phase = 0, sl_phase = 0, ph = 0;
+      uint32_t stage = 0, phase = 0, sl_phase = 0;
       int tn = 0;
-      const uint32_t a_base = smem_u32(bufA), x_base = smem_u32(bufX), r_base = smem_u32(ring);
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 0; l < L; ++l, ++ph) {
-          const uint32_t acc_col = tmem + (ph & 1) * 256;
-          const bool last = (l == L - 1);
-          trace_ev(p.trace, 1, tn, 100 + l);
-          if (l == 0) {  // K = 16, un-swizzled images
-            mbar_wait(x_ready, x_phase);
-            x_phase ^= 1;
-            mbar_wait(&full[stage], phase);
+      const uint32_t a_base = smem_u32(bufA), r_base = smem_u32(ring);
+      int nt = 0;  // tiles done by this CTA
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+        if (L == 3) {  // hidden layer -> accumulator A
+          trace_ev(p.trace, 1, tn, 101);
+          // z_1 starts as 1 * b_1 (K = 16 step on the two constant images); accumulator A is free here: its
+          // previous reader, the hidden epilogue of the last tile, precedes the h_0 slabs waited for below
+          // in the hidden warps' program order — so the bias step is issued after the first slab wait
+          for (int s = 0; s < NSLAB; ++s) {
+            mbar_wait(&slab_ready[s], sl_phase);  // h_0 slab s written by the hidden warps
+            mbar_wait(&full[stage], phase);        // weight slab s landed
             tc_fence_after();
-            trace_ev(p.trace, 1, tn, 110 + l);
-            umma_bf16(acc_col, make_smem_desc(x_base, X_LBO, 128), make_smem_desc(r_base + stage * SLAB, W0_LBO, 128),
-                      IDESC_N, 0);
+            if (s == 0) trace_ev(p.trace, 1, tn, 121);
+            const uint32_t w_slab = r_base + stage * SLAB;
+            if (s == 0)
+              umma_bf16(tmem, make_smem_desc(smem_u32(onesS), kTileM * 16, 128), make_smem_desc(smem_u32(bimgS), H * 16, 128),
+                        IDESC_N, 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tmem, make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32),
+                        make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, 1);
             umma_commit(&empty[stage]);
             if (++stage == kRingF) { stage = 0; phase ^= 1; }
-          } else {
-            for (int s = 0; s < NSLAB; ++s) {
-              mbar_wait(&slab_ready[s], sl_phase);  // activation slab s written by the epilogue
-              mbar_wait(&full[stage], phase);        // weight slab s landed
-              tc_fence_after();
-              if (s == 0) trace_ev(p.trace, 1, tn, 120 + l);
-              if (s == NSLAB - 1) trace_ev(p.trace, 1, tn, 130 + l);
-              const uint32_t w_slab = r_base + stage * SLAB;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t act_desc = make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32);
-                const uint32_t acc = (s | ks) != 0;
-                if (!last) {
-                  umma_bf16(acc_col, act_desc, make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, acc);
-                } else {
-#pragma unroll
-                  for (int h = 0; h < HALVES; ++h)
-                    umma_bf16(acc_col + h * 128, make_smem_desc_sw128_k(w_slab + h * (128 * 128) + ks * 32), act_desc,
-                              IDESC_T, acc);
-                }
-              }
-              umma_commit(&empty[stage]);
-              if (++stage == kRingF) { stage = 0; phase ^= 1; }
-            }
-            sl_phase ^= 1;
           }
-          umma_commit(acc_ready);
-          trace_ev(p.trace, 1, tn, 140 + l);
+          sl_phase ^= 1;
+          umma_commit(acc_h);
+          trace_ev(p.trace, 1, tn, 141);
         }
+        // final layer (transposed) -> accumulator slot; the pool warps must have drained its previous use
+        const int slot = (L == 2) ? (nt & 1) : 0;
+        const int k = (L == 2) ? (nt >> 1) : nt;
+        if (k >= 1) {
+          mbar_wait(&pool_done[slot], (uint32_t)((k - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t accT = tmem + ((L == 2) ? slot * 256 : 256);
+        trace_ev(p.trace, 1, tn, 102);
+        for (int s = 0; s < NSLAB; ++s) {
+          mbar_wait(&slab_ready[s], sl_phase);
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (s == 0) trace_ev(p.trace, 1, tn, 122);
+          const uint32_t w_slab = r_base + stage * SLAB;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t act_desc = make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32);
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h)
+              umma_bf16(accT + h * 128, make_smem_desc_sw128_k(w_slab + h * (128 * 128) + ks * 32), act_desc, IDESC_T,
+                        (s | ks) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kRingF) { stage = 0; phase ^= 1; }
+        }
+        sl_phase ^= 1;
+        umma_commit(&acc_f[slot]);
+        trace_ev(p.trace, 1, tn, 142);
       }
     }
-  } else {
-    // ===================== epilogue warps 0-7
+  } else if (warp < kFwdHidWarps) {
+    // ===================== hidden warps 0-7: layer 0 on the FP32 pipe + hidden-layer epilogue
     const int quarter = warp & 3, grp = warp >> 2;
-    const int r = quarter * 32 + lane;  // tile row (hidden layers) / feature inside a half (final layer)
+    const int r = quarter * 32 + lane;  // tile row (hidden-layer epilogue)
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t acc_phase = 0;
     const int d = p.d;
-    float xr[kK0];
+    // layer 0: thread = 8 columns (cg) x 4 rows (rw + 32 i) of a 64-column slab, so the weights sit in
+    // registers and every shared-memory read is shared by 8 (x) or 4 (weights) lanes
+    const int cg = threadIdx.x & 7, rw = threadIdx.x >> 3;
+    // x tile -> registers -> xS (padded rows, bf16-rounded like every MMA operand: the backward recomputes
+    // this layer with MMAs): slot s = tid + 256 k covers row s / XW, column s % XW - 1
+    float xp[2 * Q];
     auto load_x = [&](int64_t tile) {
-      const int64_t row = tile * kTileM + r;
 #pragma unroll
-      for (int j = 0; j < kK0; ++j)
-        xr[j] = (grp == 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
-    };
-    auto stage_x = [&]() {  // registers -> un-swizzled [2][128][8] layer-0 operand image (group 0 owns the rows)
-      if (grp == 0) {
-        *reinterpret_cast<uint4*>(bufX + r * 16) = make_uint4(pack_bf16x2(xr[0], xr[1]), pack_bf16x2(xr[2], xr[3]),
-                                                              pack_bf16x2(xr[4], xr[5]), pack_bf16x2(xr[6], xr[7]));
-        *reinterpret_cast<uint4*>(bufX + X_LBO + r * 16) = make_uint4(pack_bf16x2(xr[8], xr[9]), pack_bf16x2(xr[10], xr[11]),
-                                                                      pack_bf16x2(xr[12], xr[13]), pack_bf16x2(xr[14], xr[15]));
+      for (int k = 0; k < 2 * Q; ++k) {
+        const int slot = threadIdx.x + kFwdHidWarps * 32 * k;
+        const int64_t row = tile * kTileM + slot / XW;
+        const int j = slot % XW - 1;
+        xp[k] = (j >= 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;  // raw: no use before store_x
       }
-      fence_proxy_async();
-      mbar_arrive_warp(x_ready);
+    };
+    auto store_x = [&](int buf) {
+#pragma unroll
+      for (int k = 0; k < 2 * Q; ++k) xS[buf * (kTileM * XW) + threadIdx.x + kFwdHidWarps * 32 * k] = bf16_round(xp[k]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // hidden warps only
     };
     load_x(blockIdx.x);
+    store_x(0);
     int tn = 0;
-    uint32_t ph = 0;
+    uint32_t acch_phase = 0;
     const bool tr0 = (threadIdx.x == 0);
-    if (blockIdx.x < p.num_tiles) {
-      stage_x();
-      load_x(blockIdx.x + gridDim.x);
-    }
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int64_t r0 = tile * kTileM;
+    int nt = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+      // ---- the activation image is free once the final layer of the previous tile has completed
+      if (nt >= 1) {
+        const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
+        const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
+        mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
+      }
       if (tr0) trace_ev(p.trace, 0, tn, 0);
-      const int b_first = __ldg(p.tile_first + tile);  // first set intersecting this tile (precomputed)
+      // ---- layer 0: h_0 = act(W_0 x + b_0), one 64-column slab at a time, handed to the MMA warp at once
+      const float* xT = xS + (nt & 1) * (kTileM * XW);
+      // next tile's inputs: issued here so that they have landed before the first fence below (the proxy fence
+      // drains every outstanding memory operation of the thread, global loads included)
+      load_x(tile + gridDim.x);
+#pragma unroll 1
+      for (int s = 0; s < NSLAB; ++s) {
+        // column pairs (2 pi, 2 pi + 1) of the thread's 8 columns as packed fp32 pairs: FFMA2 does two columns
+        // per issue slot with the row's input broadcast
+        uint64_t z[4][4];
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) {
+          ulonglong2 w[8];  // [pair][half]: {t0, t1} / {t2, t3} of quad qq, each a packed column pair
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = w0S[(qq * NSLAB + s) * 64 + e * 8 + cg];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
+            const uint64_t x0 = f32x2(xv.x, xv.x), x1 = f32x2(xv.y, xv.y), x2 = f32x2(xv.z, xv.z), x3 = f32x2(xv.w, xv.w);
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+              if (qq == 0) z[i][pi] = ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, w[2 * pi].x)));
+              else z[i][pi] = ffma2(w[2 * pi].x, x0, ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, z[i][pi]))));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t o[4];
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            float lo, hi;
+            f32x2_unpack(z[i][pi], lo, hi);
+            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
+          }
+          *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, s * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (tr0) trace_ev(p.trace, 0, tn, 50 + s);
+        fence_proxy_async();
+        mbar_arrive_warp(&slab_ready[s]);
+        if (tr0) trace_ev(p.trace, 0, tn, 60 + s);
+      }
+      if (tr0) trace_ev(p.trace, 0, tn, 5);
 
-      // ---- hidden layers: TMEM -> bias/act/residual -> bf16 image (in place); group g takes the
-      //      chunks g, g+2, ...; TMEM loads run one chunk ahead of the math; every finished 64-column
-      //      slab is handed to the MMA warp at once so the next layer's MMAs overlap this epilogue
-      for (int l = 0; l < L - 1; ++l, ++ph) {
-        mbar_wait(acc_ready, acc_phase);
-        acc_phase ^= 1;
+      // ---- hidden layer: TMEM -> bias/act/residual -> bf16 image (in place); TMEM loads run one chunk
+      //      ahead of the math; every finished 64-column slab is handed to the MMA warp at once
+      if (L == 3) {
+        mbar_wait(acc_h, acch_phase);
+        acch_phase ^= 1;
         tc_fence_after();
-        if (tr0) trace_ev(p.trace, 0, tn, 10 + l);
-        const bool res = (p.res_mask >> l) & 1;
-        const float* bl = biasS + l * H;
-        const uint32_t acc_base = lane_base + (ph & 1) * 256;
+        if (tr0) trace_ev(p.trace, 0, tn, 11);
+        const bool res = (p.res_mask >> 1) & 1;
         uint32_t va[32], vb[32];
-        tmem_ld32(acc_base + grp * 32, va);
+        tmem_ld32(lane_base + grp * 32, va);
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 4) {
           tmem_wait_ld();
-          if (c + 2 < NCHUNK) tmem_ld32(acc_base + (c + 2) * 32, vb);
-          epi_store_chunk<ACT>(va, bufA, bl, r, c, res);
+          if (c + 2 < NCHUNK) tmem_ld32(lane_base + (c + 2) * 32, vb);
+          epi_store_chunk<ACT>(va, bufA, r, c, res);
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive_warp(&slab_ready[c >> 1]);
           if (c + 2 < NCHUNK) {
             tmem_wait_ld();
-            if (c + 4 < NCHUNK) tmem_ld32(acc_base + (c + 4) * 32, va);
-            epi_store_chunk<ACT>(vb, bufA, bl, r, c + 2, res);
+            if (c + 4 < NCHUNK) tmem_ld32(lane_base + (c + 4) * 32, va);
+            epi_store_chunk<ACT>(vb, bufA, r, c + 2, res);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive_warp(&slab_ready[(c + 2) >> 1]);
           }
         }
-        if (tr0) trace_ev(p.trace, 0, tn, 20 + l);
+        if (tr0) trace_ev(p.trace, 0, tn, 21);
       }
-      // ---- the next tile's layer-0 operand can be staged already (its MMA uses the other accumulator)
-      if (tile + gridDim.x < p.num_tiles) {
-        stage_x();
-        load_x(tile + 2 * (int64_t)gridDim.x);
-      }
-
-      // ---- final layer (transposed): thread = feature, TMEM columns = the tile's points
-      mbar_wait(acc_ready, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      if (tr0) trace_ev(p.trace, 0, tn, 30);
-      const uint32_t accT = lane_base + (ph & 1) * 256;
-      ++ph;
-      const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
-      if (grp < HALVES) {
-        const int h = grp;
-        const int f = h * 128 + r;
-        const bool is_max = (p.pooling == PCC_POOL_MAX);
-        int64_t b = b_first;
-        int64_t seg_lo = 0, seg_hi = 0;
-        if (b < p.B) { seg_lo = __ldg(p.offsets + b); seg_hi = __ldg(p.offsets + b + 1); }
+      store_x((nt + 1) & 1);  // buffer last read by h_0 of the previous tile; every warp is past it (barrier above)
+    }
+  } else if (warp < kFwdHidWarps + kFwdPoolWarps) {
+    // ===================== pool warps 8-15: thread = feature, TMEM columns = the tile's points
+    const int pw = warp - kFwdHidWarps;
+    const int quarter = warp & 3, h = pw >> 2;
+    if (h < HALVES) {
+      const int r = quarter * 32 + lane;
+      const int f = h * 128 + r;
+      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+      const bool is_max = (p.pooling == PCC_POOL_MAX);
+      const bool tr0 = (pw == 0 && lane == 0);
+      int tn = 0;
+      int nt = 0;
+      // segment lookups run one tile ahead (two dependent global loads) so they never sit on the pooling path
+      int64_t nb = 0, nlo = 0, nhi = 0;
+      auto seg_fetch = [&](int64_t tile) {
+        nb = p.B; nlo = 0; nhi = 0;
+        if (tile < p.num_tiles) {
+          nb = __ldg(p.tile_first + tile);
+          if (nb < p.B) { nlo = __ldg(p.offsets + nb); nhi = __ldg(p.offsets + nb + 1); }
+        }
+      };
+      seg_fetch(blockIdx.x);
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+        const int64_t r0 = tile * kTileM;
+        const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
+        int64_t b = nb, seg_lo = nlo, seg_hi = nhi;
+        seg_fetch(tile + gridDim.x);
+        const int slot = (L == 2) ? (nt & 1) : 0;
+        const int k = (L == 2) ? (nt >> 1) : nt;
+        mbar_wait(&acc_f[slot], (uint32_t)(k & 1));
+        tc_fence_after();
+        if (tr0) trace_ev(p.trace, 2, tn, 30);
+        const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
         float acc = is_max ? -INFINITY : 0.f;
         int arg = -1;       // column of the running max inside this tile (first occurrence)
         auto flush = [&](int64_t set) {
@@ -297,12 +397,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
           }
         };
         uint32_t va[32], vb[32];
-        tmem_ld32(accT + h * 128, va);
+        tmem_ld32(accT, va);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tmem_wait_ld();
           uint32_t (&v)[32] = (c & 1) ? vb : va;
-          if (c + 1 < 4) tmem_ld32(accT + h * 128 + (c + 1) * 32, (c & 1) ? va : vb);
+          if (c + 1 < 4) tmem_ld32(accT + (c + 1) * 32, (c & 1) ? va : vb);
           const int64_t col0 = r0 + c * 32;
           while (b < p.B && seg_lo < tile_end && seg_lo < col0 + 32) {
             const int lo = (int)((seg_lo > col0 ? seg_lo : col0) - col0);
@@ -336,15 +436,17 @@ __global__ void __launch_bounds__(kThreads, 1) phi_pool_fwd_kernel(const PhiPara
             if (b < p.B) { seg_lo = seg_hi; seg_hi = __ldg(p.offsets + b + 1); }
           }
         }
+        // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back
+        tc_fence_before();
+        mbar_arrive_warp(&pool_done[slot]);
         if (b < p.B && seg_lo < tile_end) flush(b);  // partial of the set that continues past this tile
+        if (tr0) trace_ev(p.trace, 2, tn, 40);
       }
-      tc_fence_before();
-      if (tr0) trace_ev(p.trace, 0, tn, 40);
     }
   }
 
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
+  if (warp == kFwdMmaWarp) tmem_dealloc<512>(tmem);
 }
 
 // pool accumulator -> pooled[B,H] (+ argmax): adds the final bias after pooling
@@ -391,7 +493,8 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
 }
 
 // ONE launch for everything the forward kernel needs prepared: blockIdx.y < 2L packs weight image
-// (layer y>>1, transposed if y&1); y == 2L zeroes the pool accumulator; y == 2L+1 computes tile_first
+// (layer y>>1, transposed if y&1); y == 2L zeroes the pool accumulator; y == 2L+1 computes tile_first;
+// y == 2L+2 writes the fp32 layer-0 table {b_0[c], bf16(W_0[c][0..d-1]), 0...} of the forward kernel
 __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t pool_count, const int64_t* offsets,
                                 int64_t B, int64_t num_tiles, int32_t* tile_first) {
   const int y = blockIdx.y;
@@ -427,6 +530,20 @@ __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t
   } else if (y == 2 * pk.L) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pool_count; i += (int64_t)gridDim.x * blockDim.x)
       pool[i] = 0ull;
+  } else if (y == 2 * pk.L + 2) {
+    // layer-0 table of the forward kernel, 16-byte entries [qq][slab][e = 2 pair + half][cg]: the four terms
+    // t_0..t_3 of quad qq (qq = 0: b_0, w_0, w_1, w_2; else w_{4qq-1} .. w_{4qq+2}; bf16-rounded weights, zero
+    // padded) for the column pair (c, c + 1), c = 64 slab + 8 cg + 2 pair: half 0 = {t0[c], t0[c+1], t1[c], t1[c+1]},
+    // half 1 = {t2[c], t2[c+1], t3[c], t3[c+1]}
+    float* tab = reinterpret_cast<float*>(pk.wpack + pk.w0tab_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pk.H * 4 * pk.q4; i += gridDim.x * blockDim.x) {
+      const int f = i & 3, ent = i >> 2;
+      const int cg = ent & 7, e = (ent >> 3) & 7, slab = (ent >> 6) % (pk.H / 64), qq = (ent >> 6) / (pk.H / 64);
+      const int c = 64 * slab + 8 * cg + 2 * (e >> 1) + (f & 1);
+      const int term = 2 * (e & 1) + (f >> 1);
+      const int j = 4 * qq + term - 1;
+      tab[i] = (j < 0) ? __ldg(pk.b0 + c) : (j < pk.d ? bf16_round(__ldg(pk.w[0] + (int64_t)c * pk.d + j)) : 0.f);
+    }
   } else {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < num_tiles; i += (int64_t)gridDim.x * blockDim.x) {
       const int64_t r0 = i * kTileM;
@@ -445,7 +562,7 @@ int check_phi_desc(const pcc_phi_desc* d, const char* where) {
   // the backward chain keeps z of the last hidden layer in TMEM and recomputes only z_0, which
   // covers phi = Linear(d,H) [+ one H x H hidden layer] + final Linear(H,H)
   if (d->n_layers < 2 || d->n_layers > 3) return fail(where, "fused path needs 1 or 2 hidden phi layers (+ final Linear)");
-  if (d->input_dim < 1 || d->input_dim > kK0) return fail(where, "fused path needs input_dim <= 16");
+  if (d->input_dim < 1 || d->input_dim > 7) return fail(where, "fused path needs input_dim <= 7");
   if (d->hidden != 128 && d->hidden != 256) return fail(where, "fused path needs hidden width 128 or 256");
   if (d->act != PCC_ACT_RELU && d->act != PCC_ACT_GELU && d->act != PCC_ACT_SILU)
     return fail(where, "fused path needs relu/gelu/silu");
@@ -459,10 +576,12 @@ int check_phi_desc(const pcc_phi_desc* d, const char* where) {
 static void* g_trace_buf = nullptr;  // set through pcc_debug_set_trace (diagnostics only)
 void* debug_trace_buffer() { return g_trace_buf; }
 
-template <int H, int ACT>
+static inline int q4_of(int d) { return d <= 3 ? 1 : 2; }
+
+template <int H, int ACT, int Q>
 static int launch_fwd(const PhiParams& p, cudaStream_t st) {
-  const SmemLayout lay = smem_layout(H, p.L);
-  auto kern = phi_pool_fwd_kernel<H, ACT>;
+  const SmemLayout lay = smem_layout(H, p.L, Q);
+  auto kern = phi_pool_fwd_kernel<H, ACT, Q>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_fwd", cudaGetErrorString(e));
   int dev = 0, sms = 148;
@@ -471,7 +590,7 @@ static int launch_fwd(const PhiParams& p, cudaStream_t st) {
   const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
   {
     ProfScope prof(0, st);
-    PCC_K(kern)<<<grid, kThreads, lay.total, st>>>(p);
+    PCC_K(kern)<<<grid, kFwdThreads, lay.total, st>>>(p);
   }
   return 0;
 }
@@ -515,27 +634,35 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   PackParams pk{};
   for (int l = 0; l < L; ++l) { pk.w[l] = d->w[l]; pk.w_off[l] = pl.w_off[l]; pk.wt_off[l] = pl.wt_off[l]; }
   pk.wpack = (uint8_t*)wpack; pk.d = d->input_dim; pk.H = H; pk.L = L;
+  pk.b0 = d->b[0]; pk.w0tab_off = pl.w0tab_off; pk.q4 = q4_of(d->input_dim);
 
   PhiParams p{};
   p.x = x; p.offsets = offsets; p.n = n; p.B = B; p.num_tiles = cdiv(n, kTileM);
   p.d = d->input_dim; p.L = L; p.pooling = d->pooling; p.res_mask = d->residual_mask;
   p.wpack = (const uint8_t*)wpack;
+  p.w0tab = (const float*)((const uint8_t*)wpack + pl.w0tab_off);
   for (int l = 0; l < L; ++l) { p.w_off[l] = pl.w_off[l]; p.bias[l] = d->b[l]; }
   p.pool_acc = wsb + wl.pool_off;
   p.trace = (long long*)g_trace_buf;
   p.tile_first = (const int32_t*)(wsb + wl.tile_first_off);
-  PCC_K(fwd_prep_kernel)<<<dim3(32, 2 * L + 2), 256, 0, st>>>(pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
+  PCC_K(fwd_prep_kernel)<<<dim3(32, 2 * L + 3), 256, 0, st>>>(pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
                                                              p.num_tiles, (int32_t*)(wsb + wl.tile_first_off));
   if (p.num_tiles > 0) {
     int rc = 0;
-#define PCC_DISPATCH(HH)                                                              \
+#define PCC_DISPATCH_A(HH, QQ)                                                        \
     switch (d->act) {                                                                 \
-      case PCC_ACT_RELU: rc = launch_fwd<HH, PCC_ACT_RELU>(p, st); break;             \
-      case PCC_ACT_GELU: rc = launch_fwd<HH, PCC_ACT_GELU>(p, st); break;             \
-      default: rc = launch_fwd<HH, PCC_ACT_SILU>(p, st); break;                       \
+      case PCC_ACT_RELU: rc = launch_fwd<HH, PCC_ACT_RELU, QQ>(p, st); break;         \
+      case PCC_ACT_GELU: rc = launch_fwd<HH, PCC_ACT_GELU, QQ>(p, st); break;         \
+      default: rc = launch_fwd<HH, PCC_ACT_SILU, QQ>(p, st); break;                   \
+    }
+#define PCC_DISPATCH(HH)                                                              \
+    switch (pk.q4) {                                                                  \
+      case 1: PCC_DISPATCH_A(HH, 1) break;                                            \
+      default: PCC_DISPATCH_A(HH, 2) break;                                           \
     }
     if (H == 256) { PCC_DISPATCH(256) } else { PCC_DISPATCH(128) }
 #undef PCC_DISPATCH
+#undef PCC_DISPATCH_A
     if (rc != 0) return rc;
   }
   if (B * H > 0)

@@ -56,7 +56,8 @@ CASES = [
     ("gelu", "mean", True, 256, 2, 6, [33, 1, 200, 128, 129, 64, 7, 500]),
     ("silu", "sum", True, 128, 2, 4, [31, 32, 33, 127, 128, 129, 1, 300]),
     ("relu", "sum", False, 256, 1, 3, [256, 100, 156]),
-    ("gelu", "max", True, 128, 2, 16, [700, 5, 250]),
+    ("gelu", "max", True, 128, 2, 7, [700, 5, 250]),
+    ("silu", "sum", False, 256, 2, 6, [300, 41, 129, 1]),
     ("silu", "mean", False, 128, 1, 1, [64, 64]),
 ]
 

@@ -7,23 +7,24 @@ B, N = 256, 1024
 m = pcc_b200.DeepSets(3, [256, 256], [256], 10, "relu", layer_norm=False, pooling="max", precision="bf16").cuda()
 x = torch.randn(B * N, 3, device="cuda"); idx = torch.arange(B, device="cuda").repeat_interleave(N)
 off = PF.segment_offsets(idx, B)
-buf = torch.zeros(2 * 4096, dtype=torch.int64, device="cuda")
+buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     for _ in range(2): FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
     _lib.call("pcc_debug_set_trace", _lib.ptr(buf))
     FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
     torch.cuda.synchronize()
     _lib.call("pcc_debug_set_trace", None)
-t = buf.cpu().numpy().reshape(2, 2048, 2)
+t = buf.cpu().numpy().reshape(3, 2048, 2)
 ev = []
-for role in (0, 1):
+for role in (0, 1, 2):
     for i in range(2048):
         if t[role, i, 1] == 0: break
         ev.append((int(t[role, i, 1]), role, int(t[role, i, 0])))
 ev.sort()
 t0 = ev[0][0]
 # print tiles 5..6 worth of events
-names = {0: "E x staged", 10: "E acc0 ready", 11: "E acc1 ready", 20: "E epi0 done", 21: "E epi1 done", 30: "E accF ready", 40: "E pool done"}
+names = {0: "H image free, h0 start", 5: "H h0 done", 11: "H acc1 ready", 21: "H epi1 done", 30: "P accF ready", 40: "P pool done",
+         101: "M L1 begin", 121: "M L1 first slab", 141: "M L1 issued", 102: "M L2 begin (pool drained)", 122: "M L2 first slab", 142: "M L2 issued"}
 for l in range(3):
     names[100 + l] = f"M wait operand L{l}"; names[110 + l] = f"M operand L{l} ready"; names[120 + l] = f"M first slab L{l}"
     names[130 + l] = f"M last slab L{l}"; names[140 + l] = f"M issued L{l}"
