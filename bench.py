@@ -305,7 +305,9 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: DeepSets B=256 N=1024 per GPU, phi[3-256-256]+final(256) relu, max pool, "
-                               "rho[256]-10, fwd + BCEWithLogitsLoss + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
+                               "rho[256]-10, fwd + BCEWithLogitsLoss + bwd" +
+                               ((" + gradient all-reduce (own one-shot kernel over NVLink peer memory, inside the graph)"
+                                 if gs.peer is not None else " + NCCL gradient all-reduce") if world > 1 else ""),
                    "sets_per_gpu": B_PER_GPU, "points_per_set": N_PTS, "cuda_graph": graphed,
                    "l2": f"inputs rotate over {N_ROTATE} distinct batches (166 MB) and every step streams ~0.7 GB of "
                          "staged operands, both larger than the 126 MB L2",

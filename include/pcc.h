@@ -206,7 +206,25 @@ int pcc_prof_read(int slot, double* ms_total, int64_t* count);
  *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
  *      (wgrad).  Expected values: tests/test_fused_gpu.py. */
 int pcc_selftest_umma(int mode, float* out, int device, void* stream);
-/* optional event trace of CTA 0 of the fused forward kernel into a device buffer of 2*4096 int64
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (one process per GPU, one node).
+ *      One-shot: every rank stages its flat fp32 bucket in CUDA-IPC memory mapped by all peers, publishes a
+ *      sequence number to every peer with a system-scope release, then sums all ranks' staging buffers in rank
+ *      order (bitwise identical results everywhere) and writes scale * sum back into its bucket.  A plain kernel:
+ *      capturable into the CUDA graph of the train step (an NCCL call is not, on this stack).
+ *      pcc_peer_alloc: region = 1 KB of flags + 2 staging buffers of buf_bytes, allocated with cudaMalloc by the
+ *      library (IPC export needs it — the one exception to caller-owned memory) + its 64-byte IPC handle;
+ *      pcc_peer_open / _close map / unmap a peer's region; pcc_peer_free releases the local one.
+ *      pcc_peer_allreduce: n % 4 == 0, 4 n <= buf_bytes, bucket 16-byte aligned; regions[world] in rank order;
+ *      counters = 16 zeroed bytes of local device memory that persist across calls; every rank calls it the same
+ *      number of times with the same n. */
+int pcc_peer_alloc(int64_t buf_bytes, void** region, void* ipc_handle_64, int device);
+int pcc_peer_open(const void* ipc_handle_64, void** region, int device);
+int pcc_peer_close(void* region, int device);
+int pcc_peer_free(void* region, int device);
+int pcc_peer_allreduce(float* bucket, int64_t n, void* const* regions, int64_t buf_bytes, int rank, int world,
+                       float scale, void* counters, int device, void* stream);
+
+/* optional event trace of CTA 0 of the fused forward kernel into a device buffer of 3*4096 int64
  * (role, (id, clock64) pairs); NULL disables.  Development aid. */
 int pcc_debug_set_trace(void* device_buf);
 

@@ -58,6 +58,11 @@ _SIGS = {
     "pcc_mlp_head_fwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _i64, _i32, _vp],
     "pcc_mlp_head_workspace_bytes": [C.POINTER(HeadDesc), _i64],
     "pcc_mlp_head_bwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "pcc_peer_alloc": [_i64, C.POINTER(C.c_void_p), _vp, _i32],
+    "pcc_peer_open": [_vp, C.POINTER(C.c_void_p), _i32],
+    "pcc_peer_close": [_vp, _i32],
+    "pcc_peer_free": [_vp, _i32],
+    "pcc_peer_allreduce": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp],
     "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
     "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp],
     "pcc_launch_count": [_i32],

@@ -49,6 +49,111 @@ def shard_sets(x: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, rank: int, w
     return x[r0:r1], idx[r0:r1] - b0, y[b0:b1]
 
 
+class GradArena:
+    """ONE flat fp32 buffer that holds every parameter gradient of a model.
+
+    While an arena is active (`with arena:`), the backward kernels of this package write dW / db straight
+    into its slices (the autograd Functions ask `grad_like`), and autograd adopts those views as `.grad`
+    (AccumulateGrad steals a fresh contiguous view when `.grad` is None).  The data-parallel all-reduce then
+    runs in place on `flat` — no flatten / unflatten copies, no extra launches."""
+
+    _active: "GradArena | None" = None
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        self.slices = {}
+        off = 0
+        for p in self.params:
+            off = (off + 3) // 4 * 4            # 16-byte aligned slices
+            self.slices[p.data_ptr()] = (off, p.numel(), tuple(p.shape))
+            off += p.numel()
+        self.numel = (off + 3) // 4 * 4
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+
+    def view_for(self, t: torch.Tensor):
+        ent = self.slices.get(t.data_ptr())
+        if ent is None or t.dtype != torch.float32 or tuple(t.shape) != ent[2]:
+            return None
+        return self.flat.narrow(0, ent[0], ent[1]).view(ent[2])  # a fresh view each time (so that it can be adopted)
+
+    def holds_all_grads(self) -> bool:
+        for p in self.params:
+            ent = self.slices[p.data_ptr()]
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * ent[0]:
+                return False
+        return True
+
+    def __enter__(self):
+        GradArena._active = self
+        return self
+
+    def __exit__(self, *exc):
+        GradArena._active = None
+
+
+def grad_like(t: torch.Tensor) -> torch.Tensor:
+    """gradient buffer for parameter tensor `t`: its slice of the active GradArena, else a fresh tensor"""
+    a = GradArena._active
+    if a is not None:
+        v = a.view_for(t)
+        if v is not None:
+            return v
+    return torch.empty_like(t)
+
+
+class PeerAllReduce:
+    """Average a flat fp32 bucket over the ranks of one node with the library's own one-shot all-reduce over
+    NVLink peer memory (pcc_peer.cu).  A plain kernel launch: it can be captured into the CUDA graph of the
+    train step.  The process group is only used once, to exchange the CUDA IPC handles."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import ctypes as C
+        from . import _lib as L
+        self.L, self.C = L, C
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self.numel = (numel + 3) // 4 * 4
+        self.buf_bytes = (self.numel * 4 + 255) // 256 * 256
+        region = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        L.call("pcc_peer_alloc", self.buf_bytes, C.byref(region), C.cast(handle, C.c_void_p), self.dev_index)
+        self.local = region.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.regions = (C.c_void_p * self.world)()
+        self.opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.regions[r] = self.local
+            else:
+                peer = C.c_void_p()
+                hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                L.call("pcc_peer_open", C.cast(hb, C.c_void_p), C.byref(peer), self.dev_index)
+                self.regions[r] = peer.value
+                self.opened.append(peer.value)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def run(self, flat: torch.Tensor) -> torch.Tensor:
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() == self.numel
+        L, C = self.L, self.C
+        L.call("pcc_peer_allreduce", L.ptr(flat), flat.numel(), C.cast(self.regions, C.c_void_p), self.buf_bytes,
+               self.rank, self.world, 1.0 / self.world, L.ptr(self.counters), self.dev_index, L.stream_ptr(self.dev_index))
+        return flat
+
+    def close(self):
+        if getattr(self, "local", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for ptr_ in self.opened:
+            self.L.call("pcc_peer_close", self.C.c_void_p(ptr_), self.dev_index)
+        self.L.call("pcc_peer_free", self.C.c_void_p(self.local), self.dev_index)
+        self.local, self.opened = None, []
+
+
 def flatten_grads(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
     return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
 

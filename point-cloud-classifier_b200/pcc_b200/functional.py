@@ -402,7 +402,8 @@ class MLPHeadFn(torch.autograd.Function):
         dy = L.f32c(dy)
         dev, st = _ctx(dy)
         d = _head_desc(ws, ctx.act)
-        grads = [torch.empty_like(t) for t in ws]
+        from .distributed import grad_like
+        grads = [grad_like(t) for t in ws]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = (C.c_void_p * 4)(*[grads[2 * i].data_ptr() for i in range(d.n_layers)])
         db = (C.c_void_p * 4)(*[grads[2 * i + 1].data_ptr() for i in range(d.n_layers)])

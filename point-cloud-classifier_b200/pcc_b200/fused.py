@@ -107,7 +107,8 @@ class FusedPhiPoolFn(torch.autograd.Function):
                 _VIRT["offsets"] = torch.arange(B + 1, device=x.device, dtype=torch.int64) * H
                 _VIRT["arg"] = torch.arange(B * H, device=x.device, dtype=torch.int32).view(B, H)
             offsets, arg, n = _VIRT["offsets"], _VIRT["arg"], B * H
-        grads = [torch.empty_like(t) for t in ws_]
+        from .distributed import grad_like
+        grads = [grad_like(t) for t in ws_]
         dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])
         db = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i + 1].data_ptr() for i in range(plan_len)])
         ws_bytes = call("pcc_phi_fused_workspace_bytes", C.byref(d), n, B)

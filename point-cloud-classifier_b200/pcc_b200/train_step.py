@@ -16,7 +16,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from .distributed import flatten_grads, unflatten_into_grads
+from .distributed import GradArena, PeerAllReduce, flatten_grads, unflatten_into_grads
 from .functional import BCEWithLogitsLoss
 
 
@@ -34,6 +34,24 @@ class GraphedTrainStep:
         self.static_y = example_target.clone()
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat = None
+        # data parallel: gradients land in one flat arena (no flatten / unflatten copies) that is averaged in
+        # place, by the library's own peer-memory all-reduce INSIDE the captured step when the ranks share a
+        # node (PCC_PEER_ALLREDUCE=0 forces the NCCL call after the replay)
+        self.arena = GradArena(self.params) if self.allreduce else None
+        self.peer = None
+        import os as _os
+        if self.allreduce and self.static_y.is_cuda and _os.environ.get("PCC_PEER_ALLREDUCE", "1") != "0":
+            try:
+                self.peer = PeerAllReduce(self.arena.numel, self.static_y.device)
+            except Exception as e:  # e.g. IPC not permitted: fall back to NCCL, loudly
+                import sys as _sys
+                print(f"[pcc_b200] peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=_sys.stderr)
+                self.peer = None
+            ok = torch.tensor([1 if self.peer is not None else 0], device=self.static_y.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+            if int(ok.item()) == 0 and self.peer is not None:
+                self.peer.close()
+                self.peer = None
         self.graph = None
         self.loss = None
         self.logits = None
@@ -60,19 +78,40 @@ class GraphedTrainStep:
             p.grad = None
         self.logits = self.model(*self.static_in, **self.kw)
         self.loss = self.loss_fn(self.logits, self.static_y)
-        self.loss.backward()
-        if self.allreduce:
-            # gradients gathered into one flat fp32 bucket inside the captured region; the collective itself
-            # runs right after the replay (NCCL launches are kept out of the CUDA graph)
-            self.flat = flatten_grads(self.params)
-        elif self.optimizer is not None:
-            self.optimizer.step()
+        if self.arena is not None:
+            with self.arena:
+                self.loss.backward()
+            self.in_arena = self.arena.holds_all_grads()
+            if not self.in_arena:   # some gradient came from a kernel outside this package: gather by copy
+                self.flat = flatten_grads(self.params)
+            if self.peer is not None:
+                # loss is a mean over the local batch, so gradients are averaged
+                bucket = self.arena.flat if self.in_arena else self._pad4(self.flat)
+                self.peer.run(bucket)
+                if not self.in_arena:
+                    unflatten_into_grads(bucket, self.params)
+                if self.optimizer is not None:
+                    self.optimizer.step()
+        else:
+            self.loss.backward()
+            if self.optimizer is not None:
+                self.optimizer.step()
+
+    def _pad4(self, flat):
+        if flat.numel() == self.arena.numel:
+            return flat
+        out = torch.zeros(self.arena.numel, dtype=flat.dtype, device=flat.device)
+        out[:flat.numel()] = flat
+        return out
 
     def _post(self):
-        if self.allreduce:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / self.world)   # loss is a mean over the local batch
-            unflatten_into_grads(self.flat, self.params)
+        if self.allreduce and self.peer is None:
+            # NCCL launches are kept out of the CUDA graph (capturing them hung on this stack)
+            bucket = self.arena.flat if self.in_arena else self.flat
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+            bucket.mul_(1.0 / self.world)
+            if not self.in_arena:
+                unflatten_into_grads(bucket, self.params)
             if self.optimizer is not None:
                 self.optimizer.step()
 
