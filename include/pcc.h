@@ -158,7 +158,11 @@ int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64
                               float* pooled, int32_t* argmax, void* ws, void* wpack, int device, void* stream);
 /* dpooled[B,H] -> dw[l] / db[l] (fp32, OVERWRITTEN) for every phi layer; recomputes the
  * forward per tile.  dw/db arrays follow d->w / d->b order.  wpack: the images written by the forward of
- * the same parameters. */
+ * the same parameters.
+ * Max pooling with argmax == NULL ("virtual rows"): x holds the B*H gathered argmax rows (row b*H + f is the
+ * argmax row of (b, f); n == B*H, offsets unused, no ResidualBlock).  The gradient of the final Linear's output
+ * is then one-hot per row, and the library skips that layer's dgrad and wgrad GEMMs (scaled weight rows /
+ * scaled row sums instead). */
 int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, const void* wpack, int device, void* stream);

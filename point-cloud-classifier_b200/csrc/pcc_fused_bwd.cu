@@ -33,6 +33,8 @@ struct BwdParams {
   uint8_t* stage_g[kMaxLayers];  // dZ_l images, l = 0..L-1
   float* part_w[kMaxLayers];     // per-CTA partial dW_l [grid][H][K_l]  (K_0 = 16)
   float* part_b[kMaxLayers];     // per-CTA partial db_l [grid][H]
+  int virt;                      // max pooling on pre-gathered argmax rows: row b*H+f is THE argmax row of (b, f)
+  int nbig;                      // H x H layers whose weight gradient is a GEMM over the staged images
   const int32_t* row_set;        // [n] set of each row (-1: none), seg_prep_kernel
   const float* row_scale;        // [n] pooled-gradient scale of the row's set
   long long* trace;              // optional (debug) event trace of CTA 0
@@ -86,7 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   uint64_t* a_ready = bars + 2 * kRingB;      // an operand image is ready (epilogue warps -> MMA thread)
   uint64_t* accA_ready = bars + 2 * kRingB + 1;  // z in accA complete
   uint64_t* accB_ready = bars + 2 * kRingB + 2;  // dH in accB complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingB + 3);
+  uint64_t* wf_ready = bars + 2 * kRingB + 3;    // virtual-row mode: rows of the final weight image landed in bufG
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingB + 4);
 
   constexpr uint32_t SLAB = w_slab_bytes(H);
   constexpr uint32_t X_LBO = kTileM * 16;
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     mbar_init(a_ready, kEpiWarps);
     mbar_init(accA_ready, 1);
     mbar_init(accB_ready, 1);
+    mbar_init(wf_ready, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -113,6 +117,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Virtual-row mode (max pooling, rows pre-gathered: row b*H + f is the argmax row of (b, f)): the gradient of
+  // the final Linear's output is one-hot per row, dZ_{L-1}[row] = dpooled[row] * e_f, so
+  //   dH_lh[row, :] = dpooled[row] * W_{L-1}[f, :]      (a scaled weight row: no dgrad GEMM, no dZ_{L-1} image)
+  //   dW_{L-1}[f, :] = sum_b dpooled[b, f] * h_lh[b*H + f, :]   (final_wgrad_virtual_kernel, no GEMM either)
+  // The 128 weight rows a tile needs are one contiguous 16 KB piece of every K slab of the packed image.
+  const bool virt = p.virt != 0;
 
   if (warp == kProdWarp) {
     // ===================== producer: weight slabs in consumption order
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       auto push_layer = [&](uint32_t off) { for (int s = 0; s < NSLAB; ++s) push(p.wpack + off + (size_t)s * SLAB, SLAB); };
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);        // z_0
-        push_layer(p.wt_off[L - 1]);                            // dgrad of the final layer
+        if (!virt) push_layer(p.wt_off[L - 1]);                 // dgrad of the final layer
         if (L == 3) {
           push_layer(p.w_off[1]);                               // z_1
           push_layer(p.wt_off[1]);                              // dgrad of layer 1
@@ -169,9 +179,11 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         wait_a();                                   // x tile staged
         gemm0();
         umma_commit(accA_ready);
-        wait_a();                                   // dZ of the final layer built
-        gemm(g_base, ACC_B, false);                 // dH_lh
-        umma_commit(accB_ready);
+        if (!virt) {
+          wait_a();                                 // dZ of the final layer built
+          gemm(g_base, ACC_B, false);               // dH_lh
+          umma_commit(accB_ready);
+        }
         if (L == 3) {
           wait_a();                                 // h_0 image written
           gemm(h_base, ACC_A, false);               // z_1
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     const int quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    uint32_t phA = 0, phB = 0;
+    uint32_t phA = 0, phB = 0, wf_phase = 0;
     const int d = p.d;
     float xcur[kK0], xnext[kK0];
     auto load_x = [&](int64_t tile) {
@@ -217,6 +229,17 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) { bulk_s2g(gdst, sbuf, BLOB); bulk_commit(); }
+    };
+    // slab-wise staging: `count` finished 64-column slabs (16 KB each, contiguous in the image) leave for the
+    // staging area while the epilogue works on the next ones, so the buffer hand-over waits stay short
+    auto store_slabs = [&](uint8_t* gdst, const uint8_t* sbuf, int s0, int count, uint8_t* gdst2, const uint8_t* sbuf2) {
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        bulk_s2g(gdst + (size_t)s0 * kActSlab, sbuf + (size_t)s0 * kActSlab, (uint32_t)count * kActSlab);
+        if (gdst2) bulk_s2g(gdst2 + (size_t)s0 * kActSlab, sbuf2 + (size_t)s0 * kActSlab, (uint32_t)count * kActSlab);
+        bulk_commit();
+      }
     };
     auto wait_A = [&]() { mbar_wait(accA_ready, phA); phA ^= 1; tc_fence_after(); };
     auto wait_B = [&]() { mbar_wait(accB_ready, phB); phB ^= 1; tc_fence_after(); };
@@ -286,14 +309,24 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       arrive_a();
       TRE(2);
       load_x(tile + gridDim.x);
-      // set of this thread's row (for the pooled-gradient scatter), precomputed
-      const int64_t myset = (row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
-      const float scale = (row < p.n) ? __ldg(p.row_scale + row) : 0.f;
+      // set of this thread's row (for the pooled-gradient scatter), precomputed; virtual-row mode: the row's
+      // pooled gradient itself
+      const int64_t myset = (!virt && row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
+      const float scale = (!virt && row < p.n) ? __ldg(p.row_scale + row) : 0.f;
+      const float gs = (virt && row < p.n) ? __ldg(p.dpooled + row) : 0.f;
 
       // ---- dZ of the final Linear from the pooled gradient (autograd of deep_sets.py:96-106)
       acquire();  // the previous tile's dZ_0 store has finished reading bufG
       TRE(1);
-      {
+      if (virt) {
+        // rows f0 .. f0+127 of the final weight image -> bufG (same SW128 layout as an activation image)
+        if (threadIdx.x == 0) {
+          const uint32_t f0 = (uint32_t)(r0 % H);
+          mbar_arrive_expect_tx(wf_ready, NSLAB * kActSlab);
+          for (int s = 0; s < NSLAB; ++s)
+            bulk_g2s(bufG + s * kActSlab, p.wpack + p.w_off[L - 1] + (size_t)s * SLAB + (size_t)f0 * 128, kActSlab, wf_ready);
+        }
+      } else {
         // the pooled-gradient rows of the sets that intersect this tile are staged one set at a time in a
         // scratch area of bufH (free until the h_0 epilogue) and broadcast from shared memory; a thread
         // writes its row when its own set is staged.  (Per-thread global loads here were latency bound:
@@ -338,8 +371,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         }
       }
       TRE(3);
-      store_blob(p.stage_g[L - 1] + (size_t)tile * BLOB, bufG);
-      arrive_a();
+      if (!virt) {
+        store_blob(p.stage_g[L - 1] + (size_t)tile * BLOB, bufG);
+        arrive_a();
+      }
       TRE(4);
 
       // ---- L = 3: h_0 = act(z_0 + b_0) -> bufH (over the x tile), staged; TMEM loads one chunk ahead
@@ -362,21 +397,45 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
             for (int q = 0; q < 4; ++q)
               h_chunk8(vb + q * 8, bl + (c + 2) * 32 + q * 8, bufH + act_chunk_off(r, (c + 2) * 32 + q * 8), false);
           }
+          // the two groups together have finished slabs (c - grp) / 2 and + 1
+          store_slabs(p.stage_h[0] + (size_t)tile * BLOB, bufH, (c - grp) >> 1, (c + 2 < NCHUNK) ? 2 : 1, nullptr, nullptr);
         }
         TRE(6);
-        store_blob(p.stage_h[0] + (size_t)tile * BLOB, bufH);
         arrive_a();
         TRE(7);
       }
 
       // ---- one pass over z_lh (accA) and dH_lh (accB): h_lh -> bufH, dZ_lh -> bufG, both staged
-      wait_B();
+      if (!virt) wait_B();
       TRE(8);
       wait_A();
       TRE(9);
       acquire();  // staging stores of h_0 (bufH) and dZ_{L-1} (bufG) have finished reading
       TRE(10);
-      {
+      if (virt) {
+        mbar_wait(wf_ready, wf_phase);
+        wf_phase ^= 1;
+        const bool res = (p.res_mask >> lh) & 1;
+        const float* bl = biasS + lh * H;
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 2) {
+          uint32_t z[32];
+          tmem_ld32(lane_base + ACC_A + c * 32, z);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
+            const uint4 wv = *reinterpret_cast<const uint4*>(bufG + off);  // W_{L-1}[f, 8 columns]; overwritten below
+            uint32_t g[8];
+            g[0] = __float_as_uint(gs * bf16_lo(wv.x)); g[1] = __float_as_uint(gs * bf16_hi(wv.x));
+            g[2] = __float_as_uint(gs * bf16_lo(wv.y)); g[3] = __float_as_uint(gs * bf16_hi(wv.y));
+            g[4] = __float_as_uint(gs * bf16_lo(wv.z)); g[5] = __float_as_uint(gs * bf16_hi(wv.z));
+            g[6] = __float_as_uint(gs * bf16_lo(wv.w)); g[7] = __float_as_uint(gs * bf16_hi(wv.w));
+            hdz_chunk8(z + q * 8, g, bl + c * 32 + q * 8, bufH + off, bufG + off, res);
+          }
+          store_slabs(p.stage_h[lh] + (size_t)tile * BLOB, bufH, c >> 1, 1, p.stage_g[lh] + (size_t)tile * BLOB, bufG);
+        }
+      } else {
         const bool res = (p.res_mask >> lh) & 1;
         const float* bl = biasS + lh * H;
 #pragma unroll 1
@@ -390,18 +449,16 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
             const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
             hdz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufH + off, bufG + off, res);
           }
+          store_slabs(p.stage_h[lh] + (size_t)tile * BLOB, bufH, c >> 1, 1, p.stage_g[lh] + (size_t)tile * BLOB, bufG);
         }
       }
       TRE(11);
-      store_blob(p.stage_h[lh] + (size_t)tile * BLOB, bufH);
-      store_blob(p.stage_g[lh] + (size_t)tile * BLOB, bufG);
       TRE(12);
 
       if (L == 3) {
         arrive_a();  // dZ_1 image complete: the dgrad of layer 1 can start while the staging stores drain
-        // h_1 (the older of the two stores) staged out of bufH: its head can take the x tile again; the
-        // dZ_1 store may still be reading bufG
-        if (threadIdx.x == 0) bulk_wait_read1();
+        // h_1 staged out of bufH: its head can take the x tile again
+        if (threadIdx.x == 0) bulk_wait_read0();  // slab-wise stores: only the last slab pair can still be in flight
         asm volatile("bar.sync 1, 256;" ::: "memory");
         TRE(13);
         stage_x();
@@ -422,9 +479,9 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + act_chunk_off(r, c * 32 + q * 8));
+          store_slabs(p.stage_g[0] + (size_t)tile * BLOB, bufG, c >> 1, 1, nullptr, nullptr);
         }
         TRE(16);
-        store_blob(p.stage_g[0] + (size_t)tile * BLOB, bufG);
         TRE(17);
       }
     }
@@ -449,18 +506,17 @@ struct WgradJob {
   int64_t first, stride;
   int slot;  // index of this CTA's partial inside the layer's partial array
 };
-__host__ __device__ inline int wgrad_members(int grid, int L, int layer) {  // CTAs that work on `layer`
+// nbig = number of H x H layers handled as GEMM jobs: layers 1 .. nbig (L-1, or L-2 in virtual-row mode)
+__host__ __device__ inline int wgrad_members(int grid, int nbig, int layer) {  // CTAs that work on `layer`
   if (layer == 0) return grid;
-  const int nbig = L - 1;
   return (grid - (layer - 1) + nbig - 1) / nbig;
 }
-__device__ inline WgradJob wgrad_job(int j, int cta, int grid, int L) {
+__device__ inline WgradJob wgrad_job(int j, int cta, int grid, int nbig) {
   WgradJob w;
   if (j == 0) {
-    const int nbig = L - 1;
     w.layer = 1 + cta % nbig;
     w.first = cta / nbig;
-    w.stride = wgrad_members(grid, L, w.layer);
+    w.stride = wgrad_members(grid, nbig, w.layer);
     w.slot = cta / nbig;
   } else {
     w.layer = 0; w.first = cta; w.stride = grid; w.slot = cta;
@@ -488,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = p.L;
+  const int j0 = (p.nbig == 0) ? 1 : 0;  // no H x H GEMM job (one hidden layer in virtual-row mode): layer 0 only
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], kEpiWarps); mbar_init(&x_empty[i], 1); }
@@ -511,8 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         bulk_g2s(slots + stage * BLOB, src, BLOB, &full[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
       };
-      for (int j = 0; j < 2; ++j) {
-        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+      for (int j = j0; j < 2; ++j) {
+        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
         for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
           push(p.stage_g[l] + (size_t)tile * BLOB);
@@ -524,12 +580,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0 /* bit i = phase of x buffer i */, free_phase = 0;
       const uint32_t s_base = smem_u32(slots), x_base = smem_u32(bufX);
-      for (int j = 0; j < 2; ++j) {
-        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+      for (int j = j0; j < 2; ++j) {
+        const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
         const int Np = (l == 0) ? kK0 : H;
         const uint32_t idesc = make_idesc_bf16(128, Np, 1, 1);
-        if (j > 0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
+        if (j > j0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
         bool first = true;
         for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
           const uint32_t g_stage = stage;
@@ -572,8 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0, acc_phase = 0;
     const int d = p.d;
-    for (int j = 0; j < 2; ++j) {
-      const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, L);
+    for (int j = j0; j < 2; ++j) {
+      const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
       const int l = jb.layer;
       const int Np = (l == 0) ? kK0 : H;
       float dbacc[CPW][8];
@@ -660,6 +716,63 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
+}
+
+// Virtual-row mode: weight gradient of the final Linear without a GEMM.  dZ_{L-1}[b*H + f] = dpooled[b, f] * e_f, so
+//   dW_{L-1}[f, :] = sum_b dpooled[b, f] * h_lh[b*H + f, :]      db_{L-1}[f] = sum_b dpooled[b, f]
+// One CTA per output feature f; thread = (8-column chunk, b group); the h rows come from the staged SW128 images.
+template <int H>
+__global__ void __launch_bounds__(256) final_wgrad_virtual_kernel(const uint8_t* __restrict__ stage_h,
+                                                                  const float* __restrict__ dpooled, int64_t B,
+                                                                  float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int CH = H / 8, NG = 256 / CH;
+  constexpr uint32_t BLOB = kTileM * H * 2;
+  __shared__ float red[NG][CH][8];
+  __shared__ float redb[NG];
+  const int f = blockIdx.x;
+  const int kc = threadIdx.x % CH, bg = threadIdx.x / CH;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float gsum = 0.f;
+  // 8 independent (gradient, row chunk) loads in flight per thread: the loop is latency bound
+  for (int64_t b0 = bg; b0 < B; b0 += 8 * NG) {
+    float g[8];
+    uint4 u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t b = b0 + (int64_t)i * NG;
+      const int64_t row = (b < B ? b : 0) * H + f;
+      g[i] = (b < B) ? __ldg(dpooled + row) : 0.f;
+      u[i] = __ldg(reinterpret_cast<const uint4*>(stage_h + (size_t)(row / kTileM) * BLOB +
+                                                  act_chunk_off((int)(row % kTileM), kc * 8)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0] = fmaf(g[i], bf16_lo(u[i].x), acc[0]); acc[1] = fmaf(g[i], bf16_hi(u[i].x), acc[1]);
+      acc[2] = fmaf(g[i], bf16_lo(u[i].y), acc[2]); acc[3] = fmaf(g[i], bf16_hi(u[i].y), acc[3]);
+      acc[4] = fmaf(g[i], bf16_lo(u[i].z), acc[4]); acc[5] = fmaf(g[i], bf16_hi(u[i].z), acc[5]);
+      acc[6] = fmaf(g[i], bf16_lo(u[i].w), acc[6]); acc[7] = fmaf(g[i], bf16_hi(u[i].w), acc[7]);
+      gsum += g[i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[bg][kc][j] = acc[j];
+  if (kc == 0) redb[bg] = gsum;
+  __syncthreads();
+  if (threadIdx.x < H) {
+    const int c = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) s += red[g][c][j];
+    dw[(size_t)f * H + threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) s += redb[g];
+    db[f] = s;
+  }
 }
 
 // sum the per-CTA partials of ALL layers in one launch: dW_l[H, K] (K = real in-features), db_l[H].
@@ -781,9 +894,13 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
                                          float* const* db, void* ws, const void* wpack, int device, void* stream) {
   PCC_ENTER(device);
   if (check_phi_desc(d, __func__) != 0) return -1;
-  PCC_REQUIRE(d->pooling != PCC_POOL_MAX || argmax != nullptr, "argmax required for max pooling");
   cudaStream_t st = (cudaStream_t)stream;
   const int H = d->hidden, L = d->n_layers;
+  // max pooling with argmax == NULL: the caller passes the B*H argmax rows themselves (row b*H + f = argmax row
+  // of (b, f)); offsets are not read
+  const bool virt = d->pooling == PCC_POOL_MAX && argmax == nullptr;
+  PCC_REQUIRE(!virt || n == B * H, "max pooling without argmax: x must hold the B*H gathered argmax rows");
+  PCC_REQUIRE(!virt || d->residual_mask == 0, "max pooling without argmax: not available with ResidualBlocks");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const BwdWs wl = bwd_ws(d, n, sms);
@@ -815,8 +932,11 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   p.trace = (long long*)debug_trace_buffer();
   p.row_set = (const int32_t*)(wsb + wl.row_set);
   p.row_scale = (const float*)(wsb + wl.row_scale);
-  PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(offsets, n, B, tiles, d->pooling, nullptr,
-                                                                (int32_t*)(wsb + wl.row_set), (float*)(wsb + wl.row_scale));
+  p.virt = virt ? 1 : 0;
+  p.nbig = virt ? L - 2 : L - 1;
+  if (!virt)
+    PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(offsets, n, B, tiles, d->pooling, nullptr,
+                                                                  (int32_t*)(wsb + wl.row_set), (float*)(wsb + wl.row_scale));
   int rc = 0;
 #define PCC_DISPATCH(HH)                                                                 \
   switch (d->act) {                                                                      \
@@ -829,18 +949,23 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
   if (rc != 0) return rc;
+  if (virt) {  // final Linear: scaled row sums instead of a GEMM
+    auto fk = (H == 256) ? final_wgrad_virtual_kernel<256> : final_wgrad_virtual_kernel<128>;
+    PCC_K(fk)<<<H, 256, 0, st>>>(p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
+  }
   ReduceParams rp{};
-  rp.L = L; rp.H = H;
+  const int Lr = virt ? L - 1 : L;  // layers whose per-CTA partials are reduced
+  rp.L = Lr; rp.H = H;
   int items = 0;
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; l < Lr; ++l) {
     rp.part_w[l] = p.part_w[l]; rp.part_b[l] = p.part_b[l]; rp.dw[l] = dw[l]; rp.db[l] = db[l];
     rp.K[l] = (l == 0) ? d->input_dim : H;
     rp.Kp[l] = (l == 0) ? kK0 : H;
-    rp.np[l] = wgrad_members(wl.grid, L, l);
+    rp.np[l] = wgrad_members(wl.grid, p.nbig, l);
     rp.vec_begin[l] = items;
     items += (rp.Kp[l] + 1) * (H / 4);
   }
-  rp.vec_begin[L] = items;
+  rp.vec_begin[Lr] = items;
   PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv(items, 32), 256, 0, st>>>(rp);
   return check_launch(__func__);
 }

@@ -106,7 +106,9 @@ class FusedPhiPoolFn(torch.autograd.Function):
                 _VIRT["key"] = key
                 _VIRT["offsets"] = torch.arange(B + 1, device=x.device, dtype=torch.int64) * H
                 _VIRT["arg"] = torch.arange(B * H, device=x.device, dtype=torch.int32).view(B, H)
-            offsets, arg, n = _VIRT["offsets"], _VIRT["arg"], B * H
+            # without ResidualBlocks the library exploits the one-hot structure of these rows (argmax = None):
+            # no dgrad / wgrad GEMM for the final Linear
+            offsets, arg, n = _VIRT["offsets"], (_VIRT["arg"] if res_mask else None), B * H
         from .distributed import grad_like
         grads = [grad_like(t) for t in ws_]
         dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])
