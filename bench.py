@@ -288,12 +288,17 @@ def run_ours(args):
     peaks = measured_peaks()
     pts = B_PER_GPU * N_PTS
     flops = {"phi_pool_fwd_kernel": FLOP_FWD_PT, "phi_bwd_chain_kernel": FLOP_CHAIN_PT, "phi_wgrad_kernel": FLOP_WGRAD_PT}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):   # dram bytes per launch from the committed `ncu --set full` capture (tools/summarize_profile.py)
+        traffic = json.load(open(tpath)).get("kernels", {})
     roof = None
     if kern:
         dom = max(kern, key=kern.get)
         ach = flops[dom] * pts / (kern[dom] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": ach / peaks["tflops"], "traffic": traffic.get(dom), "traffic_unit": "dram bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
+                "peak_source": peaks["source"],
                 "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
                 "algorithmic_flop_per_point": flops[dom]}
     step_tf = FLOP_TRAIN_PT * pts / (ms_dev * 1e-3) / 1e12

@@ -152,7 +152,10 @@ int pcc_phi_fused_supported(const pcc_phi_desc* d);
 int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B);
 /* bytes of the packed bf16 weight images (forward + transposed) the forward writes and the backward reads */
 int64_t pcc_phi_packed_bytes(const pcc_phi_desc* d);
-/* x[n,d] fp32, offsets[B+1] -> pooled[B,H] (+ argmax[B,H] for MAX).  ws: workspace; wpack: caller buffer of
+/* x[n,d] fp32, offsets[B+1] -> pooled[B,H] (+ argmax[B,H] for MAX).  For SUM / MEAN a non-NULL `argmax` is an
+ * aux [B,H] fp32 buffer: the kernel then pools the last hidden activations (sum_i (W h_i + b) = W sum_i h_i + n b),
+ * applies the final Linear to the [B,H] result and leaves the scaled pooled activations in aux for the backward.
+ * ws: workspace; wpack: caller buffer of
  * pcc_phi_packed_bytes() that RECEIVES the packed weight images (keep it for the backward of the same step). */
 int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
                               float* pooled, int32_t* argmax, void* ws, void* wpack, int device, void* stream);
@@ -160,9 +163,11 @@ int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, const int64
  * forward per tile.  dw/db arrays follow d->w / d->b order.  wpack: the images written by the forward of
  * the same parameters.
  * Max pooling with argmax == NULL ("virtual rows"): x holds the B*H gathered argmax rows (row b*H + f is the
- * argmax row of (b, f); n == B*H, offsets unused, no ResidualBlock).  The gradient of the final Linear's output
- * is then one-hot per row, and the library skips that layer's dgrad and wgrad GEMMs (scaled weight rows /
- * scaled row sums instead). */
+ * argmax row of (b, f); n == B*H, offsets unused).  The gradient of the final Linear's output is then one-hot
+ * per row, and the library skips that layer's dgrad and wgrad GEMMs (scaled weight rows / scaled row sums).
+ * Sum / mean pooling with argmax != NULL: the buffer is the aux [B,H] fp32 array the forward filled when it was
+ * given one (pooled hidden activations; pooling commuted with the final Linear); the backward then needs no
+ * per-point GEMM for the final Linear either.  argmax == NULL keeps the plain per-point formulation. */
 int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, const int64_t* offsets, int64_t n, int64_t B,
                               const float* dpooled, const int32_t* argmax, float* const* dw, float* const* db,
                               void* ws, const void* wpack, int device, void* stream);

@@ -38,6 +38,8 @@ struct PhiParams {
   void* pool_acc;                // float[B*H] (sum/mean) or uint64[B*H] (max)
   long long* trace;              // optional (debug): CTA 0 event timestamps, see trace_ev in pcc_fused_phi.cu
   const int32_t* tile_first;     // [num_tiles] first set intersecting each 128-row tile (seg_prep_kernel)
+  const int32_t* tile_last;      // [num_tiles] last set intersecting the tile (poolh mode)
+  int poolh;                     // sum / mean pooling commuted with the final Linear: pool the last HIDDEN activations
 };
 
 // Segment lookups hoisted out of the persistent kernels (a dependent binary search on the epilogue's
@@ -204,6 +206,6 @@ __device__ __forceinline__ float act_grad_t(float z) {
 
 int check_phi_desc(const pcc_phi_desc* d, const char* where);
 void* debug_trace_buffer();  // device buffer set through pcc_debug_set_trace, or null
-int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n);
+int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B);
 
 }  // namespace pcc

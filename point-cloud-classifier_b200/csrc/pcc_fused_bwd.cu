@@ -14,6 +14,7 @@
 //     the staged blobs, fp32 accumulation in TMEM across all tiles of a CTA, one partial
 //     per CTA, column sums (db) on the epilogue warps; a small kernel reduces the partials.
 #include "pcc_fused.cuh"
+#include "pcc_head.cuh"
 
 namespace pcc {
 
@@ -33,7 +34,9 @@ struct BwdParams {
   uint8_t* stage_g[kMaxLayers];  // dZ_l images, l = 0..L-1
   float* part_w[kMaxLayers];     // per-CTA partial dW_l [grid][H][K_l]  (K_0 = 16)
   float* part_b[kMaxLayers];     // per-CTA partial db_l [grid][H]
-  int virt;                      // max pooling on pre-gathered argmax rows: row b*H+f is THE argmax row of (b, f)
+  int virt;                      // 1: max pooling on pre-gathered argmax rows (row b*H+f is THE argmax row of (b, f));
+                                 // 2: sum / mean pooling commuted with the final Linear: dpooled holds
+                                 //    G = dpooled W_{L-1} [B, H] and dH_lh[row] = scale(row) * G[set(row)]
   int nbig;                      // H x H layers whose weight gradient is a GEMM over the staged images
   const int32_t* row_set;        // [n] set of each row (-1: none), seg_prep_kernel
   const float* row_scale;        // [n] pooled-gradient scale of the row's set
@@ -122,7 +125,11 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   //   dH_lh[row, :] = dpooled[row] * W_{L-1}[f, :]      (a scaled weight row: no dgrad GEMM, no dZ_{L-1} image)
   //   dW_{L-1}[f, :] = sum_b dpooled[b, f] * h_lh[b*H + f, :]   (final_wgrad_virtual_kernel, no GEMM either)
   // The 128 weight rows a tile needs are one contiguous 16 KB piece of every K slab of the packed image.
-  const bool virt = p.virt != 0;
+  // Mode 2 (sum / mean): the final Linear was applied AFTER pooling (forward kernel, poolh), so its dgrad is the
+  // [B, H] product G computed by the host and dH_lh of a row is its set's row of G times the pooling scale: the
+  // same per-tile flow as mode 1 with the dH image built from G; h_lh is not needed by any weight gradient.
+  const bool virt = p.virt != 0;     // no per-point dgrad / wgrad GEMM for the final Linear
+  const bool vmax = p.virt == 1, bcast = p.virt == 2;
 
   if (warp == kProdWarp) {
     // ===================== producer: weight slabs in consumption order
@@ -311,14 +318,14 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       load_x(tile + gridDim.x);
       // set of this thread's row (for the pooled-gradient scatter), precomputed; virtual-row mode: the row's
       // pooled gradient itself
-      const int64_t myset = (!virt && row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
-      const float scale = (!virt && row < p.n) ? __ldg(p.row_scale + row) : 0.f;
-      const float gs = (virt && row < p.n) ? __ldg(p.dpooled + row) : 0.f;
+      const int64_t myset = (!vmax && row < p.n) ? (int64_t)__ldg(p.row_set + row) : -1;
+      const float scale = (!vmax && row < p.n) ? __ldg(p.row_scale + row) : 0.f;
+      const float gs = vmax ? ((row < p.n) ? __ldg(p.dpooled + row) : 0.f) : 1.f;
 
       // ---- dZ of the final Linear from the pooled gradient (autograd of deep_sets.py:96-106)
       acquire();  // the previous tile's dZ_0 store has finished reading bufG
       TRE(1);
-      if (virt) {
+      if (vmax) {
         // rows f0 .. f0+127 of the final weight image -> bufG (same SW128 layout as an activation image)
         if (threadIdx.x == 0) {
           const uint32_t f0 = (uint32_t)(r0 % H);
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         int* aS = reinterpret_cast<int*>(bufH + 16384 + H * 4);
         const int64_t last_row = (r0 + kTileM - 1 < p.n - 1) ? r0 + kTileM - 1 : p.n - 1;
         const int64_t b_lo = __ldg(p.row_set + r0), b_hi = __ldg(p.row_set + last_row);
-        const bool is_max = (p.pooling == PCC_POOL_MAX);
+        const bool is_max = (p.pooling == PCC_POOL_MAX) && !bcast;
         if (myset < 0) {  // rows past the last set carry no gradient
           for (int kc = grp; kc < H / 8; kc += 2)
             *reinterpret_cast<uint4*>(bufG + act_chunk_off(r, kc * 8)) = make_uint4(0u, 0u, 0u, 0u);
@@ -413,28 +420,38 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       acquire();  // staging stores of h_0 (bufH) and dZ_{L-1} (bufG) have finished reading
       TRE(10);
       if (virt) {
-        mbar_wait(wf_ready, wf_phase);
-        wf_phase ^= 1;
+        if (vmax) {
+          mbar_wait(wf_ready, wf_phase);
+          wf_phase ^= 1;
+        }
         const bool res = (p.res_mask >> lh) & 1;
         const float* bl = biasS + lh * H;
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 2) {
-          uint32_t z[32];
+          uint32_t z[32], g[32];
           tmem_ld32(lane_base + ACC_A + c * 32, z);
+          // dH_lh chunk: mode 1: W_{L-1}[f, 32 columns] * dpooled[row]; mode 2: the image built from G (overwritten below)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(bufG + act_chunk_off(r, c * 32 + q * 8));
+            g[q * 8 + 0] = __float_as_uint(gs * bf16_lo(wv.x)); g[q * 8 + 1] = __float_as_uint(gs * bf16_hi(wv.x));
+            g[q * 8 + 2] = __float_as_uint(gs * bf16_lo(wv.y)); g[q * 8 + 3] = __float_as_uint(gs * bf16_hi(wv.y));
+            g[q * 8 + 4] = __float_as_uint(gs * bf16_lo(wv.z)); g[q * 8 + 5] = __float_as_uint(gs * bf16_hi(wv.z));
+            g[q * 8 + 6] = __float_as_uint(gs * bf16_lo(wv.w)); g[q * 8 + 7] = __float_as_uint(gs * bf16_hi(wv.w));
+          }
+          // ResidualBlock: dH_{lh-1} = dZ_lh W_lh + dH_lh — the dgrad MMA accumulates onto accB, so dH_lh goes there
+          if (res) tmem_st32(lane_base + ACC_B + c * 32, g);
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
-            const uint4 wv = *reinterpret_cast<const uint4*>(bufG + off);  // W_{L-1}[f, 8 columns]; overwritten below
-            uint32_t g[8];
-            g[0] = __float_as_uint(gs * bf16_lo(wv.x)); g[1] = __float_as_uint(gs * bf16_hi(wv.x));
-            g[2] = __float_as_uint(gs * bf16_lo(wv.y)); g[3] = __float_as_uint(gs * bf16_hi(wv.y));
-            g[4] = __float_as_uint(gs * bf16_lo(wv.z)); g[5] = __float_as_uint(gs * bf16_hi(wv.z));
-            g[6] = __float_as_uint(gs * bf16_lo(wv.w)); g[7] = __float_as_uint(gs * bf16_hi(wv.w));
-            hdz_chunk8(z + q * 8, g, bl + c * 32 + q * 8, bufH + off, bufG + off, res);
+            if (bcast) dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + off);
+            else hdz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufH + off, bufG + off, res);
           }
-          store_slabs(p.stage_h[lh] + (size_t)tile * BLOB, bufH, c >> 1, 1, p.stage_g[lh] + (size_t)tile * BLOB, bufG);
+          if (bcast) store_slabs(p.stage_g[lh] + (size_t)tile * BLOB, bufG, c >> 1, 1, nullptr, nullptr);
+          else store_slabs(p.stage_h[lh] + (size_t)tile * BLOB, bufH, c >> 1, 1, p.stage_g[lh] + (size_t)tile * BLOB, bufG);
         }
+        if (res) tmem_wait_st();
       } else {
         const bool res = (p.res_mask >> lh) & 1;
         const float* bl = biasS + lh * H;
@@ -830,12 +847,12 @@ __global__ void zero_f32_kernel_b(float* p, int64_t n) {
 // ------------------------------------------------------------------ host side
 struct BwdWs {
   int64_t stage_h[kMaxLayers], stage_g[kMaxLayers], part_w[kMaxLayers], part_b[kMaxLayers];
-  int64_t row_set, row_scale;
+  int64_t row_set, row_scale, gmat, bscale;
   int64_t total;
   int grid;
 };
 constexpr int kGridCap = 160;  // upper bound on persistent CTAs used for sizing the partial buffers
-static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms) {
+static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms, int64_t B = 0) {
   BwdWs w{};
   const int H = d->hidden, L = d->n_layers;
   const int64_t tiles = cdiv(n, kTileM);
@@ -854,11 +871,21 @@ static BwdWs bwd_ws(const pcc_phi_desc* d, int64_t n, int sms) {
   }
   w.row_set = take(n * 4);
   w.row_scale = take(n * 4);
+  w.gmat = take(B * H * 4);
+  w.bscale = take(B * 4);
   w.total = o;
   return w;
 }
 
-int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n) { return bwd_ws(d, n, kGridCap).total; }
+int64_t phi_bwd_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B) { return bwd_ws(d, n, kGridCap, B).total; }
+
+// bscale[b] = n_b * rs_b (sqrt(n) for sum pooling, 1 for mean): the factor of the final bias inside pooled[b]
+__global__ void set_bscale_kernel(const int64_t* __restrict__ offsets, int64_t B, int pooling, float* __restrict__ bscale) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float n = (float)(offsets[b + 1] - offsets[b]);
+  bscale[b] = (n <= 0.f) ? 0.f : (pooling == PCC_POOL_SUM ? sqrtf(n) : 1.f);
+}
 
 template <int H, int ACT>
 static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
@@ -900,12 +927,13 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   // of (b, f)); offsets are not read
   const bool virt = d->pooling == PCC_POOL_MAX && argmax == nullptr;
   PCC_REQUIRE(!virt || n == B * H, "max pooling without argmax: x must hold the B*H gathered argmax rows");
-  PCC_REQUIRE(!virt || d->residual_mask == 0, "max pooling without argmax: not available with ResidualBlocks");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const BwdWs wl = bwd_ws(d, n, sms);
+  const BwdWs wl = bwd_ws(d, n, sms, B);
   uint8_t* wsb = (uint8_t*)ws;
   const int64_t tiles = cdiv(n, kTileM);
+  // sum / mean pooling with the aux buffer of the forward (argmax slot = ph [B, H] fp32): commuted final Linear
+  const bool bcast = d->pooling != PCC_POOL_MAX && argmax != nullptr;
   if (tiles == 0) {
     for (int l = 0; l < L; ++l) {
       const int64_t cnt = (int64_t)H * (l == 0 ? d->input_dim : H);
@@ -932,9 +960,33 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   p.trace = (long long*)debug_trace_buffer();
   p.row_set = (const int32_t*)(wsb + wl.row_set);
   p.row_scale = (const float*)(wsb + wl.row_scale);
-  p.virt = virt ? 1 : 0;
-  p.nbig = virt ? L - 2 : L - 1;
-  if (!virt)
+  p.virt = virt ? 1 : (bcast ? 2 : 0);
+  p.nbig = (virt || bcast) ? L - 2 : L - 1;
+  if (bcast) {
+    // dW_{L-1} = dpooled^T ph, db_{L-1} = sum_b bscale_b dpooled[b], G = dpooled W_{L-1}: three [B, H]-sized products
+    float* bscale = (float*)(wsb + wl.bscale);
+    float* G = (float*)(wsb + wl.gmat);
+    const float* ph = reinterpret_cast<const float*>(argmax);
+    PCC_K(set_bscale_kernel)<<<(unsigned)cdiv(B, 256), 256, 0, st>>>(offsets, B, d->pooling, bscale);
+    HeadTileParams hp{};
+    hp.act = PCC_ACT_RELU;
+    HeadTileProb& pw = hp.prob[0];
+    pw.A = HeadOperand{dpooled, nullptr, 1, H, 0, 0, 0};
+    pw.B = HeadOperand{ph, nullptr, 1, H, 0, 0, 0};
+    pw.I = H; pw.J = H; pw.KK = (int)B;
+    pw.C = dw[L - 1]; pw.ldc = H; pw.colsum = db[L - 1]; pw.colsum_w = bscale;
+    head_set_tiles(pw);
+    HeadTileProb& pg = hp.prob[1];
+    pg.A = HeadOperand{dpooled, nullptr, H, 1, 0, 0, 0};
+    pg.B = HeadOperand{d->w[L - 1], nullptr, 1, H, 0, 0, 0};
+    pg.I = (int)B; pg.J = H; pg.KK = H;
+    pg.C = G; pg.ldc = H;
+    head_set_tiles(pg);
+    launch_head_tiles(hp, pw.tiles + pg.tiles, st);
+    p.dpooled = G;
+    p.argmax = nullptr;
+  }
+  if (!virt)  // (also in mode 2: row -> set and pooling scale)
     PCC_K(seg_prep_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(offsets, n, B, tiles, d->pooling, nullptr,
                                                                   (int32_t*)(wsb + wl.row_set), (float*)(wsb + wl.row_scale));
   int rc = 0;
@@ -954,7 +1006,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
     PCC_K(fk)<<<H, 256, 0, st>>>(p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
   }
   ReduceParams rp{};
-  const int Lr = virt ? L - 1 : L;  // layers whose per-CTA partials are reduced
+  const int Lr = (virt || bcast) ? L - 1 : L;  // layers whose per-CTA partials are reduced
   rp.L = Lr; rp.H = H;
   int items = 0;
   for (int l = 0; l < Lr; ++l) {

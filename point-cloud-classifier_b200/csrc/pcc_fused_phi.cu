@@ -17,6 +17,7 @@
 //                         cp.async.bulk (TMA engine).
 // Per-point activations never leave the SM.
 #include "pcc_fused.cuh"
+#include "pcc_head.cuh"
 
 namespace pcc {
 
@@ -25,14 +26,16 @@ constexpr int kFwdHidWarps = 8, kFwdPoolWarps = 8;
 constexpr int kFwdProdWarp = 16, kFwdMmaWarp = 17;
 constexpr int kFwdThreads = 18 * 32;  // register cap 96: warps are allocated in groups of 4 (20 x 32 x 96 <= 64 K)
 
+constexpr uint32_t kIndBytes = 2 * 128 * 128;  // set-indicator operand of the pooling MMA: [2 slabs][<=128 sets][64 points] bf16
 struct SmemLayout {
-  uint32_t bufA, ring, ones, bimg, w0, xs, bars, total;
+  uint32_t bufA, ring, ind, ones, bimg, w0, xs, bars, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int H, int L, int Q) {
+__host__ __device__ inline SmemLayout smem_layout(int H, int L, int Q, int poolh) {
   SmemLayout s;
   uint32_t o = 0;
   s.bufA = o; o += kTileM * H * 2;             // activation image, 1024-aligned slabs
-  s.ring = o; o += kRingF * w_slab_bytes(H);   // weight slabs, 1024-aligned
+  s.ring = o; o += (poolh ? kRingF - 1 : kRingF) * w_slab_bytes(H);   // weight slabs, 1024-aligned
+  s.ind = o;  o += poolh ? kIndBytes : 0;
   s.ones = o; o += kTileM * kK0 * 2;           // un-swizzled [2][128][8] bf16 image: columns 0,1 = 1, rest 0
   s.bimg = o; o += (uint32_t)H * kK0 * 2;      // un-swizzled [2][H][8] bf16 image: hidden-layer bias as (hi, lo, 0 ...)
   s.w0 = o;   o += (uint32_t)H * 4 * Q * 4;    // layer-0 table (see fwd_prep_kernel)
@@ -93,11 +96,12 @@ __device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t
 // L = 2 (phi = Linear, final Linear) or 3 (one H x H hidden layer / ResidualBlock in between).
 // TMEM: L = 3: hidden accumulator = columns [0,256), final accumulator = [256,512);
 //       L = 2: the final accumulator alternates between the two halves from tile to tile.
-template <int H, int ACT, int Q>
+template <int H, int ACT, int Q, bool POOLH>
 __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout lay = smem_layout(H, p.L, Q);
+  const SmemLayout lay = smem_layout(H, p.L, Q, POOLH ? 1 : 0);
   uint8_t* bufA = smem + lay.bufA;
+  uint8_t* indS = smem + lay.ind;
   uint8_t* ring = smem + lay.ring;
   const ulonglong2* w0S = reinterpret_cast<const ulonglong2*>(smem + lay.w0);
   float* xS = reinterpret_cast<float*>(smem + lay.xs);
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
   uint64_t* acc_h = bars + 2 * kRingF + 4;      // hidden-layer accumulator complete
   uint64_t* acc_f = bars + 2 * kRingF + 5;      // [2] final accumulator (slot) complete
   uint64_t* pool_done = bars + 2 * kRingF + 7;  // [2] final accumulator (slot) drained by the pool warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 9);
+  uint64_t* ind_ready = bars + 2 * kRingF + 9;  // poolh: set-indicator operand of this tile built by the pool warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 10);
+  volatile uint32_t* nsetsS = tmem_slot + 1;    // poolh: padded number of sets (MMA N) of the current tile
 
   constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
   constexpr int HALVES = H / 128;              // M halves of the transposed final layer
@@ -120,6 +126,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L;
+  // poolh (sum / mean pooling): sum_i (W h_i + b) = W (sum_i h_i) + n b, so the final Linear leaves the per-point
+  // path: the kernel pools the last HIDDEN activations with one small MMA per tile,
+  //   D[feature, set] += h^T[feature, point] * 1[point in set]      (A = MN-major view of the activation image,
+  // B = 0/1 indicator built by the pool warps, N = sets intersecting the tile rounded up to 16), and the host
+  // applies W_{L-1} to the [B, H] result.  No transposed final layer, 8x fewer accumulator columns to read.
+  constexpr bool poolh = POOLH;
+  const int ringn = poolh ? kRingF - 1 : kRingF;
+  const int l_end = poolh ? L - 1 : L;   // layers streamed through the ring: 1 .. l_end-1
 
   // constant operands of the bias K step of the hidden layer: A = [128 x 16] with ones in columns 0, 1;
   // B = [H x 16] with (bf16 hi, bf16 lo) of b_1 in columns 0, 1 (hi + lo carries ~16 mantissa bits)
@@ -143,6 +157,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], kFwdHidWarps);
     mbar_init(acc_h, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_f[i], 1); mbar_init(&pool_done[i], 4 * HALVES); }
+    mbar_init(ind_ready, kFwdPoolWarps);
     fence_mbar_init();
   }
   if (warp == kFwdMmaWarp) tmem_alloc<512>(tmem_slot);
@@ -157,12 +172,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int l = 1; l < L; ++l) {
+        for (int l = 1; l < l_end; ++l) {
           for (int s = 0; s < NSLAB; ++s) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], SLAB);
             bulk_g2s(ring + stage * SLAB, p.wpack + p.w_off[l] + (size_t)s * SLAB, SLAB, &full[stage]);
-            if (++stage == kRingF) { stage = 0; phase ^= 1; }
+            if (++stage == (uint32_t)ringn) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     if (lane == 0) {
       constexpr uint32_t IDESC_N = make_idesc_bf16(128, H, 0, 0);    // points x features
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, 0, 0);  // features(128) x points
-      uint32_t stage = 0, phase = 0, sl_phase = 0;
+      uint32_t stage = 0, phase = 0, sl_phase = 0, ind_phase = 0;
       int tn = 0;
       const uint32_t a_base = smem_u32(bufA), r_base = smem_u32(ring);
       int nt = 0;  // tiles done by this CTA
@@ -196,7 +211,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
               umma_bf16(tmem, make_smem_desc_sw128_k(a_base + s * kActSlab + ks * 32),
                         make_smem_desc_sw128_k(w_slab + ks * 32), IDESC_N, 1);
             umma_commit(&empty[stage]);
-            if (++stage == kRingF) { stage = 0; phase ^= 1; }
+            if (++stage == (uint32_t)ringn) { stage = 0; phase ^= 1; }
           }
           sl_phase ^= 1;
           umma_commit(acc_h);
@@ -211,6 +226,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
         }
         const uint32_t accT = tmem + ((L == 2) ? slot * 256 : 256);
         trace_ev(p.trace, 1, tn, 102);
+        if (poolh) {
+          for (int s = 0; s < NSLAB; ++s) mbar_wait(&slab_ready[s], sl_phase);  // the whole activation image (K = points)
+          sl_phase ^= 1;
+          mbar_wait(ind_ready, ind_phase);
+          ind_phase ^= 1;
+          tc_fence_after();
+          const uint32_t N = *nsetsS;
+          const uint32_t idesc = make_idesc_bf16(128, (int)N, 1, 0);
+          const uint32_t i_base = smem_u32(indS);
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h)
+#pragma unroll
+            for (int ks = 0; ks < kTileM / 16; ++ks)
+              umma_bf16(accT + h * 128, make_smem_desc_sw128_mn(a_base + h * (2 * kActSlab) + ks * 2048, kActSlab),
+                        make_smem_desc_sw128_k(i_base + (ks >> 2) * (N * 128) + (ks & 3) * 32), idesc, ks != 0);
+          umma_commit(&acc_f[slot]);
+          trace_ev(p.trace, 1, tn, 142);
+          continue;
+        }
         for (int s = 0; s < NSLAB; ++s) {
           mbar_wait(&slab_ready[s], sl_phase);
           mbar_wait(&full[stage], phase);
@@ -226,7 +260,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
                         (s | ks) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kRingF) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)ringn) { stage = 0; phase ^= 1; }
         }
         sl_phase ^= 1;
         umma_commit(&acc_f[slot]);
@@ -352,7 +386,59 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     // ===================== pool warps 8-15: thread = feature, TMEM columns = the tile's points
     const int pw = warp - kFwdHidWarps;
     const int quarter = warp & 3, h = pw >> 2;
-    if (h < HALVES) {
+    if (poolh) {
+      // ---- poolh: build the 0/1 set-indicator operand of the tile, then read the few pooled columns
+      const int pt = pw * 32 + lane;  // 0..255
+      const int f = h * 128 + quarter * 32 + lane;
+      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+      const bool tr0 = (pw == 0 && lane == 0);
+      float* hsum = reinterpret_cast<float*>(p.pool_acc);
+      int tn = 0, nt = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+        const int64_t r0 = tile * kTileM;
+        const int b_first = __ldg(p.tile_first + tile), b_last = __ldg(p.tile_last + tile);
+        const int nsets = b_last - b_first + 1;
+        const uint32_t N = (uint32_t)((nsets + 15) & ~15);   // MMA N: multiple of 16, >= 16, <= 128
+        // the previous pooling MMA (which read the indicator) is complete: this warp waited for its accumulator below
+        for (uint32_t q = pt; q < N * 16; q += 32 * kFwdPoolWarps) {
+          const uint32_t sidx = q >> 4, kc = q & 15;   // set slot, 8-point chunk
+          int64_t lo = 0, hi = 0;
+          if ((int)sidx < nsets) { lo = __ldg(p.offsets + b_first + sidx); hi = __ldg(p.offsets + b_first + sidx + 1); }
+          const int64_t p0 = r0 + kc * 8;
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t b0 = (p0 + 2 * j >= lo && p0 + 2 * j < hi) ? 0x3F80u : 0u;          // bf16 1.0
+            const uint32_t b1 = (p0 + 2 * j + 1 >= lo && p0 + 2 * j + 1 < hi) ? 0x3F80u : 0u;
+            w[j] = b0 | (b1 << 16);
+          }
+          *reinterpret_cast<uint4*>(indS + (kc >> 3) * (N * 128) + sidx * 128 + (((kc & 7) ^ (sidx & 7)) << 4)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (pt == 0) *nsetsS = N;
+        fence_proxy_async();
+        mbar_arrive_warp(ind_ready);
+        const int slot = (L == 2) ? (nt & 1) : 0;
+        const int k = (L == 2) ? (nt >> 1) : nt;
+        mbar_wait(&acc_f[slot], (uint32_t)(k & 1));
+        tc_fence_after();
+        if (tr0) trace_ev(p.trace, 2, tn, 30);
+        if (h < HALVES) {
+          const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
+          for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(accT + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((int)(c0 + j) < nsets) atomicAdd(hsum + (int64_t)(b_first + c0 + j) * H + f, __uint_as_float(v[j]));
+          }
+          tc_fence_before();
+          mbar_arrive_warp(&pool_done[slot]);
+        }
+        if (tr0) trace_ev(p.trace, 2, tn, 40);
+      }
+    } else if (h < HALVES) {
       const int r = quarter * 32 + lane;
       const int f = h * 128 + r;
       const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -478,7 +564,7 @@ __global__ void pool_finalize_kernel(const void* __restrict__ pool_acc, const in
 
 // ------------------------------------------------------------------ host side
 struct WsLayout {
-  int64_t pool_off, tile_first_off, total;
+  int64_t pool_off, tile_first_off, tile_last_off, bscale_off, total;
 };
 static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
   WsLayout w{};
@@ -488,6 +574,12 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
   o = (o + 255) / 256 * 256;
   w.tile_first_off = o;
   o += cdiv(n, kTileM) * 4;
+  o = (o + 255) / 256 * 256;
+  w.tile_last_off = o;
+  o += cdiv(n, kTileM) * 4;
+  o = (o + 255) / 256 * 256;
+  w.bscale_off = o;
+  o += B * 4;
   w.total = (o + 255) / 256 * 256;
   return w;
 }
@@ -496,7 +588,7 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
 // (layer y>>1, transposed if y&1); y == 2L zeroes the pool accumulator; y == 2L+1 computes tile_first;
 // y == 2L+2 writes the fp32 layer-0 table {b_0[c], bf16(W_0[c][0..d-1]), 0...} of the forward kernel
 __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t pool_count, const int64_t* offsets,
-                                int64_t B, int64_t num_tiles, int32_t* tile_first) {
+                                int64_t B, int64_t num_tiles, int32_t* tile_first, int32_t* tile_last, int64_t n) {
   const int y = blockIdx.y;
   if (y < 2 * pk.L) {
     const int l = y >> 1;
@@ -553,8 +645,29 @@ __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t
         if (__ldg(offsets + mid + 1) <= r0) lo = mid + 1; else hi = mid;
       }
       tile_first[i] = (int32_t)lo;
+      // last set intersecting the tile = set of its last valid row
+      const int64_t rl = (r0 + kTileM - 1 < n - 1) ? r0 + kTileM - 1 : n - 1;
+      int64_t lo2 = lo, hi2 = B;
+      while (lo2 < hi2) {
+        int64_t mid = (lo2 + hi2) >> 1;
+        if (__ldg(offsets + mid + 1) <= rl) lo2 = mid + 1; else hi2 = mid;
+      }
+      tile_last[i] = (int32_t)(lo2 < B ? lo2 : B - 1);
     }
   }
+}
+
+// poolh: hsum[b,:] (sum over the set's points of the last hidden activations) -> ph[b,:] = rs_b * hsum[b,:] with
+// rs = 1/sqrt(n) (sum pooling, deep_sets.py:99) or 1/n (mean, :102); bscale[b] = n * rs_b multiplies the final bias
+__global__ void poolh_finalize_kernel(const float* __restrict__ hsum, const int64_t* __restrict__ offsets, int64_t B, int H,
+                                      int pooling, float* __restrict__ ph, float* __restrict__ bscale) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int64_t b = i / H;
+  const float n = (float)(offsets[b + 1] - offsets[b]);
+  const float rs = (n <= 0.f) ? 0.f : (pooling == PCC_POOL_SUM ? rsqrtf(n) : 1.f / n);
+  ph[i] = rs * hsum[i];
+  if (i % H == 0) bscale[b] = n * rs;
 }
 
 int check_phi_desc(const pcc_phi_desc* d, const char* where) {
@@ -580,8 +693,8 @@ static inline int q4_of(int d) { return d <= 3 ? 1 : 2; }
 
 template <int H, int ACT, int Q>
 static int launch_fwd(const PhiParams& p, cudaStream_t st) {
-  const SmemLayout lay = smem_layout(H, p.L, Q);
-  auto kern = phi_pool_fwd_kernel<H, ACT, Q>;
+  const SmemLayout lay = smem_layout(H, p.L, Q, p.poolh);
+  auto kern = p.poolh ? phi_pool_fwd_kernel<H, ACT, Q, true> : phi_pool_fwd_kernel<H, ACT, Q, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_fwd", cudaGetErrorString(e));
   int dev = 0, sms = 148;
@@ -608,7 +721,7 @@ extern "C" int pcc_phi_fused_supported(const pcc_phi_desc* d) { return check_phi
 
 extern "C" int64_t pcc_phi_fused_workspace_bytes(const pcc_phi_desc* d, int64_t n, int64_t B) {
   if (check_phi_desc(d, __func__) != 0) return -1;
-  const int64_t fwd = ws_layout(d, n, B).total, bwd = phi_bwd_workspace_bytes(d, n);
+  const int64_t fwd = ws_layout(d, n, B).total, bwd = phi_bwd_workspace_bytes(d, n, B);
   return fwd > bwd ? fwd : bwd;  // one query serves both directions
 }
 
@@ -645,8 +758,13 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   p.pool_acc = wsb + wl.pool_off;
   p.trace = (long long*)g_trace_buf;
   p.tile_first = (const int32_t*)(wsb + wl.tile_first_off);
+  p.tile_last = (const int32_t*)(wsb + wl.tile_last_off);
+  // sum / mean pooling with an aux buffer: pooling commuted with the final Linear (see the kernel)
+  const bool poolh = d->pooling != PCC_POOL_MAX && argmax != nullptr;
+  p.poolh = poolh ? 1 : 0;
   PCC_K(fwd_prep_kernel)<<<dim3(32, 2 * L + 3), 256, 0, st>>>(pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
-                                                             p.num_tiles, (int32_t*)(wsb + wl.tile_first_off));
+                                                             p.num_tiles, (int32_t*)(wsb + wl.tile_first_off),
+                                                             (int32_t*)(wsb + wl.tile_last_off), n);
   if (p.num_tiles > 0) {
     int rc = 0;
 #define PCC_DISPATCH_A(HH, QQ)                                                        \
@@ -665,9 +783,25 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
 #undef PCC_DISPATCH_A
     if (rc != 0) return rc;
   }
-  if (B * H > 0)
+  if (B * H > 0 && poolh) {
+    // pooled = ph W_{L-1}^T + bscale (x) b_{L-1}  with ph = rs * hsum kept in the aux buffer for the backward
+    float* ph = reinterpret_cast<float*>(argmax);
+    float* bscale = reinterpret_cast<float*>(wsb + wl.bscale_off);
+    PCC_K(poolh_finalize_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>((const float*)(wsb + wl.pool_off), offsets, B, H,
+                                                                      d->pooling, ph, bscale);
+    HeadTileParams hp{};
+    hp.act = PCC_ACT_RELU;
+    HeadTileProb& pr = hp.prob[0];
+    pr.A = HeadOperand{ph, nullptr, H, 1, 0, 0, 0};
+    pr.B = HeadOperand{d->w[L - 1], nullptr, H, 1, 0, 0, 0};
+    pr.I = (int)B; pr.J = H; pr.KK = H;
+    pr.C = pooled; pr.ldc = H; pr.bias = d->b[L - 1]; pr.bias_scale = bscale;
+    head_set_tiles(pr);
+    launch_head_tiles(hp, pr.tiles, st);
+  } else if (B * H > 0) {
     PCC_K(pool_finalize_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>(wsb + wl.pool_off, offsets, d->b[L - 1], B, H,
                                                                      d->pooling, pooled, argmax);
+  }
   return check_launch(__func__);
 }
 

@@ -12,7 +12,7 @@
 //                        dW_l = dz_l^T in_l , db_l = colsum(dz_l)      (tiles over [N_l, K_l])
 //                        g_{l-1} = dz_l W_l                            (tiles over [M,   K_l])
 // No atomics, no zero-fill launches, bitwise deterministic.
-#include "pcc_common.cuh"
+#include "pcc_head.cuh"
 
 namespace pcc {
 
@@ -21,29 +21,6 @@ constexpr int kHeadMaxLayers = 4;
 constexpr int kHT = 32;    // output tile edge
 constexpr int kHK = 64;    // contraction tile
 constexpr int kHThreads = 256;
-
-// operand element (i, kk): i = output index of the tile problem, kk = contraction index
-struct HeadOperand {
-  const float* p;
-  const float* q;     // act' argument (mode 2)
-  int64_t si, sk;     // element strides of p along i / kk (one of them is 1)
-  int64_t qi, qk;
-  int mode;           // 0: p   1: act(p)   2: p * act'(q)
-};
-// C[i][j] = sum_kk A(i,kk) B(j,kk) (+ bias[j]);  colsum[i] = sum_kk A(i,kk)
-struct HeadTileProb {
-  HeadOperand A, B;
-  int I, J, KK;
-  float* C;
-  int64_t ldc;
-  const float* bias;
-  float* colsum;
-  int tiles_j, tiles;
-};
-struct HeadTileParams {
-  HeadTileProb prob[2];
-  int act;
-};
 
 // The raw loads of a K tile are issued as one unconditional batch (memory-level parallelism: the loop is
 // latency bound); the elementwise transforms run afterwards, with the mode tests hoisted out of the loops.
@@ -167,8 +144,14 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
         acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
       }
       if (want_colsum && tid < kHT) {
+        if (pr.colsum_w) {
+          const int kb = kbase + tl * kHK;
 #pragma unroll 16
-        for (int k = 0; k < kHK; ++k) csum += As[k][tid];
+          for (int k = 0; k < kHK; ++k) csum += As[k][tid] * (kb + k < KK ? __ldg(pr.colsum_w + kb + k) : 0.f);
+        } else {
+#pragma unroll 16
+          for (int k = 0; k < kHK; ++k) csum += As[k][tid];
+        }
       }
     }
   }
@@ -190,7 +173,8 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
         const int j = j0 + lj + b;
         if (j >= J) continue;
         float v = (red[0][li][lj + b] + red[1][li][lj + b]) + (red[2][li][lj + b] + red[3][li][lj + b]);
-        if (pr.bias) v += __ldg(pr.bias + j);
+        if (pr.row_scale) v *= __ldg(pr.row_scale + i);
+        if (pr.bias) v += (pr.bias_scale ? __ldg(pr.bias_scale + i) : 1.f) * __ldg(pr.bias + j);
         pr.C[(int64_t)i * pr.ldc + j] = v;
       }
     }
@@ -198,7 +182,7 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
   if (want_colsum && tid < kHT && i0 + tid < I) pr.colsum[i0 + tid] = csum;
 }
 
-static void launch_head_tiles(const HeadTileParams& hp, int tiles, cudaStream_t st) {
+void launch_head_tiles(const HeadTileParams& hp, int tiles, cudaStream_t st) {
   if (tiles <= 0) return;
   auto kern = head_tile_kernel<PCC_ACT_TANH>;
   switch (hp.act) {
@@ -237,10 +221,11 @@ static HeadGeom head_geom(const pcc_head_desc* d) {
   return g;
 }
 
-static void set_tiles(HeadTileProb& p) {
+void head_set_tiles(HeadTileProb& p) {
   p.tiles_j = (int)cdiv(p.J, kHT);
   p.tiles = (int)cdiv(p.I, kHT) * p.tiles_j;
 }
+static void set_tiles(HeadTileProb& p) { head_set_tiles(p); }
 
 }  // namespace pcc
 

@@ -71,7 +71,9 @@ class FusedPhiPoolFn(torch.autograd.Function):
         ws_bytes = call("pcc_phi_fused_workspace_bytes", C.byref(d), n, B)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
         pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
-        arg = torch.empty((B, H), dtype=torch.int32, device=x.device) if pooling == "max" else None
+        # max: argmax rows; sum / mean: aux buffer that receives the pooled hidden activations (pooling is commuted
+        # with the final Linear, include/pcc.h) and is handed back to the backward in the same slot
+        arg = torch.empty((B, H), dtype=torch.int32 if pooling == "max" else torch.float32, device=x.device)
         wpack = torch.empty(call("pcc_phi_packed_bytes", C.byref(d)), dtype=torch.uint8, device=x.device)
         call("pcc_deepsets_phi_pool_fwd", C.byref(d), ptr(x), ptr(offsets), n, B, ptr(pooled), ptr(arg), ptr(ws), ptr(wpack),
              dev, st)
@@ -106,9 +108,9 @@ class FusedPhiPoolFn(torch.autograd.Function):
                 _VIRT["key"] = key
                 _VIRT["offsets"] = torch.arange(B + 1, device=x.device, dtype=torch.int64) * H
                 _VIRT["arg"] = torch.arange(B * H, device=x.device, dtype=torch.int32).view(B, H)
-            # without ResidualBlocks the library exploits the one-hot structure of these rows (argmax = None):
-            # no dgrad / wgrad GEMM for the final Linear
-            offsets, arg, n = _VIRT["offsets"], (_VIRT["arg"] if res_mask else None), B * H
+            # the library exploits the one-hot structure of these rows (argmax = None): no dgrad / wgrad GEMM for
+            # the final Linear
+            offsets, arg, n = _VIRT["offsets"], None, B * H
         from .distributed import grad_like
         grads = [grad_like(t) for t in ws_]
         dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])

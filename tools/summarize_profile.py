@@ -40,12 +40,21 @@ def full(rep, out):
             'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
             'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active']
     idx = [i for i, h in enumerate(hdr) if h in want]
+    traffic = {}
+    ki, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     with open(out, 'w') as f:
         f.write("# ncu --set full --clock-control none, one launch of each fused kernel (B=256, N=1024, H=256, relu+max)\n")
         for r in rows[2:]:
             f.write("=====\n")
             for i in idx:
                 f.write(f"{hdr[i]:80s} {units[i]:14s} {r[i][:70]}\n")
+            name = r[ki].split('(')[0].split('<')[0].replace('void ', '').replace('pcc::', '')
+            byts = float(r[ri].replace(',', '')) * scale.get(units[ri], 1.0) + float(r[wi].replace(',', '')) * scale.get(units[wi], 1.0)
+            traffic.setdefault(name, byts)   # first launch of each kernel
+    import json
+    json.dump({"source": out, "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "kernels": traffic},
+              open("profiles/ncu_traffic.json", "w"), indent=1)
     print(open(out).read())
 
 if __name__ == "__main__":
