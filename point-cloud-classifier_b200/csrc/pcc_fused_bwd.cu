@@ -999,12 +999,12 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (H == 256) { PCC_DISPATCH(256) } else { PCC_DISPATCH(128) }
 #undef PCC_DISPATCH
   if (rc != 0) return rc;
-  rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
-  if (rc != 0) return rc;
-  if (virt) {  // final Linear: scaled row sums instead of a GEMM
+  if (virt) {  // final Linear: scaled row sums instead of a GEMM; right after the chain, while its h images are in L2
     auto fk = (H == 256) ? final_wgrad_virtual_kernel<256> : final_wgrad_virtual_kernel<128>;
     PCC_K(fk)<<<H, 256, 0, st>>>(p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
   }
+  rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
+  if (rc != 0) return rc;
   ReduceParams rp{};
   const int Lr = (virt || bcast) ? L - 1 : L;  // layers whose per-CTA partials are reduced
   rp.L = Lr; rp.H = H;

@@ -72,9 +72,18 @@ __global__ void __launch_bounds__(kPeerThreads, 1) peer_allreduce_kernel(const P
   float4* out = reinterpret_cast<float4*>(p.bucket);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.world; ++r) {
-      const float4 v = ld_cv_f4(reinterpret_cast<const float4*>(p.stage[r] + 1024 + (seq & 1) * p.buf_bytes) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    // all peers' loads of a batch are issued before the first add: one NVLink round trip, not `world` of them
+#pragma unroll 1
+    for (int rb = 0; rb < p.world; rb += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rb + j;
+        v[j] = (r < p.world) ? ld_cv_f4(reinterpret_cast<const float4*>(p.stage[r] + 1024 + (seq & 1) * p.buf_bytes) + i)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
     }
     out[i] = make_float4(acc.x * p.scale, acc.y * p.scale, acc.z * p.scale, acc.w * p.scale);
   }
