@@ -24,87 +24,170 @@ struct GemmArgs {
   int64_t k_chunk;  // K range per blockIdx.z
 };
 
+// 3xTF32 on the tensor cores (mma.sync m16n8k8): x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and
+// a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi — error ~2^-21 relative per product, fp32 accumulation: the fp32 parity
+// path (rtol 1e-4 against the reference) keeps its accuracy at several times the FFMA rate.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// four consecutive floats p[0..3]; `nvalid` leading ones are in range; one 128-bit load when possible
+__device__ __forceinline__ float4 gemm_ld4(const float* p, bool vec, int nvalid) {
+  if (vec && nvalid == 4) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) v.x = __ldg(p);
+  if (nvalid > 1) v.y = __ldg(p + 1);
+  if (nvalid > 2) v.z = __ldg(p + 2);
+  if (nvalid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
 // A_T=false: A(m,k)=A[m*lda+k] ; A_T=true: A(m,k)=A[k*lda+m]
 // B_T=false: B(k,n)=B[k*ldb+n] ; B_T=true: B(k,n)=B[n*ldb+k]
+// 256 threads = 8 warps laid out 2 (M) x 4 (N); a warp owns a (BM/2) x (BN/4) sub-tile as m16n8 fragments.
+// Operands are staged without transposition — one contiguous along k as [row][k] (stride BK+4), one contiguous
+// along its row index as [k][row] (stride B+8): 128-bit global loads and stores either way, and both layouts are
+// conflict free for the k-strided fragment loads.  The next K step's loads are in flight (registers) under the
+// math of the current one.  TM / TN are unused legacy parameters (the tile shape is BM x BN x BK).
 template <int BM, int BN, int BK, int TM, int TN, bool A_T, bool B_T>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(GemmArgs p) {
-  constexpr int NT = (BM / TM) * (BN / TN);
-  constexpr int GM = TM / 4, GN = TN / 4;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs p) {
+  constexpr int NT = 256;
+  constexpr int WM = BM / 2, WN = BN / 4;      // warp tile
+  constexpr int MT = WM / 16, NTL = WN / 8;    // m16 / n8 fragments per warp
+  constexpr bool A_KC = !A_T, B_KC = B_T;      // contiguous along k
+  constexpr int ASZ = A_KC ? BM * (BK + 4) : BK * (BM + 8);
+  constexpr int BSZ = B_KC ? BN * (BK + 4) : BK * (BN + 8);
+  constexpr int AV = BM * BK / 4 / NT, BV = BN * BK / 4 / NT;  // float4 per thread and K step
+  __shared__ __align__(16) float As[ASZ];
+  __shared__ __align__(16) float Bs[BSZ];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp & 1) * WM, wn0 = (warp >> 1) * WN;
+  const int fg = lane >> 2, ft = lane & 3;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   const int64_t kbeg = (int64_t)blockIdx.z * p.k_chunk;
   const int64_t kend = (kbeg + p.k_chunk < p.K) ? kbeg + p.k_chunk : p.K;
+  const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+  const bool b_vec = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
+  // element (row, k) of a staged operand
+  constexpr int A_FR = A_KC ? BK + 4 : 1, A_FK = A_KC ? 1 : BM + 8;
+  constexpr int B_FR = B_KC ? BK + 4 : 1, B_FK = B_KC ? 1 : BN + 8;
 
-  float acc[TM][TN];
+  float4 ra[AV], rb[BV];
+  auto fetch = [&](int64_t k0) {
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+    for (int e = 0; e < AV; ++e) {
+      const int id = tid + NT * e;
+      int row, k;
+      if (A_KC) { row = id / (BK / 4); k = 4 * (id % (BK / 4)); } else { k = id / (BM / 4); row = 4 * (id % (BM / 4)); }
+      const int64_t gr = m0 + row, gk = k0 + k;
+      const int64_t lim = A_KC ? kend - gk : p.M - gr;
+      const bool ok = A_KC ? (gr < p.M) : (gk < kend);
+      const int nv = ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : (int)lim)) : 0;
+      ra[e] = gemm_ld4(p.A + (nv ? (A_KC ? gr * p.lda + gk : gk * p.lda + gr) : 0), a_vec, nv);
+    }
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int e = 0; e < BV; ++e) {
+      const int id = tid + NT * e;
+      int row, k;
+      if (B_KC) { row = id / (BK / 4); k = 4 * (id % (BK / 4)); } else { k = id / (BN / 4); row = 4 * (id % (BN / 4)); }
+      const int64_t gr = n0 + row, gk = k0 + k;
+      const int64_t lim = B_KC ? kend - gk : p.N - gr;
+      const bool ok = B_KC ? (gr < p.N) : (gk < kend);
+      const int nv = ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : (int)lim)) : 0;
+      rb[e] = gemm_ld4(p.B + (nv ? (B_KC ? gr * p.ldb + gk : gk * p.ldb + gr) : 0), b_vec, nv);
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int e = 0; e < AV; ++e) {
+      const int id = tid + NT * e;
+      if (A_KC) *reinterpret_cast<float4*>(As + (id / (BK / 4)) * (BK + 4) + 4 * (id % (BK / 4))) = ra[e];
+      else *reinterpret_cast<float4*>(As + (id / (BM / 4)) * (BM + 8) + 4 * (id % (BM / 4))) = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < BV; ++e) {
+      const int id = tid + NT * e;
+      if (B_KC) *reinterpret_cast<float4*>(Bs + (id / (BK / 4)) * (BK + 4) + 4 * (id % (BK / 4))) = rb[e];
+      else *reinterpret_cast<float4*>(Bs + (id / (BN / 4)) * (BN + 8) + 4 * (id % (BN / 4))) = rb[e];
+    }
+  };
 
+  float acc[MT][NTL][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NTL; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  if (kbeg < kend) fetch(kbeg);
   for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-    // ---- stage A tile
-    for (int i = tid; i < BM * BK; i += NT) {
-      int m, k;
-      if (A_T) { m = i % BM; k = i / BM; } else { m = i / BK; k = i % BK; }
-      int64_t gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < p.M && gk < kend) v = A_T ? __ldg(p.A + gk * p.lda + gm) : __ldg(p.A + gm * p.lda + gk);
-      As[k][m] = v;
-    }
-    for (int i = tid; i < BN * BK; i += NT) {
-      int n, k;
-      if (B_T) { n = i / BK; k = i % BK; } else { n = i % BN; k = i / BN; }
-      int64_t gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < p.N && gk < kend) v = B_T ? __ldg(p.B + gn * p.ldb + gk) : __ldg(p.B + gk * p.ldb + gn);
-      Bs[k][n] = v;
-    }
+    if (k0 > kbeg) __syncthreads();  // the previous tiles have been consumed
+    stage();
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);
+    const float* ar = As + (wm0 + fg) * A_FR + ft * A_FK;
+    const float* br = Bs + (wn0 + fg) * B_FR + ft * B_FK;
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[TM], b[TN];
+    for (int k8 = 0; k8 < BK; k8 += 8) {
+      uint32_t bh[NTL][2], bl[NTL][2];
 #pragma unroll
-      for (int g = 0; g < GM; ++g) {
-        float4 t = *reinterpret_cast<const float4*>(&As[k][g * (BM / GM) + ty * 4]);
-        a[g * 4 + 0] = t.x; a[g * 4 + 1] = t.y; a[g * 4 + 2] = t.z; a[g * 4 + 3] = t.w;
+      for (int j = 0; j < NTL; ++j) {
+        split_tf32(br[j * 8 * B_FR + k8 * B_FK], bh[j][0], bl[j][0]);
+        split_tf32(br[j * 8 * B_FR + (k8 + 4) * B_FK], bh[j][1], bl[j][1]);
       }
 #pragma unroll
-      for (int g = 0; g < GN; ++g) {
-        float4 t = *reinterpret_cast<const float4*>(&Bs[k][g * (BN / GN) + tx * 4]);
-        b[g * 4 + 0] = t.x; b[g * 4 + 1] = t.y; b[g * 4 + 2] = t.z; b[g * 4 + 3] = t.w;
+      for (int i = 0; i < MT; ++i) {
+        uint32_t ah[4], al[4];
+        split_tf32(ar[(i * 16) * A_FR + k8 * A_FK], ah[0], al[0]);
+        split_tf32(ar[(i * 16 + 8) * A_FR + k8 * A_FK], ah[1], al[1]);
+        split_tf32(ar[(i * 16) * A_FR + (k8 + 4) * A_FK], ah[2], al[2]);
+        split_tf32(ar[(i * 16 + 8) * A_FR + (k8 + 4) * A_FK], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+          mma_tf32(acc[i][j], al, bh[j]);
+          mma_tf32(acc[i][j], ah, bl[j]);
+          mma_tf32(acc[i][j], ah, bh[j]);
+        }
       }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
   }
 
+  // fragment element e: row = fg + 8 (e >> 1), column = 2 ft + (e & 1)
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int64_t gm = m0 + (i / 4) * (BM / GM) + ty * 4 + (i % 4);
-    if (gm >= p.M) continue;
+  for (int i = 0; i < MT; ++i) {
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int64_t gn = n0 + (j / 4) * (BN / GN) + tx * 4 + (j % 4);
-      if (gn >= p.N) continue;
-      const int64_t o = gm * p.ldc + gn;
-      float v = acc[i][j];
-      if (p.atomic) {
-        atomicAdd(p.C + o, v);
-        continue;
+    for (int e2 = 0; e2 < 2; ++e2) {
+      const int64_t gm = m0 + wm0 + i * 16 + fg + 8 * e2;
+      if (gm >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+        for (int e1 = 0; e1 < 2; ++e1) {
+          const int64_t gn = n0 + wn0 + j * 8 + 2 * ft + e1;
+          if (gn >= p.N) continue;
+          const int64_t o = gm * p.ldc + gn;
+          float v = acc[i][j][e2 * 2 + e1];
+          if (p.atomic) {
+            atomicAdd(p.C + o, v);
+            continue;
+          }
+          if (p.bias) v += __ldg(p.bias + gn);
+          if (p.pre_add) v += __ldg(p.pre_add + o);
+          if (p.z_out) p.z_out[o] = v;
+          v = act_fwd(p.act, v);
+          if (p.residual) v += __ldg(p.residual + o);
+          if (p.accumulate) v += p.C[o];
+          p.C[o] = v;
+        }
       }
-      if (p.bias) v += __ldg(p.bias + gn);
-      if (p.pre_add) v += __ldg(p.pre_add + o);
-      if (p.z_out) p.z_out[o] = v;
-      v = act_fwd(p.act, v);
-      if (p.residual) v += __ldg(p.residual + o);
-      if (p.accumulate) v += p.C[o];
-      p.C[o] = v;
     }
   }
 }
@@ -188,10 +271,10 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   p.atomic = split > 1 ? 1 : 0;
   if (cfg == 0) {
     dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
-    pcc::note_launch(1), sgemm_kernel<128, 128, 16, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_kernel<128, 128, 32, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
   } else if (cfg == 1) {
     dim3 grid((unsigned)cdiv(p.N, 64), (unsigned)cdiv(p.M, 64), (unsigned)split);
-    pcc::note_launch(1), sgemm_kernel<64, 64, 16, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
+    pcc::note_launch(1), sgemm_kernel<64, 64, 32, 4, 4, A_T, B_T><<<grid, 256, 0, st>>>(p);
   } else {
     dim3 grid((unsigned)cdiv(p.N, 32), (unsigned)cdiv(p.M, 32), (unsigned)split);
     pcc::note_launch(1), sgemm_small_kernel<A_T, B_T><<<grid, 256, 0, st>>>(p);
@@ -207,7 +290,10 @@ static void plan_gemm(const GemmArgs& p, int64_t want_split, int* cfg_out, int64
   if (p.M * p.N <= 512 * 512) cfg = 2;                  // head-sized outputs: many small CTAs
   int64_t split = 1;
   if (want_split > 1) {
-    // reduction-dominated (wgrad): spread K over ~2 waves of CTAs
+    // reduction-dominated (wgrad): spread K over ~2 waves of CTAs.  With a long reduction the output tile should
+    // be as large as the output allows: a [128 x 128] weight gradient over 262k rows read through 32 x 32 tiles
+    // re-reads both operands four times (1 GB instead of 268 MB)
+    if (p.K >= 8192) cfg = min_mn >= 128 ? 0 : (min_mn >= 64 ? 1 : 2);
     split = cdiv(296, tiles[cfg]);
     int64_t max_split = cdiv(p.K, 256);
     if (split > max_split) split = max_split;
