@@ -18,6 +18,7 @@
 // Per-point activations never leave the SM.
 #include "pcc_fused.cuh"
 #include "pcc_head.cuh"
+#include <stdlib.h>
 
 namespace pcc {
 
@@ -535,6 +536,348 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
   if (warp == kFwdMmaWarp) tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------ forward kernel, CTA pairs (H = 256, max pooling)
+// Same three roles as above, but two CTAs (one cluster, two SMs of a TPC) work on two consecutive tiles with
+// cta_group::2 MMAs, each CTA holding HALF of every weight matrix resident in shared memory:
+//   hidden layer   D[256 points, 256 features]: A = each CTA's own activation image, B = W_1 split by output feature;
+//   final layer    D[256 features, 256 points]: A = W_{L-1} split by output feature, B = each CTA's own image
+//                  -> CTA c pools ITS 128 features over BOTH tiles.
+// What this buys (profiles/notes_r1.md: the single-CTA kernel is bound by shared-memory bandwidth): no weight
+// stream at all (256 KB per tile written into shared memory before), the transposed final layer becomes one
+// M = 256 MMA per K step reading 64 B/clk per SM instead of two M = 128 MMAs reading 128 B/clk, and the hidden
+// layer reads 64 instead of 96 B/clk.
+constexpr int kPairMmaWarp = 16;
+constexpr int kPairThreads = 17 * 32;
+
+struct PairSmem {
+  uint32_t bufA, w1h, w2h, ones, bimg, w0, xs, bars, total;
+};
+__host__ __device__ inline PairSmem pair_smem(int Q) {
+  PairSmem s;
+  uint32_t o = 0;
+  s.bufA = o; o += kTileM * 256 * 2;           // activation image of this CTA's tile
+  s.w1h = o;  o += 4 * kActSlab;               // rows [128 rank, +128) of the hidden weight image, 4 K slabs
+  s.w2h = o;  o += 4 * kActSlab;               // same rows of the final weight image
+  s.ones = o; o += kTileM * kK0 * 2;
+  s.bimg = o; o += kTileM * kK0 * 2;           // [2][128][8]: (hi, lo) of b_1 for this CTA's 128 features
+  s.w0 = o;   o += 256u * 4 * Q * 4;
+  s.xs = o;   o += 2u * kTileM * 4 * Q * 4;
+  s.bars = o; o += 256;
+  s.total = o;
+  return s;
+}
+
+template <int ACT, int Q>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi_pool_fwd_pair_kernel(const PhiParams p) {
+  constexpr int H = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const PairSmem lay = pair_smem(Q);
+  uint8_t* bufA = smem + lay.bufA;
+  uint8_t* w1h = smem + lay.w1h;
+  uint8_t* w2h = smem + lay.w2h;
+  __nv_bfloat16* onesS = reinterpret_cast<__nv_bfloat16*>(smem + lay.ones);
+  __nv_bfloat16* bimgS = reinterpret_cast<__nv_bfloat16*>(smem + lay.bimg);
+  const ulonglong2* w0S = reinterpret_cast<const ulonglong2*>(smem + lay.w0);
+  float* xS = reinterpret_cast<float*>(smem + lay.xs);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  uint64_t* slab_ready = bars;        // [4] (leader's copy is used) slab of BOTH images written: 16 warp arrivals
+  uint64_t* acc_h = bars + 4;         // hidden accumulator complete (multicast commit: both CTAs)
+  uint64_t* acc_f = bars + 5;         // [2] final accumulator (slot) complete (multicast)
+  uint64_t* pool_done = bars + 7;     // [2] (leader's copy) final accumulator drained in BOTH CTAs: 16 warp arrivals
+  uint64_t* wres = bars + 9;          // this CTA's weight halves have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a full weight image (256 rows)
+  constexpr int NSLAB = H / 64, NCHUNK = H / 32;
+  constexpr int XW = 4 * Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t npairs = gridDim.x >> 1, pair0 = blockIdx.x >> 1;
+  const int64_t ntp = (p.num_tiles + 1) >> 1;  // tile pairs
+
+  // ---- constants: ones image, bias halves, layer-0 table
+  for (int i = threadIdx.x; i < kTileM * kK0; i += kPairThreads) {
+    const int kc = i / (kTileM * 8), row = (i / 8) % kTileM, k8 = i % 8;
+    onesS[i] = __float2bfloat16_rn((kc == 0 && k8 < 2) ? 1.f : 0.f);
+    float v = 0.f;
+    if (L == 3 && kc == 0 && k8 < 2) {
+      const float b = __ldg(p.bias[1] + rank * 128 + row);
+      const float hi = bf16_round(b);
+      v = (k8 == 0) ? hi : (b - hi);
+    }
+    bimgS[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = threadIdx.x; i < H * 4 * Q; i += kPairThreads) reinterpret_cast<float*>(smem + lay.w0)[i] = __ldg(p.w0tab + i);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], 2 * kFwdHidWarps);
+    mbar_init(acc_h, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_f[i], 1); mbar_init(&pool_done[i], 2 * kFwdPoolWarps); }
+    mbar_init(wres, 1);
+    fence_mbar_init();
+    // resident weight halves: rows [128 rank, +128) of every K slab = one contiguous 16 KB piece per slab
+    const uint32_t nb = (uint32_t)((L == 3 ? 2 : 1) * NSLAB) * kActSlab;
+    mbar_arrive_expect_tx(wres, nb);
+    for (int sidx = 0; sidx < NSLAB; ++sidx) {
+      if (L == 3) bulk_g2s(w1h + sidx * kActSlab, p.wpack + p.w_off[1] + (size_t)sidx * SLAB + (size_t)rank * 128 * 128, kActSlab, wres);
+      bulk_g2s(w2h + sidx * kActSlab, p.wpack + p.w_off[L - 1] + (size_t)sidx * SLAB + (size_t)rank * 128 * 128, kActSlab, wres);
+    }
+  }
+  if (warp == kPairMmaWarp) tmem_alloc_pair<512>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrival; both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(wres, 0);
+
+  if (warp == kPairMmaWarp) {
+    // ===================== MMA issuer: one thread of the leader CTA drives both tensor cores
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t IDESC = make_idesc_bf16(256, 256, 0, 0);
+      uint32_t sl_phase = 0;
+      const uint32_t a_base = smem_u32(bufA), w1_base = smem_u32(w1h), w2_base = smem_u32(w2h);
+      int tn = 0, nt = 0;
+      for (int64_t tp = pair0; tp < ntp; tp += npairs, ++nt) {
+        if (L == 3) {
+          trace_ev(p.trace, 1, tn, 101);
+          for (int sidx = 0; sidx < NSLAB; ++sidx) {
+            mbar_wait_cluster(&slab_ready[sidx], sl_phase);  // h_0 slab of both tiles
+            tc_fence_after();
+            if (sidx == 0) {
+              trace_ev(p.trace, 1, tn, 121);
+              umma_bf16_pair(tmem, make_smem_desc(smem_u32(onesS), kTileM * 16, 128), make_smem_desc(smem_u32(bimgS), kTileM * 16, 128),
+                             IDESC, 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_pair(tmem, make_smem_desc_sw128_k(a_base + sidx * kActSlab + ks * 32),
+                             make_smem_desc_sw128_k(w1_base + sidx * kActSlab + ks * 32), IDESC, 1);
+          }
+          sl_phase ^= 1;
+          umma_commit_pair(acc_h);
+          trace_ev(p.trace, 1, tn, 141);
+        }
+        const int slot = (L == 2) ? (nt & 1) : 0;
+        const int k = (L == 2) ? (nt >> 1) : nt;
+        if (k >= 1) {
+          mbar_wait_cluster(&pool_done[slot], (uint32_t)((k - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t accT = tmem + ((L == 2) ? slot * 256 : 256);
+        trace_ev(p.trace, 1, tn, 102);
+        for (int sidx = 0; sidx < NSLAB; ++sidx) {
+          mbar_wait_cluster(&slab_ready[sidx], sl_phase);
+          tc_fence_after();
+          if (sidx == 0) trace_ev(p.trace, 1, tn, 122);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_pair(accT, make_smem_desc_sw128_k(w2_base + sidx * kActSlab + ks * 32),
+                           make_smem_desc_sw128_k(a_base + sidx * kActSlab + ks * 32), IDESC, (sidx | ks) != 0);
+        }
+        sl_phase ^= 1;
+        umma_commit_pair(&acc_f[slot]);
+        trace_ev(p.trace, 1, tn, 142);
+      }
+    }
+  } else if (warp < kFwdHidWarps) {
+    // ===================== hidden warps: layer 0 on the FP32 pipe + hidden-layer epilogue (this CTA's tile)
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int d = p.d;
+    const int cg = threadIdx.x & 7, rw = threadIdx.x >> 3;
+    float xp[2 * Q];
+    auto load_x = [&](int64_t tile) {
+#pragma unroll
+      for (int k = 0; k < 2 * Q; ++k) {
+        const int slot = threadIdx.x + kFwdHidWarps * 32 * k;
+        const int64_t row = tile * kTileM + slot / XW;
+        const int j = slot % XW - 1;
+        xp[k] = (j >= 0 && j < d && row < p.n && tile < p.num_tiles) ? __ldg(p.x + row * d + j) : 0.f;
+      }
+    };
+    auto store_x = [&](int buf) {
+#pragma unroll
+      for (int k = 0; k < 2 * Q; ++k) xS[buf * (kTileM * XW) + threadIdx.x + kFwdHidWarps * 32 * k] = bf16_round(xp[k]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    load_x(2 * pair0 + rank);
+    store_x(0);
+    int tn = 0, nt = 0;
+    uint32_t acch_phase = 0;
+    const bool tr0 = (threadIdx.x == 0 && rank == 0);
+    for (int64_t tp = pair0; tp < ntp; tp += npairs, ++nt) {
+      if (nt >= 1) {  // the image is free once the previous final layer has completed (multicast commit)
+        const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
+        const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
+        mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
+      }
+      if (tr0) trace_ev(p.trace, 0, tn, 0);
+      const float* xT = xS + (nt & 1) * (kTileM * XW);
+      load_x(2 * (tp + npairs) + rank);
+#pragma unroll 1
+      for (int sidx = 0; sidx < NSLAB; ++sidx) {
+        uint64_t z[4][4];
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) {
+          ulonglong2 w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = w0S[(qq * NSLAB + sidx) * 64 + e * 8 + cg];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
+            const uint64_t x0 = f32x2(xv.x, xv.x), x1 = f32x2(xv.y, xv.y), x2 = f32x2(xv.z, xv.z), x3 = f32x2(xv.w, xv.w);
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+              if (qq == 0) z[i][pi] = ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, w[2 * pi].x)));
+              else z[i][pi] = ffma2(w[2 * pi].x, x0, ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, z[i][pi]))));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t o[4];
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            float lo, hi;
+            f32x2_unpack(z[i][pi], lo, hi);
+            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
+          }
+          *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, sidx * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive_warp_remote(&slab_ready[sidx], 0);
+      }
+      if (tr0) trace_ev(p.trace, 0, tn, 5);
+      if (L == 3) {
+        mbar_wait(acc_h, acch_phase);
+        acch_phase ^= 1;
+        tc_fence_after();
+        if (tr0) trace_ev(p.trace, 0, tn, 11);
+        const bool res = (p.res_mask >> 1) & 1;
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + grp * 32, va);
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 4) {
+          tmem_wait_ld();
+          if (c + 2 < NCHUNK) tmem_ld32(lane_base + (c + 2) * 32, vb);
+          epi_store_chunk<ACT>(va, bufA, r, c, res);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive_warp_remote(&slab_ready[c >> 1], 0);
+          if (c + 2 < NCHUNK) {
+            tmem_wait_ld();
+            if (c + 4 < NCHUNK) tmem_ld32(lane_base + (c + 4) * 32, va);
+            epi_store_chunk<ACT>(vb, bufA, r, c + 2, res);
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive_warp_remote(&slab_ready[(c + 2) >> 1], 0);
+          }
+        }
+        if (tr0) trace_ev(p.trace, 0, tn, 21);
+      }
+      store_x((nt + 1) & 1);
+    }
+  } else {
+    // ===================== pool warps: thread = one of THIS CTA's 128 features, columns = points of tile 2 tp + h
+    const int pw = warp - kFwdHidWarps;
+    const int quarter = warp & 3, h = pw >> 2;
+    const int f = (int)rank * 128 + quarter * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    const bool is_max = (p.pooling == PCC_POOL_MAX);
+    const bool tr0 = (pw == 0 && lane == 0 && rank == 0);
+    int tn = 0, nt = 0;
+    int64_t nb = 0, nlo = 0, nhi = 0;
+    auto seg_fetch = [&](int64_t tile) {
+      nb = p.B; nlo = 0; nhi = 0;
+      if (tile < p.num_tiles) {
+        nb = __ldg(p.tile_first + tile);
+        if (nb < p.B) { nlo = __ldg(p.offsets + nb); nhi = __ldg(p.offsets + nb + 1); }
+      }
+    };
+    seg_fetch(2 * pair0 + h);
+    for (int64_t tp = pair0; tp < ntp; tp += npairs, ++nt) {
+      const int64_t tile = 2 * tp + h;
+      const int64_t r0 = tile * kTileM;
+      const int64_t tile_end = (r0 + kTileM < p.n) ? r0 + kTileM : p.n;
+      int64_t b = nb, seg_lo = nlo, seg_hi = nhi;
+      seg_fetch(2 * (tp + npairs) + h);
+      const int slot = (L == 2) ? (nt & 1) : 0;
+      const int k = (L == 2) ? (nt >> 1) : nt;
+      mbar_wait(&acc_f[slot], (uint32_t)(k & 1));
+      tc_fence_after();
+      if (tr0) trace_ev(p.trace, 2, tn, 30);
+      const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
+      float acc = is_max ? -INFINITY : 0.f;
+      int arg = -1;
+      auto flush = [&](int64_t set) {
+        if (is_max) {
+          if (arg >= 0) {
+            unsigned long long key = ((unsigned long long)float_ordered(acc) << 32) |
+                                     (unsigned long long)(0xFFFFFFFFu - (uint32_t)(r0 + arg));
+            atomicMax(reinterpret_cast<unsigned long long*>(p.pool_acc) + set * H + f, key);
+          }
+          acc = -INFINITY; arg = -1;
+        } else {
+          atomicAdd(reinterpret_cast<float*>(p.pool_acc) + set * H + f, acc);
+          acc = 0.f;
+        }
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld32(accT, va);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_wait_ld();
+        uint32_t (&v)[32] = (c & 1) ? vb : va;
+        if (c + 1 < 4) tmem_ld32(accT + (c + 1) * 32, (c & 1) ? va : vb);
+        const int64_t col0 = r0 + c * 32;
+        while (b < p.B && seg_lo < tile_end && seg_lo < col0 + 32) {
+          const int lo = (int)((seg_lo > col0 ? seg_lo : col0) - col0);
+          const int hi = (int)((seg_hi < col0 + 32 ? seg_hi : col0 + 32) - col0);
+          if (lo == 0 && hi == 32) {
+            if (is_max) {
+              const float m = fmaxf(fmaxf(max8(v), max8(v + 8)), fmaxf(max8(v + 16), max8(v + 24)));
+              if (m > acc || arg < 0) {
+                int j0 = 31;
+#pragma unroll
+                for (int j = 30; j >= 0; --j) j0 = (__uint_as_float(v[j]) == m) ? j : j0;
+                acc = m;
+                arg = c * 32 + j0;
+              }
+            } else {
+              acc += (sum8(v) + sum8(v + 8)) + (sum8(v + 16) + sum8(v + 24));
+            }
+          } else if (is_max) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float val = __uint_as_float(v[j]);
+              if (j >= lo && j < hi && (val > acc || arg < 0)) { acc = val; arg = c * 32 + j; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc += (j >= lo && j < hi) ? __uint_as_float(v[j]) : 0.f;
+          }
+          if (seg_hi > col0 + 32) break;
+          flush(b);
+          ++b;
+          if (b < p.B) { seg_lo = seg_hi; seg_hi = __ldg(p.offsets + b + 1); }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp_remote(&pool_done[slot], 0);
+      if (b < p.B && seg_lo < tile_end) flush(b);
+      if (tr0) trace_ev(p.trace, 2, tn, 40);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == kPairMmaWarp) tmem_dealloc_pair<512>(tmem);
+}
+
 // pool accumulator -> pooled[B,H] (+ argmax): adds the final bias after pooling
 // (max(z+b) = max(z)+b, mean(z+b) = mean(z)+b, sum(z+b)/sqrt(n) = sum(z)/sqrt(n) + b*sqrt(n))
 __global__ void pool_finalize_kernel(const void* __restrict__ pool_acc, const int64_t* __restrict__ offsets,
@@ -691,8 +1034,37 @@ void* debug_trace_buffer() { return g_trace_buf; }
 
 static inline int q4_of(int d) { return d <= 3 ? 1 : 2; }
 
+template <int ACT, int Q>
+static int launch_fwd_pair(const PhiParams& p, cudaStream_t st) {
+  const PairSmem lay = pair_smem(Q);
+  auto kern = phi_pool_fwd_pair_kernel<ACT, Q>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+  if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_fwd", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntp = (p.num_tiles + 1) / 2;
+  int64_t pairs = sms / 2;
+  if (pairs > ntp) pairs = ntp;
+  {
+    ProfScope prof(0, st);
+    PCC_K(kern)<<<(unsigned)(2 * pairs), kPairThreads, lay.total, st>>>(p);
+  }
+  return 0;
+}
+
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PCC_FWD_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int H, int ACT, int Q>
 static int launch_fwd(const PhiParams& p, cudaStream_t st) {
+  if (H == 256 && !p.poolh && p.num_tiles >= 2 && use_pair_kernel()) return launch_fwd_pair<ACT, Q>(p, st);
   const SmemLayout lay = smem_layout(H, p.L, Q, p.poolh);
   auto kern = p.poolh ? phi_pool_fwd_kernel<H, ACT, Q, true> : phi_pool_fwd_kernel<H, ACT, Q, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
