@@ -236,6 +236,9 @@ int pcc_peer_allreduce(float* bucket, int64_t n, void* const* regions, int64_t b
 /* optional event trace of CTA 0 of the fused forward kernel into a device buffer of 3*4096 int64
  * (role, (id, clock64) pairs); NULL disables.  Development aid. */
 int pcc_debug_set_trace(void* device_buf);
+/* forward kernel selection for H = 256 without commuted pooling: 1 = CTA-pair kernel (cta_group::2, default; env
+ * PCC_FWD_PAIR=0 disables), 0 = one CTA per SM.  Both compute the same function; tests compare them. */
+int pcc_debug_set_fwd_pair(int on);
 
 #ifdef __cplusplus
 }

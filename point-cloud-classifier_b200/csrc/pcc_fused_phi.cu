@@ -1053,13 +1053,13 @@ static int launch_fwd_pair(const PhiParams& p, cudaStream_t st) {
   return 0;
 }
 
+static int g_fwd_pair = -1;  // -1: read PCC_FWD_PAIR on first use; pcc_debug_set_fwd_pair overrides
 static bool use_pair_kernel() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_fwd_pair < 0) {
     const char* e = getenv("PCC_FWD_PAIR");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_fwd_pair = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  return g_fwd_pair == 1;
 }
 
 template <int H, int ACT, int Q>
@@ -1086,6 +1086,11 @@ using namespace pcc;
 
 extern "C" int pcc_debug_set_trace(void* device_buf_2x4096_i64) {
   pcc::g_trace_buf = device_buf_2x4096_i64;
+  return 0;
+}
+
+extern "C" int pcc_debug_set_fwd_pair(int on) {
+  pcc::g_fwd_pair = on ? 1 : 0;
   return 0;
 }
 

@@ -213,3 +213,52 @@ def test_deeper_phi_falls_back_to_fp32_path():
     x, idx = ragged_batch([50, 60], 3, seed=1)
     m(x.cuda(), idx.cuda()).sum().backward()
     assert m.last_path == "fp32"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [[1024] * 8, [300, 1, 129, 700, 64, 5], [128] * 3])
+def test_pair_kernel_matches_single_cta_kernel(sizes):
+    """H = 256 + max pooling runs on CTA pairs (cta_group::2, weight halves resident); the one-CTA kernel computes
+    the same function with the same operand rounding: pooled values agree to fp32 accumulation-order noise and the
+    argmax rows are the same (odd tile counts exercise the dummy second tile of the last pair)."""
+    from pcc_b200 import _lib
+    cfg = dict(input_dim=3, phi_layers=[256, 256], rho_layers=[64], output_dim=3, activation="relu", layer_norm=False,
+               residual_block=False, pooling="max")
+    torch.manual_seed(3)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    x, idx = ragged_batch(sizes, 3, seed=11, device="cuda")
+    outs = []
+    try:
+        for pair in (1, 0):
+            _lib.call("pcc_debug_set_fwd_pair", pair)
+            with torch.no_grad():
+                logits = m(x, idx)
+            outs.append((logits.clone(), m._last_pooled.clone() if hasattr(m, "_last_pooled") else None))
+    finally:
+        _lib.call("pcc_debug_set_fwd_pair", 1)
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_single_rank(tmp_path):
+    """The library's peer all-reduce (CUDA IPC staging + flags) on a one-rank group: alloc / kernel / free and the
+    averaging arithmetic; multi-rank runs are tools/test_peer_allreduce.py (2 and 8 GPUs, bit-exact vs NCCL)."""
+    import torch.distributed as dist
+    from pcc_b200.distributed import PeerAllReduce, GradArena
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/rdzv", rank=0, world_size=1)
+    try:
+        peer = PeerAllReduce(1001, torch.device("cuda", 0))
+        a = torch.randn(peer.numel, device="cuda")
+        ref = a.clone()
+        for _ in range(3):          # the sequence number / staging parity advances per call
+            peer.run(a)
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref)
+        peer.close()
+        lin = torch.nn.Linear(5, 3).cuda()
+        arena = GradArena(list(lin.parameters()))
+        assert arena.numel % 4 == 0 and arena.view_for(lin.weight).shape == lin.weight.shape
+        assert arena.view_for(torch.zeros(2, 2, device="cuda")) is None
+    finally:
+        dist.destroy_process_group()
