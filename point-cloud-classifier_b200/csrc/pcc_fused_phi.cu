@@ -717,6 +717,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
       if (tr0) trace_ev(p.trace, 0, tn, 0);
       const float* xT = xS + (nt & 1) * (kTileM * XW);
       load_x(2 * (tp + npairs) + rank);
+      float4 xrow[Q][4];  // the thread's four input rows stay in registers for all slabs
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xrow[qq][i] = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
 #pragma unroll 1
       for (int sidx = 0; sidx < NSLAB; ++sidx) {
         uint64_t z[4][4];
@@ -727,7 +732,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
           for (int e = 0; e < 8; ++e) w[e] = w0S[(qq * NSLAB + sidx) * 64 + e * 8 + cg];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 xv = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
+            const float4 xv = xrow[qq][i];
             const uint64_t x0 = f32x2(xv.x, xv.x), x1 = f32x2(xv.y, xv.y), x2 = f32x2(xv.z, xv.z), x3 = f32x2(xv.w, xv.w);
 #pragma unroll
             for (int pi = 0; pi < 4; ++pi) {
