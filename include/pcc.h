@@ -60,6 +60,10 @@ int pcc_segment_pool_fwd(const float* x, const int64_t* offsets, int64_t n, int6
 int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets, const int32_t* argmax, int64_t n, int64_t B,
                          int64_t H, int pooling, float* dx, int device, void* stream);
 
+/* precision of the large-tile dense kernels behind pcc_linear_*: 0 (default) = fp32-grade 3xTF32 mma.sync
+ * (x = hi + lo split, error ~2^-21 per product: the parity mode), 1 = single TF32 (operands rounded to 10 mantissa
+ * bits, ~1e-3 relative, 3x fewer MMAs).  Library-wide switch; the small-tile (batch-sized) kernels stay exact fp32. */
+int pcc_set_dense_precision(int mode);
 /* ---- dense layer, fp32 SIMT path: replaces nn.Linear (+ fused activation / residual)
  *      inside phi / rho (deep_sets.py:89,112), GraphConv's lin_rel / lin_root and fc1 /
  *      fc2 (graph_net.py:73,82,87,98,102).

@@ -21,8 +21,13 @@ struct GemmArgs {
   int act;
   int accumulate;   // C += result
   int atomic;       // split-K partial sums: atomicAdd into C
+  int tf32x1;       // one TF32 MMA per product (operands rounded to 10 mantissa bits) instead of the 3xTF32 split
   int64_t k_chunk;  // K range per blockIdx.z
 };
+
+// library-wide precision of the dense (pcc_linear_*) path: 0 = fp32-grade 3xTF32 (default, parity mode),
+// 1 = single TF32 (~1e-3 relative, better than the bf16 operands of the fused DeepSets path; 3x fewer MMAs)
+static int g_dense_tf32x1 = 0;
 
 // 3xTF32 on the tensor cores (mma.sync m16n8k8): x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and
 // a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi — error ~2^-21 relative per product, fp32 accumulation: the fp32 parity
@@ -152,8 +157,10 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs p) {
         split_tf32(ar[(i * 16 + 8) * A_FR + (k8 + 4) * A_FK], ah[3], al[3]);
 #pragma unroll
         for (int j = 0; j < NTL; ++j) {
-          mma_tf32(acc[i][j], al, bh[j]);
-          mma_tf32(acc[i][j], ah, bl[j]);
+          if (!p.tf32x1) {
+            mma_tf32(acc[i][j], al, bh[j]);
+            mma_tf32(acc[i][j], ah, bl[j]);
+          }
           mma_tf32(acc[i][j], ah, bh[j]);
         }
       }
@@ -269,6 +276,7 @@ static int launch_gemm(GemmArgs p, int64_t want_split, cudaStream_t st) {
   int64_t split;
   plan_gemm(p, want_split, &cfg, &split, &p.k_chunk);
   p.atomic = split > 1 ? 1 : 0;
+  p.tf32x1 = g_dense_tf32x1;
   if (cfg == 0) {
     dim3 grid((unsigned)cdiv(p.N, 128), (unsigned)cdiv(p.M, 128), (unsigned)split);
     pcc::note_launch(1), sgemm_kernel<128, 128, 32, 8, 8, A_T, B_T><<<grid, 256, 0, st>>>(p);
@@ -514,6 +522,12 @@ static inline unsigned ew_blocks(int64_t total) {
 }  // namespace pcc
 
 using namespace pcc;
+
+extern "C" int pcc_set_dense_precision(int mode) {
+  if (mode != 0 && mode != 1) return fail(__func__, "mode must be 0 (fp32-grade 3xTF32) or 1 (single TF32)");
+  pcc::g_dense_tf32x1 = mode;
+  return 0;
+}
 
 extern "C" int pcc_linear_fwd(const float* x, const float* w, const float* bias, const float* pre_add,
                               const float* residual, float* y, float* z_out, int64_t M, int64_t N, int64_t K, int act,

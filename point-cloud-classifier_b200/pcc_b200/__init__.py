@@ -9,3 +9,11 @@ from . import functional
 from . import _lib
 
 __all__ = ["DeepSets", "ResidualBlock", "GraphNet", "GraphConv", "knn_graph", "functional"]
+
+import os as _os
+
+if _os.environ.get("PCC_DENSE", "").lower() == "tf32":   # single-TF32 dense layers (functional.set_dense_precision)
+    try:
+        functional.set_dense_precision("tf32")
+    except Exception:  # library not built yet: the first real call reports it
+        pass

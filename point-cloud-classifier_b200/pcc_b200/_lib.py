@@ -39,6 +39,7 @@ _SIGS = {
     "pcc_index_max": [_vp, _i64, _vp, _i32, _vp],
     "pcc_segment_pool_fwd": [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_segment_pool_bwd": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp],
+    "pcc_set_dense_precision": [_i32],
     "pcc_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
     "pcc_linear_bwd_data": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "pcc_linear_bwd_weight": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp],

@@ -416,3 +416,10 @@ class MLPHeadFn(torch.autograd.Function):
 
 def mlp_head(x, act: str, params):
     return MLPHeadFn.apply(x, act, *params)
+
+
+def set_dense_precision(mode: str) -> None:
+    """precision of the large dense layers behind Linear / GraphConv on the fp32 path: "fp32" (default, 3xTF32 on
+    the tensor cores: fp32-grade, the parity mode) or "tf32" (single TF32: ~1e-3 relative, about 3x faster GEMMs).
+    Library-wide (pcc_set_dense_precision); env PCC_DENSE=tf32 selects it at import."""
+    call("pcc_set_dense_precision", {"fp32": 0, "tf32": 1}[mode])

@@ -118,3 +118,34 @@ def test_graphnet_train_step_matches_oracle(act, aggr, deepchem, use_w, hidden, 
     sd_eval = {k: v.cpu() for k, v in m.state_dict().items()}
     ref_ev = GO.graphnet_forward(sd_eval, cfg, x, memb, edges, w, training=False)
     torch.testing.assert_close(ev.cpu(), ref_ev, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_graphnet_tf32_dense_mode():
+    """functional.set_dense_precision("tf32"): single-TF32 tensor-core GEMMs for the node-level layers.  Stated
+    tolerance: operands rounded to 10 mantissa bits -> logits within 2e-2 of max|ref|, gradients within 5e-2
+    (relative Frobenius); the default 3xTF32 mode is the one held to 1e-4 above."""
+    from helpers import rel_l2
+    cfg = dict(input_dim=4, hidden_dim=128, output_dim=1, activation="tanh", use_gat=False, gat_heads=4,
+               sag_pool=False, pool_ratio=0.5, local_pooling="add", global_pooling="mean", deepchem_style=True)
+    sizes = [300, 200, 400, 256]          # > 128 nodes: the large-tile kernels are the ones that switch
+    feats, memb, off = _clouds(sizes, seed=31, F=4)
+    nbr, _ = KO.knn_neighbours(feats[:, 1:4].numpy(), off, 8)
+    edges = torch.from_numpy(KO.knn_edges(nbr))
+    gen = torch.Generator().manual_seed(32)
+    y = (torch.rand(len(sizes), 1, generator=gen) > 0.5).float()
+    sd = GO.init_state_dict(cfg, seed=33)
+    ref_logits, _, ref_grads, _ = GO.graphnet_train_step(sd, cfg, feats, memb, edges, None, y)
+    m = pcc_b200.GraphNet(**cfg).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    PF.set_dense_precision("tf32")
+    try:
+        logits = m(feats.cuda(), memb.cuda(), edges.cuda())
+        torch.nn.BCEWithLogitsLoss()(logits, y.cuda()).backward()
+        torch.cuda.synchronize()
+    finally:
+        PF.set_dense_precision("fp32")
+    assert rel_err(logits.detach().cpu(), ref_logits) < 2e-2
+    for k, ref in ref_grads.items():
+        assert rel_l2(dict(m.named_parameters())[k].grad, ref) < 5e-2, k

@@ -44,12 +44,24 @@ def run(B, N=1024, k=20):
         m.zero_grad(set_to_none=True)
         loss.backward()
     t_step = timeit(step, steps=5, warmup=2)
+    # the same step captured in a CUDA graph (101 launches per step: eager mode is launch bound)
+    t_graph = float("nan")
+    try:
+        from pcc_b200.train_step import GraphedTrainStep
+        gs = GraphedTrainStep(m, [feats, memb, edges], y, forward_kwargs={"num_graphs": B})
+        t_graph = timeit(gs.run, steps=5, warmup=2)
+    except Exception as e:  # noqa: BLE001
+        print(f"  (graph capture failed: {type(e).__name__}: {e})")
     pairs = B * N * N
     print(f"GraphNet B={B:4d} N={N} k={k}: kNN {t_knn:8.3f} ms ({pairs / t_knn / 1e6:8.1f} Gpairs/s) | "
-          f"train step {t_step:8.3f} ms = {B / t_step * 1e3:8.0f} graphs/s, E={edges.shape[1]}", flush=True)
+          f"train step eager {t_step:8.3f} ms, CUDA graph {t_graph:8.3f} ms = {B / t_graph * 1e3:8.0f} graphs/s, "
+          f"E={edges.shape[1]}", flush=True)
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        PF.set_dense_precision(sys.argv[1])   # "tf32": single-TF32 node-level GEMMs
+        print(f"dense precision: {sys.argv[1]}")
     run(32)
     run(256)
     for N in (256, 4096):
