@@ -19,21 +19,55 @@ namespace pcc {
 constexpr int kHeadMaxDim = 1024;
 constexpr int kHeadMaxLayers = 4;
 constexpr int kHT = 32;    // output tile edge
-constexpr int kHK = 64;    // contraction tile
 constexpr int kHThreads = 256;
 
-// The raw loads of a K tile are issued as one unconditional batch (memory-level parallelism: the loop is
-// latency bound); the elementwise transforms run afterwards, with the mode tests hoisted out of the loops.
-// Math: 256 threads = 4 k-groups x 64 threads; a group covers the whole 32x32 tile with 4x4 register
-// micro-tiles (two LDS.128 per 16 FMA) over a quarter of every K tile; the four partial tiles are summed
-// through shared memory at the end (fixed order).  Operand staging is bank-conflict free both ways: rows
-// of 36 floats, lanes laid out 8 (kk) x 4 (i) when the operand is contiguous along kk.
+// hi = x truncated to TF32 (top 19 bits), lo = x - hi (exact in fp32; the tensor core reads its top 19 bits).
+// `cvt.rna.tf32.f32` is emulated with ~6 ALU instructions on this part — the rounding conversion made the split
+// 13 instructions per operand element and the kernels ALU bound (profiles/notes_r1.md); truncation costs 2 and
+// leaves a relative error of ~2^-20 per product.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// four consecutive floats p[0..3]; `nvalid` leading ones are in range; one 128-bit load when possible
+__device__ __forceinline__ float4 head_ld4(const float* p, bool vec, int nvalid) {
+  if (vec && nvalid == 4) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) v.x = __ldg(p);
+  if (nvalid > 1) v.y = __ldg(p + 1);
+  if (nvalid > 2) v.z = __ldg(p + 2);
+  if (nvalid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
+// One 32 x 32 output tile per CTA, K consumed in chunks of 256.  The kernel runs once per CTA with 8 warps on an
+// otherwise empty SM, so it is bound by dependent-latency chains, not by throughput (tools/head_micro.py: 3.2 us
+// fixed + a per-K slope that did not depend on the instruction mix until the chains were broken):
+//   * 128-bit operand loads along each operand's contiguous direction, 8 per thread, operand and chunk: a 256-wide
+//     layer is ONE round trip, the next chunk's loads are in flight under the math of the current one;
+//   * no transposition: an operand contiguous along kk is staged as [i][kk] (rows of 260 floats), one contiguous
+//     along i as [kk][i] (rows of 40 floats) — both conflict free for the float4 stores AND for the k-strided
+//     fragment loads; the activation / act' transforms happen in registers on the way;
+//   * 8 warps, one m16n8 output tile each, 3xTF32 mma.sync (x = hi + lo, a b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi,
+//     error ~2^-21 relative: fp32-grade, the parity path depends on it), four K steps unrolled with six
+//     independent accumulator fragments so that LDS -> cvt -> HMMA chains of different steps overlap.
+constexpr int kHC = 256;            // K chunk
+constexpr int kHSk = kHC + 4;       // row of an [i][kk] staged operand
+constexpr int kHSi = kHT + 8;       // row of a [kk][i] staged operand
+constexpr int kHOp = (kHT * kHSk > kHC * kHSi) ? kHT * kHSk : kHC * kHSi;  // floats per staged operand
+constexpr int kHNV = kHT * kHC / 4 / kHThreads;  // float4 per thread, operand and chunk (8)
+constexpr int kHeadSmem = 2 * kHOp * (int)sizeof(float);
+
 template <int ACT>
 __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTileParams hp) {
-  constexpr int S = kHT + 4;
-  __shared__ __align__(16) float smem_f[2 * kHK * S];
-  float (*As)[S] = reinterpret_cast<float (*)[S]>(smem_f);
-  float (*Bs)[S] = reinterpret_cast<float (*)[S]>(smem_f + kHK * S);
+  extern __shared__ __align__(16) float smem_f[];
+  float* As = smem_f;
+  float* Bs = smem_f + kHOp;
   int t = blockIdx.x;
   const bool second = t >= hp.prob[0].tiles;
   if (second) t -= hp.prob[0].tiles;
@@ -41,142 +75,129 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
   const int I = pr.I, J = pr.J, KK = pr.KK;
   const int i0 = (t / pr.tiles_j) * kHT, j0 = (t % pr.tiles_j) * kHT;
   const int tid = threadIdx.x;
-  const int grp = tid >> 6, tyq = (tid & 63) >> 3, txq = tid & 7;  // group: rows 4 tyq.., columns 4 txq..
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 1) * 16, wn = (warp >> 1) * 8;  // 16 x 8 output tile of this warp
+  const int fg = lane >> 2, ft = lane & 3;              // mma fragment coordinates
   const float* __restrict__ ap = pr.A.p;
   const float* __restrict__ aq = pr.A.q;
   const float* __restrict__ bp = pr.B.p;
-  const int64_t a_si = pr.A.si, a_sk = pr.A.sk, a_qi = pr.A.qi, a_qk = pr.A.qk, b_si = pr.B.si, b_sk = pr.B.sk;
   const int a_mode = pr.A.mode, b_mode = pr.B.mode;
-  const bool a_kc = a_sk == 1, b_kc = b_sk == 1;  // contiguous along kk -> lanes run along kk
-  constexpr int PER = kHT * kHK / kHThreads;       // 8 elements per thread per operand
-  // element e (0..7) of this thread inside a 32 (i) x 64 (kk) operand tile: contiguous-along-kk operands use
-  // lanes 8 (kk) x 4 (i): i = ((tid >> 3) & 3) + 4 e, kk = ((tid >> 5) << 3 | (tid & 7)); the others use lanes
-  // along i: i = tid & 31, kk = (tid >> 5) + 8 e.  Global and shared addresses are base + e * step.
-  const int ai_f = a_kc ? ((tid >> 3) & 3) : (tid & 31), ai_s = a_kc ? 4 : 0;
-  const int ak_f = a_kc ? (((tid >> 5) << 3) | (tid & 7)) : (tid >> 5), ak_s = a_kc ? 0 : 8;
-  const int bi_f = b_kc ? ((tid >> 3) & 3) : (tid & 31), bi_s = b_kc ? 4 : 0;
-  const int bk_f = b_kc ? (((tid >> 5) << 3) | (tid & 7)) : (tid >> 5), bk_s = b_kc ? 0 : 8;
-  const int64_t a_step_e = ai_s * a_si + ak_s * a_sk, a_step_t = kHK * a_sk;
-  const int64_t q_step_e = ai_s * a_qi + ak_s * a_qk, q_step_t = kHK * a_qk;
-  const int64_t b_step_e = bi_s * b_si + bk_s * b_sk, b_step_t = kHK * b_sk;
-  float* const a_sts = &As[ak_f][ai_f];
-  float* const b_sts = &Bs[bk_f][bi_f];
-  const int a_sstep = ak_s * S + ai_s, b_sstep = bk_s * S + bi_s;
+  const bool a_kc = pr.A.sk == 1, b_kc = pr.B.sk == 1;  // contiguous along kk (else along i)
+  const int64_t a_ld = a_kc ? pr.A.si : pr.A.sk, q_ld = a_kc ? pr.A.qi : pr.A.qk, b_ld = b_kc ? pr.B.si : pr.B.sk;
+  const bool a_vec = (a_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0);
+  const bool q_vec = (q_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(aq) & 15) == 0);
+  const bool b_vec = (b_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0);
+  // float4 e (0..7) of this thread inside an operand chunk: kk-contiguous: row i = (tid >> 6) + 4 e, kk = 4 (tid & 63);
+  // i-contiguous: row kk = (tid >> 3) + 32 e, i = 4 (tid & 7).  (major, minor) = (row, offset inside the row)
+  const int a_maj = a_kc ? (tid >> 6) : (tid >> 3), a_mstep = a_kc ? 4 : 32, a_min = a_kc ? 4 * (tid & 63) : 4 * (tid & 7);
+  const int b_maj = b_kc ? (tid >> 6) : (tid >> 3), b_mstep = b_kc ? 4 : 32, b_min = b_kc ? 4 * (tid & 63) : 4 * (tid & 7);
+  const int a_srow = a_kc ? kHSk : kHSi, b_srow = b_kc ? kHSk : kHSi;
+  // fragment strides: element (i, k) of a staged operand
+  const int a_fi = a_kc ? kHSk : 1, a_fk = a_kc ? 1 : kHSi, b_fi = b_kc ? kHSk : 1, b_fk = b_kc ? 1 : kHSi;
 
-  // All loads of a 256-wide K range (4 staging tiles) are in flight at once: a dependent global round trip
-  // costs more than the math of a whole tile, so the K loop must not serialise them.
-  constexpr int NT = 4;
-  float ra[NT][PER], rq[NT][PER], rb[NT][PER];
-  auto fetch = [&](int kbase) {
-    const float* pa = ap + (i0 + ai_f) * a_si + (kbase + ak_f) * a_sk;
-    const float* pb = bp + (j0 + bi_f) * b_si + (kbase + bk_f) * b_sk;
-    const float* pq = aq + (i0 + ai_f) * a_qi + (kbase + ak_f) * a_qk;
-    if (i0 + kHT <= I && j0 + kHT <= J && kbase + NT * kHK <= KK) {  // interior: no predicates
+  float4 ra[kHNV], rq[kHNV], rb[kHNV];
+  auto fetch = [&](int k0) {
 #pragma unroll
-      for (int tl = 0; tl < NT; ++tl)
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-          ra[tl][e] = __ldg(pa + tl * a_step_t + e * a_step_e);
-          rb[tl][e] = __ldg(pb + tl * b_step_t + e * b_step_e);
+    for (int e = 0; e < kHNV; ++e) {
+      {
+        const int maj = a_maj + e * a_mstep;
+        const int gi = a_kc ? i0 + maj : i0 + a_min, gk = a_kc ? k0 + a_min : k0 + maj;   // first component
+        const int lim = a_kc ? KK - gk : I - gi;                                            // along the vector
+        const bool row_ok = a_kc ? (gi < I) : (gk < KK);
+        const int nv = row_ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : lim)) : 0;
+        const int64_t off = a_kc ? (int64_t)gi * a_ld + gk : (int64_t)gk * a_ld + gi;
+        ra[e] = head_ld4(ap + (nv ? off : 0), a_vec, nv);
+        if (a_mode == 2) {
+          const int64_t qoff = a_kc ? (int64_t)gi * q_ld + gk : (int64_t)gk * q_ld + gi;
+          rq[e] = head_ld4(aq + (nv ? qoff : 0), q_vec, nv);
         }
-      if (a_mode == 2) {
-#pragma unroll
-        for (int tl = 0; tl < NT; ++tl)
-#pragma unroll
-          for (int e = 0; e < PER; ++e) rq[tl][e] = __ldg(pq + tl * q_step_t + e * q_step_e);
       }
-    } else {
-#pragma unroll
-      for (int tl = 0; tl < NT; ++tl)
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-          const bool oka = (i0 + ai_f + e * ai_s < I) && (kbase + tl * kHK + ak_f + e * ak_s < KK);
-          const bool okb = (j0 + bi_f + e * bi_s < J) && (kbase + tl * kHK + bk_f + e * bk_s < KK);
-          ra[tl][e] = oka ? __ldg(pa + tl * a_step_t + e * a_step_e) : 0.f;
-          rb[tl][e] = okb ? __ldg(pb + tl * b_step_t + e * b_step_e) : 0.f;
-          rq[tl][e] = (oka && a_mode == 2) ? __ldg(pq + tl * q_step_t + e * q_step_e) : 0.f;
-        }
+      {
+        const int maj = b_maj + e * b_mstep;
+        const int gj = b_kc ? j0 + maj : j0 + b_min, gk = b_kc ? k0 + b_min : k0 + maj;
+        const int lim = b_kc ? KK - gk : J - gj;
+        const bool row_ok = b_kc ? (gj < J) : (gk < KK);
+        const int nv = row_ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : lim)) : 0;
+        const int64_t off = b_kc ? (int64_t)gj * b_ld + gk : (int64_t)gk * b_ld + gj;
+        rb[e] = head_ld4(bp + (nv ? off : 0), b_vec, nv);
+      }
     }
   };
-  float acc[4][4];
+
+  // six independent accumulator fragments (3 product terms x even / odd k step) keep the HMMA latency chains
+  // short; fragment layout c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+  float acc[6][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 6; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   float csum = 0.f;
   const bool want_colsum = pr.colsum != nullptr && j0 == 0;
 
-  for (int kbase = 0; kbase < KK; kbase += NT * kHK) {
-    fetch(kbase);
+  if (KK > 0) fetch(0);
+#pragma unroll 1
+  for (int k0 = 0; k0 < KK; k0 += kHC) {
+    // ---- transforms in registers, then stage
 #pragma unroll
-    for (int tl = 0; tl < NT; ++tl) {
-      if (kbase + tl * kHK >= KK) break;
+    for (int e = 0; e < kHNV; ++e) {
       if (a_mode == 1) {
-#pragma unroll
-        for (int e = 0; e < PER; ++e) ra[tl][e] = act_fwd(ACT, ra[tl][e]);
+        ra[e].x = act_fwd(ACT, ra[e].x); ra[e].y = act_fwd(ACT, ra[e].y); ra[e].z = act_fwd(ACT, ra[e].z); ra[e].w = act_fwd(ACT, ra[e].w);
       } else if (a_mode == 2) {
-#pragma unroll
-        for (int e = 0; e < PER; ++e) ra[tl][e] *= act_grad(ACT, rq[tl][e]);
+        ra[e].x *= act_grad(ACT, rq[e].x); ra[e].y *= act_grad(ACT, rq[e].y); ra[e].z *= act_grad(ACT, rq[e].z); ra[e].w *= act_grad(ACT, rq[e].w);
       }
       if (b_mode == 1) {
-#pragma unroll
-        for (int e = 0; e < PER; ++e) rb[tl][e] = act_fwd(ACT, rb[tl][e]);
+        rb[e].x = act_fwd(ACT, rb[e].x); rb[e].y = act_fwd(ACT, rb[e].y); rb[e].z = act_fwd(ACT, rb[e].z); rb[e].w = act_fwd(ACT, rb[e].w);
       }
-      if (tl > 0 || kbase > 0) __syncthreads();  // the previous tile has been consumed
+    }
+    if (k0 > 0) __syncthreads();  // the previous chunk has been consumed
 #pragma unroll
-      for (int e = 0; e < PER; ++e) {
-        a_sts[e * a_sstep] = ra[tl][e];
-        b_sts[e * b_sstep] = rb[tl][e];
-      }
-      __syncthreads();
+    for (int e = 0; e < kHNV; ++e) {
+      *reinterpret_cast<float4*>(As + (a_maj + e * a_mstep) * a_srow + a_min) = ra[e];
+      *reinterpret_cast<float4*>(Bs + (b_maj + e * b_mstep) * b_srow + b_min) = rb[e];
+    }
+    __syncthreads();
+    if (k0 + kHC < KK) fetch(k0 + kHC);  // in flight under the math below
+    const int kend = (KK - k0 < kHC) ? ((KK - k0 + 31) & ~31) : kHC;  // zero filled beyond KK
+    const float* ar = As + (wm + fg) * a_fi + ft * a_fk;
+    const float* br = Bs + (wn + fg) * b_fi + ft * b_fk;
+#pragma unroll 1
+    for (int k32 = 0; k32 < kend; k32 += 32) {
 #pragma unroll
-      for (int kk = 0; kk < kHK / 4; ++kk) {
-        const int k = grp * (kHK / 4) + kk;
-        const float4 a = *reinterpret_cast<const float4*>(&As[k][tyq * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][txq * 4]);
-        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-        acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
-        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-        acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
-        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
-        acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
-        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
-        acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+      for (int h = 0; h < 4; ++h) {
+        const int k8 = k32 + 8 * h;
+        const float av[4] = {ar[k8 * a_fk], ar[k8 * a_fk + 8 * a_fi], ar[(k8 + 4) * a_fk], ar[(k8 + 4) * a_fk + 8 * a_fi]};
+        const float bv[2] = {br[k8 * b_fk], br[(k8 + 4) * b_fk]};
+        uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) split_tf32(bv[i], bh[i], bl[i]);
+        mma_tf32(acc[3 * (h & 1) + 0], al, bh);
+        mma_tf32(acc[3 * (h & 1) + 1], ah, bl);
+        mma_tf32(acc[3 * (h & 1) + 2], ah, bh);
       }
-      if (want_colsum && tid < kHT) {
-        if (pr.colsum_w) {
-          const int kb = kbase + tl * kHK;
-#pragma unroll 16
-          for (int k = 0; k < kHK; ++k) csum += As[k][tid] * (kb + k < KK ? __ldg(pr.colsum_w + kb + k) : 0.f);
-        } else {
-#pragma unroll 16
-          for (int k = 0; k < kHK; ++k) csum += As[k][tid];
-        }
+    }
+    if (want_colsum && tid < kHT) {
+      const float* ac = As + tid * a_fi;
+      if (pr.colsum_w) {
+#pragma unroll 4
+        for (int k = 0; k < kend; ++k) csum += ac[k * a_fk] * (k0 + k < KK ? __ldg(pr.colsum_w + k0 + k) : 0.f);
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < kend; ++k) csum += ac[k * a_fk];
       }
     }
   }
-  __syncthreads();
 
-  // ---- sum the four k-group partials (reusing the staging memory: 4 x 32 x 33 floats) and store
-  float (*red)[kHT][kHT + 1] = reinterpret_cast<float (*)[kHT][kHT + 1]>(smem_f);
+  // ---- store: each warp owns its 16 x 8 outputs
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) red[grp][tyq * 4 + a][txq * 4 + b] = acc[a][b];
-  __syncthreads();
-  {
-    const int li = tid >> 3, lj = (tid & 7) * 4;
-    const int i = i0 + li;
-    if (i < I) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int j = j0 + lj + b;
-        if (j >= J) continue;
-        float v = (red[0][li][lj + b] + red[1][li][lj + b]) + (red[2][li][lj + b] + red[3][li][lj + b]);
-        if (pr.row_scale) v *= __ldg(pr.row_scale + i);
-        if (pr.bias) v += (pr.bias_scale ? __ldg(pr.bias_scale + i) : 1.f) * __ldg(pr.bias + j);
-        pr.C[(int64_t)i * pr.ldc + j] = v;
-      }
+  for (int e = 0; e < 4; ++e) {
+    const int i = i0 + wm + fg + (e >> 1) * 8, j = j0 + wn + 2 * ft + (e & 1);
+    if (i < I && j < J) {
+      float v = ((acc[0][e] + acc[3][e]) + (acc[1][e] + acc[4][e])) + (acc[2][e] + acc[5][e]);  // small terms first
+      if (pr.row_scale) v *= __ldg(pr.row_scale + i);
+      if (pr.bias) v += (pr.bias_scale ? __ldg(pr.bias_scale + i) : 1.f) * __ldg(pr.bias + j);
+      pr.C[(int64_t)i * pr.ldc + j] = v;
     }
   }
   if (want_colsum && tid < kHT && i0 + tid < I) pr.colsum[i0 + tid] = csum;
@@ -191,7 +212,8 @@ void launch_head_tiles(const HeadTileParams& hp, int tiles, cudaStream_t st) {
     case PCC_ACT_SILU: kern = head_tile_kernel<PCC_ACT_SILU>; break;
     default: break;
   }
-  PCC_K(kern)<<<tiles, kHThreads, 0, st>>>(hp);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+  PCC_K(kern)<<<tiles, kHThreads, kHeadSmem, st>>>(hp);
 }
 
 static int check_head(const pcc_head_desc* d, const char* where) {
