@@ -61,7 +61,7 @@ constexpr int kHSk = kHC + 4;       // row of an [i][kk] staged operand
 constexpr int kHSi = kHT + 8;       // row of a [kk][i] staged operand
 constexpr int kHOp = (kHT * kHSk > kHC * kHSi) ? kHT * kHSk : kHC * kHSi;  // floats per staged operand
 constexpr int kHNV = kHT * kHC / 4 / kHThreads;  // float4 per thread, operand and chunk (8)
-constexpr int kHeadSmem = 2 * kHOp * (int)sizeof(float);
+constexpr int kHeadSmem = 3 * kHOp * (int)sizeof(float);  // A, B, act' argument
 
 template <int ACT>
 __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTileParams hp) {
@@ -95,31 +95,65 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
   // fragment strides: element (i, k) of a staged operand
   const int a_fi = a_kc ? kHSk : 1, a_fk = a_kc ? 1 : kHSi, b_fi = b_kc ? kHSk : 1, b_fk = b_kc ? 1 : kHSi;
 
-  float4 ra[kHNV], rq[kHNV], rb[kHNV];
-  auto fetch = [&](int k0) {
-#pragma unroll
+  // staging: the operand (and act' argument) float4s go global -> shared with 16-byte cp.async from ROLLED loops
+  // (all of a chunk's loads in flight, no registers held, little code: this kernel runs once per CTA and every
+  // instruction is an instruction-cache miss); operands that are not 16-byte loadable take a scalar path
+  float* Qs = smem_f + 2 * kHOp;
+  auto stage_operand = [&](const float* __restrict__ gp, float* sdst, bool kc, bool vec, int64_t ld, int maj0, int mstep,
+                           int mn, int srow, int lim_row, int lim_vec, int row0, int vec0) {
+    // row0 / vec0: global index of the first row / first vector component of this thread's float4 0
+#pragma unroll 1
     for (int e = 0; e < kHNV; ++e) {
-      {
-        const int maj = a_maj + e * a_mstep;
-        const int gi = a_kc ? i0 + maj : i0 + a_min, gk = a_kc ? k0 + a_min : k0 + maj;   // first component
-        const int lim = a_kc ? KK - gk : I - gi;                                            // along the vector
-        const bool row_ok = a_kc ? (gi < I) : (gk < KK);
-        const int nv = row_ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : lim)) : 0;
-        const int64_t off = a_kc ? (int64_t)gi * a_ld + gk : (int64_t)gk * a_ld + gi;
-        ra[e] = head_ld4(ap + (nv ? off : 0), a_vec, nv);
-        if (a_mode == 2) {
-          const int64_t qoff = a_kc ? (int64_t)gi * q_ld + gk : (int64_t)gk * q_ld + gi;
-          rq[e] = head_ld4(aq + (nv ? qoff : 0), q_vec, nv);
-        }
+      const int maj = maj0 + e * mstep;
+      const int grow = row0 + e * mstep, gvec = vec0;
+      const int lim = lim_vec - gvec;
+      const int nv = (grow < lim_row) ? (lim > 4 ? 4 : (lim < 0 ? 0 : lim)) : 0;
+      float* d = sdst + maj * srow + mn;
+      const float* g = gp + (int64_t)grow * ld + gvec;
+      if (vec && nv == 4) {
+        const uint32_t da = (uint32_t)__cvta_generic_to_shared(d);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(g) : "memory");
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nv > 0) v.x = __ldg(g);
+        if (nv > 1) v.y = __ldg(g + 1);
+        if (nv > 2) v.z = __ldg(g + 2);
+        if (nv > 3) v.w = __ldg(g + 3);
+        *reinterpret_cast<float4*>(d) = v;
       }
-      {
-        const int maj = b_maj + e * b_mstep;
-        const int gj = b_kc ? j0 + maj : j0 + b_min, gk = b_kc ? k0 + b_min : k0 + maj;
-        const int lim = b_kc ? KK - gk : J - gj;
-        const bool row_ok = b_kc ? (gj < J) : (gk < KK);
-        const int nv = row_ok ? (lim > 4 ? 4 : (lim < 0 ? 0 : lim)) : 0;
-        const int64_t off = b_kc ? (int64_t)gj * b_ld + gk : (int64_t)gk * b_ld + gj;
-        rb[e] = head_ld4(bp + (nv ? off : 0), b_vec, nv);
+    }
+  };
+  auto fetch = [&](int k0) {
+    // kk-contiguous: rows = i (limit I / J), vector along kk (limit KK); i-contiguous: rows = kk, vector along i
+    stage_operand(ap, As, a_kc, a_vec, a_ld, a_maj, a_mstep, a_min, a_srow, a_kc ? I : KK, a_kc ? KK : I,
+                  a_kc ? i0 + a_maj : k0 + a_maj, a_kc ? k0 + a_min : i0 + a_min);
+    if (a_mode == 2)
+      stage_operand(aq, Qs, a_kc, q_vec, q_ld, a_maj, a_mstep, a_min, a_srow, a_kc ? I : KK, a_kc ? KK : I,
+                    a_kc ? i0 + a_maj : k0 + a_maj, a_kc ? k0 + a_min : i0 + a_min);
+    stage_operand(bp, Bs, b_kc, b_vec, b_ld, b_maj, b_mstep, b_min, b_srow, b_kc ? J : KK, b_kc ? KK : J,
+                  b_kc ? j0 + b_maj : k0 + b_maj, b_kc ? k0 + b_min : j0 + b_min);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto transform = [&]() {  // in place, on the float4s this thread staged
+    if (a_mode == 0 && b_mode == 0) return;
+#pragma unroll 1
+    for (int e = 0; e < kHNV; ++e) {
+      float4* pa = reinterpret_cast<float4*>(As + (a_maj + e * a_mstep) * a_srow + a_min);
+      if (a_mode == 1) {
+        float4 v = *pa;
+        v.x = act_fwd(ACT, v.x); v.y = act_fwd(ACT, v.y); v.z = act_fwd(ACT, v.z); v.w = act_fwd(ACT, v.w);
+        *pa = v;
+      } else if (a_mode == 2) {
+        float4 v = *pa;
+        const float4 q = *reinterpret_cast<const float4*>(Qs + (a_maj + e * a_mstep) * a_srow + a_min);
+        v.x *= act_grad(ACT, q.x); v.y *= act_grad(ACT, q.y); v.z *= act_grad(ACT, q.z); v.w *= act_grad(ACT, q.w);
+        *pa = v;
+      }
+      if (b_mode == 1) {
+        float4* pb = reinterpret_cast<float4*>(Bs + (b_maj + e * b_mstep) * b_srow + b_min);
+        float4 v = *pb;
+        v.x = act_fwd(ACT, v.x); v.y = act_fwd(ACT, v.y); v.z = act_fwd(ACT, v.z); v.w = act_fwd(ACT, v.w);
+        *pb = v;
       }
     }
   };
@@ -134,29 +168,13 @@ __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTilePara
   float csum = 0.f;
   const bool want_colsum = pr.colsum != nullptr && j0 == 0;
 
-  if (KK > 0) fetch(0);
 #pragma unroll 1
   for (int k0 = 0; k0 < KK; k0 += kHC) {
-    // ---- transforms in registers, then stage
-#pragma unroll
-    for (int e = 0; e < kHNV; ++e) {
-      if (a_mode == 1) {
-        ra[e].x = act_fwd(ACT, ra[e].x); ra[e].y = act_fwd(ACT, ra[e].y); ra[e].z = act_fwd(ACT, ra[e].z); ra[e].w = act_fwd(ACT, ra[e].w);
-      } else if (a_mode == 2) {
-        ra[e].x *= act_grad(ACT, rq[e].x); ra[e].y *= act_grad(ACT, rq[e].y); ra[e].z *= act_grad(ACT, rq[e].z); ra[e].w *= act_grad(ACT, rq[e].w);
-      }
-      if (b_mode == 1) {
-        rb[e].x = act_fwd(ACT, rb[e].x); rb[e].y = act_fwd(ACT, rb[e].y); rb[e].z = act_fwd(ACT, rb[e].z); rb[e].w = act_fwd(ACT, rb[e].w);
-      }
-    }
     if (k0 > 0) __syncthreads();  // the previous chunk has been consumed
-#pragma unroll
-    for (int e = 0; e < kHNV; ++e) {
-      *reinterpret_cast<float4*>(As + (a_maj + e * a_mstep) * a_srow + a_min) = ra[e];
-      *reinterpret_cast<float4*>(Bs + (b_maj + e * b_mstep) * b_srow + b_min) = rb[e];
-    }
+    fetch(k0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    transform();
     __syncthreads();
-    if (k0 + kHC < KK) fetch(k0 + kHC);  // in flight under the math below
     const int kend = (KK - k0 < kHC) ? ((KK - k0 + 31) & ~31) : kHC;  // zero filled beyond KK
     const float* ar = As + (wm + fg) * a_fi + ft * a_fk;
     const float* br = Bs + (wn + fg) * b_fi + ft * b_fk;
