@@ -7,14 +7,18 @@ def launches(path, out):
     data = rows[1:]
     names = [r[ci['Kernel Name']] for r in data]
     idxs = [i for i, n in enumerate(names) if 'phi_pool_fwd' in n]
-    # last full step: from the segment-offset kernels preceding the last forward kernel to the end
-    start = idxs[-1]
+    # one full step in the middle of the run: from the kernels that follow a wgrad_reduce up to the next one
+    mid = idxs[len(idxs) // 2]
+    start = mid
     while start > 0 and 'wgrad_reduce' not in names[start - 1]:
         start -= 1
-    step = data[start:]
+    end = mid
+    while end < len(names) - 1 and 'wgrad_reduce' not in names[end]:
+        end += 1
+    step = data[start:end + 1]
     tot = sum(float(r[ci['Metric Value']]) for r in step)
     with open(out, 'w') as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none: launches of ONE eager train step\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 2 --warmup 3: launches of ONE train step\n")
         f.write(f"# (cold-cache, serialised: compare shares, not absolutes).  total {tot/1e3:.1f} us, {len(step)} launches\n")
         f.write("#   ns      share  kernel\n")
         for r in step:
@@ -49,7 +53,7 @@ def full(rep, out):
             f.write("=====\n")
             for i in idx:
                 f.write(f"{hdr[i]:80s} {units[i]:14s} {r[i][:70]}\n")
-            name = r[ki].split('(')[0].split('<')[0].replace('void ', '').replace('pcc::', '')
+            name = r[ki].split('(')[0].split('<')[0].replace('void ', '').replace('pcc::', '').replace('phi_pool_fwd_pair_kernel', 'phi_pool_fwd_kernel')
             byts = float(r[ri].replace(',', '')) * scale.get(units[ri], 1.0) + float(r[wi].replace(',', '')) * scale.get(units[wi], 1.0)
             traffic.setdefault(name, byts)   # first launch of each kernel
     import json
