@@ -31,6 +31,9 @@ struct PeerParams {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -58,8 +61,10 @@ __global__ void __launch_bounds__(kPeerThreads, 1) peer_allreduce_kernel(const P
     __threadfence_system();
     const unsigned int arrived = atomicAdd(p.counters + 1, 1u) + 1;
     if (arrived == gridDim.x * seq) {  // the arrival counter is never reset: seq-th multiple of the grid size
+      // ONE system-scope fence, then relaxed flag stores: a release per peer serialised `world` fences (43 us at 8
+      // ranks against 23 us at 2)
       __threadfence_system();
-      for (int r = 0; r < p.world; ++r) st_release_sys(reinterpret_cast<unsigned int*>(p.stage[r]) + p.rank, seq);
+      for (int r = 0; r < p.world; ++r) st_relaxed_sys(reinterpret_cast<unsigned int*>(p.stage[r]) + p.rank, seq);
     }
   }
   if (threadIdx.x < p.world) {
