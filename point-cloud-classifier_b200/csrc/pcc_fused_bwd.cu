@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t phA = 0, phB = 0, wf_phase = 0;
     const int d = p.d;
-    float xcur[kK0], xnext[kK0];
+    float xcur[kK0] = {}, xnext[kK0];
     auto load_x = [&](int64_t tile) {
       const int64_t row = tile * kTileM + r;
 #pragma unroll

@@ -244,9 +244,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
                         make_smem_desc_sw128_k(i_base + (ks >> 2) * (N * 128) + (ks & 3) * 32), idesc, ks != 0);
           umma_commit(&acc_f[slot]);
           trace_ev(p.trace, 1, tn, 142);
-          continue;
         }
-        for (int s = 0; s < NSLAB; ++s) {
+        for (int s = 0; !poolh && s < NSLAB; ++s) {
           mbar_wait(&slab_ready[s], sl_phase);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -263,9 +262,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
           umma_commit(&empty[stage]);
           if (++stage == (uint32_t)ringn) { stage = 0; phase ^= 1; }
         }
-        sl_phase ^= 1;
-        umma_commit(&acc_f[slot]);
-        trace_ev(p.trace, 1, tn, 142);
+        if (!poolh) {
+          sl_phase ^= 1;
+          umma_commit(&acc_f[slot]);
+          trace_ev(p.trace, 1, tn, 142);
+        }
       }
     }
   } else if (warp < kFwdHidWarps) {
