@@ -59,6 +59,11 @@ CASES = [
     ("gelu", "max", True, 128, 2, 7, [700, 5, 250]),
     ("silu", "sum", False, 256, 2, 6, [300, 41, 129, 1]),
     ("silu", "mean", False, 128, 1, 1, [64, 64]),
+    # H = 256 + max pooling = the CTA-pair forward kernel: other activations, ResidualBlock, one hidden layer
+    # (alternating final accumulators), d > 3 (two-quad layer-0 table), odd tile counts
+    ("gelu", "max", True, 256, 2, 3, [300, 129, 1, 700, 64]),
+    ("silu", "max", False, 256, 1, 6, [128, 128, 128, 5, 250]),
+    ("relu", "max", False, 256, 1, 3, [1000, 24]),
 ]
 
 
