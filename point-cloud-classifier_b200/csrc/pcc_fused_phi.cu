@@ -710,11 +710,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
     uint32_t acch_phase = 0;
     const bool tr0 = (threadIdx.x == 0 && rank == 0);
     for (int64_t tp = pair0; tp < ntp; tp += npairs, ++nt) {
-      if (nt >= 1) {  // the image is free once the previous final layer has completed (multicast commit)
-        const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
-        const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
-        mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
-      }
       if (tr0) trace_ev(p.trace, 0, tn, 0);
       const float* xT = xS + (nt & 1) * (kTileM * XW);
       load_x(2 * (tp + npairs) + rank);
@@ -742,17 +737,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
             }
           }
         }
+        uint32_t o[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t o[4];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int pi = 0; pi < 4; ++pi) {
             float lo, hi;
             f32x2_unpack(z[i][pi], lo, hi);
-            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
+            o[i][pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
           }
-          *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, sidx * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+        // The image is free once the previous final layer has completed (multicast commit).  The first slab of the
+        // new tile has been computed in registers by now: its math hides under the tail of that final layer.
+        if (sidx == 0 && nt >= 1) {
+          const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
+          const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
+          mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, sidx * 64 + cg * 8)) =
+              make_uint4(o[i][0], o[i][1], o[i][2], o[i][3]);
         fence_proxy_async();
         mbar_arrive_warp_remote(&slab_ready[sidx], 0);
       }
