@@ -24,6 +24,40 @@ __global__ void histogram_kernel(const int64_t* __restrict__ idx, int64_t n, int
   if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&counts[v], (unsigned long long)__popc(mask));
 }
 
+// histogram + exclusive scan in ONE launch: every block adds its warp-aggregated counts into offsets[0..B) (zeroed
+// by a memset node), takes a ticket in offsets[B], and the last block to finish scans the counts in place
+// (offsets[b] = number of rows with idx < b, offsets[B] = n) — the reference's bincount + split bookkeeping
+// (/root/reference/models/deep_sets.py:91-92) without a host sync and without three dependent launches.
+__global__ void __launch_bounds__(1024) segment_offsets_fused_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t B,
+                                                                     int64_t* __restrict__ offsets) {
+  __shared__ bool s_last;
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(offsets);
+  for (int64_t i0 = (int64_t)blockIdx.x * 1024; i0 < n; i0 += (int64_t)gridDim.x * 1024) {
+    const int64_t i = i0 + threadIdx.x;
+    const int64_t v = (i < n) ? idx[i] : -1;
+    const bool valid = (v >= 0 && v < B);
+    const unsigned mask = __match_any_sync(0xffffffffu, valid ? v : -1 - (int64_t)(threadIdx.x & 31));
+    const int leader = __ffs(mask) - 1;
+    if (valid && (int)(threadIdx.x & 31) == leader) atomicAdd(&counts[v], (unsigned long long)__popc(mask));
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counts[B], 1ull) == (unsigned long long)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  long long carry = 0;
+  for (int64_t base = 0; base < B; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const long long v = (i < B) ? (long long)*reinterpret_cast<volatile unsigned long long*>(&counts[i]) : 0;
+    long long tot;
+    const long long ex = block_exclusive_scan_1024(v, &tot);
+    if (i < B) offsets[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) offsets[B] = carry;
+}
+
 __global__ void index_max_kernel(const int64_t* __restrict__ idx, int64_t n, long long* __restrict__ out) {
   long long m = LLONG_MIN;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -205,10 +239,11 @@ extern "C" int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int
   PCC_REQUIRE(n >= 0 && B >= 0, "negative size");
   PCC_REQUIRE(B + 1 <= (int64_t)PCC_SCAN_SINGLE_MAX, "too many segments for the single-block scan");
   cudaStream_t st = (cudaStream_t)stream;
-  PCC_K(zero_i64_kernel)<<<(unsigned)cdiv(B + 1, 256), 256, 0, st>>>(offsets, B + 1);
-  if (n > 0)
-    PCC_K(histogram_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(idx, n, B, (unsigned long long*)offsets);
-  PCC_K(exclusive_scan_single_block_kernel)<<<1, 1024, 0, st>>>(offsets, B + 1);
+  PCC_CUDA(cudaMemsetAsync(offsets, 0, (size_t)(B + 1) * sizeof(int64_t), st));
+  int64_t blocks = cdiv(n, 1024);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 592) blocks = 592;
+  PCC_K(segment_offsets_fused_kernel)<<<(unsigned)blocks, 1024, 0, st>>>(idx, n, B, offsets);
   return check_launch(__func__);
 }
 
