@@ -136,6 +136,15 @@ int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offsets, int64_
             float* d2, int device, void* stream);
 /* edge_index[2,n*k] from nbr (row0 = neighbour, row1 = centre); all slots must be valid */
 int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge_index, int device, void* stream);
+/* Gaussian edge weights of the reference's graph dataset (/root/reference/utils/data.py:835-845,
+ * Step2PointGraph._compute_weights, called once per graph at :814) for a batch of graphs on device:
+ * d_e = ||pos[src_e] - pos[dst_e]|| (fp32), sigma_g = median over the graph's edges + eps (exact order statistics,
+ * mean of the two middle ones for an even count, like np.median), w_e = exp(-d_e^2 / (2 sigma_g^2)).
+ * pos: xyz at pos[i * pos_stride + 0..2]; edges [2,E] (node-offset, graphs back to back, utils/data.py:1228-1261);
+ * edge_offsets [G+1]: first edge of every graph; sigma_out [G] optional; ws: pcc_edge_weights_workspace_bytes. */
+int64_t pcc_edge_weights_workspace_bytes(int64_t E, int64_t G);
+int pcc_edge_weights(const float* pos, int64_t pos_stride, const int64_t* edges, int64_t E, const int64_t* edge_offsets,
+                     int64_t G, float eps, float* weights, float* sigma_out, void* ws, int device, void* stream);
 
 /* ---- fused DeepSets phi + pool, tcgen05 / TMEM path (bf16 operands, fp32 accumulate).
  *      Replaces deep_sets.py:89-106 and its autograd in two launches; per-point

@@ -342,3 +342,108 @@ extern "C" int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge
   PCC_K(knn_edges_kernel)<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(nbr, total, k, edge_index);
   return check_launch(__func__);
 }
+
+// ====================================================================== Gaussian edge weights
+//   reference: /root/reference/utils/data.py:835-845 (Step2PointGraph._compute_weights), one call per graph (:814):
+//     dists = ||pos[src] - pos[dst]||  (float32),  sigma = median(dists) + eps,  w = exp(-dists^2 / (2 sigma^2)).
+//   Device version for batched graphs (edges of graph g = [eoff[g], eoff[g+1])): distances once, an EXACT per-graph
+//   median by radix selection on the float bit patterns (distances are >= 0, so the uint32 order is the float
+//   order; np.median = mean of the two middle order statistics for an even count), then the weights.  All
+//   arithmetic in fp32 with round-to-nearest and no FMA contraction, like numpy.
+namespace pcc {
+
+__global__ void edge_dist_kernel(const float* __restrict__ pos, int64_t pos_stride, const int64_t* __restrict__ edges,
+                                 int64_t E, float* __restrict__ dist) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t s = edges[e], t = edges[E + e];
+  const float dx = __fsub_rn(pos[s * pos_stride + 0], pos[t * pos_stride + 0]);
+  const float dy = __fsub_rn(pos[s * pos_stride + 1], pos[t * pos_stride + 1]);
+  const float dz = __fsub_rn(pos[s * pos_stride + 2], pos[t * pos_stride + 2]);
+  const float ss = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  dist[e] = __fsqrt_rn(ss);
+}
+
+// order statistic `rank` (0-based) of d[0..m): 4 passes of 8-bit radix selection, one CTA per graph
+__device__ uint32_t radix_select_u32(const float* __restrict__ d, int64_t m, int64_t rank, unsigned int* hist /*[256]*/) {
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint32_t u = __float_as_uint(d[i]);
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    // every thread walks the 256 bins (cheap, keeps the result uniform without another broadcast)
+    int64_t cum = 0;
+    uint32_t bin = 0;
+    for (int b = 0; b < 256; ++b) {
+      const int64_t c = hist[b];
+      if (cum + c > rank) { bin = (uint32_t)b; break; }
+      cum += c;
+    }
+    rank -= cum;
+    prefix |= bin << shift;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(1024) edge_sigma_kernel(const float* __restrict__ dist, const int64_t* __restrict__ eoff,
+                                                          float eps, float* __restrict__ sigma) {
+  __shared__ unsigned int hist[256];
+  const int64_t g = blockIdx.x;
+  const int64_t lo = eoff[g], m = eoff[g + 1] - lo;
+  if (m <= 0) {
+    if (threadIdx.x == 0) sigma[g] = __int_as_float(0x7fc00000);  // np.median of an empty array: nan
+    return;
+  }
+  const float* d = dist + lo;
+  float med;
+  if (m & 1) {
+    med = __uint_as_float(radix_select_u32(d, m, m / 2, hist));
+  } else {
+    const float a = __uint_as_float(radix_select_u32(d, m, m / 2 - 1, hist));
+    const float b = __uint_as_float(radix_select_u32(d, m, m / 2, hist));
+    med = __fmul_rn(__fadd_rn(a, b), 0.5f);  // np.mean of the two middle elements, float32
+  }
+  if (threadIdx.x == 0) sigma[g] = __fadd_rn(med, eps);
+}
+
+__global__ void edge_weight_kernel(const float* __restrict__ dist, const int64_t* __restrict__ eoff, int64_t G, int64_t E,
+                                   const float* __restrict__ sigma, float* __restrict__ w) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t lo = 0, hi = G;  // graph of edge e: last g with eoff[g] <= e
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (eoff[mid] <= e) lo = mid; else hi = mid;
+  }
+  const float s = sigma[lo], d = dist[e];
+  const float den = __fmul_rn(2.f, __fmul_rn(s, s));
+  w[e] = expf(-__fdiv_rn(__fmul_rn(d, d), den));
+}
+
+}  // namespace pcc
+
+extern "C" int64_t pcc_edge_weights_workspace_bytes(int64_t E, int64_t G) {
+  return ((E > 0 ? E : 1) * 4 + 255) / 256 * 256 + ((G > 0 ? G : 1) * 4 + 255) / 256 * 256;
+}
+
+extern "C" int pcc_edge_weights(const float* pos, int64_t pos_stride, const int64_t* edges, int64_t E,
+                                const int64_t* edge_offsets, int64_t G, float eps, float* weights, float* sigma_out,
+                                void* ws, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(E >= 0 && G >= 0 && pos_stride >= 3, "bad sizes");
+  if (E == 0 || G == 0) return 0;
+  PCC_REQUIRE(ws != nullptr, "workspace required (pcc_edge_weights_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dist = (float*)ws;
+  float* sigma = sigma_out ? sigma_out : (float*)((uint8_t*)ws + (E * 4 + 255) / 256 * 256);
+  PCC_K(edge_dist_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(pos, pos_stride, edges, E, dist);
+  PCC_K(edge_sigma_kernel)<<<(unsigned)G, 1024, 0, st>>>(dist, edge_offsets, eps, sigma);
+  PCC_K(edge_weight_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(dist, edge_offsets, G, E, sigma, weights);
+  return check_launch(__func__);
+}

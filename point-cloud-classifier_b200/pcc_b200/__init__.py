@@ -4,11 +4,11 @@ Host-side mirror of the reference's model interface (models/deep_sets.py,
 models/graph_net.py) over the C-ABI library lib/libpcc.so.  See DESIGN.md.
 """
 from .deep_sets import DeepSets, ResidualBlock
-from .graph_net import GraphNet, GraphConv, knn_graph
+from .graph_net import GraphNet, GraphConv, knn_graph, gaussian_edge_weights
 from . import functional
 from . import _lib
 
-__all__ = ["DeepSets", "ResidualBlock", "GraphNet", "GraphConv", "knn_graph", "functional"]
+__all__ = ["DeepSets", "ResidualBlock", "GraphNet", "GraphConv", "knn_graph", "gaussian_edge_weights", "functional"]
 
 import os as _os
 

@@ -55,6 +55,8 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_edge_weights_workspace_bytes": [_i64, _i64],
+    "pcc_edge_weights": [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _vp, _vp, _vp, _i32, _vp],
     "pcc_mlp_head_supported": [C.POINTER(HeadDesc)],
     "pcc_mlp_head_fwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _i64, _i32, _vp],
     "pcc_mlp_head_workspace_bytes": [C.POINTER(HeadDesc), _i64],
@@ -79,7 +81,8 @@ _SIGS = {
     "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
 _RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64,
-             "pcc_phi_packed_bytes": _i64, "pcc_mlp_head_workspace_bytes": _i64}
+             "pcc_phi_packed_bytes": _i64, "pcc_mlp_head_workspace_bytes": _i64,
+             "pcc_edge_weights_workspace_bytes": _i64}
 EXPORTS = tuple(_SIGS) + ("pcc_last_error",)
 
 _lib = None

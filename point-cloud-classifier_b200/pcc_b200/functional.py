@@ -317,6 +317,23 @@ def knn_edges(nbr: torch.Tensor) -> torch.Tensor:
     return ei
 
 
+def edge_weights(pos: torch.Tensor, edges: torch.Tensor, edge_offsets: torch.Tensor, eps: float = 1e-6,
+                 return_sigma: bool = False):
+    """Gaussian edge weights of the reference's graph dataset (utils/data.py:835-845) for batched graphs on device:
+    one sigma = median edge length + eps per graph (edges of graph g = [edge_offsets[g], edge_offsets[g+1]))."""
+    pos = pos if (pos.dtype == torch.float32 and pos.stride(1) == 1) else pos.float().contiguous()
+    edges = L.i64c(edges)
+    edge_offsets = L.i64c(edge_offsets)
+    dev, st = _ctx(pos, edges, edge_offsets)
+    E, G = edges.shape[1], edge_offsets.numel() - 1
+    w = torch.empty(E, dtype=torch.float32, device=pos.device)
+    sigma = torch.empty(max(G, 1), dtype=torch.float32, device=pos.device)
+    ws = torch.empty(max(int(call("pcc_edge_weights_workspace_bytes", E, G)), 16), dtype=torch.uint8, device=pos.device)
+    call("pcc_edge_weights", ptr(pos), pos.stride(0), ptr(edges), E, ptr(edge_offsets), G, float(eps), ptr(w), ptr(sigma),
+         ptr(ws), dev, st)
+    return (w, sigma[:G]) if return_sigma else w
+
+
 # ------------------------------------------------------------------ fused loss, row gather
 class BCEWithLogitsFn(torch.autograd.Function):
     """nn.BCEWithLogitsLoss(reduction='mean') (wrapper.py:38) with its gradient produced in the same pass."""

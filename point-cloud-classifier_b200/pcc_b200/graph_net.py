@@ -123,3 +123,16 @@ def knn_graph(features: torch.Tensor, membership: torch.Tensor, k: int = 20, pos
     pos = features[:, pos_cols[0]:pos_cols[1]]
     nbr, d2 = PF.knn(pos, offsets, k)
     return PF.knn_edges(nbr), d2
+
+
+def gaussian_edge_weights(features: torch.Tensor, edges: torch.Tensor, membership: torch.Tensor,
+                          num_graphs: Optional[int] = None, pos_cols=(1, 4), eps: float = 1e-6) -> torch.Tensor:
+    """Edge weights of the reference's graph dataset (utils/data.py:835-845, `use_weights: true`) computed on the
+    device for a collated batch (utils/data.py:1228-1261: graphs back to back, node-offset edges): one
+    sigma = median edge length + eps per graph.  The edges of a graph must be contiguous (what the collate and
+    `knn_graph` produce)."""
+    if num_graphs is None:
+        num_graphs = PF.index_max(membership) + 1
+    edge_graph = membership[edges[1]].contiguous()            # graph of every edge (by its centre node)
+    edge_offsets = PF.segment_offsets(edge_graph, num_graphs)
+    return PF.edge_weights(features[:, pos_cols[0]:pos_cols[1]], edges, edge_offsets, eps)

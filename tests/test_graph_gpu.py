@@ -149,3 +149,36 @@ def test_graphnet_tf32_dense_mode():
     assert rel_err(logits.detach().cpu(), ref_logits) < 2e-2
     for k, ref in ref_grads.items():
         assert rel_l2(dict(m.named_parameters())[k].grad, ref) < 5e-2, k
+
+
+@pytest.mark.gpu
+def test_gaussian_edge_weights_match_reference_golden_and_oracle():
+    """pcc_edge_weights (utils/data.py:835-845 on device, batched): edge lengths and the per-graph median sigma are
+    bit-exact against the oracle (which is pinned to the reference's own function by tests/golden/edge_weights.npz);
+    the weights differ only by the exp implementation (a few ulp: rtol 2e-6)."""
+    import os
+    from oracle import edge_weights_oracle as EO
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edge_weights.npz"))
+    feats, edges, eoff, gold, node0 = [], [], [0], [], 0
+    for gi in range(int(z["count"])):
+        f, e = z[f"features_{gi}"], z[f"edges_{gi}"]
+        feats.append(f); edges.append(e + node0); gold.append(z[f"weights_{gi}"])
+        node0 += f.shape[0]; eoff.append(eoff[-1] + e.shape[1])
+    feats, edges, gold = np.concatenate(feats), np.concatenate(edges, axis=1), np.concatenate(gold)
+    eoff = np.asarray(eoff, dtype=np.int64)
+    ref_w, ref_sigma, ref_d = EO.compute_weights_batched(feats, edges, eoff)
+    assert np.array_equal(ref_w, gold)                      # batched oracle == reference goldens
+    f_gpu = torch.from_numpy(feats).cuda()
+    w, sigma = PF.edge_weights(f_gpu[:, 1:4], torch.from_numpy(edges).cuda(), torch.from_numpy(eoff).cuda(),
+                               return_sigma=True)
+    assert np.array_equal(sigma.cpu().numpy(), ref_sigma)   # exact medians (odd and even counts)
+    np.testing.assert_allclose(w.cpu().numpy(), gold, rtol=2e-6, atol=1e-30)
+    # through the module-level helper on a kNN batch (membership -> per-graph edge ranges), incl. an empty graph id
+    sizes = [300, 77, 512]
+    fb, memb, off = _clouds(sizes, seed=41, F=4)
+    nbr, _ = KO.knn_neighbours(fb[:, 1:4].numpy(), off, 8)
+    e2 = KO.knn_edges(nbr)
+    eo2 = np.asarray([0] + list(np.cumsum([s * 8 for s in sizes])), dtype=np.int64)
+    w2_ref, _, _ = EO.compute_weights_batched(fb.numpy(), e2, eo2)
+    w2 = pcc_b200.gaussian_edge_weights(fb.cuda(), torch.from_numpy(e2).cuda(), memb.cuda())
+    np.testing.assert_allclose(w2.cpu().numpy(), w2_ref, rtol=2e-6, atol=1e-30)
