@@ -146,6 +146,14 @@ int64_t pcc_edge_weights_workspace_bytes(int64_t E, int64_t G);
 int pcc_edge_weights(const float* pos, int64_t pos_stride, const int64_t* edges, int64_t E, const int64_t* edge_offsets,
                      int64_t G, float eps, float* weights, float* sigma_out, void* ws, int device, void* stream);
 
+/* ---- device-side collate helpers.  pcc_expand_segments: idx[i] = segment of row i from
+ *      offsets[B+1] — the `cat(full((n_i,), i))` of /root/reference/utils/data.py:658-659 (_collate_sparse) and
+ *      :1245 (_graph_collate membership) without the per-sample loop.  pcc_offset_edges: per-graph local edge lists
+ *      stored back to back -> batched edge_index (edges_i + node offset, utils/data.py:1240). */
+int pcc_expand_segments(const int64_t* offsets, int64_t B, int64_t n, int64_t* idx, int device, void* stream);
+int pcc_offset_edges(const int64_t* edges, int64_t E, const int64_t* edge_offsets, const int64_t* node_offsets, int64_t G,
+                     int64_t* out, int device, void* stream);
+
 /* ---- fused DeepSets phi + pool, tcgen05 / TMEM path (bf16 operands, fp32 accumulate).
  *      Replaces deep_sets.py:89-106 and its autograd in two launches; per-point
  *      activations never reach HBM.  See DESIGN.md §3 for the layer descriptor. */

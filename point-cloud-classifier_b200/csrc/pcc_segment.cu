@@ -280,3 +280,56 @@ extern "C" int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets
                                                                                      pooling, dx);
   return check_launch(__func__);
 }
+
+// ====================================================================== device-side collate helpers
+//   reference: /root/reference/utils/data.py:651-663 (_collate_sparse: idx = cat(full((n_i,), i))) and :1228-1261
+//   (_graph_collate: membership = cat(full((n_i,), i)), edges_i + node offset).  The per-sample python loops become
+//   two launches over the concatenated arrays.
+namespace pcc {
+
+// idx[i] = segment of row i (last s with offsets[s] <= i); offsets[B+1]
+__global__ void expand_segments_kernel(const int64_t* __restrict__ offsets, int64_t B, int64_t n, int64_t* __restrict__ idx) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+  }
+  idx[i] = lo;
+}
+
+// edges[2,E] hold per-graph LOCAL node ids, graphs back to back (edge_offsets[G+1]); out = edges + node_offsets[graph]
+__global__ void offset_edges_kernel(const int64_t* __restrict__ edges, int64_t E, const int64_t* __restrict__ edge_offsets,
+                                    const int64_t* __restrict__ node_offsets, int64_t G, int64_t* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t lo = 0, hi = G;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(edge_offsets + mid) <= e) lo = mid; else hi = mid;
+  }
+  const int64_t off = __ldg(node_offsets + lo);
+  out[e] = edges[e] + off;
+  out[E + e] = edges[E + e] + off;
+}
+
+}  // namespace pcc
+
+extern "C" int pcc_expand_segments(const int64_t* offsets, int64_t B, int64_t n, int64_t* idx, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(B >= 1 || n == 0, "rows without a segment");
+  if (n == 0) return 0;
+  PCC_K(expand_segments_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(offsets, B, n, idx);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_offset_edges(const int64_t* edges, int64_t E, const int64_t* edge_offsets, const int64_t* node_offsets,
+                                int64_t G, int64_t* out, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(G >= 1 || E == 0, "edges without a graph");
+  if (E == 0) return 0;
+  PCC_K(offset_edges_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, (cudaStream_t)stream>>>(edges, E, edge_offsets, node_offsets,
+                                                                                  G, out);
+  return check_launch(__func__);
+}

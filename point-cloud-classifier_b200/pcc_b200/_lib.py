@@ -55,6 +55,8 @@ _SIGS = {
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_expand_segments": [_vp, _i64, _i64, _vp, _i32, _vp],
+    "pcc_offset_edges": [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _vp],
     "pcc_edge_weights_workspace_bytes": [_i64, _i64],
     "pcc_edge_weights": [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _vp, _vp, _vp, _i32, _vp],
     "pcc_mlp_head_supported": [C.POINTER(HeadDesc)],
