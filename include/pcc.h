@@ -236,6 +236,16 @@ int pcc_prof_read(int slot, double* ms_total, int64_t* count);
  *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
  *      (wgrad).  Expected values: tests/test_fused_gpu.py. */
 int pcc_selftest_umma(int mode, float* out, int device, void* stream);
+/* ---- fused multi-tensor Adam / AdamW step: torch.optim.Adam / AdamW as constructed at
+ *      /root/reference/models/wrapper.py:30-33 (default betas / eps; weight_decay 0 / 0.01), every parameter
+ *      tensor in one launch.  table (device, [n_tensors][4] int64): {param pointer, grad pointer (0 = no gradient:
+ *      skipped), numel, offset of the tensor's moments inside exp_avg / exp_avg_sq [total]} sorted by offset;
+ *      step: device int64 scalar, incremented by the call (bias corrections use the incremented value);
+ *      decoupled: 1 = AdamW, 0 = Adam (L2 term added to the gradient).  Capturable in a CUDA graph. */
+int pcc_adam_step(const int64_t* table, int n_tensors, int64_t total, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, int device,
+                  void* stream);
+
 /* ---- gradient all-reduce over NVLink / NVSwitch peer memory (one process per GPU, one node).
  *      One-shot: every rank stages its flat fp32 bucket in CUDA-IPC memory mapped by all peers, publishes a
  *      sequence number to every peer with a system-scope release, then sums all ranks' staging buffers in rank

@@ -63,6 +63,7 @@ _SIGS = {
     "pcc_mlp_head_fwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _i64, _i32, _vp],
     "pcc_mlp_head_workspace_bytes": [C.POINTER(HeadDesc), _i64],
     "pcc_mlp_head_bwd": [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "pcc_adam_step": [_vp, _i32, _i64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _vp],
     "pcc_peer_alloc": [_i64, C.POINTER(C.c_void_p), _vp, _i32],
     "pcc_peer_open": [_vp, C.POINTER(C.c_void_p), _i32],
     "pcc_peer_close": [_vp, _i32],
