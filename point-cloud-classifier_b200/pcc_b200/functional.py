@@ -335,16 +335,22 @@ def edge_weights(pos: torch.Tensor, edges: torch.Tensor, edge_offsets: torch.Ten
 
 
 # ------------------------------------------------------------------ fused loss, row gather
+def bce_logits_loss_and_grad(logits, target):
+    """(mean BCE-with-logits loss, d loss / d logits) from one kernel launch; no autograd node"""
+    logits, target = L.f32c(logits.detach()), L.f32c(target)
+    dev, st = _ctx(logits, target)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    call("pcc_bce_logits", ptr(logits), ptr(target), logits.numel(), ptr(loss), ptr(dlogits), dev, st)
+    return loss, dlogits
+
+
 class BCEWithLogitsFn(torch.autograd.Function):
     """nn.BCEWithLogitsLoss(reduction='mean') (wrapper.py:38) with its gradient produced in the same pass."""
 
     @staticmethod
     def forward(ctx, logits, target):
-        logits, target = L.f32c(logits), L.f32c(target)
-        dev, st = _ctx(logits, target)
-        loss = torch.empty((), dtype=torch.float32, device=logits.device)
-        dlogits = torch.empty_like(logits)
-        call("pcc_bce_logits", ptr(logits), ptr(target), logits.numel(), ptr(loss), ptr(dlogits), dev, st)
+        loss, dlogits = bce_logits_loss_and_grad(logits, target)
         ctx.save_for_backward(dlogits)
         return loss
 

@@ -57,6 +57,8 @@ def test_no_cpu_fallback():
     g = pcc_b200.GraphNet(4, 16, 1, "tanh")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         g(torch.randn(4, 4), torch.zeros(4, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pcc_b200.FusedAdam(m.parameters(), lr=1e-3)
 
 
 def test_graphnet_state_dict_and_out_of_scope_branches():
