@@ -10,6 +10,14 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 static std::atomic<long long> g_launches{0};
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("PCC_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
 void note_launch(int kernels) { g_launches.fetch_add(kernels, std::memory_order_relaxed); }
 
 static std::atomic<int> g_prof_on{0};
@@ -59,6 +67,11 @@ extern "C" int pcc_prof_read(int slot, double* ms_total, int64_t* count) {
 }
 
 extern "C" const char* pcc_last_error(void) { return pcc::g_last_error.c_str(); }
+
+extern "C" int pcc_debug_set_pdl(int on) {
+  pcc::g_pdl = on ? 1 : 0;
+  return 0;
+}
 
 extern "C" int pcc_version(void) { return 100; }
 

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // the prologue read only parameters; rows, gradients and images come from the predecessors in the stream
   // Virtual-row mode (max pooling, rows pre-gathered: row b*H + f is the argmax row of (b, f)): the gradient of
   // the final Linear's output is one-hot per row, dZ_{L-1}[row] = dpooled[row] * e_f, so
   //   dH_lh[row, :] = dpooled[row] * W_{L-1}[f, :]      (a scaled weight row: no dgrad GEMM, no dZ_{L-1} image)
@@ -574,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // barriers and TMEM are set up while the predecessor drains; the images below are its output
 
   if (warp == kProdWarp) {
     if (lane == 0) {
@@ -742,6 +744,7 @@ template <int H>
 __global__ void __launch_bounds__(256) final_wgrad_virtual_kernel(const uint8_t* __restrict__ stage_h,
                                                                   const float* __restrict__ dpooled, int64_t B,
                                                                   float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
   constexpr int CH = H / 8, NG = 256 / CH;
   constexpr uint32_t BLOB = kTileM * H * 2;
   __shared__ float red[NG][CH][8];
@@ -805,6 +808,7 @@ struct ReduceParams {
   int L, H;
 };
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams p) {
+  pdl_enter();
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int item = blockIdx.x * 32 + lane;
@@ -895,7 +899,7 @@ static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
   {
     ProfScope prof(1, st);
-    PCC_K(kern)<<<grid, kThreads, lay.total, st>>>(p);
+    launch_dep(kern, dim3(grid), dim3(kThreads), lay.total, st, p);
   }
   return 0;
 }
@@ -907,7 +911,7 @@ static int launch_wgrad(const BwdParams& p, int grid, cudaStream_t st) {
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
   {
     ProfScope prof(2, st);
-    PCC_K(kern)<<<grid, kThreads, smem_bytes, st>>>(p);
+    launch_dep(kern, dim3(grid), dim3(kThreads), smem_bytes, st, p);
   }
   return 0;
 }
@@ -1001,7 +1005,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   if (virt) {  // final Linear: scaled row sums instead of a GEMM; right after the chain, while its h images are in L2
     auto fk = (H == 256) ? final_wgrad_virtual_kernel<256> : final_wgrad_virtual_kernel<128>;
-    PCC_K(fk)<<<H, 256, 0, st>>>(p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
+    launch_dep(fk, dim3(H), dim3(256), 0, st, p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
   }
   rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
   if (rc != 0) return rc;
@@ -1018,6 +1022,6 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
     items += (rp.Kp[l] + 1) * (H / 4);
   }
   rp.vec_begin[Lr] = items;
-  PCC_K(wgrad_reduce_kernel)<<<(unsigned)cdiv(items, 32), 256, 0, st>>>(rp);
+  launch_dep(wgrad_reduce_kernel, dim3((unsigned)cdiv(items, 32)), dim3(256), 0, st, rp);
   return check_launch(__func__);
 }

@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     }
     bimgS[i] = __float2bfloat16_rn(v);
   }
+  if (warp == kFwdMmaWarp) tmem_alloc<512>(tmem_slot);
+  // everything above reads only parameters; the packed weights, the layer-0 table, the pool accumulator and the
+  // tile tables below are written by fwd_prep_kernel, the predecessor in the stream (see pdl_enter)
+  pdl_wait();
   for (int i = threadIdx.x; i < H * 4 * Q; i += kFwdThreads) reinterpret_cast<float*>(smem + lay.w0)[i] = __ldg(p.w0tab + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -161,7 +165,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     mbar_init(ind_ready, kFwdPoolWarps);
     fence_mbar_init();
   }
-  if (warp == kFwdMmaWarp) tmem_alloc<512>(tmem_slot);
   fence_proxy_async();  // the two constant images are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
@@ -609,6 +612,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
     }
     bimgS[i] = __float2bfloat16_rn(v);
   }
+  if (warp == kPairMmaWarp) tmem_alloc_pair<512>(tmem_slot);
+  // everything above reads only parameters; what follows was written by fwd_prep_kernel, the predecessor in the stream
+  pdl_wait();
   for (int i = threadIdx.x; i < H * 4 * Q; i += kPairThreads) reinterpret_cast<float*>(smem + lay.w0)[i] = __ldg(p.w0tab + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&slab_ready[i], 2 * kFwdHidWarps);
@@ -624,7 +630,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
       bulk_g2s(w2h + sidx * kActSlab, p.wpack + p.w_off[L - 1] + (size_t)sidx * SLAB + (size_t)rank * 128 * 128, kActSlab, wres);
     }
   }
-  if (warp == kPairMmaWarp) tmem_alloc_pair<512>(tmem_slot);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -893,6 +898,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
 __global__ void pool_finalize_kernel(const void* __restrict__ pool_acc, const int64_t* __restrict__ offsets,
                                      const float* __restrict__ bias, int64_t B, int H, int pooling,
                                      float* __restrict__ pooled, int32_t* __restrict__ argmax) {
+  pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int64_t b = i / H;
@@ -942,6 +948,7 @@ static WsLayout ws_layout(const pcc_phi_desc* d, int64_t n, int64_t B) {
 // y == 2L+2 writes the fp32 layer-0 table {b_0[c], bf16(W_0[c][0..d-1]), 0...} of the forward kernel
 __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t pool_count, const int64_t* offsets,
                                 int64_t B, int64_t num_tiles, int32_t* tile_first, int32_t* tile_last, int64_t n) {
+  pdl_enter();
   const int y = blockIdx.y;
   if (y < 2 * pk.L) {
     const int l = y >> 1;
@@ -1014,6 +1021,7 @@ __global__ void fwd_prep_kernel(PackParams pk, unsigned long long* pool, int64_t
 // rs = 1/sqrt(n) (sum pooling, deep_sets.py:99) or 1/n (mean, :102); bscale[b] = n * rs_b multiplies the final bias
 __global__ void poolh_finalize_kernel(const float* __restrict__ hsum, const int64_t* __restrict__ offsets, int64_t B, int H,
                                       int pooling, float* __restrict__ ph, float* __restrict__ bscale) {
+  pdl_enter();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int64_t b = i / H;
@@ -1058,7 +1066,7 @@ static int launch_fwd_pair(const PhiParams& p, cudaStream_t st) {
   if (pairs > ntp) pairs = ntp;
   {
     ProfScope prof(0, st);
-    PCC_K(kern)<<<(unsigned)(2 * pairs), kPairThreads, lay.total, st>>>(p);
+    launch_dep(kern, dim3((unsigned)(2 * pairs)), dim3(kPairThreads), lay.total, st, p);
   }
   return 0;
 }
@@ -1085,7 +1093,7 @@ static int launch_fwd(const PhiParams& p, cudaStream_t st) {
   const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
   {
     ProfScope prof(0, st);
-    PCC_K(kern)<<<grid, kFwdThreads, lay.total, st>>>(p);
+    launch_dep(kern, dim3(grid), dim3(kFwdThreads), lay.total, st, p);
   }
   return 0;
 }
@@ -1149,9 +1157,8 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
   // sum / mean pooling with an aux buffer: pooling commuted with the final Linear (see the kernel)
   const bool poolh = d->pooling != PCC_POOL_MAX && argmax != nullptr;
   p.poolh = poolh ? 1 : 0;
-  PCC_K(fwd_prep_kernel)<<<dim3(32, 2 * L + 3), 256, 0, st>>>(pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
-                                                             p.num_tiles, (int32_t*)(wsb + wl.tile_first_off),
-                                                             (int32_t*)(wsb + wl.tile_last_off), n);
+  launch_dep(fwd_prep_kernel, dim3(32, 2 * L + 3), dim3(256), 0, st, pk, (unsigned long long*)(wsb + wl.pool_off), B * H, offsets, B,
+             p.num_tiles, (int32_t*)(wsb + wl.tile_first_off), (int32_t*)(wsb + wl.tile_last_off), n);
   if (p.num_tiles > 0) {
     int rc = 0;
 #define PCC_DISPATCH_A(HH, QQ)                                                        \
@@ -1174,8 +1181,8 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
     // pooled = ph W_{L-1}^T + bscale (x) b_{L-1}  with ph = rs * hsum kept in the aux buffer for the backward
     float* ph = reinterpret_cast<float*>(argmax);
     float* bscale = reinterpret_cast<float*>(wsb + wl.bscale_off);
-    PCC_K(poolh_finalize_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>((const float*)(wsb + wl.pool_off), offsets, B, H,
-                                                                      d->pooling, ph, bscale);
+    launch_dep(poolh_finalize_kernel, dim3((unsigned)cdiv(B * H, 256)), dim3(256), 0, st, (const float*)(wsb + wl.pool_off), offsets, B, H,
+               d->pooling, ph, bscale);
     HeadTileParams hp{};
     hp.act = PCC_ACT_RELU;
     HeadTileProb& pr = hp.prob[0];
@@ -1186,8 +1193,8 @@ extern "C" int pcc_deepsets_phi_pool_fwd(const pcc_phi_desc* d, const float* x, 
     head_set_tiles(pr);
     launch_head_tiles(hp, pr.tiles, st);
   } else if (B * H > 0) {
-    PCC_K(pool_finalize_kernel)<<<(unsigned)cdiv(B * H, 256), 256, 0, st>>>(wsb + wl.pool_off, offsets, d->b[L - 1], B, H,
-                                                                     d->pooling, pooled, argmax);
+    launch_dep(pool_finalize_kernel, dim3((unsigned)cdiv(B * H, 256)), dim3(256), 0, st, wsb + wl.pool_off, offsets, d->b[L - 1], B, H,
+               d->pooling, pooled, argmax);
   }
   return check_launch(__func__);
 }

@@ -65,6 +65,7 @@ constexpr int kHeadSmem = 3 * kHOp * (int)sizeof(float);  // A, B, act' argument
 
 template <int ACT>
 __global__ void __launch_bounds__(kHThreads) head_tile_kernel(const HeadTileParams hp) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem_f[];
   float* As = smem_f;
   float* Bs = smem_f + kHOp;
@@ -231,7 +232,7 @@ void launch_head_tiles(const HeadTileParams& hp, int tiles, cudaStream_t st) {
     default: break;
   }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
-  PCC_K(kern)<<<tiles, kHThreads, kHeadSmem, st>>>(hp);
+  launch_dep(kern, dim3(tiles), dim3(kHThreads), kHeadSmem, st, hp);
 }
 
 static int check_head(const pcc_head_desc* d, const char* where) {

@@ -30,6 +30,7 @@ __global__ void histogram_kernel(const int64_t* __restrict__ idx, int64_t n, int
 // (/root/reference/models/deep_sets.py:91-92) without a host sync and without three dependent launches.
 __global__ void __launch_bounds__(1024) segment_offsets_fused_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t B,
                                                                      int64_t* __restrict__ offsets) {
+  pdl_enter();
   __shared__ bool s_last;
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(offsets);
   for (int64_t i0 = (int64_t)blockIdx.x * 1024; i0 < n; i0 += (int64_t)gridDim.x * 1024) {
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256) segment_pool_bwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y,
                                                          int64_t count, float* __restrict__ loss,
                                                          float* __restrict__ dz) {
+  pdl_enter();
   __shared__ float red[8];
   const float inv = 1.f / (float)count;
   float s = 0.f;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 // out[i, :] = x[clamp(idx[i], 0, n-1), :]  (rows of d floats)
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t count, int d,
                                    int64_t n, float* __restrict__ out) {
+  pdl_enter();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= count * d) return;
   const int64_t i = t / d;
@@ -220,7 +223,7 @@ extern "C" int pcc_bce_logits(const float* logits, const float* target, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   PCC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   const int blocks = (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
-  PCC_K(bce_logits_kernel)<<<blocks, 256, 0, st>>>(logits, target, count, loss, dlogits);
+  launch_dep(bce_logits_kernel, dim3(blocks), dim3(256), 0, st, logits, target, count, loss, dlogits);
   return check_launch(__func__);
 }
 
@@ -229,7 +232,7 @@ extern "C" int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count
   PCC_ENTER(device);
   if (count == 0 || d == 0) return 0;
   PCC_REQUIRE(n > 0, "gather from an empty tensor");
-  PCC_K(gather_rows_kernel)<<<(unsigned)cdiv(count * d, 256), 256, 0, (cudaStream_t)stream>>>(x, idx, count, d, n, out);
+  launch_dep(gather_rows_kernel, dim3((unsigned)cdiv(count * d, 256)), dim3(256), 0, (cudaStream_t)stream, x, idx, count, d, n, out);
   return check_launch(__func__);
 }
 
@@ -243,7 +246,7 @@ extern "C" int pcc_segment_offsets(const int64_t* idx, int64_t n, int64_t B, int
   int64_t blocks = cdiv(n, 1024);
   if (blocks < 1) blocks = 1;
   if (blocks > 592) blocks = 592;
-  PCC_K(segment_offsets_fused_kernel)<<<(unsigned)blocks, 1024, 0, st>>>(idx, n, B, offsets);
+  launch_dep(segment_offsets_fused_kernel, dim3((unsigned)blocks), dim3(1024), 0, st, idx, n, B, offsets);
   return check_launch(__func__);
 }
 

@@ -76,6 +76,7 @@ _SIGS = {
     "pcc_prof_read": [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "pcc_debug_set_trace": [_vp],
     "pcc_debug_set_fwd_pair": [_i32],
+    "pcc_debug_set_pdl": [_i32],
     "pcc_selftest_umma": [_i32, _vp, _i32, _vp],
     "pcc_phi_fused_supported": [C.POINTER(PhiDesc)],
     "pcc_phi_fused_workspace_bytes": [C.POINTER(PhiDesc), _i64, _i64],

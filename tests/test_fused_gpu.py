@@ -267,3 +267,40 @@ def test_peer_allreduce_single_rank(tmp_path):
         assert arena.view_for(torch.zeros(2, 2, device="cuda")) is None
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pooling,act", [("max", "relu"), ("mean", "gelu")])
+def test_dependent_launch_matches_stream_ordered_launch(pooling, act):
+    """The kernels of the train step are launched with programmatic dependent launch (each one is scheduled while
+    its predecessor drains and waits for it before its first global access).  Replays of the captured step over
+    changing batches must give bit-identical gradients to plain stream-ordered launches of the same kernels
+    (everything except the loss scalar's float atomics is order-deterministic)."""
+    from pcc_b200 import _lib
+    from pcc_b200.train_step import GraphedTrainStep
+    B, N, d = 64, 256, 3
+    batches = []
+    g = torch.Generator().manual_seed(5)
+    for _ in range(6):
+        batches.append((torch.randn(B * N, d, generator=g).cuda(), (torch.rand(B, 2, generator=g) > 0.5).float().cuda()))
+    idx = torch.arange(B, device="cuda").repeat_interleave(N)
+    grads = []
+    try:
+        for pdl in (1, 0):
+            _lib.call("pcc_debug_set_pdl", pdl)
+            torch.manual_seed(1)
+            m = pcc_b200.DeepSets(d, [256, 256], [256], 2, act, layer_norm=False, residual_block=False, pooling=pooling,
+                                  precision="bf16").cuda()
+            gs = GraphedTrainStep(m, (batches[0][0], idx), batches[0][1], forward_kwargs={"num_sets": B}, warmup=2)
+            out = []
+            for rep in range(3):
+                for x, y in batches:
+                    gs.step((x, idx), y)
+                    out.append([p.grad.clone() for p in m.parameters()])
+            torch.cuda.synchronize()
+            grads.append(out)
+    finally:
+        _lib.call("pcc_debug_set_pdl", 1)
+    for a, b in zip(*grads):
+        for ga, gb in zip(a, b):
+            assert torch.equal(ga, gb)
