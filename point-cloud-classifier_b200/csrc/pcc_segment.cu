@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int j = 0; j < 8; ++j) t += red[j];
-    atomicAdd(loss, t * inv);
+    if (gridDim.x == 1) *loss = t * inv;  // one block: plain store, no zero-fill before the launch, deterministic
+    else atomicAdd(loss, t * inv);
   }
 }
 
@@ -221,8 +222,10 @@ extern "C" int pcc_bce_logits(const float* logits, const float* target, int64_t 
   PCC_ENTER(device);
   PCC_REQUIRE(count > 0, "empty logits");
   cudaStream_t st = (cudaStream_t)stream;
-  PCC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  const int blocks = (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
+  // up to 16 K logits (the train step's [B, out] is a few thousand): ONE block, so the launch needs no memset node
+  // in front of it and stays a programmatic dependent of the head kernel before it
+  const int blocks = (count <= 16384) ? 1 : (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
+  if (blocks > 1) PCC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   launch_dep(bce_logits_kernel, dim3(blocks), dim3(256), 0, st, logits, target, count, loss, dlogits);
   return check_launch(__func__);
 }
