@@ -177,11 +177,11 @@ __global__ void __launch_bounds__(256) segment_pool_bwd_kernel(const float* __re
 // ------------------------------------------------------------------ fused loss + row gather
 // BCEWithLogitsLoss(reduction=mean) forward and its gradient in one pass (wrapper.py:38,64-67):
 // loss = mean(max(z,0) - z*y + log1p(exp(-|z|))), dlogits = (sigmoid(z) - y) / count
-__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y,
+__global__ void __launch_bounds__(1024) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ y,
                                                          int64_t count, float* __restrict__ loss,
                                                          float* __restrict__ dz) {
   pdl_enter();
-  __shared__ float red[8];
+  __shared__ float red[32];
   const float inv = 1.f / (float)count;
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int j = 0; j < 8; ++j) t += red[j];
+    for (int j = 0; j < (int)(blockDim.x >> 5); ++j) t += red[j];
     if (gridDim.x == 1) *loss = t * inv;  // one block: plain store, no zero-fill before the launch, deterministic
     else atomicAdd(loss, t * inv);
   }
@@ -222,11 +222,11 @@ extern "C" int pcc_bce_logits(const float* logits, const float* target, int64_t 
   PCC_ENTER(device);
   PCC_REQUIRE(count > 0, "empty logits");
   cudaStream_t st = (cudaStream_t)stream;
-  // up to 16 K logits (the train step's [B, out] is a few thousand): ONE block, so the launch needs no memset node
+  // up to 4 K logits (the train step's [B, out] is 256 .. 2560): ONE block, so the launch needs no memset node
   // in front of it and stays a programmatic dependent of the head kernel before it
-  const int blocks = (count <= 16384) ? 1 : (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
+  const int blocks = (count <= 4096) ? 1 : (int)(cdiv(count, 256) < 148 ? cdiv(count, 256) : 148);
   if (blocks > 1) PCC_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  launch_dep(bce_logits_kernel, dim3(blocks), dim3(256), 0, st, logits, target, count, loss, dlogits);
+  launch_dep(bce_logits_kernel, dim3(blocks), dim3(blocks == 1 ? 1024 : 256), 0, st, logits, target, count, loss, dlogits);
   return check_launch(__func__);
 }
 

@@ -125,7 +125,7 @@ def test_fused_bce_loss_and_gather():
     (ref * 2.0).backward()
     torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(z.grad, z2.grad, rtol=1e-5, atol=1e-8)
-    zb = (torch.randn(2500, 10, generator=g) * 3).cuda()     # > 16 K logits: the multi-block (atomic) variant
+    zb = (torch.randn(2500, 10, generator=g) * 3).cuda()     # > 4 K logits: the multi-block (atomic) variant
     yb = (torch.rand(2500, 10, generator=g) > 0.5).float().cuda()
     torch.testing.assert_close(PF.bce_with_logits(zb, yb), torch.nn.BCEWithLogitsLoss()(zb, yb), rtol=1e-5, atol=1e-6)
     x = torch.randn(1000, 3, generator=g).cuda()
