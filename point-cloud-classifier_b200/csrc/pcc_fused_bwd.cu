@@ -740,12 +740,13 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
 // Virtual-row mode: weight gradient of the final Linear without a GEMM.  dZ_{L-1}[b*H + f] = dpooled[b, f] * e_f, so
 //   dW_{L-1}[f, :] = sum_b dpooled[b, f] * h_lh[b*H + f, :]      db_{L-1}[f] = sum_b dpooled[b, f]
 // One CTA per output feature f; thread = (8-column chunk, b group); the h rows come from the staged SW128 images.
+constexpr int kFwvThreads = 512;
 template <int H>
-__global__ void __launch_bounds__(256) final_wgrad_virtual_kernel(const uint8_t* __restrict__ stage_h,
+__global__ void __launch_bounds__(kFwvThreads) final_wgrad_virtual_kernel(const uint8_t* __restrict__ stage_h,
                                                                   const float* __restrict__ dpooled, int64_t B,
                                                                   float* __restrict__ dw, float* __restrict__ db) {
   pdl_enter();
-  constexpr int CH = H / 8, NG = 256 / CH;
+  constexpr int CH = H / 8, NG = kFwvThreads / CH;
   constexpr uint32_t BLOB = kTileM * H * 2;
   __shared__ float red[NG][CH][8];
   __shared__ float redb[NG];
@@ -1005,7 +1006,7 @@ extern "C" int pcc_deepsets_phi_pool_bwd(const pcc_phi_desc* d, const float* x, 
   if (rc != 0) return rc;
   if (virt) {  // final Linear: scaled row sums instead of a GEMM; right after the chain, while its h images are in L2
     auto fk = (H == 256) ? final_wgrad_virtual_kernel<256> : final_wgrad_virtual_kernel<128>;
-    launch_dep(fk, dim3(H), dim3(256), 0, st, p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
+    launch_dep(fk, dim3(H), dim3(kFwvThreads), 0, st, p.stage_h[L - 2], dpooled, B, dw[L - 1], db[L - 1]);
   }
   rc = (H == 256) ? launch_wgrad<256>(p, wl.grid, st) : launch_wgrad<128>(p, wl.grid, st);
   if (rc != 0) return rc;
