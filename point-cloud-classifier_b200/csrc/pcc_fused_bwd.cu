@@ -542,6 +542,13 @@ __device__ inline WgradJob wgrad_job(int j, int cta, int grid, int nbig) {
   return w;
 }
 
+// Tiles are consumed in DESCENDING order: the chain kernel wrote the images in ascending order just before, so the
+// high tiles are the ones still in L2 (reading upwards starts with the evicted ones and pushes the rest out).
+__device__ __forceinline__ int64_t wgrad_last_tile(const WgradJob& jb, int64_t num_tiles) {
+  if (jb.first >= num_tiles) return jb.first - jb.stride;  // no tile: the loop condition fails at once
+  return jb.first + (num_tiles - 1 - jb.first) / jb.stride * jb.stride;
+}
+
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
       for (int j = j0; j < 2; ++j) {
         const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
-        for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
+        for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
           push(p.stage_g[l] + (size_t)tile * BLOB);
           if (l >= 1) push(p.stage_h[l - 1] + (size_t)tile * BLOB);
         }
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         const uint32_t idesc = make_idesc_bf16(128, Np, 1, 1);
         if (j > j0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
         bool first = true;
-        for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
+        for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
           const uint32_t g_stage = stage;
           mbar_wait(&full[stage], phase);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
@@ -656,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
       for (int i = 0; i < CPW; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dbacc[i][j] = 0.f;
-      for (int64_t tile = jb.first; tile < p.num_tiles; tile += jb.stride) {
+      for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
         if (l == 0) {  // x tile -> [2][128][8] bf16 image (group 0 owns the rows)
           mbar_wait(&x_empty[xpar], ((xphase >> xpar) & 1) ^ 1);
           xphase ^= 1u << xpar;
@@ -757,7 +764,8 @@ __global__ void __launch_bounds__(kFwvThreads) final_wgrad_virtual_kernel(const 
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   float gsum = 0.f;
   // 8 independent (gradient, row chunk) loads in flight per thread: the loop is latency bound
-  for (int64_t b0 = bg; b0 < B; b0 += 8 * NG) {
+  // highest sets first: their rows were written last by the chain kernel and are the likeliest to still be in L2
+  for (int64_t b0 = (B - 1) / (8 * NG) * (8 * NG) + bg; b0 >= 0; b0 -= 8 * NG) {
     float g[8];
     uint4 u[8];
 #pragma unroll
