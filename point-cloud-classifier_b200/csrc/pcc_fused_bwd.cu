@@ -513,7 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
 }
 
 // ====================================================================== K2: wgrad
-constexpr int kSlots = 3;
+// staged images travel through the ring as HALF images (64 of a tile's 128 rows = 4 of the 8 K steps): six 32 KB
+// slots instead of three 64 KB ones keep the same bytes in shared memory but let the loads of the next one and a
+// half tiles overlap the MMAs of the current half instead of waiting for a whole image to drain
+constexpr int kSlots = 6;
 
 // Work split of the wgrad kernel.  Each CTA runs two jobs: (0) ONE of the H x H layers (layers 1..L-1
 // are dealt round-robin over the CTAs) on every members-th tile, (1) layer 0 (K = 16) on every grid-th
@@ -553,13 +556,16 @@ template <int H>
 __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t BLOB = kTileM * H * 2;
+  constexpr uint32_t HBLOB = BLOB / 2;       // half image: rows [64 hf, +64) of every 64-column slab, packed
+  constexpr uint32_t HSLAB = kActSlab / 2;   // 64 rows x 128 B
+  constexpr int NSL = H / 64;                // slabs per image
   constexpr uint32_t XBLOB = kTileM * kK0 * 2;
   constexpr int HALVES = H / 128;
   constexpr int CH = H / 8;            // 16-byte feature chunks per image row
   constexpr int CPW = CH / kEpiWarps;  // chunks per epilogue warp for the db column sums
-  uint8_t* slots = smem;                                   // kSlots images (1024-aligned)
-  uint8_t* bufX = smem + kSlots * BLOB;                    // 2 x-images (tile parity)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSlots * BLOB + 2 * XBLOB);
+  uint8_t* slots = smem;                                   // kSlots half images (1024-aligned)
+  uint8_t* bufX = smem + kSlots * HBLOB;                   // 2 x-images (tile parity)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSlots * HBLOB + 2 * XBLOB);
   uint64_t* full = bars;                       // [kSlots]
   uint64_t* empty = bars + kSlots;             // [kSlots] count 1 (MMA commit) + 256 (epilogue readers)
   uint64_t* x_full = bars + 2 * kSlots;        // [2] count 256
@@ -587,18 +593,21 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
   if (warp == kProdWarp) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      auto push = [&](const uint8_t* src) {
+      auto push = [&](const uint8_t* src, int hf) {
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], BLOB);
-        bulk_g2s(slots + stage * BLOB, src, BLOB, &full[stage]);
+        mbar_arrive_expect_tx(&full[stage], HBLOB);
+        for (int sl = 0; sl < NSL; ++sl)
+          bulk_g2s(slots + stage * HBLOB + sl * HSLAB, src + (size_t)sl * kActSlab + (size_t)hf * HSLAB, HSLAB, &full[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
       };
       for (int j = j0; j < 2; ++j) {
         const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
         for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
-          push(p.stage_g[l] + (size_t)tile * BLOB);
-          if (l >= 1) push(p.stage_h[l - 1] + (size_t)tile * BLOB);
+          for (int hf = 0; hf < 2; ++hf) {
+            push(p.stage_g[l] + (size_t)tile * BLOB, hf);
+            if (l >= 1) push(p.stage_h[l - 1] + (size_t)tile * BLOB, hf);
+          }
         }
       }
     }
@@ -614,35 +623,39 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
         if (j > j0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
         bool first = true;
         for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
-          const uint32_t g_stage = stage;
-          mbar_wait(&full[stage], phase);
-          if (++stage == kSlots) { stage = 0; phase ^= 1; }
-          uint32_t in_addr = 0, in_stage = 0;
-          if (l >= 1) {
-            in_stage = stage;
-            mbar_wait(&full[stage], phase);
-            if (++stage == kSlots) { stage = 0; phase ^= 1; }
-            in_addr = s_base + in_stage * BLOB;
-          } else {
+          uint32_t x_addr = 0;
+          if (l == 0) {
             mbar_wait(&x_full[xpar], (xphase >> xpar) & 1);
             xphase ^= 1u << xpar;
-            in_addr = x_base + xpar * XBLOB;
+            x_addr = x_base + xpar * XBLOB;
           }
-          tc_fence_after();
-          const uint32_t g_addr = s_base + g_stage * BLOB;
-          // D[out(128 per half), in] += dZ^T (MN-major view of the dZ image) * In (MN-major view)
-#pragma unroll
-          for (int o = 0; o < HALVES; ++o)
-            for (int ks = 0; ks < kTileM / 16; ++ks) {
-              const uint64_t a_desc = make_smem_desc_sw128_mn(g_addr + o * (2 * kActSlab) + ks * 2048, kActSlab);
-              const uint64_t b_desc = (l >= 1) ? make_smem_desc_sw128_mn(in_addr + ks * 2048, kActSlab)
-                                               : make_smem_desc(in_addr + ks * 256, 128, kTileM * 16);
-              umma_bf16(tmem + o * Np, a_desc, b_desc, idesc, !(first && ks == 0));
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t g_stage = stage;
+            mbar_wait(&full[stage], phase);
+            if (++stage == kSlots) { stage = 0; phase ^= 1; }
+            uint32_t in_addr = 0, in_stage = 0;
+            if (l >= 1) {
+              in_stage = stage;
+              mbar_wait(&full[stage], phase);
+              if (++stage == kSlots) { stage = 0; phase ^= 1; }
+              in_addr = s_base + in_stage * HBLOB;
             }
+            tc_fence_after();
+            const uint32_t g_addr = s_base + g_stage * HBLOB;
+            // D[out(128 per half), in] += dZ^T (MN-major view of the dZ half image) * In (MN-major view)
+#pragma unroll
+            for (int o = 0; o < HALVES; ++o)
+              for (int ks = 0; ks < kTileM / 32; ++ks) {
+                const uint64_t a_desc = make_smem_desc_sw128_mn(g_addr + o * (2 * HSLAB) + ks * 2048, HSLAB);
+                const uint64_t b_desc = (l >= 1) ? make_smem_desc_sw128_mn(in_addr + ks * 2048, HSLAB)
+                                                 : make_smem_desc(x_addr + (hf * (kTileM / 32) + ks) * 256, 128, kTileM * 16);
+                umma_bf16(tmem + o * Np, a_desc, b_desc, idesc, !(first && hf == 0 && ks == 0));
+              }
+            umma_commit(&empty[g_stage]);
+            if (l >= 1) umma_commit(&empty[in_stage]);
+          }
           first = false;
-          umma_commit(&empty[g_stage]);
-          if (l >= 1) umma_commit(&empty[in_stage]);
-          else { umma_commit(&x_empty[xpar]); xpar ^= 1; }
+          if (l == 0) { umma_commit(&x_empty[xpar]); xpar ^= 1; }
         }
         umma_commit(acc_ready);
       }
@@ -683,27 +696,30 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
           mbar_arrive_warp(&x_full[xpar]);
           xpar ^= 1;
         }
-        // column sums of the dZ image: warp w owns chunks w, w+8, ...; lane owns rows lane, lane+32, ...
-        mbar_wait(&full[stage], phase);
-        const uint8_t* gb = slots + stage * BLOB;
-#pragma unroll
-        for (int i = 0; i < CPW; ++i) {
-          const int c = warp + kEpiWarps * i;
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int rw = lane + 32 * rr;
-            const uint4 u = *reinterpret_cast<const uint4*>(gb + act_chunk_off(rw, c * 8));
-            dbacc[i][0] += bf16_lo(u.x); dbacc[i][1] += bf16_hi(u.x); dbacc[i][2] += bf16_lo(u.y); dbacc[i][3] += bf16_hi(u.y);
-            dbacc[i][4] += bf16_lo(u.z); dbacc[i][5] += bf16_hi(u.z); dbacc[i][6] += bf16_lo(u.w); dbacc[i][7] += bf16_hi(u.w);
-          }
-        }
-        mbar_arrive_warp(&empty[stage]);
-        if (++stage == kSlots) { stage = 0; phase ^= 1; }
-        if (l >= 1) {  // the input image slot is only read by the tensor core; wait for THIS use of the slot
-          // to be filled before releasing it, otherwise the arrival could land in the previous phase
+        // column sums of the dZ half images: warp w owns chunks w, w+8, ...; lane owns rows lane, lane+32 of the half
+        for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&full[stage], phase);
+          const uint8_t* gb = slots + stage * HBLOB;
+#pragma unroll
+          for (int i = 0; i < CPW; ++i) {
+            const int c = warp + kEpiWarps * i;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int rw = lane + 32 * rr;
+              const uint4 u = *reinterpret_cast<const uint4*>(gb + (uint32_t)(c >> 3) * HSLAB + (uint32_t)rw * 128u +
+                                                              ((uint32_t)((c & 7) ^ (rw & 7)) << 4));
+              dbacc[i][0] += bf16_lo(u.x); dbacc[i][1] += bf16_hi(u.x); dbacc[i][2] += bf16_lo(u.y); dbacc[i][3] += bf16_hi(u.y);
+              dbacc[i][4] += bf16_lo(u.z); dbacc[i][5] += bf16_hi(u.z); dbacc[i][6] += bf16_lo(u.w); dbacc[i][7] += bf16_hi(u.w);
+            }
+          }
           mbar_arrive_warp(&empty[stage]);
           if (++stage == kSlots) { stage = 0; phase ^= 1; }
+          if (l >= 1) {  // the input half image is only read by the tensor core; wait for THIS use of the slot
+            // to be filled before releasing it, otherwise the arrival could land in the previous phase
+            mbar_wait(&full[stage], phase);
+            mbar_arrive_warp(&empty[stage]);
+            if (++stage == kSlots) { stage = 0; phase ^= 1; }
+          }
         }
       }
       // ---- db partial: reduce over lanes, lane 0 writes
@@ -914,7 +930,7 @@ static int launch_chain(const BwdParams& p, int grid, cudaStream_t st) {
 }
 template <int H>
 static int launch_wgrad(const BwdParams& p, int grid, cudaStream_t st) {
-  const int smem_bytes = kSlots * kTileM * H * 2 + 2 * kTileM * kK0 * 2 + 256;
+  const int smem_bytes = kSlots * (kTileM * H * 2 / 2) + 2 * kTileM * kK0 * 2 + 256;
   auto kern = phi_wgrad_kernel<H>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return fail("pcc_deepsets_phi_pool_bwd", cudaGetErrorString(e));
