@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
           bulk_g2s(slots + stage * HBLOB + sl * HSLAB, src + (size_t)sl * kActSlab + (size_t)hf * HSLAB, HSLAB, &full[stage]);
         if (++stage == kSlots) { stage = 0; phase ^= 1; }
       };
-      for (int j = j0; j < 2; ++j) {
+      for (int j = 1; j >= j0; --j) {  // layer 0 first: its accumulator flush (32 columns) is the short one to wait for
         const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
         for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
@@ -615,12 +615,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0 /* bit i = phase of x buffer i */, free_phase = 0;
       const uint32_t s_base = smem_u32(slots), x_base = smem_u32(bufX);
-      for (int j = j0; j < 2; ++j) {
+      for (int j = 1; j >= j0; --j) {  // layer 0 first: its accumulator flush (32 columns) is the short one to wait for
         const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
         const int l = jb.layer;
         const int Np = (l == 0) ? kK0 : H;
         const uint32_t idesc = make_idesc_bf16(128, Np, 1, 1);
-        if (j > j0) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
+        if (j < 1) { mbar_wait(acc_free, free_phase); free_phase ^= 1; tc_fence_after(); }
         bool first = true;
         for (int64_t tile = wgrad_last_tile(jb, p.num_tiles); tile >= jb.first; tile -= jb.stride) {
           uint32_t x_addr = 0;
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_wgrad_kernel(const BwdParams 
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     uint32_t stage = 0, phase = 0, xpar = 0, xphase = 0, acc_phase = 0;
     const int d = p.d;
-    for (int j = j0; j < 2; ++j) {
+    for (int j = 1; j >= j0; --j) {  // layer 0 first: its accumulator flush (32 columns) is the short one to wait for
       const WgradJob jb = wgrad_job(j, blockIdx.x, gridDim.x, p.nbig);
       const int l = jb.layer;
       const int Np = (l == 0) ? kK0 : H;
