@@ -11,7 +11,14 @@ from ._lib import call, ptr
 
 
 class FusedAdam(torch.optim.Optimizer):
-    """decoupled=True: torch.optim.AdamW (default weight_decay 0.01); decoupled=False: torch.optim.Adam (0.0)."""
+    """decoupled=True: torch.optim.AdamW (default weight_decay 0.01); decoupled=False: torch.optim.Adam (0.0).
+
+    Used the way models/wrapper.py uses its optimizer: zero_grad() and step().  Not carried over from torch.optim:
+    * `state_dict()` holds the hyper-parameters only — the moments live in two flat device buffers and are not
+      checkpointed (the reference never saves optimizer state);
+    * hyper-parameters are passed to the kernel by value, so a step captured in a CUDA graph keeps the lr it was
+      captured with (the reference trains with a constant lr; re-capture after changing it);
+    * one step counter per parameter group."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, decoupled=True):
         if weight_decay is None:
