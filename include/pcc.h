@@ -217,11 +217,12 @@ int pcc_mlp_head_bwd(const pcc_head_desc* d, const float* x, const float* zsave,
  *      pcc_bce_logits: nn.BCEWithLogitsLoss(reduction="mean") forward AND its gradient in one pass
  *      (/root/reference/models/wrapper.py:38,64-67): loss[1], dlogits[count] = (sigmoid(z) - y) / count.
  *      pcc_gather_rows: out[i,:] = x[clamp(idx[i]),:] for rows of d floats (argmax-row backward of max
- *      pooling). */
+ *      pooling).  Optional g_in / g_out [count]: g_out[i] = idx[i] >= 0 ? g_in[i] : 0 — the pooled
+ *      gradient with the entries of empty sets (argmax -1, autograd routes nothing there) zeroed. */
 int pcc_bce_logits(const float* logits, const float* target, int64_t count, float* loss, float* dlogits, int device,
                    void* stream);
-int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count, int d, int64_t n, float* out, int device,
-                    void* stream);
+int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count, int d, int64_t n, float* out,
+                    const float* g_in, float* g_out, int device, void* stream);
 
 /* ---- accounting / measurement helpers used by bench.py.
  *      pcc_launch_count: kernels launched by this library since the last reset.

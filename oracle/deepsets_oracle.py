@@ -74,9 +74,25 @@ def _layer_norm(z: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 
     return (z - mu) * torch.rsqrt(var + eps) * w + b
 
 
-def mlp_forward(sd: Dict[str, torch.Tensor], plan: List[dict], activation: str, h: torch.Tensor) -> torch.Tensor:
+def _round_bf16_ste(t: torch.Tensor) -> torch.Tensor:
+    """value rounded to bf16 (round-to-nearest-even), identity gradient (straight-through)"""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def mlp_forward(sd: Dict[str, torch.Tensor], plan: List[dict], activation: str, h: torch.Tensor,
+                operand_rounding: Optional[str] = None, round_final_weight: bool = True) -> torch.Tensor:
+    """operand_rounding="bf16": the STATED arithmetic of the product's bf16 precision mode — both operands of
+    every Linear are rounded to bf16, products and sums stay fp32 (tensor-core bf16 x bf16 -> fp32), bias /
+    activation / residual in fp32.  Same reference algorithm (deep_sets.py:44-57,149-160), different stated
+    operand precision; used by the parity tests to separate "the kernel computes what it says" (tight bound)
+    from "bf16 operands differ from fp32 operands" (a property of the mode: ReLU masks flip where |z| is below
+    the rounding noise)."""
+    q = _round_bf16_ste if operand_rounding == "bf16" else (lambda t: t)
     for L in plan:
-        z = F.linear(h, sd[L["lin"] + ".weight"], sd[L["lin"] + ".bias"])
+        w = sd[L["lin"] + ".weight"]
+        if L["kind"] != "final" or round_final_weight:
+            w = q(w)
+        z = F.linear(q(h), w, sd[L["lin"] + ".bias"])
         if L["kind"] == "final":
             h = z
             continue
@@ -122,8 +138,9 @@ def segment_pool(phi_x: torch.Tensor, offsets: torch.Tensor, pooling: str
 
 
 def deepsets_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, idx: torch.Tensor,
-                     return_aux: bool = False):
-    """cfg keys = the reference ctor kwargs (deep_sets.py:6-16)."""
+                     return_aux: bool = False, phi_operand_rounding: Optional[str] = None, argmax_rows=None):
+    """cfg keys = the reference ctor kwargs (deep_sets.py:6-16).  phi_operand_rounding: see mlp_forward (phi only;
+    the set head stays fp32, like the product's).  argmax_rows [B,H]: evaluate max pooling at these rows."""
     ln = cfg.get("layer_norm", True)
     phi = layer_plan("phi", cfg["input_dim"], list(cfg["phi_layers"]),
                      cfg["phi_layers"][-1] if cfg["phi_layers"] else cfg["input_dim"],
@@ -133,9 +150,15 @@ def deepsets_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, id
     pooling = cfg.get("pooling", "sum")
     if pooling not in POOLS:
         raise ValueError("pooling must be 'mean', 'sum', or 'max'")
-    phi_x = mlp_forward(sd, phi, cfg["activation"], x)
+    # sum / mean in the product's bf16 mode: pooling is commuted with the final Linear, which is then applied
+    # to the pooled [B,H] activations by the fp32-grade head kernel — its weight is not rounded
+    phi_x = mlp_forward(sd, phi, cfg["activation"], x, phi_operand_rounding, round_final_weight=(pooling == "max"))
     offsets = segment_offsets(idx)
-    pooled, arg = segment_pool(phi_x, offsets, pooling)
+    if argmax_rows is not None and pooling == "max":
+        arg = argmax_rows
+        pooled = phi_x[arg, torch.arange(phi_x.shape[1]).expand(arg.shape[0], -1)]
+    else:
+        pooled, arg = segment_pool(phi_x, offsets, pooling)
     logits = mlp_forward(sd, rho, cfg["activation"], pooled)
     if return_aux:
         return logits, {"phi_x": phi_x, "pooled": pooled, "argmax": arg, "offsets": offsets}
@@ -143,14 +166,15 @@ def deepsets_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, id
 
 
 def deepsets_train_step(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, idx: torch.Tensor,
-                        y: torch.Tensor):
+                        y: torch.Tensor, phi_operand_rounding: Optional[str] = None, argmax_rows=None):
     """forward + BCEWithLogitsLoss(mean) + backward (wrapper.py:58-67).
 
     Returns (logits, loss, grads{name: tensor}, aux).  Gradients come from torch
     autograd over the restated forward above.
     """
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    logits, aux = deepsets_forward(leaves, cfg, x, idx, return_aux=True)
+    logits, aux = deepsets_forward(leaves, cfg, x, idx, return_aux=True, phi_operand_rounding=phi_operand_rounding,
+                                   argmax_rows=argmax_rows)
     loss = F.binary_cross_entropy_with_logits(logits, y)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}

@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
   uint64_t* acc_f = bars + 2 * kRingF + 5;      // [2] final accumulator (slot) complete
   uint64_t* pool_done = bars + 2 * kRingF + 7;  // [2] final accumulator (slot) drained by the pool warps
   uint64_t* ind_ready = bars + 2 * kRingF + 9;  // poolh: set-indicator operand of this tile built by the pool warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 10);
-  volatile uint32_t* nsetsS = tmem_slot + 1;    // poolh: padded number of sets (MMA N) of the current tile
+  uint64_t* img_free = bars + 2 * kRingF + 10;  // poolh: every pooling MMA of the tile has finished reading the activation image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRingF + 11);
+  volatile uint32_t* nsetsS = tmem_slot + 1;    // poolh: padded number of sets (MMA N) of the current chunk
 
   constexpr uint32_t SLAB = w_slab_bytes(H);   // K = 64 slab of a weight image
   constexpr int HALVES = H / 128;              // M halves of the transposed final layer
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     mbar_init(acc_h, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_f[i], 1); mbar_init(&pool_done[i], 4 * HALVES); }
     mbar_init(ind_ready, kFwdPoolWarps);
+    mbar_init(img_free, 1);
     fence_mbar_init();
   }
   fence_proxy_async();  // the two constant images are read by the tensor core (async proxy)
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
       constexpr uint32_t IDESC_N = make_idesc_bf16(128, H, 0, 0);    // points x features
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, 0, 0);  // features(128) x points
       uint32_t stage = 0, phase = 0, sl_phase = 0, ind_phase = 0;
+      uint32_t use = 0;  // poolh: running count of final-accumulator uses (one per chunk of <= 128 sets)
       int tn = 0;
       const uint32_t a_base = smem_u32(bufA), r_base = smem_u32(ring);
       int nt = 0;  // tiles done by this CTA
@@ -221,6 +224,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
           umma_commit(acc_h);
           trace_ev(p.trace, 1, tn, 141);
         }
+        if (poolh) {
+          // The sets that intersect the tile (interior empty ones included) are pooled in chunks of <= 128: one
+          // pooling MMA group (N <= 128 columns) per chunk, each a separate use of a final-accumulator slot.
+          const int nsets_t = __ldg(p.tile_last + tile) - __ldg(p.tile_first + tile) + 1;
+          const int nch = (nsets_t + 127) >> 7;
+          for (int s = 0; s < NSLAB; ++s) mbar_wait(&slab_ready[s], sl_phase);  // the whole activation image (K = points)
+          sl_phase ^= 1;
+          for (int ch = 0; ch < nch; ++ch, ++use) {
+            const int slot = (L == 2) ? (int)(use & 1) : 0;
+            const uint32_t k = (L == 2) ? (use >> 1) : use;
+            if (k >= 1) mbar_wait(&pool_done[slot], (k - 1) & 1);
+            const uint32_t accT = tmem + ((L == 2) ? slot * 256 : 256);
+            if (ch == 0) trace_ev(p.trace, 1, tn, 102);
+            mbar_wait(ind_ready, ind_phase);
+            ind_phase ^= 1;
+            tc_fence_after();
+            const uint32_t N = *nsetsS;
+            const uint32_t idesc = make_idesc_bf16(128, (int)N, 1, 0);
+            const uint32_t i_base = smem_u32(indS);
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h)
+#pragma unroll
+              for (int ks = 0; ks < kTileM / 16; ++ks)
+                umma_bf16(accT + h * 128, make_smem_desc_sw128_mn(a_base + h * (2 * kActSlab) + ks * 2048, kActSlab),
+                          make_smem_desc_sw128_k(i_base + (ks >> 2) * (N * 128) + (ks & 3) * 32), idesc, ks != 0);
+            umma_commit(&acc_f[slot]);
+          }
+          umma_commit(img_free);
+          trace_ev(p.trace, 1, tn, 142);
+          continue;
+        }
         // final layer (transposed) -> accumulator slot; the pool warps must have drained its previous use
         const int slot = (L == 2) ? (nt & 1) : 0;
         const int k = (L == 2) ? (nt >> 1) : nt;
@@ -230,24 +264,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
         }
         const uint32_t accT = tmem + ((L == 2) ? slot * 256 : 256);
         trace_ev(p.trace, 1, tn, 102);
-        if (poolh) {
-          for (int s = 0; s < NSLAB; ++s) mbar_wait(&slab_ready[s], sl_phase);  // the whole activation image (K = points)
-          sl_phase ^= 1;
-          mbar_wait(ind_ready, ind_phase);
-          ind_phase ^= 1;
-          tc_fence_after();
-          const uint32_t N = *nsetsS;
-          const uint32_t idesc = make_idesc_bf16(128, (int)N, 1, 0);
-          const uint32_t i_base = smem_u32(indS);
-#pragma unroll
-          for (int h = 0; h < HALVES; ++h)
-#pragma unroll
-            for (int ks = 0; ks < kTileM / 16; ++ks)
-              umma_bf16(accT + h * 128, make_smem_desc_sw128_mn(a_base + h * (2 * kActSlab) + ks * 2048, kActSlab),
-                        make_smem_desc_sw128_k(i_base + (ks >> 2) * (N * 128) + (ks & 3) * 32), idesc, ks != 0);
-          umma_commit(&acc_f[slot]);
-          trace_ev(p.trace, 1, tn, 142);
-        }
         for (int s = 0; !poolh && s < NSLAB; ++s) {
           mbar_wait(&slab_ready[s], sl_phase);
           mbar_wait(&full[stage], phase);
@@ -307,9 +323,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
       // ---- the activation image is free once the final layer of the previous tile has completed
       if (nt >= 1) {
-        const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
-        const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
-        mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
+        if (poolh) {
+          mbar_wait(img_free, (uint32_t)((nt - 1) & 1));
+        } else {
+          const int pslot = (L == 2) ? ((nt - 1) & 1) : 0;
+          const int pk = (L == 2) ? ((nt - 1) >> 1) : (nt - 1);
+          mbar_wait(&acc_f[pslot], (uint32_t)(pk & 1));
+        }
       }
       if (tr0) trace_ev(p.trace, 0, tn, 0);
       // ---- layer 0: h_0 = act(W_0 x + b_0), one 64-column slab at a time, handed to the MMA warp at once
@@ -398,50 +418,56 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
       const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
       const bool tr0 = (pw == 0 && lane == 0);
       float* hsum = reinterpret_cast<float*>(p.pool_acc);
-      int tn = 0, nt = 0;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+      int tn = 0;
+      uint32_t use = 0;  // running count of final-accumulator uses, in step with the MMA thread
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int64_t r0 = tile * kTileM;
-        const int b_first = __ldg(p.tile_first + tile), b_last = __ldg(p.tile_last + tile);
-        const int nsets = b_last - b_first + 1;
-        const uint32_t N = (uint32_t)((nsets + 15) & ~15);   // MMA N: multiple of 16, >= 16, <= 128
-        // the previous pooling MMA (which read the indicator) is complete: this warp waited for its accumulator below
-        for (uint32_t q = pt; q < N * 16; q += 32 * kFwdPoolWarps) {
-          const uint32_t sidx = q >> 4, kc = q & 15;   // set slot, 8-point chunk
-          int64_t lo = 0, hi = 0;
-          if ((int)sidx < nsets) { lo = __ldg(p.offsets + b_first + sidx); hi = __ldg(p.offsets + b_first + sidx + 1); }
-          const int64_t p0 = r0 + kc * 8;
-          uint32_t w[4];
+        const int b_first0 = __ldg(p.tile_first + tile), b_last = __ldg(p.tile_last + tile);
+        const int nsets_t = b_last - b_first0 + 1;
+        // chunks of <= 128 sets (a tile of 128 one-point sets plus interior empty sets holds more than 128)
+        for (int c0s = 0; c0s < nsets_t; c0s += 128, ++use) {
+          const int b_first = b_first0 + c0s;
+          const int nsets = (nsets_t - c0s < 128) ? nsets_t - c0s : 128;
+          const uint32_t N = (uint32_t)((nsets + 15) & ~15);   // MMA N: multiple of 16, >= 16, <= 128
+          // the previous pooling MMA (which read the indicator) is complete: this warp waited for its accumulator below
+          for (uint32_t q = pt; q < N * 16; q += 32 * kFwdPoolWarps) {
+            const uint32_t sidx = q >> 4, kc = q & 15;   // set slot, 8-point chunk
+            int64_t lo = 0, hi = 0;
+            if ((int)sidx < nsets) { lo = __ldg(p.offsets + b_first + sidx); hi = __ldg(p.offsets + b_first + sidx + 1); }
+            const int64_t p0 = r0 + kc * 8;
+            uint32_t w[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t b0 = (p0 + 2 * j >= lo && p0 + 2 * j < hi) ? 0x3F80u : 0u;          // bf16 1.0
-            const uint32_t b1 = (p0 + 2 * j + 1 >= lo && p0 + 2 * j + 1 < hi) ? 0x3F80u : 0u;
-            w[j] = b0 | (b1 << 16);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t b0 = (p0 + 2 * j >= lo && p0 + 2 * j < hi) ? 0x3F80u : 0u;          // bf16 1.0
+              const uint32_t b1 = (p0 + 2 * j + 1 >= lo && p0 + 2 * j + 1 < hi) ? 0x3F80u : 0u;
+              w[j] = b0 | (b1 << 16);
+            }
+            *reinterpret_cast<uint4*>(indS + (kc >> 3) * (N * 128) + sidx * 128 + (((kc & 7) ^ (sidx & 7)) << 4)) =
+                make_uint4(w[0], w[1], w[2], w[3]);
           }
-          *reinterpret_cast<uint4*>(indS + (kc >> 3) * (N * 128) + sidx * 128 + (((kc & 7) ^ (sidx & 7)) << 4)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        if (pt == 0) *nsetsS = N;
-        fence_proxy_async();
-        mbar_arrive_warp(ind_ready);
-        const int slot = (L == 2) ? (nt & 1) : 0;
-        const int k = (L == 2) ? (nt >> 1) : nt;
-        mbar_wait(&acc_f[slot], (uint32_t)(k & 1));
-        tc_fence_after();
-        if (tr0) trace_ev(p.trace, 2, tn, 30);
-        if (h < HALVES) {
-          const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
-          for (uint32_t c0 = 0; c0 < N; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(accT + c0, v);
-            tmem_wait_ld();
+          if (pt == 0) *nsetsS = N;
+          fence_proxy_async();
+          mbar_arrive_warp(ind_ready);
+          const int slot = (L == 2) ? (int)(use & 1) : 0;
+          const uint32_t k = (L == 2) ? (use >> 1) : use;
+          mbar_wait(&acc_f[slot], k & 1);
+          tc_fence_after();
+          if (tr0) trace_ev(p.trace, 2, tn, 30);
+          if (h < HALVES) {
+            const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
+            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(accT + c0, v);
+              tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if ((int)(c0 + j) < nsets) atomicAdd(hsum + (int64_t)(b_first + c0 + j) * H + f, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; ++j)
+                if ((int)(c0 + j) < nsets) atomicAdd(hsum + (int64_t)(b_first + c0 + j) * H + f, __uint_as_float(v[j]));
+            }
+            tc_fence_before();
+            mbar_arrive_warp(&pool_done[slot]);
           }
-          tc_fence_before();
-          mbar_arrive_warp(&pool_done[slot]);
+          if (tr0) trace_ev(p.trace, 2, tn, 40);
         }
-        if (tr0) trace_ev(p.trace, 2, tn, 40);
       }
     } else if (h < HALVES) {
       const int r = quarter * 32 + lane;

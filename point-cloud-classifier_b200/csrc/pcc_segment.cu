@@ -202,13 +202,17 @@ __global__ void __launch_bounds__(1024) bce_logits_kernel(const float* __restric
 
 // out[i, :] = x[clamp(idx[i], 0, n-1), :]  (rows of d floats)
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t count, int d,
-                                   int64_t n, float* __restrict__ out) {
+                                   int64_t n, float* __restrict__ out, const float* __restrict__ g_in,
+                                   float* __restrict__ g_out) {
   pdl_enter();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= count * d) return;
   const int64_t i = t / d;
   const int j = (int)(t - i * d);
   int64_t r = idx[i];
+  // a negative index marks "no row" (argmax of an empty set): its gradient entry is zeroed so that the clamped
+  // row contributes nothing downstream
+  if (g_out && j == 0) g_out[i] = (r >= 0) ? g_in[i] : 0.f;
   r = r < 0 ? 0 : (r >= n ? n - 1 : r);
   out[t] = __ldg(x + r * d + j);
 }
@@ -231,11 +235,12 @@ extern "C" int pcc_bce_logits(const float* logits, const float* target, int64_t 
 }
 
 extern "C" int pcc_gather_rows(const float* x, const int32_t* idx, int64_t count, int d, int64_t n, float* out,
+                               const float* g_in, float* g_out,
                                int device, void* stream) {
   PCC_ENTER(device);
   if (count == 0 || d == 0) return 0;
   PCC_REQUIRE(n > 0, "gather from an empty tensor");
-  launch_dep(gather_rows_kernel, dim3((unsigned)cdiv(count * d, 256)), dim3(256), 0, (cudaStream_t)stream, x, idx, count, d, n, out);
+  launch_dep(gather_rows_kernel, dim3((unsigned)cdiv(count * d, 256)), dim3(256), 0, (cudaStream_t)stream, x, idx, count, d, n, out, g_in, g_out);
   return check_launch(__func__);
 }
 

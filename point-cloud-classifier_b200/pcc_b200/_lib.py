@@ -70,7 +70,7 @@ _SIGS = {
     "pcc_peer_free": [_vp, _i32],
     "pcc_peer_allreduce": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp],
     "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
-    "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp],
+    "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _i32, _vp],
     "pcc_launch_count": [_i32],
     "pcc_prof_enable": [_i32],
     "pcc_prof_read": [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],

@@ -116,23 +116,42 @@ class PeerAllReduce:
         self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
         self.numel = (numel + 3) // 4 * 4
         self.buf_bytes = (self.numel * 4 + 255) // 256 * 256
-        region = C.c_void_p()
+        self.local, self.opened = None, []
+        # Every rank runs the same collective sequence (gather handles, gather status, barrier) whatever fails
+        # locally, so a rank that cannot allocate or map IPC memory makes ALL ranks raise together instead of
+        # leaving the healthy ones in a barrier.
+        err = None
         handle = (C.c_ubyte * 64)()
-        L.call("pcc_peer_alloc", self.buf_bytes, C.byref(region), C.cast(handle, C.c_void_p), self.dev_index)
-        self.local = region.value
+        try:
+            region = C.c_void_p()
+            L.call("pcc_peer_alloc", self.buf_bytes, C.byref(region), C.cast(handle, C.c_void_p), self.dev_index)
+            self.local = region.value
+        except Exception as e:
+            err = e
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
         self.regions = (C.c_void_p * self.world)()
-        self.opened = []
-        for r in range(self.world):
-            if r == self.rank:
-                self.regions[r] = self.local
-            else:
-                peer = C.c_void_p()
-                hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-                L.call("pcc_peer_open", C.cast(hb, C.c_void_p), C.byref(peer), self.dev_index)
-                self.regions[r] = peer.value
-                self.opened.append(peer.value)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.regions[r] = self.local
+                    else:
+                        peer = C.c_void_p()
+                        hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                        L.call("pcc_peer_open", C.cast(hb, C.c_void_p), C.byref(peer), self.dev_index)
+                        self.regions[r] = peer.value
+                        self.opened.append(peer.value)
+            except Exception as e:
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer rank could not allocate its IPC region")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            self.close()
+            raise RuntimeError(f"peer all-reduce setup failed on rank(s) {[r for r, o in enumerate(oks) if not o]}"
+                               + (f": {type(err).__name__}: {err}" if err is not None else ""))
         self.counters = torch.zeros(4, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
@@ -145,12 +164,13 @@ class PeerAllReduce:
         return flat
 
     def close(self):
-        if getattr(self, "local", None) is None:
+        if getattr(self, "local", None) is None and not getattr(self, "opened", None):
             return
         torch.cuda.synchronize(self.device)
         for ptr_ in self.opened:
             self.L.call("pcc_peer_close", self.C.c_void_p(ptr_), self.dev_index)
-        self.L.call("pcc_peer_free", self.C.c_void_p(self.local), self.dev_index)
+        if self.local is not None:
+            self.L.call("pcc_peer_free", self.C.c_void_p(self.local), self.dev_index)
         self.local, self.opened = None, []
 
 
@@ -186,16 +206,29 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int | None 
 
 
 def attach_allreduce_hooks(model: torch.nn.Module) -> List:
-    """Data-parallel training under the UNCHANGED reference loop: when the last parameter gradient of
-    a backward pass has been accumulated, all gradients are averaged across ranks (one flat bucket).
-    Returns the hook handles."""
+    """Data-parallel training under the UNCHANGED reference loop (wrapper.py:51-74): at the END of every backward
+    pass all gradients are averaged across ranks (one flat bucket).  Returns the hook handles.
+
+    The first parameter hook of a pass queues an end-of-backward callback on the autograd engine, so the
+    collective fires exactly once per pass whatever subset of the parameters received a gradient (a parameter
+    without one contributes zeros, as in `flatten_grads`): every rank issues the same collective sequence even
+    when a branch leaves some parameters unused, and a backward that raises midway leaves no stale count
+    behind (the flag is cleared when the next pass starts queuing)."""
+    from torch.autograd import Variable
     params = [p for p in model.parameters() if p.requires_grad]
-    state = {"seen": 0}
+    state = {"queued": False}
+
+    def finish():
+        state["queued"] = False
+        allreduce_gradients(params)
 
     def hook(_p):
-        state["seen"] += 1
-        if state["seen"] == len(params):
-            state["seen"] = 0
-            allreduce_gradients(params)
+        if not state["queued"]:
+            state["queued"] = True
+            try:
+                Variable._execution_engine.queue_callback(finish)
+            except Exception:
+                state["queued"] = False
+                raise
 
     return [p.register_post_accumulate_grad_hook(hook) for p in params]

@@ -371,14 +371,17 @@ class BCEWithLogitsLoss(torch.nn.Module):
         return bce_with_logits(logits, target)
 
 
-def gather_rows(x: torch.Tensor, idx_i32: torch.Tensor) -> torch.Tensor:
-    """out[i] = x[clamp(idx[i])] for int32 row ids (used by the argmax-row backward of max pooling)"""
+def gather_rows(x: torch.Tensor, idx_i32: torch.Tensor, grad: Optional[torch.Tensor] = None):
+    """out[i] = x[clamp(idx[i])] for int32 row ids (used by the argmax-row backward of max pooling).  With `grad`
+    (one value per index) also returns grad with the entries of negative indices (empty sets) zeroed, from the
+    same launch."""
     x = L.f32c(x)
     dev, st = _ctx(x, idx_i32)
     flat = idx_i32.reshape(-1)
     out = torch.empty((flat.numel(), x.shape[1]), dtype=torch.float32, device=x.device)
-    call("pcc_gather_rows", ptr(x), ptr(flat), flat.numel(), x.shape[1], x.shape[0], ptr(out), dev, st)
-    return out
+    gm = torch.empty_like(grad) if grad is not None else None
+    call("pcc_gather_rows", ptr(x), ptr(flat), flat.numel(), x.shape[1], x.shape[0], ptr(out), ptr(grad), ptr(gm), dev, st)
+    return out if grad is None else (out, gm)
 
 
 # ------------------------------------------------------------------ fused rho head

@@ -57,6 +57,11 @@ class FusedPhiPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, offsets, meta, *params):
         plan_len, act, pooling, res_mask = meta
+        if ctx.needs_input_grad[0]:
+            # the fused backward produces parameter gradients only (the reference never asks for dx: the collate's
+            # x does not require grad); failing loudly beats returning a silent None
+            raise RuntimeError("the fused bf16 phi+pool path does not produce a gradient for x; use precision='fp32' "
+                               "or detach x")
         x = L.f32c(x)
         dev = L.require_cuda(x, offsets, *params)
         st = L.stream_ptr(dev)
@@ -102,15 +107,12 @@ class FusedPhiPoolFn(torch.autograd.Function):
             # virtual rows b*H .. b*H+H-1 and feature f's argmax is virtual row b*H+f, so the same kernels
             # produce the identical sums with n/(B*H) times less work.
             from .functional import gather_rows
-            x = gather_rows(x, arg)
-            key = (B, H, x.device)
-            if _VIRT.get("key") != key:
-                _VIRT["key"] = key
-                _VIRT["offsets"] = torch.arange(B + 1, device=x.device, dtype=torch.int64) * H
-                _VIRT["arg"] = torch.arange(B * H, device=x.device, dtype=torch.int32).view(B, H)
+            # an empty set has argmax -1 and receives no gradient: its pooled-gradient entries are zeroed by the
+            # same launch, so the (clamped) gathered row contributes nothing
+            x, dpooled = gather_rows(x, arg, dpooled)
             # the library exploits the one-hot structure of these rows (argmax = None): no dgrad / wgrad GEMM for
-            # the final Linear
-            offsets, arg, n = _VIRT["offsets"], None, B * H
+            # the final Linear; offsets are not read in this mode
+            arg, n = None, B * H
         from .distributed import grad_like
         grads = [grad_like(t) for t in ws_]
         dw = (C.c_void_p * L.MAX_PHI_LAYERS)(*[grads[2 * i].data_ptr() for i in range(plan_len)])
@@ -121,8 +123,6 @@ class FusedPhiPoolFn(torch.autograd.Function):
              C.cast(dw, C.c_void_p), C.cast(db, C.c_void_p), ptr(ws), ptr(wpack), dev, st)
         return (None, None, None, *grads)
 
-
-_VIRT = {}  # cached index tensors of the virtual-row backward (static per (B, H, device))
 
 
 def phi_pool(x, offsets, plan: List[dict], act: str, pooling: str):

@@ -43,20 +43,22 @@ class GraphedTrainStep:
         import os as _os
         if self.allreduce and self.static_y.is_cuda and _os.environ.get("PCC_PEER_ALLREDUCE", "1") != "0":
             try:
+                # collective-safe: every rank runs the same collective sequence inside and either all ranks get a
+                # working instance or all ranks raise (and have released what they had mapped)
                 self.peer = PeerAllReduce(self.arena.numel, self.static_y.device)
             except Exception as e:  # e.g. IPC not permitted: fall back to NCCL, loudly
                 import sys as _sys
                 print(f"[pcc_b200] peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=_sys.stderr)
                 self.peer = None
-            ok = torch.tensor([1 if self.peer is not None else 0], device=self.static_y.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
-            if int(ok.item()) == 0 and self.peer is not None:
-                self.peer.close()
-                self.peer = None
         self.graph = None
         self.loss = None
         self.logits = None
 
+        # The warm-up steps run the real step (optimizer and all-reduce included) on the example batch.  They must
+        # not become part of the training trajectory (the reference loop, wrapper.py:51-74, has no hidden steps), so
+        # parameters, buffers (BatchNorm running statistics, num_batches_tracked) and the optimizer state are
+        # snapshotted here and restored IN PLACE after the capture (the graph holds their addresses).
+        snap = self._snapshot() if optimizer is not None or any(True for _ in model.buffers()) else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -72,6 +74,39 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph):
                 self._step_body()
             torch.cuda.synchronize()
+        if snap is not None:
+            self._restore(snap)
+            torch.cuda.synchronize()
+
+    def _optimizer_tensors(self):
+        opt = self.optimizer
+        if opt is None:
+            return []
+        out = []
+        for st in getattr(opt, "_groups", None) or []:       # FusedAdam: flat moment buffers + device step counter
+            if st is not None:
+                out += [st["exp_avg"], st["exp_avg_sq"], st["step"]]
+        for st in opt.state.values():                         # torch.optim: per-parameter state tensors
+            if isinstance(st, dict):
+                out += [v for v in st.values() if torch.is_tensor(v)]
+        return out
+
+    def _snapshot(self):
+        with torch.no_grad():
+            model_t = list(self.model.parameters()) + list(self.model.buffers())
+            return {"model": [(t, t.detach().clone()) for t in model_t],
+                    "opt": {id(t): (t, t.detach().clone()) for t in self._optimizer_tensors()}}
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for t, c in snap["model"]:
+                t.copy_(c)
+            for t in self._optimizer_tensors():
+                ent = snap["opt"].get(id(t))
+                if ent is not None:
+                    t.copy_(ent[1])
+                else:            # state created lazily by the warm-up steps: back to its initial value (zeros)
+                    t.zero_()
 
     # one training step on the static buffers
     def _step_body(self):

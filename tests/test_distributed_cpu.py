@@ -60,6 +60,27 @@ def _worker(rank, world, port, q):
     ok2 = all(torch.allclose(p.grad, b, atol=1e-6) for p, b in zip(lin.parameters(), ref))
     for h in handles:
         h.remove()
+    # (2b) a parameter that gets no gradient in one pass (unused branch) must neither skip that pass's all-reduce
+    #      nor shift the next one: two modules, the second one only used in the second pass
+    both = torch.nn.ModuleList([lin, torch.nn.Linear(3, 1)])
+    with torch.no_grad():
+        both[1].weight.fill_(-0.25); both[1].bias.fill_(0.3)
+    handles = D.attach_allreduce_hooks(both)
+    both.zero_grad()
+    local_loss(xs, ids, ys).backward()                       # pass 1: both[1] unused -> no grad for it
+    ok2 = ok2 and all(torch.allclose(p.grad, b, atol=1e-6) for p, b in zip(lin.parameters(), ref))
+    both.zero_grad()
+
+    def loss2(xa, ia, ya):
+        pooled = torch.zeros(ya.shape[0], 3).index_add(0, ia, xa)
+        return ((lin(pooled) + both[1](pooled) - ya) ** 2).sum()
+    loss2(xs, ids, ys).backward()                            # pass 2: every parameter used
+    got2 = [p.grad.clone() for p in both.parameters()]
+    for h in handles:
+        h.remove()
+    both.zero_grad()
+    loss2(x, idx, y).backward()
+    ok2 = ok2 and all(torch.allclose(a, p.grad / world, atol=1e-6) for a, p in zip(got2, both.parameters()))
     # (3) shards are disjoint, ordered, re-based
     total_rows = torch.tensor([xs.shape[0]])
     dist.all_reduce(total_rows)

@@ -1,6 +1,9 @@
-"""GPU, BASELINE.json's full sizes (B = 256 sets x N = 1024 points, H = 256): the oracle cannot run these in
-seconds, so the CUDA path is checked through size-independent properties of the reference's DeepSets
-(models/deep_sets.py:89-112):
+"""GPU, BASELINE.json's full sizes (B = 256 sets x N = 1024 points, H = 256).
+(1) `test_graphed_train_step_matches_oracle_full_size`: the thing bench.py times — `GraphedTrainStep` (fused BCE
+    loss, CUDA-graph replay of forward + loss + backward) — against the pinned oracle on the same batch: logits and
+    every parameter gradient, for the headline relu + max model and the reference's yaml default (gelu + residual
+    + mean, d = 6, out = 1); ~1 s of CPU per oracle evaluation.  Tolerances and their derivation: test_fused_gpu.py.
+(2) size-independent properties of the reference's DeepSets (models/deep_sets.py:89-112):
   * permutation invariance: shuffling the points inside every set leaves the logits unchanged — bit-exact for max
     pooling (every point's row is computed independently and the maximum does not depend on the order), to
     accumulation-order noise for sum / mean;
@@ -16,7 +19,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "point-cloud-classifier_b200"))
 
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pcc_b200  # noqa: E402
+from oracle import deepsets_oracle as O  # noqa: E402
+from pcc_b200 import functional as PF  # noqa: E402
+from pcc_b200.train_step import GraphedTrainStep  # noqa: E402
+from test_fused_gpu import _fused_argmax, check_step_against_oracles  # noqa: E402
 
 B, N, D, H, OUT = 256, 1024, 3, 256, 10
 pytestmark = pytest.mark.gpu
@@ -98,3 +107,38 @@ def test_pooled_maxima_match_fp32_full_size():
         true_max = h.view(B, N, H).max(dim=1).values
     gap = (pooled - true_max).abs().max() / true_max.abs().max()
     assert float(gap) < 3e-2   # the stated bf16 tolerance of tests/test_fused_gpu.py
+
+
+FULL_CFGS = {
+    "relu_max": dict(input_dim=3, phi_layers=[H, H], rho_layers=[H], output_dim=10, activation="relu", layer_norm=False,
+                     residual_block=False, pooling="max"),
+    "yaml_gelu_res_mean": dict(input_dim=6, phi_layers=[H, H], rho_layers=[H], output_dim=1, activation="gelu",
+                               layer_norm=False, residual_block=True, pooling="mean"),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_CFGS))
+def test_graphed_train_step_matches_oracle_full_size(name):
+    cfg = FULL_CFGS[name]
+    d, out = cfg["input_dim"], cfg["output_dim"]
+    sd = O.init_state_dict(cfg, seed=71)
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(B * N, d, generator=g)
+    idx = torch.arange(B).repeat_interleave(N)
+    y = (torch.rand(B, out, generator=g) > 0.5).float()
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    xc, ic, yc = x.cuda(), idx.cuda(), y.cuda()
+    # the captured step is built on a DIFFERENT batch and then fed this one through its static buffers
+    gs = GraphedTrainStep(m, (torch.randn_like(xc), ic), torch.zeros_like(yc), forward_kwargs={"num_sets": B})
+    assert gs.graph is not None and m.last_path == "fused-bf16"
+    loss = gs.step((xc, ic), yc)
+    torch.cuda.synchronize()
+    arg = None
+    if cfg["pooling"] == "max":
+        arg = _fused_argmax(m, xc, PF.segment_offsets(ic, B), cfg["activation"])
+    r32 = O.deepsets_train_step(sd, cfg, x, idx, y, argmax_rows=arg)
+    r16 = O.deepsets_train_step(sd, cfg, x, idx, y, phi_operand_rounding="bf16", argmax_rows=arg)
+    assert abs(float(loss) - float(r16[1])) < 2e-3 * abs(float(r16[1]))
+    check_step_against_oracles(f"GraphedTrainStep full size {name}", cfg["activation"],
+                               {k: p.grad for k, p in m.named_parameters()}, gs.logits, (r32[0], r32[2]), (r16[0], r16[2]))

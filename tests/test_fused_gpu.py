@@ -1,16 +1,26 @@
 """GPU: the fused tcgen05 / TMEM phi+pool path (bf16 operands, fp32 accumulate).
 
-Stated bf16 tolerance (north_star "or a stated bf16 tolerance"): operands are rounded to
-bf16 (8-bit mantissa) before every tensor-core contraction.  Forward values (pooled
-features, logits) are compared against the fp32 oracle with
-    max|got - ref| <= BF16_TOL * max|ref|,   BF16_TOL = 3e-2      (measured: 1e-3..4e-3)
-and parameter gradients with the relative Frobenius error
-    ||got - ref||_F <= BF16_GRAD_TOL * ||ref||_F,   BF16_GRAD_TOL = 5e-2   (measured: 2e-3..8e-3)
-(max-norm is not meaningful for gradients across precisions: one flipped relu mask or argmax
-row moves a single entry by O(1)).  Max pooling: a precision change can move an argmax between
-near-tied rows, so (a) argmax rows must lie in their set and be maximal in fp32 within
-BF16_TOL, with > 97 % identical to the fp32 oracle's, and (b) gradients are checked against
-an fp32 oracle evaluated with the SAME argmax rows the kernel selected.
+Stated bf16 tolerance (north_star "or a stated bf16 tolerance").  The bf16 mode rounds both operands of every phi
+Linear to bf16 (8-bit mantissa) and accumulates in fp32.  Two comparisons, both against the pinned oracle
+(oracle/deepsets_oracle.py), per tensor, printed by every test:
+
+ (1) oracle evaluated with the SAME stated operand rounding (`phi_operand_rounding="bf16"`: operands rounded to
+     bf16, everything else fp32) — "the kernel computes what it says".  Measured on B200 (tools/grad_err_report.py,
+     profiles/grad_err_r2.txt): logits <= 2.5e-3 of max|ref| (relu: <= 3e-4; gelu / silu carry the tanh.approx
+     activation, 1e-3 .. 2.5e-3), parameter gradients <= 4.4e-3 relative Frobenius error over all 11 cases and both
+     full-size configurations.  Tolerances = 2x measured:
+         logits  max|got - ref| <= BF16_TOL * max|ref|,        BF16_TOL = 5e-3
+         grads   ||got - ref||_F <= BF16_GRAD_TOL * ||ref||_F,  BF16_GRAD_TOL = 1e-2
+ (2) the fp32 oracle (the reference's own arithmetic): logits <= FP32_TOL = 1.5e-2 (measured <= 6.5e-3).  Gradients:
+     smooth activations (gelu / silu) <= FP32_GRAD_TOL_SMOOTH = 1e-2 (measured <= 4.4e-3); ReLU <=
+     FP32_GRAD_TOL_RELU = 0.16 (measured 7.6e-3 .. 7.8e-2).  The ReLU figure is a property of bf16 operands, not of the
+     kernel (comparison (1) holds to 2.9e-3 on the same cases): rounding the operands moves every pre-activation by
+     ~2e-3 of its scale, so ~0.5 % of the ReLU masks flip, each flip changes one gradient term by O(1), and with
+     random labels the gradient is an incoherent sum, so the relative error is ~sqrt(flip fraction) ~ 7e-2 whatever
+     the batch size (rho.0.bias at B=256 shows the same 7e-2 as phi.0.weight).
+Max pooling: a precision change can move an argmax between near-tied rows, so (a) argmax rows must lie in their set
+and be maximal in fp32 within FP32_TOL, with > 97 % identical to the fp32 oracle's, and (b) gradients are checked
+against oracles evaluated with the SAME argmax rows the kernel selected.
 """
 import ctypes as C
 
@@ -25,8 +35,34 @@ import pcc_b200
 from pcc_b200 import _lib, functional as PF, fused as FZ
 
 pytestmark = pytest.mark.gpu
-BF16_TOL = 3e-2
-BF16_GRAD_TOL = 5e-2
+BF16_TOL = 5e-3
+BF16_GRAD_TOL = 1e-2
+FP32_TOL = 1.5e-2
+FP32_GRAD_TOL_SMOOTH = 1e-2
+FP32_GRAD_TOL_RELU = 0.16
+
+
+def check_step_against_oracles(tag, act, named_grads, logits, ref32, ref16):
+    """ref32 / ref16 = (logits, grads) of the fp32 oracle and of the oracle with bf16 operand rounding.
+    Prints the per-tensor errors and the worst case, asserts the stated tolerances."""
+    e_l16, e_l32 = rel_err(logits, ref16[0]), rel_err(logits, ref32[0])
+    rows, worst16, worst32 = [], ("", 0.0), ("", 0.0)
+    for k, r16 in ref16[1].items():
+        got = named_grads[k]
+        assert got is not None, k
+        e16, e32 = rel_l2(got, r16), rel_l2(got, ref32[1][k])
+        rows.append(f"{k}={e16:.1e}/{e32:.1e}")
+        if e16 > worst16[1]:
+            worst16 = (k, e16)
+        if e32 > worst32[1]:
+            worst32 = (k, e32)
+    print(f"{tag}: logits {e_l16:.1e}/{e_l32:.1e} (vs bf16-operand oracle / fp32 oracle); grads rel-L2 "
+          f"worst {worst16[0]} {worst16[1]:.1e} / {worst32[0]} {worst32[1]:.1e}; " + " ".join(rows))
+    assert e_l16 < BF16_TOL, ("logits vs bf16-operand oracle", e_l16)
+    assert e_l32 < FP32_TOL, ("logits vs fp32 oracle", e_l32)
+    assert worst16[1] < BF16_GRAD_TOL, ("grad vs bf16-operand oracle",) + worst16
+    tol32 = FP32_GRAD_TOL_RELU if act == "relu" else FP32_GRAD_TOL_SMOOTH
+    assert worst32[1] < tol32, ("grad vs fp32 oracle",) + worst32
 
 
 def _st_a(i, k):
@@ -84,9 +120,13 @@ def test_fused_forward_matches_oracle(act, pool, res, H, depth, d, sizes):
     off = PF.segment_offsets(idx.cuda(), len(sizes))
     with torch.no_grad():
         pooled = FZ.phi_pool(x.cuda(), off, m._phi_plan, act, pool)
-    err = rel_err(pooled, aux["pooled"])
-    print(f"fused fwd {act}/{pool}/res={res}/H={H}/depth={depth}: rel err {err:.2e}")
-    assert err < BF16_TOL
+    _, aux16 = O.deepsets_forward(sd, cfg, x, idx, return_aux=True, phi_operand_rounding="bf16")
+    err, err16 = rel_err(pooled, aux["pooled"]), rel_err(pooled, aux16["pooled"])
+    print(f"fused fwd {act}/{pool}/res={res}/H={H}/depth={depth}: pooled rel err {err16:.2e} vs bf16-operand oracle, "
+          f"{err:.2e} vs fp32 oracle")
+    assert err < FP32_TOL
+    if pool != "max":   # (max: a near-tie can pick another row than the free-running oracle; covered with pinned rows below)
+        assert err16 < BF16_TOL
 
 
 def test_fused_argmax_consistent_with_fp32_oracle():
@@ -114,7 +154,7 @@ def test_fused_argmax_consistent_with_fp32_oracle():
     phi = aux["phi_x"]
     picked = phi[arg, torch.arange(H).expand(B, -1)]        # fp32 value at the row the kernel picked
     gap = (aux["pooled"] - picked).abs().max() / aux["pooled"].abs().max()
-    assert float(gap) < BF16_TOL                            # picked rows are (near-)maximal in fp32 too
+    assert float(gap) < FP32_TOL                            # picked rows are (near-)maximal in fp32 too
     agree = (arg == aux["argmax"]).float().mean()
     print(f"argmax agreement with fp32 oracle: {float(agree):.3f}")
     assert float(agree) > 0.97
@@ -132,7 +172,7 @@ def test_fused_large_config2_properties():
     with torch.no_grad():
         pooled = FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
         ref = m._mlp(m._phi_plan, x).view(B, N, -1).max(dim=1)[0]   # fp32 CUDA path
-    assert rel_err(pooled, ref) < BF16_TOL
+    assert rel_err(pooled, ref) < FP32_TOL
 
 
 def _fused_argmax(m, x, off, act):
@@ -148,20 +188,6 @@ def _fused_argmax(m, x, off, act):
     return arg.cpu().long()
 
 
-def _oracle_step_with_argmax(sd, cfg, x, idx, y, arg):
-    """fp32 oracle train step with max pooling pinned to given argmax rows."""
-    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    phi = O.layer_plan("phi", cfg["input_dim"], list(cfg["phi_layers"]), cfg["phi_layers"][-1], False,
-                       cfg["residual_block"])
-    rho = O.layer_plan("rho", phi[-1]["out"], list(cfg["rho_layers"]), cfg["output_dim"], False, False)
-    phi_x = O.mlp_forward(leaves, phi, cfg["activation"], x)
-    pooled = phi_x[arg, torch.arange(phi_x.shape[1]).expand(arg.shape[0], -1)]
-    logits = O.mlp_forward(leaves, rho, cfg["activation"], pooled)
-    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
-    loss.backward()
-    return logits.detach(), {k: v.grad for k, v in leaves.items()}
-
-
 @pytest.mark.parametrize("act,pool,res,H,depth,d,sizes", CASES)
 def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
     """forward + BCEWithLogitsLoss + backward through the fused kernels vs the fp32 oracle."""
@@ -171,27 +197,18 @@ def test_fused_train_step_matches_oracle(act, pool, res, H, depth, d, sizes):
     y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(53)) > 0.5).float()
     m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
     m.load_state_dict(sd)
+    arg = None
     if pool == "max":
         off = PF.segment_offsets(idx.cuda(), len(sizes))
         arg = _fused_argmax(m, x.cuda(), off, act)
-        ref_logits, ref_grads = _oracle_step_with_argmax(sd, cfg, x, idx, y, arg)
-    else:
-        ref_logits, _, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
+    r32 = O.deepsets_train_step(sd, cfg, x, idx, y, argmax_rows=arg)
+    r16 = O.deepsets_train_step(sd, cfg, x, idx, y, phi_operand_rounding="bf16", argmax_rows=arg)
     logits = m(x.cuda(), idx.cuda())
     assert m.last_path == "fused-bf16"
     loss = torch.nn.BCEWithLogitsLoss()(logits, y.cuda())
     loss.backward()
-    assert rel_err(logits, ref_logits) < BF16_TOL
-    worst = 0.0
-    for k, ref in ref_grads.items():
-        got = dict(m.named_parameters())[k].grad
-        assert got is not None, k
-        e = rel_l2(got, ref)
-        worst = max(worst, e)
-        # max pooling routes the gradient through few rows, so relu-mask flips average out less
-        assert e < (2 * BF16_GRAD_TOL if pool == "max" else BF16_GRAD_TOL), (k, e)
-    print(f"fused train {act}/{pool}/res={res}/H={H}/depth={depth}: logits {rel_err(logits, ref_logits):.2e} "
-          f"worst grad rel-L2 {worst:.2e}")
+    check_step_against_oracles(f"fused train {act}/{pool}/res={res}/H={H}/depth={depth}", act,
+                               {k: p.grad for k, p in m.named_parameters()}, logits, (r32[0], r32[2]), (r16[0], r16[2]))
 
 
 def test_fused_multi_tile_per_cta_backward():
@@ -201,14 +218,14 @@ def test_fused_multi_tile_per_cta_backward():
     sizes = [1024] * 40
     x, idx = ragged_batch(sizes, 3, seed=62)
     y = (torch.rand(len(sizes), 3, generator=torch.Generator().manual_seed(63)) > 0.5).float()
-    ref_logits, _, ref_grads, _ = O.deepsets_train_step(sd, cfg, x, idx, y)
+    r32 = O.deepsets_train_step(sd, cfg, x, idx, y)
+    r16 = O.deepsets_train_step(sd, cfg, x, idx, y, phi_operand_rounding="bf16")
     m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
     m.load_state_dict(sd)
     logits = m(x.cuda(), idx.cuda())
     torch.nn.BCEWithLogitsLoss()(logits, y.cuda()).backward()
-    assert rel_err(logits, ref_logits) < BF16_TOL
-    for k, ref in ref_grads.items():
-        assert rel_l2(dict(m.named_parameters())[k].grad, ref) < BF16_GRAD_TOL, k
+    check_step_against_oracles("multi-tile relu/mean", "relu", {k: p.grad for k, p in m.named_parameters()}, logits,
+                               (r32[0], r32[2]), (r16[0], r16[2]))
 
 
 def test_deeper_phi_falls_back_to_fp32_path():
@@ -304,3 +321,58 @@ def test_dependent_launch_matches_stream_ordered_launch(pooling, act):
     for a, b in zip(*grads):
         for ga, gb in zip(a, b):
             assert torch.equal(ga, gb)
+
+
+@pytest.mark.parametrize("pool,H", [("sum", 128), ("mean", 256), ("max", 256)])
+def test_interior_empty_sets(pool, H):
+    """Sets without points inside the index range (a gap in idx, or an explicit num_sets): the library defines their
+    pooled row as 0 and they receive no gradient.  One 128-row tile here intersects 328 sets (64 one-point sets,
+    200 EMPTY ones, 64 one-point sets): the commuted sum / mean pooling runs its pooling MMA in chunks of <= 128 sets;
+    max pooling must not route the gradient of an empty set (argmax -1) to row 0."""
+    d, act = 3, "gelu"
+    cfg = _cfg(act, pool, False, H, 2, d)
+    sd = O.init_state_dict(cfg, seed=91)
+    ids = list(range(64)) + list(range(264, 328)) + [328] * 300 + [330] * 5
+    num_sets = 480                                           # 149 trailing empty sets as well
+    idx = torch.tensor(ids, dtype=torch.long)
+    g = torch.Generator().manual_seed(92)
+    x = torch.randn(len(ids), d, generator=g)
+    wt = torch.randn(num_sets, H, generator=g)
+    m = pcc_b200.DeepSets(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    off = PF.segment_offsets(idx.cuda(), num_sets)
+    pooled = FZ.phi_pool(x.cuda(), off, m._phi_plan, act, pool)
+    (pooled * wt.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    # oracle on the compacted batch (non-empty sets only), same stated operand rounding
+    nonempty = sorted(set(ids))
+    remap = {b: i for i, b in enumerate(nonempty)}
+    cidx = torch.tensor([remap[b] for b in ids], dtype=torch.long)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    plan = O.layer_plan("phi", d, [H, H], H, False, False)
+    phi_x = O.mlp_forward(leaves, plan, act, x, "bf16", round_final_weight=(pool == "max"))
+    if pool == "max":   # evaluate at the rows the kernel selected (near-ties may resolve differently, see the header)
+        arg = _fused_argmax(m, x.cuda(), off, act)
+        assert bool((arg[[b for b in range(num_sets) if b not in remap]] == -1).all())
+        ref = phi_x[arg[nonempty], torch.arange(H).expand(len(nonempty), -1)]
+    else:
+        ref, _ = O.segment_pool(phi_x, O.segment_offsets(cidx), pool)
+    (ref * wt[nonempty]).sum().backward()
+    got = pooled.detach().cpu()
+    empty = torch.ones(num_sets, dtype=torch.bool)
+    empty[nonempty] = False
+    assert bool((got[empty] == 0).all())
+    assert rel_err(got[nonempty], ref) < BF16_TOL
+    for i, Lr in enumerate(m._phi_plan):
+        for nm, p in (("weight", Lr["lin"].weight), ("bias", Lr["lin"].bias)):
+            r = leaves[f"{plan[i]['lin']}.{nm}"].grad
+            e = rel_l2(p.grad, r)
+            assert e < BF16_GRAD_TOL, (pool, plan[i]["lin"], nm, e)
+
+
+def test_fused_path_refuses_input_gradient():
+    m = pcc_b200.DeepSets(3, [128, 128], [64], 2, "relu", layer_norm=False, pooling="mean", precision="bf16").cuda()
+    x = torch.randn(200, 3, device="cuda", requires_grad=True)
+    idx = torch.arange(2, device="cuda").repeat_interleave(100)
+    with pytest.raises(RuntimeError, match="gradient for x"):
+        m(x, idx)

@@ -78,7 +78,9 @@ def test_fused_adam_in_captured_train_step():
     for _ in range(n_graph):
         gs.run()
     torch.cuda.synchronize()
-    total = int(opt._groups[0]["step"].item())        # warm-up + capture + replays
+    # building the captured step must not advance the trajectory: its warm-up steps are rolled back
+    total = int(opt._groups[0]["step"].item())
+    assert total == n_graph
     o_ref = torch.optim.AdamW(ref.parameters(), lr=1e-3)
     lf = torch.nn.BCEWithLogitsLoss()
     for _ in range(total):
