@@ -15,6 +15,14 @@ network).  Their published semantics are restated below:
       aggregates to 0 (PyG scatter with include_self=False on a zero-filled output).
   global_mean_pool(x, batch): segment mean of rows by `batch`, size = batch.max()+1.
 
+Pinned all the same, as far as the reference itself reaches (tests/test_oracle_golden.py, CPU):
+  * the control flow, BatchNorm / Linear / activation arithmetic and state_dict keys against outputs of the
+    reference's OWN models/graph_net.py, run by oracle/gen_golden_graphnet.py with an independent loop-based
+    stand-in for the absent torch_geometric kernels (tests/golden/graphnet_*.npz: logits, loss, every gradient,
+    running statistics, eval logits);
+  * `_bn` against torch.nn.BatchNorm1d, `graph_aggregate` / `global_mean_pool` against torch.scatter_reduce
+    (include_self=False on a zero-filled output), values and gradients.
+
 Control flow follows /root/reference/models/graph_net.py:65-104 (activation BEFORE
 BatchNorm, :75-76; forward hard-codes global_mean_pool in both branches, :92,:96;
 fc1 width 256 hard-coded, :61).  BatchNorm1d is torch's own (train-mode batch

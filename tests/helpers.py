@@ -46,3 +46,17 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     operand precision causes."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def load_graphnet_golden(name):
+    """tests/golden/graphnet_*.npz: outputs of the reference's own models/graph_net.py (oracle/gen_golden_graphnet.py)"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    out = {"cfg": json.loads(str(z["cfg_json"])),
+           "sd": {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")},
+           "grads": {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")},
+           "after": {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("after/")},
+           "weights": torch.from_numpy(z["weights"]) if "weights" in z.files else None}
+    for k in ("x", "membership", "edges", "y", "logits", "logits_eval"):
+        out[k] = torch.from_numpy(z[k])
+    out["loss"] = float(z["loss"])
+    return out
