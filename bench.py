@@ -1,25 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native DeepSets hot path.
+"""bench.py — benchmark of the B200-native point-set encoder hot path.
 
 Metric (BASELINE.json): train samples/sec (fwd+bwd), DeepSets B=256 N=1024 per GPU.
-A "step" = forward + BCEWithLogitsLoss + backward of one batch (+ gradient all-reduce
-when N > 1) of the workload BASELINE.json's configs[1] names: phi [3->256->256]+final,
-ReLU, max pool, rho [256]->10, bf16 tensor-core path, 1xB200 (weak scaling for N > 1:
-256 sets per GPU).
+A "step" = forward + BCEWithLogitsLoss + backward of one batch (+ gradient all-reduce when N > 1).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo (CUDA)
-  python bench.py --impl reference [...]                         # reference CPU path (oracle port)
-  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # headline: configs[1] (relu + max, bf16 path)
+  python bench.py --config yaml|ragged|graphnet|sweep [...]       # the other BASELINE configs (see WORKLOADS)
+  python bench.py --impl reference [...]                          # reference CPU path (oracle port) on the host cores
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # one rank per GPU (weak scaling)
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  The timed loop is repeated `--repeats` times (each window = exactly K steps between
+barrier + synchronize); `value` is the MEDIAN window, all windows are listed in `windows_ms`.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -29,15 +28,154 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-B_PER_GPU, N_PTS, D_IN, H, OUT = 256, 1024, 3, 256, 10
-CFG = dict(input_dim=D_IN, phi_layers=[H, H], rho_layers=[H], output_dim=OUT, activation="relu", layer_norm=False,
-           residual_block=False, pooling="max")
-# algorithmic FLOP per point, reference formulation, recompute not credited
-FLOP_FWD_PT = 2 * (H * D_IN + 2 * H * H)               # 263,680
-FLOP_TRAIN_PT = 3 * FLOP_FWD_PT - 2 * H * D_IN          # 789,504
-FLOP_CHAIN_PT = 2 * (2 * H * H)                         # dgrad of the two H x H layers
-FLOP_WGRAD_PT = FLOP_FWD_PT                             # wgrad of all three layers
-N_ROTATE = 32                                           # distinct input batches (166 MB > 126 MB L2)
+N_ROTATE = 32   # distinct input batches per rank (headline: 166 MB > 126 MB L2)
+
+
+# ---------------------------------------------------------------------------- workloads
+def _lognormal_sizes(B, seed=2):
+    """N_i = clamp(round(exp(N(ln 1500, 0.8^2))), 16, 4096)"""
+    g = torch.Generator().manual_seed(seed)
+    s = torch.exp(torch.randn(B, generator=g) * 0.8 + math.log(1500.0)).round().clamp(16, 4096)
+    return [int(v) for v in s]
+
+
+class DeepSetsWorkload:
+    kind = "deepsets"
+
+    def __init__(self, name, B, N, d, out, act, pool, res, ragged=False, H=256, desc=""):
+        self.name, self.B, self.N, self.d, self.out, self.H, self.ragged = name, B, N, d, out, H, ragged
+        self.cfg = dict(input_dim=d, phi_layers=[H, H], rho_layers=[H], output_dim=out, activation=act, layer_norm=False,
+                        residual_block=res, pooling=pool)
+        self.sizes = _lognormal_sizes(B) if ragged else [N] * B
+        self.points = sum(self.sizes)
+        self.desc = desc
+        # SURVEY.md section 8(d): algorithmic FLOP per point, reference formulation, recompute not credited
+        self.flop_fwd_pt = 2 * (H * d + 2 * H * H)
+        self.flop_train_pt = 3 * self.flop_fwd_pt - 2 * H * d
+        self.kernel_flop_pt = {"phi_pool_fwd_kernel": self.flop_fwd_pt, "phi_bwd_chain_kernel": 2 * (2 * H * H),
+                               "phi_wgrad_kernel": self.flop_fwd_pt}
+        self.unit_name = "sets"
+
+    def forward_kwargs(self):
+        return {"num_sets": self.B}
+
+    def build_model(self, dev, precision):
+        import pcc_b200
+        return pcc_b200.DeepSets(**self.cfg, precision=precision).to(dev)
+
+    def expected_path(self, precision):
+        return "fused-bf16" if precision == "bf16" else "fp32"
+
+    def make_batches(self, n_batches, seed, pin=True, B=None):
+        """[(inputs tuple, target)] on the host, in the layout of the reference collate (utils/data.py:651-663)"""
+        B = B or self.B
+        sizes = self.sizes[:B] if self.ragged else [self.N] * B
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+        out = []
+        for _ in range(n_batches):
+            x = torch.randn(sum(sizes), self.d, generator=g)
+            y = (torch.rand(B, self.out, generator=g) > 0.5).float()
+            ts = (x, idx, y)
+            if pin:
+                ts = tuple(t.pin_memory() for t in ts)
+            out.append((ts[:2], ts[2]))
+        return out
+
+    # reference CPU arm: oracle port (pinned to the reference module by tests/golden)
+    def cpu_state(self):
+        from oracle import deepsets_oracle as O
+        return O.init_state_dict(self.cfg, seed=0)
+
+    def cpu_step(self, sd, inputs, y):
+        from oracle import deepsets_oracle as O
+        return O.deepsets_train_step(sd, self.cfg, inputs[0], inputs[1], y)
+
+    def workload_text(self):
+        return self.desc
+
+
+class GraphNetWorkload:
+    """configs[3]: configs/graph_net.yaml model on kNN graphs (k = 20) over N = 1024-point clouds.  A step = kNN graph
+    build (pcc_knn) + CSR + forward + BCEWithLogitsLoss + backward."""
+    kind = "graphnet"
+
+    def __init__(self, name, B, N, k=20, hidden=128, desc=""):
+        self.name, self.B, self.N, self.k, self.hidden = name, B, N, k, hidden
+        self.cfg = dict(input_dim=4, hidden_dim=hidden, output_dim=1, activation="tanh", use_gat=False, gat_heads=4,
+                        sag_pool=False, pool_ratio=0.5, local_pooling="add", global_pooling="mean", deepchem_style=True)
+        self.points = B * N
+        self.desc = desc
+        C = hidden
+        # SURVEY.md section 8(d), per node: fwd 2 (2*4*C + 2*C*C + C*256) FLOP, train ~3x; aggregation gather bytes
+        # k*C*4 per conv and direction (conv1: C = 4), edges 16 B / edge
+        self.flop_fwd_pt = 2 * (2 * 4 * C + 2 * C * C + C * 256)
+        self.flop_train_pt = 3 * self.flop_fwd_pt
+        self.bytes_gather_pt = 2 * (k * 4 * 4 + k * C * 4) + 2 * k * 16
+        self.unit_name = "graphs"
+
+    def forward_kwargs(self):
+        return {"num_graphs": self.B}
+
+    def build_model(self, dev, precision):
+        import pcc_b200
+        return pcc_b200.KnnGraphNet(k=self.k, precision=precision, **self.cfg).to(dev)
+
+    def expected_path(self, precision):
+        return None
+
+    def make_batches(self, n_batches, seed, pin=True, B=None):
+        B = B or self.B
+        g = torch.Generator().manual_seed(seed)
+        memb = torch.arange(B).repeat_interleave(self.N)
+        out = []
+        for _ in range(n_batches):
+            f = torch.randn(B * self.N, 4, generator=g)          # col 0: normalised energy, cols 1:4 xyz (data.py:808-813)
+            f[:, 0] = torch.rand(B * self.N, generator=g)
+            y = (torch.rand(B, 1, generator=g) > 0.5).float()
+            ts = (f, memb, y)
+            if pin:
+                ts = tuple(t.pin_memory() for t in ts)
+            out.append((ts[:2], ts[2]))
+        return out
+
+    def cpu_state(self):
+        from oracle import graphnet_oracle as GO
+        return GO.init_state_dict(self.cfg, seed=0)
+
+    def cpu_step(self, sd, inputs, y):
+        import numpy as np
+        from oracle import graphnet_oracle as GO
+        from oracle import knn_oracle as KO
+        f, memb = inputs
+        B = int(memb.max()) + 1
+        off = np.arange(B + 1, dtype=np.int64) * self.N
+        nbr, _ = KO.knn_neighbours(f[:, 1:4].numpy(), off, self.k)
+        edges = torch.from_numpy(KO.knn_edges(nbr))
+        return GO.graphnet_train_step(sd, self.cfg, f, memb, edges, None, y)
+
+    def workload_text(self):
+        return self.desc
+
+
+def make_workload(name, B=None, N=None):
+    if name == "deepsets":
+        return DeepSetsWorkload(name, B or 256, N or 1024, 3, 10, "relu", "max", False,
+                                desc="configs[1]: DeepSets B=256 N=1024 per GPU, phi[3-256-256]+final(256) relu, max pool, "
+                                     "rho[256]-10, fwd + BCEWithLogitsLoss + bwd")
+    if name == "yaml":
+        return DeepSetsWorkload(name, B or 256, N or 1024, 6, 1, "gelu", "mean", True,
+                                desc="configs/deep_sets.yaml model (gelu + ResidualBlock + mean pool, d=6, out=1, no LayerNorm) "
+                                     "at B=256 N=1024 per GPU, fwd + BCEWithLogitsLoss + bwd")
+    if name == "ragged":
+        return DeepSetsWorkload(name, B or 256, N or 1024, 3, 10, "relu", "sum", False, ragged=True,
+                                desc="configs[2]: DeepSets variable-size sets, N_i log-normal in [16, 4096] (478 k points per "
+                                     "256 sets), sum pool (sum / sqrt(n)), relu, fwd + loss + bwd")
+    if name == "graphnet":
+        return GraphNetWorkload(name, B or 256, N or 1024,
+                                desc="configs[3]: configs/graph_net.yaml GraphNet (tanh, add aggregation, deepchem) on kNN k=20 "
+                                     "graphs, N=1024 per cloud, B=256 per GPU; step = kNN build + CSR + fwd + loss + bwd")
+    raise SystemExit(f"unknown --config {name}")
 
 
 def measured_peaks():
@@ -45,8 +183,9 @@ def measured_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
-                "hbm": float(d.get("hbm_gbs", 6650.0)), "source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"}
-    return {"tflops": 1400.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+                "tflops_burst": float(d.get("bf16_tflops", 1650.0)),
+                "hbm": float(d.get("hbm_gbs", 6650.0)), "source": "MEASURED_PEAKS.json"}
+    return {"tflops": 1400.0, "tflops_burst": 1650.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback"}
 
 
 class ClockSampler:
@@ -96,66 +235,130 @@ class ClockSampler:
         return out
 
 
-def make_batches(n_batches, B, device, seed):
-    g = torch.Generator().manual_seed(seed)
-    host = []
-    idx = torch.arange(B).repeat_interleave(N_PTS)
-    for _ in range(n_batches):
-        x = torch.randn(B * N_PTS, D_IN, generator=g)
-        y = (torch.rand(B, OUT, generator=g) > 0.5).float()
-        host.append((x.pin_memory() if device != "cpu" else x, idx.pin_memory() if device != "cpu" else idx,
-                     y.pin_memory() if device != "cpu" else y))
-    return host
-
-
-# ---------------------------------------------------------------------------- reference arm
-def cpu_reference_rate(steps, warmup, sample_sets=32, budget_s=25.0):
-    """The reference's own CPU path (oracle/deepsets_oracle.py: functional restatement of
-    models/deep_sets.py + wrapper.py:38 loss, pinned to the reference by tests/golden) on the
-    box's host cores.  One step = fwd + loss + bwd of a `sample_sets`-set sample of the workload."""
-    from oracle import deepsets_oracle as O
+# ---------------------------------------------------------------------------- reference arm (host CPU)
+def cpu_reference_rate(wl, steps, warmup, sample_units=None, budget_s=25.0):
+    """The reference's own CPU path (oracle port: functional restatement of models/deep_sets.py / graph_net.py +
+    wrapper.py:38 loss, pinned to the reference by tests/golden) on the box's host cores, all threads.
+    One step = fwd + loss + bwd of `sample_units` sets / graphs of the workload (default: the FULL per-GPU batch)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.init_state_dict(CFG, seed=0)
-    (x, idx, y), = make_batches(1, sample_sets, "cpu", seed=1)
+    units = sample_units or wl.B
+    sd = wl.cpu_state()
+    (inputs, y), = wl.make_batches(1, seed=1, pin=False, B=units)
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.deepsets_train_step(sd, CFG, x, idx, y)
+        wl.cpu_step(sd, inputs, y)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
             break
     ms = statistics.median(times) * 1e3
-    return {"value": sample_sets / ms * 1e3, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} steps of fwd+loss+bwd on {sample_sets} sets x {N_PTS} pts (same model), median",
-            "ms_per_step": ms, "steps": len(times)}
+    pts = inputs[0].shape[0]
+    return {"value": units / ms * 1e3, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} steps of fwd+loss+bwd on {units} {wl.unit_name} ({pts} points, "
+                      f"{'the full per-GPU batch' if units == wl.B else 'a sample'} of the same workload), median",
+            "ms_per_step": ms, "steps": len(times), "units": units}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_rate(args.steps, args.warmup, budget_s=120.0)
-    line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd), DeepSets B=256 N=1024", "value": cb["value"],
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup,
+    wl = make_workload(args.config if args.config != "sweep" else "deepsets")
+    # the full 256-set batch per step (same config as the CUDA arm); GraphNet's numpy kNN oracle is O(N^2): 32 graphs
+    units = None if wl.kind == "deepsets" else 32
+    cb = cpu_reference_rate(wl, args.steps, min(args.warmup, 3), sample_units=units, budget_s=150.0)
+    line = {"impl": "reference", "metric": metric_name(wl), "value": cb["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": min(args.warmup, 3),
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DeepSets phi[3-256-256]+final relu max-pool rho[256]-10, fwd+loss+bwd",
-                       "device": "host CPU", "sample_sets_per_step": 32, "points_per_set": N_PTS},
+            "config": {"workload": wl.workload_text(), "name": wl.name, "units_per_gpu": cb["units"],
+                       "points_per_gpu": wl.points if cb["units"] == wl.B else cb["units"] * wl.N, "device": "host CPU",
+                       "precision_mode": "fp32"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def metric_name(wl):
+    if wl.name == "deepsets":
+        return "train samples/sec (fwd+bwd), DeepSets B=256 N=1024"
+    return f"train samples/sec (fwd+bwd), {wl.name} B={wl.B} N={wl.N}"
+
+
+# ---------------------------------------------------------------------------- comparators (single GPU, rank 0)
+def eager_gpu_baseline(wl, dev, steps=5, warmup=2):
+    """The reference's "existing GPU path": its algorithm as stock PyTorch eager ops on the same B200 (oracle port
+    moved to cuda:0, fp32, TF32 off — the port runs at the reference module's speed)."""
+    if wl.kind != "deepsets":
+        return None
+    from oracle import deepsets_oracle as O
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {k: v.to(dev) for k, v in wl.cpu_state().items()}
+        (inputs, y), = wl.make_batches(1, seed=3, pin=False)
+        x, idx, y = inputs[0].to(dev), inputs[1].to(dev), y.to(dev)
+        for _ in range(warmup):
+            O.deepsets_train_step(sd, wl.cfg, x, idx, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            O.deepsets_train_step(sd, wl.cfg, x, idx, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return {"value": wl.B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+            "what": "reference algorithm as stock PyTorch eager ops on cuda:0 (oracle port, fp32, TF32 off): cuBLAS sgemm + "
+                    "B-iteration pooling loop + counts.tolist() sync, same batch shape"}
+
+
+def wrapper_loop_e2e(wl, dev, precision, steps=20, warmup=5):
+    """The literal training-loop sequence of the reference (models/wrapper.py:51-74) on the drop-in module: pageable
+    host tensors `.to(device)`, model(*inputs), optimizer.zero_grad(), BCEWithLogitsLoss, loss.backward(), torch AdamW
+    step, loss.item() — eager launches, no CUDA graph, no fused loss / optimizer.  Wall-clock timed."""
+    if wl.kind != "deepsets":
+        return None
+    model = wl.build_model(dev, precision)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)          # wrapper.py:33
+    criterion = torch.nn.BCEWithLogitsLoss()                       # wrapper.py:38
+    batches = wl.make_batches(4, seed=5, pin=False)
+    model.train()
+
+    def one(i):
+        inputs, y = batches[i % len(batches)]
+        inputs = [t.to(dev) for t in inputs if t is not None]      # wrapper.py:54
+        y = y.to(dev)                                              # wrapper.py:55
+        logits = model(*inputs)                                    # wrapper.py:58
+        opt.zero_grad()                                            # wrapper.py:61
+        loss = criterion(logits, y)                                # wrapper.py:64
+        loss.backward()                                            # wrapper.py:67
+        opt.step()                                                 # wrapper.py:70
+        return loss.item() + loss.item()                           # wrapper.py:73-74 (two host reads)
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(warmup + i)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    return {"value": wl.B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "precision_mode": precision,
+            "what": "wrapper.py:51-74 sequence on pcc_b200.DeepSets: pageable .to(device), eager forward, torch AdamW step, "
+                    "loss.item() x2 per step (wall clock, includes the optimizer)"}
+
+
 # ---------------------------------------------------------------------------- this repo
 def run_ours(args):
+    import ctypes as C
     import torch.distributed as dist
-    import pcc_b200
     from pcc_b200 import _lib
     from pcc_b200.train_step import GraphedTrainStep
-    import ctypes as C
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +367,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback. Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
     def log(msg):
         if rank == 0:
             print(f"[bench] {msg}", file=sys.stderr, flush=True)
@@ -172,24 +376,28 @@ def run_ours(args):
         log(f"process group up: world {world}")
     _lib.call("pcc_check_device", local)
 
+    if args.config == "sweep":
+        return run_sweep(args, dev, rank, world, log)
+    wl = make_workload(args.config, args.batch, args.points)
     torch.manual_seed(0)
-    model = pcc_b200.DeepSets(**CFG, precision=args.precision).to(dev)
-    host = make_batches(N_ROTATE, B_PER_GPU, "cuda", seed=1000 + rank)
-    devb = [tuple(t.to(dev) for t in b) for b in host]
-    kw = {"num_sets": B_PER_GPU}
+    model = wl.build_model(dev, args.precision)
+    n_rot = N_ROTATE if wl.kind == "deepsets" else 8
+    host = wl.make_batches(n_rot, seed=1000 + rank)
+    devb = [(tuple(t.to(dev) for t in ins), y.to(dev)) for ins, y in host]
+    kw = wl.forward_kwargs()
 
-    def build(use_graph):
-        return GraphedTrainStep(model, devb[0][:2], devb[0][2], forward_kwargs=kw, allreduce=world > 1,
-                                use_graph=use_graph)
+    def build(use_graph, allreduce=None):
+        return GraphedTrainStep(model, devb[0][0], devb[0][1], forward_kwargs=kw,
+                                allreduce=(world > 1) if allreduce is None else allreduce, use_graph=use_graph)
     try:
         gs = build(not args.no_graph)
         graphed = not args.no_graph
     except Exception as e:  # graph capture unavailable (e.g. NCCL capture) -> eager launches
-        if rank == 0:
-            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+        log(f"CUDA graph capture failed ({type(e).__name__}: {e}); running eager")
         gs = build(False)
         graphed = False
-    assert model.last_path == ("fused-bf16" if args.precision == "bf16" else "fp32")
+    exp = wl.expected_path(args.precision)
+    assert exp is None or model.last_path == exp, (model.last_path, exp)
     log(f"train step built (cuda graph: {graphed})")
 
     def barrier():
@@ -197,20 +405,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, repeats):
+        """`repeats` windows of exactly `steps` steps, each bracketed by barrier + synchronize, CUDA-event timed, max
+        over ranks per window; returns (median ms per step, [ms per step of every window])"""
         for i in range(warmup):
             fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        wins, it = [], warmup
+        for _ in range(repeats):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn(it)
+                it += 1
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            wins.append(float(ms.item()) / steps)
+        return statistics.median(wins), wins
 
     W = max(args.warmup, 3)
     sampler = ClockSampler(local)
@@ -219,7 +433,7 @@ def run_ours(args):
     # Both timed loops feed the captured step the same way, like a prefetching input pipeline: two captured steps
     # (GraphedTrainStep instances over the same model) own one set of static input buffers each; while step i
     # computes out of slot i%2, the copy stream moves batch i+1 straight into the other slot's static buffers.
-    #   value: the 32 rotating batches are already resident in HBM (device -> device copies);
+    #   value: the rotating batches are already resident in HBM (device -> device copies);
     #   e2e:   they sit in pinned host memory (H2D inside the timed region) and the loss of every step is copied
     #          back to pinned memory on a third stream and read by the host one step later (wrapper.py:73).
     copy_stream = torch.cuda.Stream()
@@ -234,10 +448,10 @@ def run_ours(args):
         state = {"primed": False, "seen": 0}
 
         def enqueue_copy(i):
-            b, slot = batches[i % N_ROTATE], i % 2
+            b, slot = batches[i % n_rot], i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free_ev[slot])          # the step that consumed this slot has finished with it
-                slots[slot].load(b[:2], b[2])                  # batch -> the slot's static device buffers
+                slots[slot].load(b[0], b[1])                   # batch -> the slot's static device buffers
                 staged_ev[slot].record(copy_stream)
 
         def step(i):
@@ -264,28 +478,37 @@ def run_ours(args):
         return step
 
     # ---- value: inputs resident in HBM when the timed region starts
-    ms_dev = timed(make_feed(devb, False), args.steps, W)
+    ms_dev, wins_dev = timed(make_feed(devb, False), args.steps, W, args.repeats)
     torch.cuda.synchronize()
     # ---- e2e: pinned host buffers -> H2D inside the timed region, loss read back every step
-    e2e_step = make_feed(host, True)
-    ms_e2e = timed(e2e_step, args.steps, W)
-    log(f"e2e timing done: {ms_e2e:.3f} ms/step")
+    ms_e2e, wins_e2e = timed(make_feed(host, True), args.steps, W, args.repeats)
+    log(f"timing done: {ms_dev:.4f} ms/step device-resident, {ms_e2e:.4f} ms/step e2e")
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- N > 1: every rank must hold bitwise identical averaged gradients after a step
+    grad_identical = None
+    if world > 1:
+        flat = torch.cat([p.grad.detach().reshape(-1).double() for p in model.parameters() if p.grad is not None])
+        chk = torch.stack([flat.sum(), flat.abs().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        grad_identical = all(bool(torch.equal(c, allc[0])) for c in allc)
+        assert grad_identical, "averaged gradients differ between ranks"
+
     # ---- per-kernel durations (CUDA events inside the library, eager launches of the same step)
-    eager = GraphedTrainStep(model, devb[0][:2], devb[0][2], forward_kwargs=kw, allreduce=False, use_graph=False, warmup=2)
+    eager = GraphedTrainStep(model, devb[0][0], devb[0][1], forward_kwargs=kw, allreduce=False, use_graph=False, warmup=2)
     _lib.call("pcc_launch_count", 1)
-    eager.step(devb[1][:2], devb[1][2])
+    eager.step(devb[1][0], devb[1][1])
     torch.cuda.synchronize()
     launches = int(_lib.call("pcc_launch_count", 1))
     _lib.call("pcc_prof_enable", 1)
     ksteps = min(args.steps, 20)
     for i in range(ksteps):
-        eager.step(devb[i % N_ROTATE][:2], devb[i % N_ROTATE][2])
+        eager.step(devb[i % n_rot][0], devb[i % n_rot][1])
     torch.cuda.synchronize()
     _lib.call("pcc_prof_enable", 0)
     kern = {}
-    for slot, name in ((0, "phi_pool_fwd_kernel"), (1, "phi_bwd_chain_kernel"), (2, "phi_wgrad_kernel")):
+    for slot, name in enumerate(PROF_SLOTS):
         ms_tot, cnt = C.c_double(0), C.c_int64(0)
         _lib.call("pcc_prof_read", slot, C.byref(ms_tot), C.byref(cnt))
         if cnt.value:
@@ -297,49 +520,173 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    pts = B_PER_GPU * N_PTS
-    flops = {"phi_pool_fwd_kernel": FLOP_FWD_PT, "phi_bwd_chain_kernel": FLOP_CHAIN_PT, "phi_wgrad_kernel": FLOP_WGRAD_PT}
+    pts = wl.points
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):   # dram bytes per launch from the committed `ncu --set full` capture (tools/summarize_profile.py)
         traffic = json.load(open(tpath)).get("kernels", {})
     roof = None
-    if kern:
-        dom = max(kern, key=kern.get)
-        ach = flops[dom] * pts / (kern[dom] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops"], "traffic": traffic.get(dom), "traffic_unit": "dram bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
-                "peak_source": peaks["source"],
-                "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
-                "algorithmic_flop_per_point": flops[dom]}
-    step_tf = FLOP_TRAIN_PT * pts / (ms_dev * 1e-3) / 1e12
-    cb = cpu_reference_rate(8, 2) if world == 1 else None
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    if wl.kind == "deepsets":
+        kd = {k: v for k, v in kern.items() if k in wl.kernel_flop_pt}
+        if kd:
+            dom = max(kd, key=kd.get)
+            ach = wl.kernel_flop_pt[dom] * pts / (kd[dom] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": KERNEL_SYMBOL.get(dom, dom) if wl.name == "deepsets" else dom,
+                    "achieved": ach, "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_burst"],
+                    "frac_of_sustained": ach / peaks["tflops"],
+                    "traffic": traffic.get(dom), "traffic_unit": "dram bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
+                    "peak_source": peaks["source"] + ": bf16_tflops (burst: the kernel is timed alone with CUDA events)",
+                    "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
+                    "algorithmic_flop_per_point": wl.kernel_flop_pt[dom]}
+    else:
+        kd = {k: v for k, v in kern.items() if k.startswith("graph")}
+        if kd:
+            dom = max(kd, key=kd.get)
+            nbytes = GRAPH_KERNEL_BYTES_PT(wl).get(dom, 0) * pts
+            ach = nbytes / (kd[dom] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": traffic.get(dom),
+                    "peak_source": peaks["source"] + ": hbm_gbs",
+                    "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
+                    "algorithmic_bytes_per_node": GRAPH_KERNEL_BYTES_PT(wl).get(dom, 0),
+                    "note": "algorithmic bytes count every gathered fp32 neighbour row once (SURVEY 8d); rows are re-read "
+                            "k times and mostly served by L2, so the fraction can exceed what DRAM alone would allow"}
+    step_tf = wl.flop_train_pt * pts / (ms_dev * 1e-3) / 1e12
+    extras = {}
+    if world == 1 and not args.no_baselines:
+        units = None if wl.kind == "deepsets" else 8
+        cb = cpu_reference_rate(wl, 8, 1, sample_units=units, budget_s=25.0)
+        extras["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        extras["eager_gpu_baseline"] = eager_gpu_baseline(wl, dev)
+        extras["e2e_wrapper"] = wrapper_loop_e2e(wl, dev, args.precision)
+        if wl.kind == "deepsets" and args.precision == "bf16":   # the fp32-parity mode of the same step (rtol 1e-4 path)
+            m32 = wl.build_model(dev, "fp32")
+            g32 = GraphedTrainStep(m32, devb[0][0], devb[0][1], forward_kwargs=kw, allreduce=False)
+            for _ in range(2):
+                g32.run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g32.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms32 = e0.elapsed_time(e1) / 5
+            extras["fp32_mode"] = {"value": wl.B / ms32 * 1e3, "unit": "samples/s", "ms_per_step": ms32,
+                                   "what": "same step with precision='fp32' (3xTF32 mma.sync layer-wise kernels, rtol 1e-4 parity mode)"}
+    else:
+        extras["cpu_baseline"] = None
+    h2d = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
     line = {
-        "metric": "train samples/sec (fwd+bwd), DeepSets B=256 N=1024", "value": world * B_PER_GPU / ms_dev * 1e3,
+        "metric": metric_name(wl), "value": world * wl.B / ms_dev * 1e3,
         "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_dev,
+        "repeats": args.repeats, "windows_ms": [round(w, 5) for w in wins_dev],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: DeepSets B=256 N=1024 per GPU, phi[3-256-256]+final(256) relu, max pool, "
-                               "rho[256]-10, fwd + BCEWithLogitsLoss + bwd" +
-                               ((" + gradient all-reduce (own one-shot kernel over NVLink peer memory, inside the graph)"
-                                 if gs.peer is not None else " + NCCL gradient all-reduce") if world > 1 else ""),
-                   "sets_per_gpu": B_PER_GPU, "points_per_set": N_PTS, "cuda_graph": graphed,
-                   "l2": f"inputs rotate over {N_ROTATE} distinct batches (166 MB) and every step streams ~0.7 GB of "
-                         "staged operands, both larger than the 126 MB L2",
-                   "parallelism": f"dp{world}", "precision_mode": args.precision},
-        "e2e": {"value": world * B_PER_GPU / ms_e2e * 1e3, "unit": "samples/s", "ms_per_step": ms_e2e,
+        "config": {"workload": wl.workload_text() +
+                   ((" + gradient all-reduce (own one-shot kernel over NVLink peer memory, inside the graph)"
+                     if gs.peer is not None else " + NCCL gradient all-reduce") if world > 1 else ""),
+                   "name": wl.name, "units_per_gpu": wl.B, "points_per_gpu": pts, "cuda_graph": graphed,
+                   "l2": f"inputs rotate over {n_rot} distinct batches per rank and every step streams far more than the "
+                         "126 MB L2 through the staged operands / activations",
+                   "parallelism": f"dp{world}", "precision_mode": args.precision,
+                   "timing": f"median of {args.repeats} windows of {args.steps} steps (CUDA events, max over ranks per window)"},
+        "e2e": {"value": world * wl.B / ms_e2e * 1e3, "unit": "samples/s", "ms_per_step": ms_e2e,
+                "windows_ms": [round(w, 5) for w in wins_e2e],
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "api": "GraphedTrainStep.load/run, two captured slots fed alternately from pinned host x, idx, y (H2D on a copy stream, one step ahead) + per-step loss read-back on a third stream; the device-resident value uses the same feed with device-to-device copies"},
-        "gpu_launches": launches * args.steps,
+                "api": "GraphedTrainStep.load/run, two captured slots fed alternately from pinned host inputs (H2D on a copy "
+                       "stream, one step ahead) + per-step loss read-back on a third stream; the device-resident value uses "
+                       "the same feed with device-to-device copies"},
+        "gpu_launches": launches * args.steps * args.repeats,
         "gpu_launches_per_step": launches,
         "roofline": roof,
         "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                          "frac": step_tf / peaks["tflops"], "algorithmic_flop_per_point": FLOP_TRAIN_PT},
-        "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+                          "frac": step_tf / peaks["tflops"], "algorithmic_flop_per_point": wl.flop_train_pt,
+                          "note": "reference-formulation FLOPs over the whole step against the sustained peak; for max pooling "
+                                  "the backward physically runs on the B*H argmax rows only (DESIGN.md section 4), so this "
+                                  "overstates tensor-pipe utilisation — `roofline` (forward kernel) is the honest figure"},
+        "grad_checksum_identical_on_all_ranks": grad_identical,
         "clocks": clocks,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+PROF_SLOTS = ("phi_pool_fwd_kernel", "phi_bwd_chain_kernel", "phi_wgrad_kernel", "graph_conv_fwd_kernel",
+              "graph_conv_bwd_kernel", "graph_aggregate_bwd_kernel", "knn_kernel")
+KERNEL_SYMBOL = {"phi_pool_fwd_kernel": "phi_pool_fwd_pair_kernel"}   # H = 256 + max pooling runs the CTA-pair variant
+
+
+def GRAPH_KERNEL_BYTES_PT(wl):
+    k, Cc = wl.k, wl.hidden
+    return {"graph_conv_fwd_kernel": k * Cc * 4 + 2 * Cc * 4, "graph_conv_bwd_kernel": 4 * Cc * 4,
+            "graph_aggregate_bwd_kernel": k * Cc * 4 + Cc * 4}
+
+
+# ---------------------------------------------------------------------------- configs[4]: point-count sweep
+def run_sweep(args, dev, rank, world, log):
+    """N = 256 .. 16384 at constant points per GPU and step (B = 262144 / N), DeepSets (relu + max and relu + sum)
+    and GraphNet (kNN k=20), CUDA-graph train step; CPU column = oracle port on the host cores on a bounded sample."""
+    import torch.distributed as dist
+    from pcc_b200.train_step import GraphedTrainStep
+    total = 262144
+    rows = []
+    for model_name in ("deepsets", "deepsets_sum", "graphnet"):
+        for N in (256, 512, 1024, 2048, 4096, 8192, 16384):
+            B = total // N
+            if model_name == "graphnet":
+                wl = GraphNetWorkload("graphnet", B, N)
+            else:
+                wl = DeepSetsWorkload("deepsets", B, N, 3, 10, "relu", "max" if model_name == "deepsets" else "sum", False)
+            torch.manual_seed(0)
+            model = wl.build_model(dev, args.precision)
+            (ins, y), = wl.make_batches(1, seed=7 + rank, pin=False)
+            ins, y = tuple(t.to(dev) for t in ins), y.to(dev)
+            gs = GraphedTrainStep(model, ins, y, forward_kwargs=wl.forward_kwargs(), allreduce=world > 1)
+            for _ in range(3):
+                gs.run()
+            wins = []
+            for _ in range(3):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    gs.run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+                if world > 1:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                wins.append(float(ms))
+            ms = statistics.median(wins)
+            row = {"model": model_name, "N": N, "B_per_gpu": B, "ms_per_step": round(ms, 4),
+                   "samples_per_s": world * B / ms * 1e3, "Mpoints_per_s": world * total / ms / 1e3}
+            if rank == 0 and world == 1 and not args.no_baselines:
+                units = max(2, (32768 if model_name != "graphnet" else 8192) // N)
+                cb = cpu_reference_rate(wl, 2, 1, sample_units=min(units, B), budget_s=20.0)
+                row["cpu_samples_per_s"] = cb["value"]
+                row["cpu_sample"] = cb["sample"]
+                row["cpu_cores"] = cb["cores"]
+            rows.append(row)
+            log(json.dumps(row))
+            if gs.peer is not None:
+                gs.peer.close()
+            del gs, model
+            torch.cuda.empty_cache()
+    if rank == 0:
+        head = next(r for r in rows if r["model"] == "deepsets" and r["N"] == 1024)
+        line = {"metric": "train samples/sec (fwd+bwd), point-count sweep N=256..16384 at 262144 points per GPU and step",
+                "value": head["samples_per_s"], "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": 3,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: point-count scaling sweep, DeepSets (relu+max, relu+sum) and GraphNet (kNN k=20); "
+                                       "`value` is the DeepSets relu+max N=1024 row", "name": "sweep", "parallelism": f"dp{world}"},
+                "sweep": rows}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -349,9 +696,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--repeats", type=int, default=5, help="timed windows of --steps steps; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="deepsets", choices=["deepsets", "yaml", "ragged", "graphnet", "sweep"])
+    ap.add_argument("--batch", type=int, default=None, help="sets / graphs per GPU (default 256)")
+    ap.add_argument("--points", type=int, default=None, help="points per set / cloud (default 1024)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU / wrapper-loop comparator legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -106,7 +106,7 @@ def mlp_forward(sd: Dict[str, torch.Tensor], plan: List[dict], activation: str, 
 def segment_offsets(idx: torch.Tensor) -> torch.Tensor:
     """deep_sets.py:91-92: only the histogram of idx matters; the split is contiguous."""
     counts = torch.bincount(idx)
-    off = torch.zeros(counts.numel() + 1, dtype=torch.int64)
+    off = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=idx.device)
     off[1:] = torch.cumsum(counts, 0)
     return off
 

@@ -4,12 +4,12 @@ Host-side mirror of the reference's model interface (models/deep_sets.py,
 models/graph_net.py) over the C-ABI library lib/libpcc.so.  See DESIGN.md.
 """
 from .deep_sets import DeepSets, ResidualBlock
-from .graph_net import GraphNet, GraphConv, knn_graph, gaussian_edge_weights
+from .graph_net import GraphNet, GraphConv, KnnGraphNet, knn_graph, gaussian_edge_weights
 from . import functional
 from .optim import FusedAdam
 from . import _lib
 
-__all__ = ["DeepSets", "ResidualBlock", "GraphNet", "GraphConv", "knn_graph", "gaussian_edge_weights", "FusedAdam", "functional"]
+__all__ = ["DeepSets", "ResidualBlock", "GraphNet", "GraphConv", "KnnGraphNet", "knn_graph", "gaussian_edge_weights", "FusedAdam", "functional"]
 
 import os as _os
 

@@ -55,8 +55,13 @@ class GraphNet(nn.Module):
                  pool_ratio=0.5,
                  local_pooling="add",
                  global_pooling="mean",
-                 deepchem_style=False):
+                 deepchem_style=False,
+                 precision: Optional[str] = None):
         super().__init__()
+        import os
+        self.precision = precision or os.environ.get("PCC_GRAPH_PRECISION", "fp32")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         if use_gat:
             raise NotImplementedError("use_gat=True (GATConv, graph_net.py:47-48) is outside the B200 hot path")
         if sag_pool:
@@ -85,7 +90,8 @@ class GraphNet(nn.Module):
         self.bn3 = nn.BatchNorm1d(256)
         self.fc2 = nn.Linear(256, output_dim)
 
-    def forward(self, x, membership, edges, weights=None, num_graphs: Optional[int] = None):
+    def forward(self, x, membership, edges, weights=None, num_graphs: Optional[int] = None,
+                edges_sorted_by_target: bool = False):
         if not x.is_cuda:
             raise RuntimeError("pcc_b200.GraphNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)")
         if not hasattr(self, "activation"):
@@ -110,6 +116,24 @@ class GraphNet(nn.Module):
             h = PF.linear_act(h, self.fc1.weight, self.fc1.bias, None, act)
             h = PF.batchnorm(h, self.bn3)
         return PF.linear_act(h, self.fc2.weight, self.fc2.bias, None, "none")
+
+
+class KnnGraphNet(nn.Module):
+    """GraphNet on a kNN graph built on the device from the node positions (north_star: "kNN graph build, ...,
+    scatter aggregation"): forward(features[n, F], membership[n]) = GraphNet(features, membership,
+    knn_graph(features, membership, k)).  The reference builds its edges offline (utils/data.py:847-929); this module
+    is the on-device equivalent for raw point clouds and carries the same parameters / state_dict keys under `net.`."""
+
+    def __init__(self, k: int = 20, pos_cols=(1, 4), precision: Optional[str] = None, **graphnet_kwargs):
+        super().__init__()
+        self.k, self.pos_cols = k, tuple(pos_cols)
+        self.net = GraphNet(**graphnet_kwargs, precision=precision)
+
+    def forward(self, features, membership, num_graphs: Optional[int] = None):
+        if num_graphs is None:
+            num_graphs = PF.index_max(membership) + 1
+        edges, _ = knn_graph(features, membership, self.k, self.pos_cols, num_graphs)
+        return self.net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True)
 
 
 def knn_graph(features: torch.Tensor, membership: torch.Tensor, k: int = 20, pos_cols=(1, 4),
