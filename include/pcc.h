@@ -213,6 +213,74 @@ int pcc_mlp_head_fwd(const pcc_head_desc* d, const float* x, float* y, float* zs
 int pcc_mlp_head_bwd(const pcc_head_desc* d, const float* x, const float* zsave, const float* dy, float* dx,
                      float* const* dw, float* const* db, void* ws, int64_t M, int device, void* stream);
 
+/* ---- fused bf16 GraphNet path (tcgen05 / TMEM): the neighbour stage of /root/reference/models/graph_net.py:73-92 for
+ *      hidden_dim = 128 (configs/graph_net.yaml), deepchem_style = true, aggregation add / mean, activations tanh / relu /
+ *      gelu.  Pipeline and data layout: DESIGN.md section 4 (GraphNet) and csrc/pcc_gnn.cuh.  CSR arguments: rowptr[M+1]
+ *      int64, col[E] int32 = neighbour node per CSR slot, w[E] fp32 edge weight per slot or NULL.  *_bf16 = bf16 [M,128]
+ *      row-major.  "partials" are per-CTA partial sums, [nblk][...]; *nblk_out (host int) receives the block count used.
+ *      Every buffer is caller-owned.
+ *   pcc_gnn_pack_weights : conv2 lin_rel / lin_root [128,128] and fc1 [256,128] fp32 -> packed bf16 operand images
+ *                          (pcc_gnn_packed_bytes() bytes); w_fc1 may be NULL.
+ *   pcc_gnn_conv1_fwd    : GraphConv 1 (graph_net.py:73; K = 2 input_dim <= 16, CUDA cores): agg_out[M,F], z_out[M,128],
+ *                          partials [nblk][2][128] = sums of act(z), act(z)^2 (BatchNorm statistics, :76).
+ *   pcc_gnn_bn_finalize  : partial sums -> scale = gamma*invstd, shift = beta - mean*scale, mean, invstd; updates the
+ *                          running statistics (momentum, unbiased variance) when the pointers are non-NULL.
+ *   pcc_gnn_bn_eval      : scale / shift from the running statistics (eval mode).
+ *   pcc_gnn_bn_apply     : h = bf16(act(z)*scale + shift)            (activation BEFORE BatchNorm, graph_net.py:75-76)
+ *   pcc_gnn_conv_fwd     : GraphConv 2 (:82) in ONE kernel: CSR gather-reduce of bf16 neighbour rows into the shared-
+ *                          memory A image [agg | h], tcgen05 GEMM with [W_rel ; W_root], z (fp32) + BatchNorm partial
+ *                          sums in the epilogue; agg_out keeps the aggregate for the weight gradient.
+ *   pcc_gnn_fc1_pool_fwd : fc1 + act + bn3 statistics + global_mean_pool (:87-92): psum[B,256] = per-graph sums of
+ *                          act(fc1(h)), partials [nblk][2][256]; the per-node [M,256] tensor never reaches HBM. */
+int64_t pcc_gnn_packed_bytes(void);
+int pcc_gnn_max_blocks(void);
+int pcc_gnn_pack_weights(const float* w_rel2, const float* w_root2, const float* w_fc1, void* packed, int device, void* stream);
+int pcc_gnn_conv1_fwd(const float* x, int F, const int64_t* rowptr, const int32_t* col, const float* w, int mean,
+                      const float* w_rel, const float* w_root, const float* bias, int64_t M, int act, float* agg_out,
+                      float* z_out, float* partials, int* nblk_out, int device, void* stream);
+int pcc_gnn_bn_finalize(const float* partials, int nblk, int Cn, int64_t rows, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                        float* mean_out, float* invstd_out, int device, void* stream);
+int pcc_gnn_bn_eval(const float* running_mean, const float* running_var, const float* gamma, const float* beta, float eps,
+                    int Cn, float* scale, float* shift, int device, void* stream);
+int pcc_gnn_bn_apply(const float* z, const float* scale, const float* shift, int64_t M, int act, void* h_bf16, int device,
+                     void* stream);
+int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, const int32_t* col, const float* w, int mean,
+                     const void* packed, const float* bias, int64_t M, int act, void* agg_out_bf16, float* z_out,
+                     float* partials, int* nblk_out, int device, void* stream);
+int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership, int64_t M,
+                         int64_t B, int act, float* psum, float* partials, int* nblk_out, int device, void* stream);
+/*   backward (autograd of the above).  One block z = A W^T + b, a = act(z), h = a*scale + shift has
+ *      dz = scale (dh - c1 - xhat c2) act'(z),  c1 = sum(dh)/M,  c2 = sum(dh xhat)/M,  xhat = (a - mean) invstd;
+ *   the kernel that produces a gradient tensor dh also accumulates the two sums (partials [nblk][2][128]).
+ *   pcc_gnn_bn_bwd_finalize : partial sums -> c1, c2, dgamma, dbeta.
+ *   pcc_gnn_reduce          : out[i] = sum_b part[b*count + i] (weight-gradient partials).
+ *   pcc_gnn_fc1_bwd         : recomputes z3 per tile; dz3 = (gs[graph] - kap - lam*xhat3) act'(z3) (gs / kap / lam carry the
+ *                             mean-pool + bn3 backward, computed by the caller from [B,256]-sized data); dh_out = dz3 Wfc1
+ *                             (fp32) + its bn2 sums; dw_part [nblk][256][128], db_part [nblk][256].
+ *   pcc_gnn_conv_bwd        : dz in the operand prologue; dagg_out (bf16) | droot_out (fp32) = dz [W_rel | W_root];
+ *                             dw_part [nblk][128][256] = dz^T [agg | h_in] accumulated in TMEM; db_part [nblk][128].
+ *   pcc_gnn_agg_bwd         : dh_inout[j] += sum_{e: src(e)=j} w_e dagg[dst(e)] (CSR by source) + the bn sums of the
+ *                             previous block (z_prev, its mean / invstd).
+ *   pcc_gnn_conv1_bwd       : partials [nblk][128][2F+1] = (dW_rel | dW_root | db) of GraphConv 1. */
+int pcc_gnn_bn_bwd_finalize(const float* partials, int nblk, int Cn, int64_t rows, float* c1, float* c2, float* dgamma,
+                            float* dbeta, int device, void* stream);
+int pcc_gnn_reduce(const float* part, int nblk, int64_t count, float* out, int device, void* stream);
+int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership, const float* gs,
+                    const float* kap, const float* lam, const float* mu3, const float* r3, const float* z_prev,
+                    const float* mu_prev, const float* r_prev, int64_t M, int act, float* dh_out, float* stat_part,
+                    float* dw_part, float* db_part, int* nblk_out, int device, void* stream);
+int pcc_gnn_conv_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
+                     const float* bn_c1, const float* bn_c2, const void* agg_bf16, const void* h_in_bf16, const void* packed,
+                     int64_t M, int act, void* dagg_out_bf16, float* droot_out, float* dw_part, float* db_part, int* nblk_out,
+                     int device, void* stream);
+int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src, const int32_t* col_src, const float* w_src,
+                    float* dh_inout, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M, int act,
+                    float* partials, int* nblk_out, int device, void* stream);
+int pcc_gnn_conv1_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
+                      const float* bn_c1, const float* bn_c2, const float* agg, const float* x, int F, int64_t M, int act,
+                      float* partials, int* nblk_out, int device, void* stream);
+
 /* ---- loss and row gather.
  *      pcc_bce_logits: nn.BCEWithLogitsLoss(reduction="mean") forward AND its gradient in one pass
  *      (/root/reference/models/wrapper.py:38,64-67): loss[1], dlogits[count] = (sigmoid(z) - y) / count.

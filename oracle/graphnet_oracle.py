@@ -68,10 +68,18 @@ def graph_aggregate(x: torch.Tensor, edges: torch.Tensor, weights: Optional[torc
     return out
 
 
-def graphconv(sd, prefix: str, x, edges, weights, aggr: str) -> torch.Tensor:
+def _round_bf16_ste(t: torch.Tensor) -> torch.Tensor:
+    """value rounded to bf16 (round-to-nearest-even), identity gradient"""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def graphconv(sd, prefix: str, x, edges, weights, aggr: str, q=None) -> torch.Tensor:
+    """q: operand rounding of the product's bf16 mode (aggregate and weights rounded to bf16; x arrives rounded)"""
     agg = graph_aggregate(x, edges, weights, aggr)
-    return F.linear(agg, sd[prefix + ".lin_rel.weight"], sd[prefix + ".lin_rel.bias"]) + \
-        F.linear(x, sd[prefix + ".lin_root.weight"])
+    w_rel, w_root = sd[prefix + ".lin_rel.weight"], sd[prefix + ".lin_root.weight"]
+    if q is not None:
+        agg, w_rel, w_root = q(agg), q(w_rel), q(w_root)
+    return F.linear(agg, w_rel, sd[prefix + ".lin_rel.bias"]) + F.linear(x, w_root)
 
 
 def global_mean_pool(x: torch.Tensor, membership: torch.Tensor) -> torch.Tensor:
@@ -98,19 +106,28 @@ def _bn(sd, prefix: str, x: torch.Tensor, training: bool, stats_out: Optional[di
 
 
 def graphnet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x, membership, edges, weights=None,
-                     training: bool = True, stats_out: Optional[dict] = None) -> torch.Tensor:
+                     training: bool = True, stats_out: Optional[dict] = None,
+                     operand_rounding: Optional[str] = None) -> torch.Tensor:
     """cfg keys = the reference ctor kwargs (graph_net.py:10-22); only the
-    use_gat=False, sag_pool=False branch (configs/graph_net.yaml:6,8) is restated."""
+    use_gat=False, sag_pool=False branch (configs/graph_net.yaml:6,8) is restated.
+    operand_rounding="bf16": the STATED arithmetic of the product's bf16 GraphNet mode (deepchem_style only) — the
+    normalised activations h1 / h2, the conv2 aggregate and the conv2 / fc1 weights are rounded to bf16, products and
+    sums, pre-activations, BatchNorm statistics and conv1 stay fp32.  Same algorithm, stated operand precision."""
     if cfg.get("use_gat", False) or cfg.get("sag_pool", False):
         raise NotImplementedError("GATConv / SAGPooling branches are out of scope (SURVEY.md §2 row 3)")
     act = cfg["activation"]
     aggr = cfg.get("local_pooling", "add")
+    q = _round_bf16_ste if operand_rounding == "bf16" else None
     h = graphconv(sd, "conv1", x, edges, weights, aggr)
     h = _bn(sd, "bn1", _act(act, h), training, stats_out)
-    h = graphconv(sd, "conv2", h, edges, weights, aggr)
+    if q is not None:
+        h = q(h)
+    h = graphconv(sd, "conv2", h, edges, weights, aggr, q)
     h = _bn(sd, "bn2", _act(act, h), training, stats_out)
+    if q is not None:
+        h = q(h)
     if cfg.get("deepchem_style", False):
-        h = F.linear(h, sd["fc1.weight"], sd["fc1.bias"])
+        h = F.linear(h, q(sd["fc1.weight"]) if q is not None else sd["fc1.weight"], sd["fc1.bias"])
         h = _bn(sd, "bn3", _act(act, h), training, stats_out)
         h = global_mean_pool(h, membership)
     else:
@@ -126,10 +143,11 @@ TRAINABLE = ("conv1.lin_rel.weight", "conv1.lin_rel.bias", "conv1.lin_root.weigh
              "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")
 
 
-def graphnet_train_step(sd, cfg, x, membership, edges, weights, y):
+def graphnet_train_step(sd, cfg, x, membership, edges, weights, y, operand_rounding: Optional[str] = None):
     leaves = {k: (v.detach().clone().requires_grad_(True) if k in TRAINABLE else v) for k, v in sd.items()}
     stats = {}
-    logits = graphnet_forward(leaves, cfg, x, membership, edges, weights, training=True, stats_out=stats)
+    logits = graphnet_forward(leaves, cfg, x, membership, edges, weights, training=True, stats_out=stats,
+                              operand_rounding=operand_rounding)
     loss = F.binary_cross_entropy_with_logits(logits, y)
     loss.backward()
     grads = {k: leaves[k].grad for k in TRAINABLE}

@@ -1,0 +1,728 @@
+// Fused bf16 GraphNet path, backward kernels (autograd of /root/reference/models/graph_net.py:73-92), see pcc_gnn.cuh.
+//
+// One block  z = A W^T + b,  a = act(z),  h = BN(a) = a s + t  (s = gamma invstd, t = beta - mean s,  xhat = (a - mean) invstd):
+//   dgamma = sum dh xhat,  dbeta = sum dh,  dz = s (dh - dbeta/M - xhat dgamma/M) act'(z)
+// so every backward kernel needs the two column sums (dbeta, dgamma) of ITS incoming gradient before it can form dz: the
+// kernel that PRODUCES a gradient tensor also accumulates those two sums (per-CTA partials, reduced by
+// gnn_bn_bwd_finalize), and the consumer folds the BatchNorm / activation backward into its operand prologue.
+//   fc1 bwd  (tcgen05): recompute z3 = h2 Wfc1^T per tile, dz3 (bn3 + mean-pool backward are per-graph / per-channel
+//                       terms), dh2 = dz3 Wfc1, dWfc1 += dz3^T h2 in TMEM, sums for bn2
+//   conv bwd (tcgen05): dz2 in the prologue, [dagg2 | droot] = dz2 [W_rel | W_root], dW += dz2^T [agg2 | h1] in TMEM
+//   agg bwd  (CUDA cores): dh1 = droot + A^T dagg2 (CSR by source, bf16 rows), sums for bn1
+//   conv1 bwd (CUDA cores): dz1, dW_rel1 / dW_root1 / db1 (K = 2F)
+#include "pcc_gnn.cuh"
+
+namespace pcc {
+namespace gnn {
+
+// bnb arrays: [5][Cn] = {mean, invstd, scale, c1 = dbeta/M, c2 = dgamma/M}
+struct BnBack {
+  const float* mean;
+  const float* invstd;
+  const float* scale;
+  const float* c1;
+  const float* c2;
+};
+
+// partial sums [nblk][2][Cn] (sum dh, sum dh xhat) -> c1, c2, dgamma, dbeta
+__global__ void __launch_bounds__(256) gnn_bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int Cn, int64_t rows,
+                                           float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta) {
+  __shared__ double red[8][2][32];
+  const int cl = threadIdx.x & 31, gq = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < Cn)
+    for (int b = gq; b < nblk; b += 8) {
+      s1 += (double)__ldg(partials + (size_t)b * 2 * Cn + c);
+      s2 += (double)__ldg(partials + (size_t)b * 2 * Cn + Cn + c);
+    }
+  red[gq][0][cl] = s1;
+  red[gq][1][cl] = s2;
+  __syncthreads();
+  if (gq != 0 || c >= Cn) return;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) { s1 += red[j][0][cl]; s2 += red[j][1][cl]; }
+  dbeta[c] = (float)s1;
+  dgamma[c] = (float)s2;
+  c1[c] = (float)(s1 / (double)rows);
+  c2[c] = (float)(s2 / (double)rows);
+}
+
+// out[i] = sum_b part[b*count + i]
+__global__ void gnn_reduce_kernel(const float* __restrict__ part, int nblk, int64_t count, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * count + i];
+  out[i] = s;
+}
+
+// ====================================================================== fc1 backward
+constexpr int kFbLoadWarps = 4, kFbEpiWarp0 = 4, kFbMmaWarp = 12, kFbThreads = 13 * 32;
+constexpr uint32_t kHImgB = kC * kTile * 2;        // 32 KB
+constexpr uint32_t kFcWImgB = kFc * kC * 2;        // 64 KB
+constexpr uint32_t kDzImg = kFc * kTile * 2;       // 64 KB: [128 rows][256 cols]
+
+struct Fc1BwdParams {
+  const __nv_bfloat16* h_in;   // h2 [M,C]
+  const uint8_t* wimg;         // [256][C]
+  const float* bias;           // fc1 bias [256]
+  const int64_t* membership;
+  const float* gs;             // [B,256]: alpha_c G[b,c] / n_b
+  const float* kap;            // [256]
+  const float* lam;            // [256]
+  const float* mu3;            // [256]
+  const float* r3;             // [256]
+  const float* z_prev;         // z2 [M,C]
+  const float* mu_prev;        // bn2 mean [C]
+  const float* r_prev;         // bn2 invstd [C]
+  float* dh_out;               // dh2 [M,C] fp32
+  float* stat_part;            // [grid][2][C]
+  float* dw_part;              // [grid][256][C]
+  float* db_part;              // [grid][256]
+  int64_t M, num_tiles;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Himg = smem;                                  // 2 x 32 KB
+  uint8_t* Wimg = smem + 2 * kHImgB;                     // 64 KB
+  uint8_t* Dimg = smem + 2 * kHImgB + kFcWImgB;          // 64 KB
+  float* cst = reinterpret_cast<float*>(smem + 2 * kHImgB + kFcWImgB + kDzImg);   // bias, kap, lam, mu3, r3 [5][256]; mu2, r2 [2][128]
+  float* scratch = cst + 5 * kFc + 2 * kC;                                        // [4][2][C] stats, [4][256] db
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 4 * 2 * kC + 4 * kFc);
+  uint64_t* full = bars;           // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* z_full = bars + 4;
+  uint64_t* z_free = bars + 5;     // 8 warps
+  uint64_t* dz_ready = bars + 6;   // 8 warps
+  uint64_t* dh_full = bars + 7;
+  uint64_t* dh_free = bars + 8;    // 8 warps
+  uint64_t* wbar = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kFbLoadWarps); mbar_init(&empty[i], 1); }
+    mbar_init(z_full, 1); mbar_init(z_free, 8); mbar_init(dz_ready, 8); mbar_init(dh_full, 1); mbar_init(dh_free, 8);
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(wbar, kFcWImgB);
+    for (int s = 0; s < 4; ++s) bulk_g2s(Wimg + s * (kFcWImgB / 4), p.wimg + (size_t)s * (kFcWImgB / 4), kFcWImgB / 4, wbar);
+  }
+  for (int i = threadIdx.x; i < kFc; i += kFbThreads) {
+    cst[i] = __ldg(p.bias + i); cst[kFc + i] = __ldg(p.kap + i); cst[2 * kFc + i] = __ldg(p.lam + i);
+    cst[3 * kFc + i] = __ldg(p.mu3 + i); cst[4 * kFc + i] = __ldg(p.r3 + i);
+  }
+  for (int i = threadIdx.x; i < kC; i += kFbThreads) { cst[5 * kFc + i] = __ldg(p.mu_prev + i); cst[5 * kFc + kC + i] = __ldg(p.r_prev + i); }
+  if (warp == kFbMmaWarp) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t T_Z = 0, T_DH = 128, T_DW = 256;
+  const int64_t my_tiles = (p.num_tiles > (int64_t)blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < kFbLoadWarps) {
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, k = it >> 1;
+      if (k >= 1) mbar_wait_b(&empty[buf], (uint32_t)((k - 1) & 1));
+      // same tile loader as the forward kernel (pcc_gnn.cu)
+      for (int c = warp * 32 + lane; c < kTile * (kC / 8); c += kFbLoadWarps * 32) {
+        const int r = c >> 4, kc = c & 15;
+        const int64_t node = tile * kTile + r;
+        const uint4 v = node < p.M ? __ldg(reinterpret_cast<const uint4*>(p.h_in + (size_t)node * kC) + kc) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(Himg + buf * kHImgB + img_chunk_off(r, kc * 8)) = v;
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(&full[buf]);
+    }
+  } else if (warp == kFbMmaWarp) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_Z = make_idesc_bf16(128, 128, 0, 0);     // z3 half: [128 rows] x [128 out]
+      constexpr uint32_t IDESC_DH = make_idesc_bf16(128, kC, 0, 1);     // dh2: dZ (K-major) x W viewed [in x out]
+      constexpr uint32_t IDESC_DW = make_idesc_bf16(128, kC, 1, 1);     // dW half: dZ^T x h2
+      mbar_wait_b(wbar, 0);
+      const uint32_t h_base = smem_u32(Himg), w_base = smem_u32(Wimg), d_base = smem_u32(Dimg);
+      int it = 0;
+      uint32_t use = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1, k = it >> 1;
+        mbar_wait_b(&full[buf], (uint32_t)(k & 1));
+        for (int half = 0; half < 2; ++half, ++use) {
+          if (use >= 1) mbar_wait_b(z_free, (use - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < kC / 64; ++s)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tmem + T_Z, make_smem_desc_sw128_k(h_base + buf * kHImgB + s * kSlab + ks * 32),
+                        make_smem_desc_sw128_k(w_base + s * (kFc * 128) + half * (128 * 128) + ks * 32), IDESC_Z, (s | ks) != 0);
+          umma_commit(z_full);
+        }
+        mbar_wait_b(dz_ready, (uint32_t)(it & 1));
+        if (it >= 1) mbar_wait_b(dh_free, (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+        // dh2[rows, in] = sum_out dZ[rows, out] W[out, in]
+#pragma unroll
+        for (int ks = 0; ks < kFc / 16; ++ks)
+          umma_bf16(tmem + T_DH, make_smem_desc_sw128_k(d_base + (ks >> 2) * kSlab + (ks & 3) * 32),
+                    make_smem_desc_sw128_mn(w_base + ks * 2048, kFc * 128), IDESC_DH, ks != 0);
+        // dW[out, in] += sum_rows dZ[rows, out] h2[rows, in]   (two halves of 128 output features)
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+          for (int ks = 0; ks < kTile / 16; ++ks)
+            umma_bf16(tmem + T_DW + o * kC, make_smem_desc_sw128_mn(d_base + o * (2 * kSlab) + ks * 2048, kSlab),
+                      make_smem_desc_sw128_mn(h_base + buf * kHImgB + ks * 2048, kSlab), IDESC_DW, (it | ks) != 0);
+        umma_commit(&empty[buf]);
+        umma_commit(dh_full);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 4-11: lane quarter q, 64-column group cg of every 128-column phase
+    const int q = warp & 3, cg = (warp - kFbEpiWarp0) >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const float* b3 = cst; const float* kap = cst + kFc; const float* lam = cst + 2 * kFc;
+    const float* mu3 = cst + 3 * kFc; const float* r3 = cst + 4 * kFc;
+    const float* mu2 = cst + 5 * kFc; const float* r2 = cst + 5 * kFc + kC;
+    float st2[4][2], db3[2][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { st2[c][0] = st2[c][1] = 0.f; db3[0][c] = db3[1][c] = 0.f; }
+    const int row = q * 32 + lane;
+    int it = 0;
+    uint32_t use = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int64_t node = tile * kTile + row;
+      const bool valid = node < p.M;
+      const int64_t gph = valid ? __ldg(p.membership + node) : 0;
+      const float* gsr = p.gs + gph * kFc;
+#pragma unroll
+      for (int half = 0; half < 2; ++half, ++use) {
+        mbar_wait_b(z_full, use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = half * 128 + cg * 64 + c * 16;
+          uint32_t v[16];
+          tmem_ld16(lane_base + T_Z + cg * 64 + c * 16, v);
+          float gq[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(gsr + col0) + j);
+            gq[4 * j] = t4.x; gq[4 * j + 1] = t4.y; gq[4 * j + 2] = t4.z; gq[4 * j + 3] = t4.w;
+          }
+          tmem_wait_ld();
+          float dz[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = col0 + j;
+            const float z = __uint_as_float(v[j]) + b3[col];
+            const float a = actf<ACT>(z);
+            const float da = gq[j] - kap[col] - lam[col] * (a - mu3[col]) * r3[col];
+            dz[j] = valid ? da * actg<ACT>(z, a) : 0.f;
+          }
+          *reinterpret_cast<uint4*>(Dimg + img_chunk_off(row, col0)) =
+              make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+          *reinterpret_cast<uint4*>(Dimg + img_chunk_off(row, col0 + 8)) =
+              make_uint4(pack_bf16x2(dz[8], dz[9]), pack_bf16x2(dz[10], dz[11]), pack_bf16x2(dz[12], dz[13]), pack_bf16x2(dz[14], dz[15]));
+          db3[half][c] += warp_transpose_sum16(dz, lane);   // (bf16 rounding of dz not applied to the bias gradient)
+        }
+        tc_fence_before();
+        mbar_arrive_warp(z_free);
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(dz_ready);
+      // ---- dh2 of the tile: TMEM -> HBM (fp32) + the two column sums the bn2 backward needs
+      mbar_wait_b(dh_full, (uint32_t)(it & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = cg * 64 + c * 16;
+        uint32_t v[16];
+        tmem_ld16(lane_base + T_DH + col0, v);
+        float zp[16];
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.z_prev + (size_t)node * kC + col0) + j);
+            zp[4 * j] = t4.x; zp[4 * j + 1] = t4.y; zp[4 * j + 2] = t4.z; zp[4 * j + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) zp[j] = 0.f;
+        }
+        tmem_wait_ld();
+        float s1[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float dh = valid ? __uint_as_float(v[j]) : 0.f;
+          const float xh = (actf<ACT>(zp[j]) - mu2[col0 + j]) * r2[col0 + j];
+          s1[j] = dh;
+          s2[j] = dh * xh;
+        }
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(p.dh_out + (size_t)node * kC + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(s1[4 * j], s1[4 * j + 1], s1[4 * j + 2], s1[4 * j + 3]);
+        }
+        st2[c][0] += warp_transpose_sum16(s1, lane);
+        st2[c][1] += warp_transpose_sum16(s2, lane);
+      }
+      tc_fence_before();
+      mbar_arrive_warp(dh_free);
+    }
+    // ---- per-CTA partials: bn2 sums, fc1 bias gradient, fc1 weight gradient (TMEM)
+    float* sstat = scratch;                 // [4 q][2][C]
+    float* sdb = scratch + 4 * 2 * kC;      // [4 q][256]
+    if (lane < 16) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sstat[(q * 2 + 0) * kC + cg * 64 + c * 16 + lane] = st2[c][0];
+        sstat[(q * 2 + 1) * kC + cg * 64 + c * 16 + lane] = st2[c][1];
+        sdb[q * kFc + 0 * 128 + cg * 64 + c * 16 + lane] = db3[0][c];
+        sdb[q * kFc + 1 * 128 + cg * 64 + c * 16 + lane] = db3[1][c];
+      }
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const int t = threadIdx.x - kFbEpiWarp0 * 32;   // 0..255
+    p.stat_part[(size_t)blockIdx.x * 2 * kC + t] = sstat[(0 * 2 + t / kC) * kC + t % kC] + sstat[(1 * 2 + t / kC) * kC + t % kC] +
+                                                   sstat[(2 * 2 + t / kC) * kC + t % kC] + sstat[(3 * 2 + t / kC) * kC + t % kC];
+    p.db_part[(size_t)blockIdx.x * kFc + t] = sdb[t] + sdb[kFc + t] + sdb[2 * kFc + t] + sdb[3 * kFc + t];
+    // dW partial [256 out][C in]: TMEM lane = out feature inside its half, column = in feature
+    if (my_tiles > 0) {
+      // the last dh_full commit covered every MMA issued before it, the dW ones included
+      for (int o = 0; o < 2; ++o) {
+        float* dst = p.dw_part + ((size_t)blockIdx.x * kFc + o * 128 + row) * kC + cg * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + T_DW + o * kC + cg * 64 + c * 16, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(dst + c * 16)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    } else {
+      for (int o = 0; o < 2; ++o) {
+        float* dst = p.dw_part + ((size_t)blockIdx.x * kFc + o * 128 + row) * kC + cg * 64;
+        for (int j = 0; j < 64; ++j) dst[j] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kFbMmaWarp) tmem_dealloc<512>(tmem);
+}
+
+// ====================================================================== conv2 backward
+constexpr int kCbLoadWarps = 16, kCbEpiWarp0 = 16, kCbMmaWarp = 20, kCbThreads = 21 * 32;
+constexpr uint32_t kDz2Img = kC * kTile * 2;          // 32 KB: [128 rows][C cols]
+constexpr uint32_t kAinImg = 2 * kC * kTile * 2;      // 64 KB: [128 rows][2C cols]
+constexpr uint32_t kCwImg = 2 * kC * kC * 2;          // 64 KB
+
+struct ConvBwdParams {
+  const float* dh;             // dL/dh of this block's output [M,C] fp32
+  const float* z;              // pre-activation of this block [M,C]
+  BnBack bn;                   // [C] arrays
+  const __nv_bfloat16* agg;    // [M,C] kept aggregate (A operand, left half)
+  const __nv_bfloat16* h_in;   // [M,C] block input (A operand, right half)
+  const uint8_t* wimg;         // [C][2C] image
+  __nv_bfloat16* dagg_out;     // [M,C] bf16
+  float* droot_out;            // [M,C] fp32
+  float* dw_part;              // [grid][C][2C]
+  float* db_part;              // [grid][C]
+  int64_t M, num_tiles;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* Dimg = smem;                            // 32 KB
+  uint8_t* Aimg = smem + kDz2Img;                  // 64 KB
+  uint8_t* Wimg = smem + kDz2Img + kAinImg;        // 64 KB
+  float* cst = reinterpret_cast<float*>(smem + kDz2Img + kAinImg + kCwImg);   // [5][C]
+  float* scratch = cst + 5 * kC;                                              // [16][C] db
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kCbLoadWarps * kC);
+  uint64_t* full = bars;        // 16 warps
+  uint64_t* empty = bars + 1;   // MMA commit
+  uint64_t* dx_full = bars + 2;
+  uint64_t* dx_free = bars + 3; // 4 warps
+  uint64_t* wbar = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(full, kCbLoadWarps); mbar_init(empty, 1); mbar_init(dx_full, 1); mbar_init(dx_free, 4); mbar_init(wbar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(wbar, kCwImg);
+    for (int s = 0; s < 4; ++s) bulk_g2s(Wimg + s * (kCwImg / 4), p.wimg + (size_t)s * (kCwImg / 4), kCwImg / 4, wbar);
+  }
+  for (int i = threadIdx.x; i < kC; i += kCbThreads) {
+    cst[i] = __ldg(p.bn.mean + i); cst[kC + i] = __ldg(p.bn.invstd + i); cst[2 * kC + i] = __ldg(p.bn.scale + i);
+    cst[3 * kC + i] = __ldg(p.bn.c1 + i); cst[4 * kC + i] = __ldg(p.bn.c2 + i);
+  }
+  if (warp == kCbMmaWarp) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t T_DX = 0, T_DW = 256;
+  const int64_t my_tiles = (p.num_tiles > (int64_t)blockIdx.x) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < kCbLoadWarps) {
+    // ===================== prologue warps: dz = s (dh - c1 - xhat c2) act'(z) -> bf16 image; [agg | h_in] image
+    const int col = 4 * lane;
+    const float4 mu = *reinterpret_cast<const float4*>(cst + col), rs = *reinterpret_cast<const float4*>(cst + kC + col);
+    const float4 sc = *reinterpret_cast<const float4*>(cst + 2 * kC + col), c1 = *reinterpret_cast<const float4*>(cst + 3 * kC + col);
+    const float4 c2 = *reinterpret_cast<const float4*>(cst + 4 * kC + col);
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (it >= 1) mbar_wait_b(empty, (uint32_t)((it - 1) & 1));
+#pragma unroll 2
+      for (int i = 0; i < kTile / kCbLoadWarps; ++i) {
+        const int r = warp + kCbLoadWarps * i;
+        const int64_t node = tile * kTile + r;
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        uint2 ag = make_uint2(0u, 0u), hr = make_uint2(0u, 0u);
+        if (node < p.M) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.dh + (size_t)node * kC) + lane);
+          const float4 z = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)node * kC) + lane);
+          ag = __ldg(reinterpret_cast<const uint2*>(p.agg + (size_t)node * kC) + lane);
+          hr = __ldg(reinterpret_cast<const uint2*>(p.h_in + (size_t)node * kC) + lane);
+          float a;
+          a = actf<ACT>(z.x); dz[0] = sc.x * (g.x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(z.x, a);
+          a = actf<ACT>(z.y); dz[1] = sc.y * (g.y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(z.y, a);
+          a = actf<ACT>(z.z); dz[2] = sc.z * (g.z - c1.z - (a - mu.z) * rs.z * c2.z) * actg<ACT>(z.z, a);
+          a = actf<ACT>(z.w); dz[3] = sc.w * (g.w - c1.w - (a - mu.w) * rs.w * c2.w) * actg<ACT>(z.w, a);
+        }
+        db[0] += dz[0]; db[1] += dz[1]; db[2] += dz[2]; db[3] += dz[3];
+        *reinterpret_cast<uint2*>(Dimg + img_chunk_off(r, col) + ((col & 7) << 1)) =
+            make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, col) + ((col & 7) << 1)) = ag;
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, kC + col) + ((col & 7) << 1)) = hr;
+      }
+      fence_proxy_async();
+      mbar_arrive_warp(full);
+    }
+    *reinterpret_cast<float4*>(scratch + warp * kC + col) = make_float4(db[0], db[1], db[2], db[3]);
+    asm volatile("bar.sync 3, 512;" ::: "memory");
+    for (int i = threadIdx.x; i < kC; i += kCbLoadWarps * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCbLoadWarps; ++w) s += scratch[w * kC + i];
+      p.db_part[(size_t)blockIdx.x * kC + i] = s;
+    }
+  } else if (warp == kCbMmaWarp) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_DX = make_idesc_bf16(128, 2 * kC, 0, 1);   // [128 rows] x [2C in]: dZ (K-major) x W viewed [in x out]
+      constexpr uint32_t IDESC_DW = make_idesc_bf16(128, 2 * kC, 1, 1);   // [C out] x [2C in]: dZ^T x [agg | h]
+      mbar_wait_b(wbar, 0);
+      const uint32_t d_base = smem_u32(Dimg), a_base = smem_u32(Aimg), w_base = smem_u32(Wimg);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait_b(full, (uint32_t)(it & 1));
+        if (it >= 1) mbar_wait_b(dx_free, (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < kC / 16; ++ks)
+          umma_bf16(tmem + T_DX, make_smem_desc_sw128_k(d_base + (ks >> 2) * kSlab + (ks & 3) * 32),
+                    make_smem_desc_sw128_mn(w_base + ks * 2048, kC * 128), IDESC_DX, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < kTile / 16; ++ks)
+          umma_bf16(tmem + T_DW, make_smem_desc_sw128_mn(d_base + ks * 2048, kSlab),
+                    make_smem_desc_sw128_mn(a_base + ks * 2048, kSlab), IDESC_DW, (it | ks) != 0);
+        umma_commit(empty);
+        umma_commit(dx_full);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 16-19: dX accumulator -> dagg (bf16) | droot (fp32)
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int64_t node = tile * kTile + row;
+      const bool valid = node < p.M;
+      mbar_wait_b(dx_full, (uint32_t)(it & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2 * kC / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + T_DX + c * 32, v);
+        tmem_wait_ld();
+        if (!valid) continue;
+        if (c < kC / 32) {
+          uint4* dst = reinterpret_cast<uint4*>(p.dagg_out + (size_t)node * kC + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+        } else {
+          float4* dst = reinterpret_cast<float4*>(p.droot_out + (size_t)node * kC + (c - kC / 32) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp(dx_free);
+    }
+    // dW partial [C out][2C]: lane = out feature
+    float* dst = p.dw_part + ((size_t)blockIdx.x * kC + row) * (2 * kC);
+    if (my_tiles > 0) {
+#pragma unroll 1
+      for (int c = 0; c < 2 * kC / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + T_DW + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst + c * 32)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    } else {
+      for (int j = 0; j < 2 * kC; ++j) dst[j] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kCbMmaWarp) tmem_dealloc<512>(tmem);
+}
+
+// ====================================================================== aggregation backward (+ sums for the bn backward)
+// dh[j] = droot[j] + sum_{e: src(e) = j} w_e dagg[dst(e)]   (CSR by source; for mean aggregation w already carries
+// 1/deg(dst)); warp per node, lane = 4 channels; writes dh IN PLACE over droot.  Also accumulates sum dh and
+// sum dh xhat of the PREVIOUS block (z_prev, its mean / invstd) per block.
+template <int ACT>
+__global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* __restrict__ dagg, GnnGraph g, float* __restrict__ dh,
+                                                          const float* __restrict__ z_prev, const float* __restrict__ mu_prev,
+                                                          const float* __restrict__ r_prev, int64_t M, float* __restrict__ partials) {
+  __shared__ float red[8][2][kC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mu_prev) + lane), rs = __ldg(reinterpret_cast<const float4*>(r_prev) + lane);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < M; node += nwarps) {
+    const int64_t pb = __ldg(g.rowptr + node), pe = __ldg(g.rowptr + node + 1);
+    float4 acc = *(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
+    const float4 z = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)node * kC) + lane);
+    for (int64_t p0 = pb; p0 < pe; p0 += 32) {
+      const int cnt = (int)((pe - p0 < 32) ? pe - p0 : 32);
+      const int myc = lane < cnt ? __ldg(g.col + p0 + lane) : 0;
+      const float myw = (g.w && lane < cnt) ? __ldg(g.w + p0 + lane) : 1.f;
+      for (int j = 0; j < cnt; j += 8) {
+        uint2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = __shfl_sync(0xffffffffu, myc, (j + u) & 31);
+          v[u] = (j + u < cnt) ? __ldg(reinterpret_cast<const uint2*>(dagg + (size_t)t * kC) + lane) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float wu = __shfl_sync(0xffffffffu, myw, (j + u) & 31);
+          acc.x = fmaf(wu, bf16_lo(v[u].x), acc.x); acc.y = fmaf(wu, bf16_hi(v[u].x), acc.y);
+          acc.z = fmaf(wu, bf16_lo(v[u].y), acc.z); acc.w = fmaf(wu, bf16_hi(v[u].y), acc.w);
+        }
+      }
+    }
+    *(reinterpret_cast<float4*>(dh + (size_t)node * kC) + lane) = acc;
+    s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
+    s2[0] += acc.x * (actf<ACT>(z.x) - mu.x) * rs.x; s2[1] += acc.y * (actf<ACT>(z.y) - mu.y) * rs.y;
+    s2[2] += acc.z * (actf<ACT>(z.z) - mu.z) * rs.z; s2[3] += acc.w * (actf<ACT>(z.w) - mu.w) * rs.w;
+  }
+  *reinterpret_cast<float4*>(&red[warp][0][4 * lane]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  *reinterpret_cast<float4*>(&red[warp][1][4 * lane]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kC; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][i / kC][i % kC];
+    partials[(size_t)blockIdx.x * 2 * kC + i] = s;
+  }
+}
+
+// ====================================================================== conv1 backward (K = 2F): CUDA cores
+// dz1 = s (dh - c1 - xhat c2) act'(z1);  dW_rel1[c,f] += dz1[c] agg1[f],  dW_root1[c,f] += dz1[c] x[f],  db1[c] += dz1[c]
+// per-block partial [C][2F+1] (rel | root | bias).
+template <int ACT, int FP>
+__global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z, BnBack bn,
+                                                            const float* __restrict__ agg, const float* __restrict__ x, int F,
+                                                            int64_t M, float* __restrict__ partials) {
+  extern __shared__ float red1[];   // [8][C][2 FP + 1]
+  constexpr int NA = 2 * FP + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(bn.invstd) + lane);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.scale) + lane), c1 = __ldg(reinterpret_cast<const float4*>(bn.c1) + lane);
+  const float4 c2 = __ldg(reinterpret_cast<const float4*>(bn.c2) + lane);
+  float acc[4][NA];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int f = 0; f < NA; ++f) acc[j][f] = 0.f;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < M; node += nwarps) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
+    const float4 zz = __ldg(reinterpret_cast<const float4*>(z + (size_t)node * kC) + lane);
+    float in[2 * FP];
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+      in[f] = f < F ? __ldg(agg + node * F + f) : 0.f;
+      in[FP + f] = f < F ? __ldg(x + node * F + f) : 0.f;
+    }
+    float dz[4], a;
+    a = actf<ACT>(zz.x); dz[0] = sc.x * (g.x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(zz.x, a);
+    a = actf<ACT>(zz.y); dz[1] = sc.y * (g.y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(zz.y, a);
+    a = actf<ACT>(zz.z); dz[2] = sc.z * (g.z - c1.z - (a - mu.z) * rs.z * c2.z) * actg<ACT>(zz.z, a);
+    a = actf<ACT>(zz.w); dz[3] = sc.w * (g.w - c1.w - (a - mu.w) * rs.w * c2.w) * actg<ACT>(zz.w, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int f = 0; f < 2 * FP; ++f) acc[j][f] = fmaf(dz[j], in[f], acc[j][f]);
+      acc[j][2 * FP] += dz[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int f = 0; f < NA; ++f) red1[(warp * kC + 4 * lane + j) * NA + f] = acc[j][f];
+  __syncthreads();
+  const int W = 2 * F + 1;
+  for (int i = threadIdx.x; i < kC * W; i += 256) {
+    const int c = i / W, f = i % W;
+    const int slot = f < F ? f : (f < 2 * F ? FP + (f - F) : 2 * FP);
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red1[(w8 * kC + c) * NA + slot];
+    partials[(size_t)blockIdx.x * kC * W + i] = s;
+  }
+}
+
+int gnn_grid(int64_t num_tiles);
+
+}  // namespace gnn
+}  // namespace pcc
+
+using namespace pcc;
+using namespace pcc::gnn;
+
+#define GNN_ACT_DISPATCH(act, ...)                        \
+  switch (act) {                                           \
+    case PCC_ACT_RELU: { constexpr int A = PCC_ACT_RELU; __VA_ARGS__; break; } \
+    case PCC_ACT_GELU: { constexpr int A = PCC_ACT_GELU; __VA_ARGS__; break; } \
+    case PCC_ACT_TANH: { constexpr int A = PCC_ACT_TANH; __VA_ARGS__; break; } \
+    default: return fail(__func__, "activation must be tanh / relu / gelu (graph_net.py:38-43)"); \
+  }
+
+extern "C" int pcc_gnn_bn_bwd_finalize(const float* partials, int nblk, int Cn, int64_t rows, float* c1, float* c2,
+                                       float* dgamma, float* dbeta, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_K(gnn_bn_bwd_finalize_kernel)<<<cdiv(Cn, 32), 256, 0, (cudaStream_t)stream>>>(partials, nblk, Cn, rows, c1, c2, dgamma, dbeta);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_reduce(const float* part, int nblk, int64_t count, float* out, int device, void* stream) {
+  PCC_ENTER(device);
+  if (count == 0) return 0;
+  PCC_K(gnn_reduce_kernel)<<<(unsigned)cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(part, nblk, count, out);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership,
+                               const float* gs, const float* kap, const float* lam, const float* mu3, const float* r3,
+                               const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M, int act,
+                               float* dh_out, float* stat_part, float* dw_part, float* db_part, int* nblk_out, int device,
+                               void* stream) {
+  PCC_ENTER(device);
+  Fc1BwdParams p{};
+  p.h_in = (const __nv_bfloat16*)h_in_bf16;
+  p.wimg = (const uint8_t*)packed + 2 * kC * kC * 2;
+  p.bias = bias; p.membership = membership; p.gs = gs; p.kap = kap; p.lam = lam; p.mu3 = mu3; p.r3 = r3;
+  p.z_prev = z_prev; p.mu_prev = mu_prev; p.r_prev = r_prev;
+  p.dh_out = dh_out; p.stat_part = stat_part; p.dw_part = dw_part; p.db_part = db_part;
+  p.M = M; p.num_tiles = cdiv(M, kTile);
+  const int grid = gnn_grid(p.num_tiles);
+  *nblk_out = grid;
+  if (grid == 0) return 0;
+  const int smem_bytes = 2 * kHImgB + kFcWImgB + kDzImg + (5 * kFc + 2 * kC + 8 * kC + 4 * kFc) * 4 + 128;
+  {
+    ProfScope prof(4, (cudaStream_t)stream);
+    GNN_ACT_DISPATCH(act, {
+      auto kern = gnn_fc1_bwd_kernel<A>;
+      PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      PCC_K(kern)<<<grid, kFbThreads, smem_bytes, (cudaStream_t)stream>>>(p);
+    });
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_conv_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd,
+                                const float* bn_scale, const float* bn_c1, const float* bn_c2, const void* agg_bf16,
+                                const void* h_in_bf16, const void* packed, int64_t M, int act, void* dagg_out_bf16,
+                                float* droot_out, float* dw_part, float* db_part, int* nblk_out, int device, void* stream) {
+  PCC_ENTER(device);
+  ConvBwdParams p{};
+  p.dh = dh; p.z = z;
+  p.bn = BnBack{bn_mean, bn_invstd, bn_scale, bn_c1, bn_c2};
+  p.agg = (const __nv_bfloat16*)agg_bf16; p.h_in = (const __nv_bfloat16*)h_in_bf16;
+  p.wimg = (const uint8_t*)packed;
+  p.dagg_out = (__nv_bfloat16*)dagg_out_bf16; p.droot_out = droot_out; p.dw_part = dw_part; p.db_part = db_part;
+  p.M = M; p.num_tiles = cdiv(M, kTile);
+  const int grid = gnn_grid(p.num_tiles);
+  *nblk_out = grid;
+  if (grid == 0) return 0;
+  const int smem_bytes = kDz2Img + kAinImg + kCwImg + (5 * kC + kCbLoadWarps * kC) * 4 + 128;
+  {
+    ProfScope prof(4, (cudaStream_t)stream);
+    GNN_ACT_DISPATCH(act, {
+      auto kern = gnn_conv_bwd_kernel<A>;
+      PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      PCC_K(kern)<<<grid, kCbThreads, smem_bytes, (cudaStream_t)stream>>>(p);
+    });
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src, const int32_t* col_src, const float* w_src,
+                               float* dh_inout, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M,
+                               int act, float* partials, int* nblk_out, int device, void* stream) {
+  PCC_ENTER(device);
+  int blocks = (int)(cdiv(M, 8) < 1184 ? cdiv(M, 8) : 1184);
+  if (blocks < 1) blocks = 1;
+  *nblk_out = blocks;
+  GnnGraph g{rowptr_src, col_src, w_src, 0};
+  {
+    ProfScope prof(5, (cudaStream_t)stream);
+    GNN_ACT_DISPATCH(act, {
+      auto kern = gnn_agg_bwd_kernel<A>;
+      PCC_K(kern)<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, dh_inout, z_prev, mu_prev, r_prev, M,
+                                                            partials);
+    });
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_conv1_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd,
+                                 const float* bn_scale, const float* bn_c1, const float* bn_c2, const float* agg, const float* x,
+                                 int F, int64_t M, int act, float* partials, int* nblk_out, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(F >= 1 && F <= 8, "fused conv1 needs input_dim <= 8");
+  int blocks = (int)(cdiv(M, 8 * 16) < 592 ? cdiv(M, 8 * 16) : 592);
+  if (blocks < 1) blocks = 1;
+  *nblk_out = blocks;
+  BnBack bn{bn_mean, bn_invstd, bn_scale, bn_c1, bn_c2};
+  const int smem_bytes = 8 * kC * (F <= 4 ? 9 : 17) * 4;
+  GNN_ACT_DISPATCH(act, {
+    auto kern = F <= 4 ? gnn_conv1_bwd_kernel<A, 4> : gnn_conv1_bwd_kernel<A, 8>;
+    PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>(dh, z, bn, agg, x, F, M, partials);
+  });
+  return check_launch(__func__);
+}

@@ -7,6 +7,7 @@
 // [E,C] message tensor is ever materialised.
 #include "pcc_common.cuh"
 #include "pcc_scan.cuh"
+#include <stdlib.h>
 
 namespace pcc {
 
@@ -38,12 +39,30 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ keys, int64_t E, int
     }
   }
 }
-// restore ascending edge order inside each row (makes float summation order reproducible)
-__global__ void csr_sort_rows_kernel(const int64_t* __restrict__ rowptr, int32_t* __restrict__ perm, int64_t n) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// restore ascending edge order inside each row (makes float summation order reproducible): one warp per row,
+// rows of up to 32 entries (kNN graphs: k <= 32) by a bitonic sort across the lanes (coalesced load / store),
+// longer rows by an insertion sort on lane 0
+__global__ void __launch_bounds__(256) csr_sort_rows_kernel(const int64_t* __restrict__ rowptr, int32_t* __restrict__ perm, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  int64_t s = rowptr[i], e = rowptr[i + 1];
-  if (e - s < 2 || e - s > 1024) return;
+  const int64_t s = rowptr[i], e = rowptr[i + 1];
+  const int64_t len = e - s;
+  if (len < 2) return;
+  if (len <= 32) {
+    int v = lane < len ? perm[s + lane] : 0x7fffffff;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+        v = (lower == up) ? min(v, other) : max(v, other);
+      }
+    if (lane < len) perm[s + lane] = v;
+    return;
+  }
+  if (lane != 0 || len > 4096) return;
   for (int64_t a = s + 1; a < e; ++a) {
     int32_t v = perm[a];
     int64_t b = a - 1;
@@ -249,6 +268,106 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ pos,
   }
 }
 
+// ------------------------------------------------------------------ kNN, shared-memory tiled (the default)
+// CTA = 256 consecutive query points; for every cloud the CTA's queries belong to, the cloud's points stream through a
+// shared-memory tile ({x, y, z} as float4, 1024 candidates) that ALL warps read (one broadcast LDS.128 per candidate
+// instead of per-lane global loads).  Thread = one query: its running top-K lives in REGISTERS as a sorted list of
+// 64-bit keys (fp32 bits of d2 << 32 | candidate id: d2 >= 0, so the unsigned order is the (d2, id) order the oracle
+// defines, ties -> lower id).  A candidate that beats the thread's current K-th key is appended to a small per-thread
+// queue in shared memory; the queues are drained warp-wide (unrolled compare-exchange chain, ~5 instructions per list
+// slot) only when some lane's queue fills, so the divergent insertion cost is paid once per ~5 accepted candidates
+// instead of once per candidate.  Distances use the oracle's arithmetic (no FMA contraction): results are bit-exact.
+constexpr int kKnnTile = 1024, kKnnQ = 8;
+template <int K>
+__global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict__ pos, int64_t pos_stride,
+                                                        const int64_t* __restrict__ offsets, int64_t n, int64_t B, int k,
+                                                        int64_t* __restrict__ nbr, float* __restrict__ d2o) {
+  __shared__ float4 tile[kKnnTile];
+  __shared__ unsigned long long queue[kKnnQ][256];
+  const int tid = threadIdx.x;
+  const int64_t q = (int64_t)blockIdx.x * 256 + tid;
+  const bool valid = q < n;
+  auto cloud_of = [&](int64_t r) {
+    int64_t lo = 0, hi = B;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid + 1) <= r) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const int64_t q_first = (int64_t)blockIdx.x * 256;
+  const int64_t q_last = (q_first + 255 < n - 1) ? q_first + 255 : n - 1;
+  const int64_t b_first = cloud_of(q_first), b_last = cloud_of(q_last);
+  unsigned long long list[K];
+#pragma unroll
+  for (int s = 0; s < K; ++s) list[s] = ~0ull;
+  int cnt = 0;
+  auto drain = [&]() {
+    const int m = __reduce_max_sync(0xffffffffu, cnt);
+    for (int i = 0; i < m; ++i) {
+      const unsigned long long key = (i < cnt) ? queue[i][tid] : ~0ull;
+      if (key < list[K - 1]) {
+        list[K - 1] = key;
+#pragma unroll
+        for (int s = K - 1; s >= 1; --s) {
+          const unsigned long long a = list[s - 1], b = list[s];
+          list[s - 1] = a < b ? a : b;
+          list[s] = a < b ? b : a;
+        }
+      }
+    }
+    cnt = 0;
+  };
+  for (int64_t b = b_first; b <= b_last && b < B; ++b) {
+    const int64_t cs = __ldg(offsets + b), ce = __ldg(offsets + b + 1);
+    const bool active = valid && q >= cs && q < ce;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+      qx = __ldg(pos + q * pos_stride); qy = __ldg(pos + q * pos_stride + 1); qz = __ldg(pos + q * pos_stride + 2);
+    }
+    const bool warp_active = __any_sync(0xffffffffu, active);
+    for (int64_t t0 = cs; t0 < ce; t0 += kKnnTile) {
+      const int tn = (int)((ce - t0 < kKnnTile) ? ce - t0 : kKnnTile);
+      __syncthreads();
+      for (int i = tid; i < tn; i += 256) {
+        const float* pp = pos + (t0 + i) * pos_stride;
+        tile[i] = make_float4(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2), 0.f);
+      }
+      __syncthreads();
+      if (!warp_active) continue;
+      const unsigned self = (unsigned)(q - t0);   // position of the query inside this tile (or out of range)
+      for (int j0 = 0; j0 < tn; j0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j < tn) {
+            const float4 c = tile[j];
+            const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)(t0 + j);
+            if (active && (unsigned)j != self && key < list[K - 1]) {
+              queue[cnt][tid] = key;
+              ++cnt;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, cnt > kKnnQ - 4)) drain();
+      }
+    }
+    if (warp_active) drain();
+  }
+  if (valid) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      if (s < k) {
+        const bool ok = list[s] != ~0ull;
+        nbr[q * k + s] = ok ? (int64_t)(list[s] & 0xffffffffull) : -1;
+        d2o[q * k + s] = ok ? __uint_as_float((unsigned)(list[s] >> 32)) : INFINITY;
+      }
+    }
+  }
+}
+
 __global__ void knn_edges_kernel(const int64_t* __restrict__ nbr, int64_t total, int k, int64_t* __restrict__ ei) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < total) {
@@ -279,7 +398,7 @@ extern "C" int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t*
   if (E > 0 && n > 0) {
     PCC_K(csr_copy_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr, cursor, n);
     PCC_K(csr_fill_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, cursor, perm);
-    PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(rowptr, perm, n);
+    PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(rowptr, perm, n);
   }
   return check_launch(__func__);
 }
@@ -329,9 +448,22 @@ extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offs
   PCC_REQUIRE(k >= 1 && k <= 32, "k must be in [1,32]");
   PCC_REQUIRE(n < (int64_t)0x7fffffff, "point count exceeds int32 range");
   if (n == 0) return 0;
-  constexpr int QW = 4;
-  const int64_t warps = cdiv(n, QW);
-  pcc::note_launch(1), knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  static int legacy = -1;   // PCC_KNN_LEGACY=1: the warp-per-4-queries kernel of round 1 (kept for comparison)
+  if (legacy < 0) { const char* e = getenv("PCC_KNN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(6, st);
+  if (legacy) {
+    constexpr int QW = 4;
+    const int64_t warps = cdiv(n, QW);
+    pcc::note_launch(1), knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+    return check_launch(__func__);
+  }
+  const unsigned grid = (unsigned)cdiv(n, 256);
+  pcc::note_launch(1);
+  if (k <= 8) knn_tiled_kernel<8><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  else if (k <= 16) knn_tiled_kernel<16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  else if (k <= 20) knn_tiled_kernel<20><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  else knn_tiled_kernel<32><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
   return check_launch(__func__);
 }
 

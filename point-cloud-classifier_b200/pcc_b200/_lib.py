@@ -71,6 +71,21 @@ _SIGS = {
     "pcc_peer_allreduce": [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _vp],
     "pcc_bce_logits": [_vp, _vp, _i64, _vp, _vp, _i32, _vp],
     "pcc_gather_rows": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _i32, _vp],
+    "pcc_gnn_packed_bytes": [],
+    "pcc_gnn_max_blocks": [],
+    "pcc_gnn_pack_weights": [_vp, _vp, _vp, _vp, _i32, _vp],
+    "pcc_gnn_conv1_fwd": [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_bn_finalize": [_vp, _i32, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "pcc_gnn_bn_eval": [_vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _i32, _vp],
+    "pcc_gnn_bn_apply": [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
+    "pcc_gnn_conv_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_fc1_pool_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_bn_bwd_finalize": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
+    "pcc_gnn_reduce": [_vp, _i32, _i64, _vp, _i32, _vp],
+    "pcc_gnn_fc1_bwd": [_vp] * 12 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_conv_bwd": [_vp] * 10 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_agg_bwd": [_vp] * 8 + [_i64, _i32, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_conv1_bwd": [_vp] * 9 + [_i32, _i64, _i32, _vp, C.POINTER(C.c_int), _i32, _vp],
     "pcc_launch_count": [_i32],
     "pcc_prof_enable": [_i32],
     "pcc_prof_read": [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
@@ -84,7 +99,7 @@ _SIGS = {
     "pcc_deepsets_phi_pool_fwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "pcc_deepsets_phi_pool_bwd": [C.POINTER(PhiDesc), _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
-_RESTYPES = {"pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64,
+_RESTYPES = {"pcc_gnn_packed_bytes": _i64, "pcc_gnn_max_blocks": C.c_int, "pcc_csr_workspace_bytes": _i64, "pcc_phi_fused_workspace_bytes": _i64, "pcc_launch_count": _i64,
              "pcc_phi_packed_bytes": _i64, "pcc_mlp_head_workspace_bytes": _i64,
              "pcc_edge_weights_workspace_bytes": _i64}
 EXPORTS = tuple(_SIGS) + ("pcc_last_error",)

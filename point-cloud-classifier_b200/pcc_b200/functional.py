@@ -239,8 +239,14 @@ class GraphCSR:
         self.dst = edges[1].contiguous()
         self.n = n
         self.E = edges.shape[1]
-        self.by_dst = self._build(self.dst)
+        self._by_dst = None
         self._by_src = None
+
+    @property
+    def by_dst(self):
+        if self._by_dst is None:
+            self._by_dst = self._build(self.dst)
+        return self._by_dst
 
     def _build(self, keys) -> Tuple[torch.Tensor, torch.Tensor]:
         dev, st = _ctx(keys)

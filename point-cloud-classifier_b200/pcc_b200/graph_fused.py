@@ -1,0 +1,194 @@
+"""Host side of the fused bf16 GraphNet path (pcc_gnn_* in libpcc.so): GraphConv -> act -> BatchNorm1d (twice),
+fc1 -> act -> bn3 -> global_mean_pool of /root/reference/models/graph_net.py:73-92 and their autograd as ONE
+autograd Function over tcgen05 kernels.  bf16 operands (normalised activations h, aggregates, weights), fp32
+accumulation, fp32 pre-activations and BatchNorm statistics.  Stated tolerance: tests/test_graph_fused_gpu.py.
+
+Supported: hidden_dim = 128, deepchem_style = True, local_pooling add / mean, input_dim <= 8, tanh / relu / gelu
+(configs/graph_net.yaml is inside).  Everything else takes the fp32 layer-wise path of graph_net.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT, call, ptr
+
+C_HID, C_FC = 128, 256
+
+
+def supported(input_dim: int, hidden_dim: int, act: str, aggr: str, deepchem: bool) -> bool:
+    return hidden_dim == C_HID and deepchem and aggr in ("add", "mean") and 1 <= input_dim <= 8 and act in ("tanh", "relu", "gelu")
+
+
+class FusedGraph:
+    """CSR views of a batched edge list in the layout the fused kernels read: rowptr int64 [n+1], col int32 [E]
+    (neighbour node per slot), w fp32 [E] or None.  by_dst feeds the forward aggregation, by_src its transpose."""
+
+    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None):
+        from .functional import GraphCSR
+        self.n, self.aggr = n, aggr
+        self.E = edges.shape[1]
+        csr = None
+        if by_dst is not None:                       # e.g. a kNN graph: k consecutive edges per target, already grouped
+            self.rowptr_d, self.col_d = by_dst
+            self.w_d = weights
+            perm_d = None
+        else:
+            csr = GraphCSR(edges, n)
+            self.rowptr_d, perm_d = csr.by_dst
+            pl = perm_d.long()
+            self.col_d = edges[0][pl].to(torch.int32)
+            self.w_d = weights[pl].contiguous() if weights is not None else None
+        self._edges, self._weights, self._csr = edges, weights, csr
+        self._src = None
+
+    def by_src(self):
+        if self._src is None:
+            from .functional import GraphCSR
+            csr = self._csr or GraphCSR(self._edges, self.n)
+            rowptr_s, perm_s = csr.by_src
+            pl = perm_s.long()
+            dst = self._edges[1][pl]
+            col_s = dst.to(torch.int32)
+            w_s = self._weights[pl] if self._weights is not None else None
+            if self.aggr == "mean":                  # d agg_i / d x_j = w_e / deg(i)
+                deg = (self.rowptr_d[1:] - self.rowptr_d[:-1]).clamp(min=1).to(torch.float32)
+                inv = (1.0 / deg)[dst]
+                w_s = inv if w_s is None else w_s * inv
+            self._src = (rowptr_s, col_s, w_s.contiguous() if w_s is not None else None)
+        return self._src
+
+
+def _nblk():
+    return C.c_int(0)
+
+
+class GraphNetFusedFn(torch.autograd.Function):
+    """(x, params...) -> y3[B,256] = bn3-normalised, mean-pooled act(fc1(.)) — everything of GraphNet.forward before fc2."""
+
+    @staticmethod
+    def forward(ctx, x, membership, graph: FusedGraph, counts, meta, bufs, *params):
+        act, training, eps, momentum = meta
+        (w_rel1, b_rel1, w_root1, w_rel2, b_rel2, w_root2, g1, be1, g2, be2, w_fc1, b_fc1, g3, be3) = [L.f32c(p) for p in params]
+        x = L.f32c(x)
+        dev = L.require_cuda(x, membership, *params)
+        st = L.stream_ptr(dev)
+        M, F = x.shape
+        B = counts.numel()
+        A = ACT[act]
+        mean = 1 if graph.aggr == "mean" else 0
+        f32 = dict(dtype=torch.float32, device=x.device)
+        bf = dict(dtype=torch.bfloat16, device=x.device)
+        nmax = call("pcc_gnn_max_blocks")
+        part = torch.empty(nmax * 2 * C_FC, **f32)
+        packed = torch.empty(call("pcc_gnn_packed_bytes"), dtype=torch.uint8, device=x.device)
+        call("pcc_gnn_pack_weights", ptr(w_rel2), ptr(w_root2), ptr(w_fc1), ptr(packed), dev, st)
+
+        def bn(layer, Cn, gamma, beta, nblk, rows):
+            rm, rv = bufs[layer]
+            sc, sh, mu, rs = (torch.empty(Cn, **f32) for _ in range(4))
+            if training:
+                call("pcc_gnn_bn_finalize", ptr(part), nblk, Cn, rows, ptr(gamma), ptr(beta), eps, momentum, ptr(rm), ptr(rv),
+                     ptr(sc), ptr(sh), ptr(mu), ptr(rs), dev, st)
+            else:
+                call("pcc_gnn_bn_eval", ptr(rm), ptr(rv), ptr(gamma), ptr(beta), eps, Cn, ptr(sc), ptr(sh), dev, st)
+                mu, rs = rm, torch.rsqrt(rv + eps)
+            return sc, sh, mu, rs
+
+        # ---- conv1 -> act -> bn1
+        agg1 = torch.empty((M, F), **f32)
+        z1 = torch.empty((M, C_HID), **f32)
+        nb = _nblk()
+        call("pcc_gnn_conv1_fwd", ptr(x), F, ptr(graph.rowptr_d), ptr(graph.col_d), ptr(graph.w_d), mean, ptr(w_rel1), ptr(w_root1),
+             ptr(b_rel1), M, A, ptr(agg1), ptr(z1), ptr(part), C.byref(nb), dev, st)
+        s1, t1, mu1, r1 = bn(0, C_HID, g1, be1, nb.value, M)
+        h1 = torch.empty((M, C_HID), **bf)
+        call("pcc_gnn_bn_apply", ptr(z1), ptr(s1), ptr(t1), M, A, ptr(h1), dev, st)
+        # ---- conv2 -> act -> bn2 (gather + GEMM + statistics in one kernel)
+        agg2 = torch.empty((M, C_HID), **bf)
+        z2 = torch.empty((M, C_HID), **f32)
+        call("pcc_gnn_conv_fwd", ptr(h1), ptr(graph.rowptr_d), ptr(graph.col_d), ptr(graph.w_d), mean, ptr(packed), ptr(b_rel2), M, A,
+             ptr(agg2), ptr(z2), ptr(part), C.byref(nb), dev, st)
+        s2, t2, mu2, r2 = bn(1, C_HID, g2, be2, nb.value, M)
+        h2 = torch.empty((M, C_HID), **bf)
+        call("pcc_gnn_bn_apply", ptr(z2), ptr(s2), ptr(t2), M, A, ptr(h2), dev, st)
+        # ---- fc1 -> act -> bn3 -> global_mean_pool: only per-graph sums and the statistics leave the kernel
+        psum = torch.empty((B, C_FC), **f32)
+        call("pcc_gnn_fc1_pool_fwd", ptr(h2), ptr(packed), ptr(b_fc1), ptr(membership), M, B, A, ptr(psum), ptr(part), C.byref(nb),
+             dev, st)
+        s3, t3, mu3, r3 = bn(2, C_FC, g3, be3, nb.value, M)
+        nb_f = counts.to(torch.float32).clamp(min=1.0).unsqueeze(1)
+        P = psum / nb_f
+        y3 = P * s3 + t3
+        ctx.save_for_backward(x, membership, agg1, z1, h1, agg2, z2, h2, P, nb_f, packed, b_fc1,
+                              s1, mu1, r1, s2, mu2, r2, s3, mu3, r3)
+        ctx.graph, ctx.meta, ctx.shapes = graph, meta, (M, F, B)
+        return y3
+
+    @staticmethod
+    def backward(ctx, G):
+        (x, membership, agg1, z1, h1, agg2, z2, h2, P, nb_f, packed, b_fc1,
+         s1, mu1, r1, s2, mu2, r2, s3, mu3, r3) = ctx.saved_tensors
+        act, training, eps, momentum = ctx.meta
+        if not training:
+            raise RuntimeError("the fused GraphNet backward uses batch statistics: call it in train() mode")
+        graph = ctx.graph
+        M, F, B = ctx.shapes
+        G = L.f32c(G)
+        dev = L.require_cuda(G)
+        st = L.stream_ptr(dev)
+        A = ACT[act]
+        f32 = dict(dtype=torch.float32, device=G.device)
+        nmax = call("pcc_gnn_max_blocks")
+        nb = _nblk()
+        # ---- bn3 + mean-pool backward: per-graph / per-channel terms (graph-sized tensors)
+        xhatP = (P - mu3) * r3
+        sumG, sumGx = G.sum(0), (G * xhatP).sum(0)
+        d_g3, d_be3 = sumGx, sumG
+        gs = (G * s3 / nb_f).contiguous()
+        kap = (s3 * sumG / M).contiguous()
+        lam = (s3 * sumGx / M).contiguous()
+        # ---- fc1 backward (+ bn2 sums)
+        dh2 = torch.empty((M, C_HID), **f32)
+        stat = torch.empty(nmax * 2 * C_HID, **f32)
+        dw_part = torch.empty(148 * C_FC * C_HID, **f32)
+        db_part = torch.empty(148 * C_FC, **f32)
+        call("pcc_gnn_fc1_bwd", ptr(h2), ptr(packed), ptr(b_fc1), ptr(membership), ptr(gs), ptr(kap), ptr(lam), ptr(mu3), ptr(r3),
+             ptr(z2), ptr(mu2), ptr(r2), M, A, ptr(dh2), ptr(stat), ptr(dw_part), ptr(db_part), C.byref(nb), dev, st)
+        d_wfc1 = torch.empty((C_FC, C_HID), **f32)
+        d_bfc1 = torch.empty(C_FC, **f32)
+        call("pcc_gnn_reduce", ptr(dw_part), nb.value, C_FC * C_HID, ptr(d_wfc1), dev, st)
+        call("pcc_gnn_reduce", ptr(db_part), nb.value, C_FC, ptr(d_bfc1), dev, st)
+        c1, c2, d_g2, d_be2 = (torch.empty(C_HID, **f32) for _ in range(4))
+        call("pcc_gnn_bn_bwd_finalize", ptr(stat), nb.value, C_HID, M, ptr(c1), ptr(c2), ptr(d_g2), ptr(d_be2), dev, st)
+        # ---- conv2 backward: dz2 in the prologue, [dagg2 | droot] and dW in one kernel
+        dagg2 = torch.empty((M, C_HID), dtype=torch.bfloat16, device=G.device)
+        droot = dh2.new_empty((M, C_HID))
+        cw_part = torch.empty(148 * C_HID * 2 * C_HID, **f32)
+        cb_part = torch.empty(148 * C_HID, **f32)
+        call("pcc_gnn_conv_bwd", ptr(dh2), ptr(z2), ptr(mu2), ptr(r2), ptr(s2), ptr(c1), ptr(c2), ptr(agg2), ptr(h1), ptr(packed), M, A,
+             ptr(dagg2), ptr(droot), ptr(cw_part), ptr(cb_part), C.byref(nb), dev, st)
+        d_w2 = torch.empty((C_HID, 2 * C_HID), **f32)
+        d_b2 = torch.empty(C_HID, **f32)
+        call("pcc_gnn_reduce", ptr(cw_part), nb.value, C_HID * 2 * C_HID, ptr(d_w2), dev, st)
+        call("pcc_gnn_reduce", ptr(cb_part), nb.value, C_HID, ptr(d_b2), dev, st)
+        d_wrel2, d_wroot2 = d_w2[:, :C_HID].contiguous(), d_w2[:, C_HID:].contiguous()
+        # ---- dh1 = droot + A^T dagg2 (+ bn1 sums)
+        rowptr_s, col_s, w_s = graph.by_src()
+        call("pcc_gnn_agg_bwd", ptr(dagg2), ptr(rowptr_s), ptr(col_s), ptr(w_s), ptr(droot), ptr(z1), ptr(mu1), ptr(r1), M, A,
+             ptr(stat), C.byref(nb), dev, st)
+        c1b, c2b, d_g1, d_be1 = (torch.empty(C_HID, **f32) for _ in range(4))
+        call("pcc_gnn_bn_bwd_finalize", ptr(stat), nb.value, C_HID, M, ptr(c1b), ptr(c2b), ptr(d_g1), ptr(d_be1), dev, st)
+        # ---- conv1 backward (weights only: x needs no gradient)
+        W1 = 2 * F + 1
+        p1 = torch.empty(592 * C_HID * W1, **f32)
+        call("pcc_gnn_conv1_bwd", ptr(droot), ptr(z1), ptr(mu1), ptr(r1), ptr(s1), ptr(c1b), ptr(c2b), ptr(agg1), ptr(x), F, M, A,
+             ptr(p1), C.byref(nb), dev, st)
+        d1 = torch.empty((C_HID, W1), **f32)
+        call("pcc_gnn_reduce", ptr(p1), nb.value, C_HID * W1, ptr(d1), dev, st)
+        d_wrel1, d_wroot1, d_b1 = d1[:, :F].contiguous(), d1[:, F:2 * F].contiguous(), d1[:, 2 * F].contiguous()
+        grads = (d_wrel1, d_b1, d_wroot1, d_wrel2, d_b2, d_wroot2, d_g1, d_be1, d_g2, d_be2, d_wfc1, d_bfc1, d_g3, d_be3)
+        return (None, None, None, None, None, None) + grads

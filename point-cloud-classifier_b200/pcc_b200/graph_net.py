@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as PF
+from . import graph_fused as GF
 
 
 class GraphConv(nn.Module):
@@ -89,6 +90,7 @@ class GraphNet(nn.Module):
         self.fc1 = nn.Linear(hidden_dim, 256)
         self.bn3 = nn.BatchNorm1d(256)
         self.fc2 = nn.Linear(256, output_dim)
+        self.last_path = None   # "fused-bf16" | "fp32": which kernels the last forward used
 
     def forward(self, x, membership, edges, weights=None, num_graphs: Optional[int] = None,
                 edges_sorted_by_target: bool = False):
@@ -98,10 +100,13 @@ class GraphNet(nn.Module):
             raise AttributeError("'GraphNet' object has no attribute 'activation'")
         act = self._act_name
         n = x.shape[0]
-        csr = PF.GraphCSR(edges, n)
         if num_graphs is None:
             num_graphs = PF.index_max(membership) + 1
         offsets = PF.segment_offsets(membership, num_graphs)
+        if self.precision == "bf16" and self.fused_supported(x.shape[1]):
+            return self._forward_fused(x, membership, edges, weights, offsets, edges_sorted_by_target)
+        self.last_path = "fp32"
+        csr = PF.GraphCSR(edges, n)
 
         h = self.conv1(x, csr, weights, act)
         h = PF.batchnorm(h, self.bn1)
@@ -134,6 +139,43 @@ class KnnGraphNet(nn.Module):
             num_graphs = PF.index_max(membership) + 1
         edges, _ = knn_graph(features, membership, self.k, self.pos_cols, num_graphs)
         return self.net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True)
+
+
+def _fused_methods():
+    def fused_supported(self, input_dim=None) -> bool:
+        F = self.conv1.in_channels if input_dim is None else input_dim
+        return GF.supported(F, self.conv2.out_channels, self._act_name, self.local_pooling, self.deepchem_style) and \
+            all(isinstance(b.momentum, float) for b in (self.bn1, self.bn2, self.bn3))
+
+    def _forward_fused(self, x, membership, edges, weights, offsets, sorted_by_target):
+        """bf16 tcgen05 path (graph_fused.py): one autograd Function for everything before fc2"""
+        n, E = x.shape[0], edges.shape[1]
+        edges = edges if edges.dtype == torch.int64 else edges.long()
+        by_dst = None
+        if sorted_by_target and n > 0 and E % n == 0:      # kNN graph: k consecutive edges per target node
+            k = E // n
+            by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, edges[0].to(torch.int32))
+        graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst)
+        counts = offsets[1:] - offsets[:-1]
+        bns = (self.bn1, self.bn2, self.bn3)
+        bufs = [(b.running_mean, b.running_var) for b in bns]
+        meta = (self._act_name, self.training, float(self.bn1.eps), float(self.bn1.momentum))
+        params = (self.conv1.lin_rel.weight, self.conv1.lin_rel.bias, self.conv1.lin_root.weight,
+                  self.conv2.lin_rel.weight, self.conv2.lin_rel.bias, self.conv2.lin_root.weight,
+                  self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias,
+                  self.fc1.weight, self.fc1.bias, self.bn3.weight, self.bn3.bias)
+        y3 = GF.GraphNetFusedFn.apply(x, membership, graph, counts, meta, bufs, *params)
+        if self.training:
+            for b in bns:
+                b.num_batches_tracked.add_(1)
+        self.last_path = "fused-bf16"
+        return PF.linear_act(y3, self.fc2.weight, self.fc2.bias, None, "none")
+
+    GraphNet.fused_supported = fused_supported
+    GraphNet._forward_fused = _forward_fused
+
+
+_fused_methods()
 
 
 def knn_graph(features: torch.Tensor, membership: torch.Tensor, k: int = 20, pos_cols=(1, 4),

@@ -1,0 +1,118 @@
+"""GPU: the fused bf16 GraphNet path (pcc_gnn_*: tcgen05 GraphConv / fc1 kernels, BatchNorm folded into producer epilogues
+and consumer prologues) against the pinned oracle (oracle/graphnet_oracle.py, fp32).
+
+Stated bf16 tolerance: the normalised activations h1 / h2, the aggregates and the conv2 / fc1 weights are rounded to bf16
+(8-bit mantissa) before every tensor-core contraction; accumulation, pre-activations and BatchNorm statistics are fp32.
+Two comparisons, per tensor, printed by the tests (measured on B200, profiles/r2/graph_fused_err.txt):
+ (1) oracle with the SAME stated operand rounding (graphnet_oracle operand_rounding="bf16"): logits <= 2.1e-4 of max|ref|;
+     gradients (relative Frobenius) <= 8.7e-3 for tanh / gelu, <= 3.3e-2 for relu (the backward additionally rounds the
+     gradient operands dz / dagg to bf16, which the oracle does not model; bias gradients are near-cancelling sums).
+     Tolerances 2x measured: logits 2e-3 (10x, floor), gradients 2e-2 (7e-2 relu).
+ (2) the fp32 oracle: logits <= 7.3e-3 -> 1.5e-2; gradients <= 2.6e-2 (tanh / gelu) -> 5e-2, <= 0.14 (relu: ReLU masks
+     flip where |z| is below the bf16 rounding noise, as in tests/test_fused_gpu.py) -> 0.3.
+The fp32 mode of the same module stays at rtol 1e-4 (tests/test_graph_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, rel_l2
+from oracle import graphnet_oracle as GO
+from oracle import knn_oracle as KO
+
+import pcc_b200
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL_Q, GRAD_TOL_Q, GRAD_TOL_Q_RELU = 2e-3, 2e-2, 7e-2   # vs the oracle with the stated bf16 operand rounding
+LOGIT_TOL, GRAD_TOL, GRAD_TOL_RELU = 1.5e-2, 5e-2, 0.3   # vs the fp32 oracle
+
+
+def _clouds(sizes, seed, F=4):
+    g = torch.Generator().manual_seed(seed)
+    n = sum(sizes)
+    feats = torch.randn(n, F, generator=g)
+    feats[:, 0] = torch.rand(n, generator=g)
+    memb = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return feats, memb, off
+
+
+def _cfg(act, aggr, F=4):
+    return dict(input_dim=F, hidden_dim=128, output_dim=1, activation=act, use_gat=False, gat_heads=4, sag_pool=False,
+                pool_ratio=0.5, local_pooling=aggr, global_pooling="mean", deepchem_style=True)
+
+
+@pytest.mark.parametrize("act,aggr,use_w,F,sizes,k", [
+    ("tanh", "add", False, 4, [300, 200, 400, 256], 8),       # configs/graph_net.yaml
+    ("relu", "mean", True, 4, [129, 1000, 77], 6),
+    ("gelu", "add", True, 1, [64, 64, 500], 5),
+    ("tanh", "add", False, 4, [1024] * 20, 20),               # more tiles than SMs: several tiles per CTA
+])
+def test_fused_graphnet_train_step_matches_oracle(act, aggr, use_w, F, sizes, k):
+    cfg = _cfg(act, aggr, F)
+    feats, memb, off = _clouds(sizes, seed=21, F=max(F, 4))
+    nbr, _ = KO.knn_neighbours(feats[:, 1:4].numpy(), off, k)
+    edges = torch.from_numpy(KO.knn_edges(nbr))
+    gen = torch.Generator().manual_seed(22)
+    perm = torch.randperm(edges.shape[1], generator=gen)      # arbitrary edge order (general CSR build)
+    edges = edges[:, perm].contiguous()
+    x = feats[:, :F].contiguous()
+    w = torch.rand(edges.shape[1], generator=gen) if use_w else None
+    y = (torch.rand(len(sizes), 1, generator=gen) > 0.5).float()
+    sd = GO.init_state_dict(cfg, seed=23)
+    ref_logits, _, ref_grads, ref_stats = GO.graphnet_train_step(sd, cfg, x, memb, edges, w, y)
+    q_logits, _, q_grads, _ = GO.graphnet_train_step(sd, cfg, x, memb, edges, w, y, operand_rounding="bf16")
+
+    m = pcc_b200.GraphNet(**cfg, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    m.train()
+    args = [x.cuda(), memb.cuda(), edges.cuda()] + ([w.cuda()] if use_w else [])
+    logits = m(*args)
+    assert m.last_path == "fused-bf16"
+    torch.nn.BCEWithLogitsLoss()(logits, y.cuda()).backward()
+    e_log, e_logq = rel_err(logits, ref_logits), rel_err(logits, q_logits)
+    worst, worstq, rows = ("", 0.0), ("", 0.0), []
+    for kname, ref in ref_grads.items():
+        got = dict(m.named_parameters())[kname].grad
+        assert got is not None, kname
+        e, eq = rel_l2(got, ref), rel_l2(got, q_grads[kname])
+        rows.append(f"{kname}={eq:.1e}/{e:.1e}")
+        if e > worst[1]:
+            worst = (kname, e)
+        if eq > worstq[1]:
+            worstq = (kname, eq)
+    print(f"fused graphnet {act}/{aggr}/w={use_w}/F={F}/n={sum(sizes)}: logits {e_logq:.1e}/{e_log:.1e} (vs bf16-operand oracle / "
+          f"fp32 oracle); worst grad {worstq[0]} {worstq[1]:.1e} / {worst[0]} {worst[1]:.1e}; " + " ".join(rows))
+    assert e_logq < LOGIT_TOL_Q and e_log < LOGIT_TOL
+    assert worstq[1] < (GRAD_TOL_Q_RELU if act == "relu" else GRAD_TOL_Q), worstq
+    assert worst[1] < (GRAD_TOL_RELU if act == "relu" else GRAD_TOL), worst
+    new_sd = m.state_dict()
+    for kname, v in ref_stats.items():
+        torch.testing.assert_close(new_sd[kname].cpu(), v, rtol=2e-2, atol=2e-3)
+    # eval mode: running statistics
+    m.eval()
+    with torch.no_grad():
+        ev = m(*args)
+    sd_eval = {kk: v.cpu() for kk, v in m.state_dict().items()}
+    ref_ev = GO.graphnet_forward(sd_eval, cfg, x, memb, edges, w, training=False)
+    assert rel_err(ev, ref_ev) < LOGIT_TOL
+
+
+def test_knn_graphnet_module_uses_fused_path_and_matches_fp32_mode():
+    """KnnGraphNet (kNN build on device + GraphNet): the bf16 fused path against the fp32 mode of the same module"""
+    cfg = _cfg("tanh", "add")
+    feats, memb, _ = _clouds([512, 300, 700], seed=5)
+    y = (torch.rand(3, 1, generator=torch.Generator().manual_seed(6)) > 0.5).float().cuda()
+    torch.manual_seed(0)
+    a = pcc_b200.KnnGraphNet(k=20, precision="bf16", **cfg).cuda()
+    b = pcc_b200.KnnGraphNet(k=20, precision="fp32", **cfg).cuda()
+    b.load_state_dict(a.state_dict())
+    outs = []
+    for m in (a, b):
+        m.train()
+        logits = m(feats.cuda(), memb.cuda(), num_graphs=3)
+        torch.nn.BCEWithLogitsLoss()(logits, y).backward()
+        outs.append((logits.detach(), {k: p.grad for k, p in m.named_parameters()}))
+    assert a.net.last_path == "fused-bf16" and b.net.last_path == "fp32"
+    assert rel_err(outs[0][0], outs[1][0]) < LOGIT_TOL
+    for k, g in outs[1][1].items():
+        assert rel_l2(outs[0][1][k], g) < GRAD_TOL, k
