@@ -35,8 +35,11 @@ __global__ void gnn_pack_kernel(const float* __restrict__ w_rel, const float* __
 }
 
 // ------------------------------------------------------------------ conv1 (K = 2F <= 16): CUDA cores
-// warp per node; lane owns output channels lane + 32 j.  Writes agg1 (kept for the weight gradient), z1 and the
-// per-block partial sums of act(z1), act(z1)^2 (BatchNorm statistics).
+// Block = 256 nodes per iteration, two phases.  (A) thread = node: gather-reduce of the node's neighbours (F <= 8
+// floats per row, independent loads -> deep memory-level parallelism, no shuffles), aggregate and own row parked in
+// shared memory.  (B) warp = 32 of those nodes in turn, lane = output channels lane + 32 j: z = b + W_rel agg + W_root x
+// from broadcast shared-memory reads, coalesced 128-byte stores of z1, per-lane column sums of act(z1), act(z1)^2
+// (BatchNorm statistics).  Writes agg1 (kept for the weight gradient).
 template <int ACT, int FP>
 __global__ void __launch_bounds__(256) gnn_conv1_fwd_kernel(const float* __restrict__ x, int F, GnnGraph g,
                                                             const float* __restrict__ w_rel, const float* __restrict__ w_root,
@@ -44,6 +47,7 @@ __global__ void __launch_bounds__(256) gnn_conv1_fwd_kernel(const float* __restr
                                                             float* __restrict__ z_out, float* __restrict__ partials) {
   constexpr int CPL = kC / 32;
   __shared__ float red[8][2][kC];
+  __shared__ float aS[256][FP], xS[256][FP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float wr[CPL][FP], wo[CPL][FP], bb[CPL];
 #pragma unroll
@@ -57,37 +61,50 @@ __global__ void __launch_bounds__(256) gnn_conv1_fwd_kernel(const float* __restr
     }
   }
   float s1[CPL] = {}, s2[CPL] = {};
-  const int64_t nwarps = (int64_t)gridDim.x * 8;
-  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < M; node += nwarps) {
-    const int64_t pb = __ldg(g.rowptr + node), pe = __ldg(g.rowptr + node + 1);
-    float a[FP] = {};
-    for (int64_t p = pb + lane; p < pe; p += 32) {       // lane = one neighbour
-      const int64_t s = (int64_t)__ldg(g.col + p);
-      const float we = g.w ? __ldg(g.w + p) : 1.f;
+  const int64_t nchunks = (M + 255) / 256;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t node = chunk * 256 + threadIdx.x;
+    float a[FP], xs[FP];
 #pragma unroll
-      for (int f = 0; f < FP; ++f)
-        if (f < F) a[f] += we * __ldg(x + s * F + f);
+    for (int f = 0; f < FP; ++f) a[f] = xs[f] = 0.f;
+    if (node < M) {
+      const int64_t pb = __ldg(g.rowptr + node), pe = __ldg(g.rowptr + node + 1);
+#pragma unroll 4
+      for (int64_t p = pb; p < pe; ++p) {
+        const int64_t sidx = (int64_t)__ldg(g.col + p);
+        const float we = g.w ? __ldg(g.w + p) : 1.f;
+#pragma unroll
+        for (int f = 0; f < FP; ++f)
+          if (f < F) a[f] = fmaf(we, __ldg(x + sidx * F + f), a[f]);
+      }
+      const float inv = (g.mean && pe > pb) ? 1.f / (float)(pe - pb) : 1.f;
+#pragma unroll
+      for (int f = 0; f < FP; ++f) {
+        a[f] *= inv;
+        if (f < F) { xs[f] = __ldg(x + node * F + f); agg_out[node * F + f] = a[f]; }
+      }
     }
-    const float inv = (g.mean && pe > pb) ? 1.f / (float)(pe - pb) : 1.f;
-    float xs[FP];
+    __syncthreads();   // phase B of the previous chunk has finished reading the shared arrays
 #pragma unroll
-    for (int f = 0; f < FP; ++f) {
-      a[f] = f < F ? warp_sum(a[f]) * inv : 0.f;
-      xs[f] = f < F ? __ldg(x + node * F + f) : 0.f;
-    }
-    float mine = 0.f;   // (a[lane] with a runtime index would send the array to local memory)
+    for (int f = 0; f < FP; ++f) { aS[threadIdx.x][f] = a[f]; xS[threadIdx.x][f] = xs[f]; }
+    __syncthreads();
+    const int64_t base = chunk * 256 + warp * 32;
+    const int nn = (int)((M - base < 32) ? (M - base < 0 ? 0 : M - base) : 32);
+#pragma unroll 2
+    for (int i = 0; i < nn; ++i) {
+      float av[FP], xv[FP];
 #pragma unroll
-    for (int f = 0; f < FP; ++f) mine = (lane == f) ? a[f] : mine;
-    if (lane < F) agg_out[node * F + lane] = mine;
+      for (int f = 0; f < FP; ++f) { av[f] = aS[warp * 32 + i][f]; xv[f] = xS[warp * 32 + i][f]; }
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-      float z = bb[j];
+      for (int j = 0; j < CPL; ++j) {
+        float z = bb[j];
 #pragma unroll
-      for (int f = 0; f < FP; ++f) z = fmaf(wr[j][f], a[f], fmaf(wo[j][f], xs[f], z));
-      z_out[node * kC + lane + 32 * j] = z;
-      const float av = actf<ACT>(z);
-      s1[j] += av;
-      s2[j] += av * av;
+        for (int f = 0; f < FP; ++f) z = fmaf(wr[j][f], av[f], fmaf(wo[j][f], xv[f], z));
+        z_out[(base + i) * kC + lane + 32 * j] = z;
+        const float act = actf<ACT>(z);
+        s1[j] += act;
+        s2[j] += act * act;
+      }
     }
   }
 #pragma unroll
@@ -113,11 +130,21 @@ __global__ void __launch_bounds__(256) gnn_bn_finalize_kernel(const float* __res
   const int cl = threadIdx.x & 31, gq = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  if (c < Cn)
-    for (int b = gq; b < nblk; b += 8) {
+  if (c < Cn) {
+    int b = gq;
+    for (; b + 24 < nblk; b += 32) {   // four independent loads per sum in flight
+      const float a0 = __ldg(partials + (size_t)b * 2 * Cn + c), a1 = __ldg(partials + (size_t)(b + 8) * 2 * Cn + c);
+      const float a2 = __ldg(partials + (size_t)(b + 16) * 2 * Cn + c), a3 = __ldg(partials + (size_t)(b + 24) * 2 * Cn + c);
+      const float q0 = __ldg(partials + (size_t)b * 2 * Cn + Cn + c), q1 = __ldg(partials + (size_t)(b + 8) * 2 * Cn + Cn + c);
+      const float q2 = __ldg(partials + (size_t)(b + 16) * 2 * Cn + Cn + c), q3 = __ldg(partials + (size_t)(b + 24) * 2 * Cn + Cn + c);
+      s1 += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      s2 += ((double)q0 + (double)q1) + ((double)q2 + (double)q3);
+    }
+    for (; b < nblk; b += 8) {
       s1 += (double)__ldg(partials + (size_t)b * 2 * Cn + c);
       s2 += (double)__ldg(partials + (size_t)b * 2 * Cn + Cn + c);
     }
+  }
   red[gq][0][cl] = s1;
   red[gq][1][cl] = s2;
   __syncthreads();
@@ -171,14 +198,23 @@ __global__ void __launch_bounds__(256) gnn_bn_apply_kernel(const float* __restri
 }
 
 // ====================================================================== conv2: gather + tcgen05 GEMM + BatchNorm partials
-// Persistent, one CTA per SM, 128-node tiles.  Warps 0-15: CSR gather-reduce of the bf16 neighbour rows (lane = 4
-// channels, 8 row loads in flight per lane) into the SW128 A image [agg | h] of the tile (double buffered) and the
-// kept copy of agg; warp 20: one thread issues the [128 x 2C] x [2C x C] MMAs (weights resident in shared memory)
-// into one of two TMEM accumulators; warps 16-19: TMEM -> + bias -> z (fp32, HBM) and the column sums of act(z),
-// act(z)^2 by transposed warp reductions.
+// Persistent, one CTA per SM, 128-node tiles.
+//   warps 0-15 : CSR gather-reduce.  The neighbour rows (256 B of bf16 each) are fetched by the TMA engine: the lanes of
+//                a warp issue one cp.async.bulk per neighbour into the warp's shared-memory slot (22 rows) and wait on
+//                the slot's mbarrier, so a node's rows are ALL in flight at once and no register holds in-flight data
+//                (ncu on the register-gather version: every memory unit below 25 % of peak, the loop was bound by the
+//                ~1.2k-cycle L2 latency times the few loads a thread can keep in registers).  The next node's neighbour
+//                ids are prefetched while the rows land.  Reduced rows go as bf16 into the SW128 A image [agg | h] of
+//                the tile and into the kept copy of agg.
+//   warp 20    : one thread issues the [128 x 2C] x [2C x C] MMAs (weights resident in shared memory) into one of two
+//                TMEM accumulators;
+//   warps 16-19: TMEM -> + bias -> z (fp32, HBM) and the column sums of act(z), act(z)^2 (transposed warp reductions).
 constexpr int kLoadWarps = 16, kEpiWarp0 = 16, kMmaWarpG = 20, kConvThreads = 21 * 32;
 constexpr uint32_t kAImg = 2 * kC * kTile * 2;   // [128 rows][2C cols] bf16 = 64 KB
 constexpr uint32_t kWImg = 2 * kC * kC * 2;      // 64 KB
+constexpr int kSlotRows = 22;                    // neighbour rows per gather slot (k = 20 fits in one round)
+constexpr uint32_t kRowB = kC * 2;               // 256 B
+constexpr uint32_t kSlotB = kSlotRows * kRowB;
 
 struct ConvFwdParams {
   const __nv_bfloat16* h_in;
@@ -194,21 +230,25 @@ struct ConvFwdParams {
 template <int ACT>
 __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const ConvFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* Aimg = smem;                       // 2 x 64 KB
-  uint8_t* Wimg = smem + 2 * kAImg;           // 64 KB
-  float* biasS = reinterpret_cast<float*>(smem + 2 * kAImg + kWImg);        // [C]
+  uint8_t* Aimg = smem;                       // 64 KB (single buffer: the MMA of a tile takes ~0.5k cycles, its gather >10k)
+  uint8_t* Wimg = smem + kAImg;               // 64 KB
+  uint8_t* slots = smem + kAImg + kWImg;      // 16 x 22 rows x 256 B
+  float* biasS = reinterpret_cast<float*>(slots + kLoadWarps * kSlotB);     // [C]
   float* scratch = biasS + kC;                                              // [4][2][C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 4 * 2 * kC);
-  uint64_t* full = bars;          // [2] A image written (16 warp arrivals)
-  uint64_t* empty = bars + 2;     // [2] MMAs that read the image complete
-  uint64_t* acc_full = bars + 4;  // [2]
-  uint64_t* acc_empty = bars + 6; // [2] 4 warp arrivals
-  uint64_t* wbar = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* full = bars;          // A image written (16 warp arrivals)
+  uint64_t* empty = bars + 1;     // MMAs that read the image complete
+  uint64_t* acc_full = bars + 2;  // [2]
+  uint64_t* acc_empty = bars + 4; // [2] 4 warp arrivals
+  uint64_t* wbar = bars + 6;
+  uint64_t* gbar = bars + 7;      // [16] gather slot of warp w landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + kLoadWarps);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kLoadWarps); mbar_init(&empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(full, kLoadWarps); mbar_init(empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < kLoadWarps; ++i) mbar_init(&gbar[i], 1);
     mbar_init(wbar, 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(wbar, kWImg);
@@ -223,76 +263,86 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
 
   if (warp < kLoadWarps) {
     // ===================== gather warps
-    const __nv_bfloat16* hin = p.h_in;
+    const uint8_t* hin = reinterpret_cast<const uint8_t*>(p.h_in);
+    uint8_t* slot = slots + warp * kSlotB;
+    uint64_t* bar = &gbar[warp];
+    uint32_t gphase = 0;
+    constexpr int NPW = kTile / kLoadWarps;   // 8 nodes per warp and tile: rows warp + 16 i
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1, k = it >> 1;
-      if (k >= 1) mbar_wait_b(&empty[buf], (uint32_t)((k - 1) & 1));
-      uint8_t* A = Aimg + buf * kAImg;
-      // two nodes per iteration: their neighbour-row loads are independent, so 16 rows are in flight per lane
+      const int64_t n0 = tile * kTile;
+      // row pointers of this warp's 8 nodes: lane i < 8 holds node i's [pb, pe)
+      int64_t pbv = 0, pev = 0;
+      if (lane < NPW && n0 + warp + kLoadWarps * lane < p.M) {
+        pbv = __ldg(p.g.rowptr + n0 + warp + kLoadWarps * lane);
+        pev = __ldg(p.g.rowptr + n0 + warp + kLoadWarps * lane + 1);
+      }
+      // neighbour ids / weights of node 0, chunk 0 (lane = CSR slot)
+      int64_t pb = __shfl_sync(0xffffffffu, pbv, 0), pe = __shfl_sync(0xffffffffu, pev, 0);
+      int cnt = (int)((pe - pb < kSlotRows) ? pe - pb : kSlotRows);
+      int myc = lane < cnt ? __ldg(p.g.col + pb + lane) : 0;
+      float myw = (p.g.w && lane < cnt) ? __ldg(p.g.w + pb + lane) : 1.f;
 #pragma unroll 1
-      for (int i = 0; i < kTile / kLoadWarps; i += 2) {
-        int rr[2];
-        int64_t node[2], pb[2], pe[2];
-        float acc[2][4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          rr[h] = warp + kLoadWarps * (i + h);
-          node[h] = tile * kTile + rr[h];
-          pb[h] = pe[h] = 0;
-          if (node[h] < p.M) { pb[h] = __ldg(p.g.rowptr + node[h]); pe[h] = __ldg(p.g.rowptr + node[h] + 1); }
-          acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
-        }
-        const int64_t dmax = (pe[0] - pb[0] > pe[1] - pb[1]) ? pe[0] - pb[0] : pe[1] - pb[1];
-        for (int64_t o = 0; o < dmax; o += 32) {
-          int cnt[2], myc[2];
-          float myw[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int64_t left = pe[h] - pb[h] - o;
-            cnt[h] = left < 0 ? 0 : (left < 32 ? (int)left : 32);
-            myc[h] = lane < cnt[h] ? __ldg(p.g.col + pb[h] + o + lane) : 0;
-            myw[h] = (p.g.w && lane < cnt[h]) ? __ldg(p.g.w + pb[h] + o + lane) : 1.f;
+      for (int i = 0; i < NPW; ++i) {
+        const int r = warp + kLoadWarps * i;
+        const bool ok = n0 + r < p.M;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t deg = pe - pb;
+        // root row of the node: issued early, used last
+        uint2 root = make_uint2(0u, 0u);
+        if (ok) root = __ldg(reinterpret_cast<const uint2*>(hin + (size_t)(n0 + r) * kRowB) + lane);
+        int64_t done = 0;
+        for (;;) {
+          // ---- issue this chunk's row copies (TMA engine), then prefetch the ids of the NEXT chunk / node
+          if (cnt > 0) {
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * kRowB);
+            __syncwarp();
+            if (lane < cnt) bulk_g2s(slot + lane * kRowB, hin + (size_t)myc * kRowB, kRowB, bar);
           }
-          const int cm = cnt[0] > cnt[1] ? cnt[0] : cnt[1];
-          for (int j = 0; j < cm; j += 8) {
-            uint2 v[2][8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int src = __shfl_sync(0xffffffffu, myc[h], (j + u) & 31);
-                v[h][u] = (j + u < cnt[h]) ? __ldg(reinterpret_cast<const uint2*>(hin + (size_t)src * kC) + lane) : make_uint2(0u, 0u);
-              }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float wu = __shfl_sync(0xffffffffu, myw[h], (j + u) & 31);
-                acc[h][0] = fmaf(wu, bf16_lo(v[h][u].x), acc[h][0]); acc[h][1] = fmaf(wu, bf16_hi(v[h][u].x), acc[h][1]);
-                acc[h][2] = fmaf(wu, bf16_lo(v[h][u].y), acc[h][2]); acc[h][3] = fmaf(wu, bf16_hi(v[h][u].y), acc[h][3]);
-              }
+          const int ccnt = cnt;
+          const float cw = myw;
+          done += cnt;
+          int64_t npb = pb + done, npe = pe;
+          bool next_node = false;
+          if (done >= deg) {   // this node is complete after this chunk: next = node i + 1
+            next_node = true;
+            const int ni = (i + 1 < NPW) ? i + 1 : 0;
+            npb = __shfl_sync(0xffffffffu, pbv, ni);
+            npe = __shfl_sync(0xffffffffu, pev, ni);
+            if (i + 1 >= NPW) { npb = 0; npe = 0; }
           }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint2 root = make_uint2(0u, 0u);
-          if (node[h] < p.M) {
-            if (p.g.mean && pe[h] > pb[h]) {
-              const float inv = 1.f / (float)(pe[h] - pb[h]);
-              acc[h][0] *= inv; acc[h][1] *= inv; acc[h][2] *= inv; acc[h][3] *= inv;
+          cnt = (int)((npe - npb < kSlotRows) ? npe - npb : kSlotRows);
+          myc = lane < cnt ? __ldg(p.g.col + npb + lane) : 0;
+          myw = (p.g.w && lane < cnt) ? __ldg(p.g.w + npb + lane) : 1.f;
+          // ---- reduce the landed rows: lane owns 4 channels (8 bytes of every row)
+          if (ccnt > 0) {
+            mbar_wait_b(bar, gphase);
+            gphase ^= 1;
+#pragma unroll 2
+            for (int u = 0; u < ccnt; ++u) {
+              const uint2 v = *reinterpret_cast<const uint2*>(slot + u * kRowB + lane * 8);
+              const float wu = __shfl_sync(0xffffffffu, cw, u);
+              acc[0] = fmaf(wu, bf16_lo(v.x), acc[0]); acc[1] = fmaf(wu, bf16_hi(v.x), acc[1]);
+              acc[2] = fmaf(wu, bf16_lo(v.y), acc[2]); acc[3] = fmaf(wu, bf16_hi(v.y), acc[3]);
             }
-            root = __ldg(reinterpret_cast<const uint2*>(hin + (size_t)node[h] * kC) + lane);
+            __syncwarp();   // every lane has read the slot before the next chunk's copies overwrite it
           }
-          const uint2 ag = make_uint2(pack_bf16x2(acc[h][0], acc[h][1]), pack_bf16x2(acc[h][2], acc[h][3]));
-          if (node[h] < p.M) reinterpret_cast<uint2*>(p.agg_out + (size_t)node[h] * kC)[lane] = ag;
-          const int col = 4 * lane;
-          *reinterpret_cast<uint2*>(A + img_chunk_off(rr[h], col) + ((col & 7) << 1)) = ag;
-          *reinterpret_cast<uint2*>(A + img_chunk_off(rr[h], kC + col) + ((col & 7) << 1)) = root;
+          if (next_node) { pb = npb; pe = npe; break; }
         }
+        if (p.g.mean && deg > 0) {
+          const float inv = 1.f / (float)deg;
+          acc[0] *= inv; acc[1] *= inv; acc[2] *= inv; acc[3] *= inv;
+        }
+        const uint2 ag = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
+        if (ok) reinterpret_cast<uint2*>(p.agg_out + (size_t)(n0 + r) * kC)[lane] = ag;
+        // the A image is free once the MMAs of the previous tile have completed
+        if (i == 0 && it >= 1) mbar_wait_b(empty, (uint32_t)((it - 1) & 1));
+        const int col = 4 * lane;
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, col) + ((col & 7) << 1)) = ag;
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, kC + col) + ((col & 7) << 1)) = root;
       }
       fence_proxy_async();
-      mbar_arrive_warp(&full[buf]);
+      mbar_arrive_warp(full);
     }
   } else if (warp == kMmaWarpG) {
     // ===================== MMA issuer
@@ -303,16 +353,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1, k = it >> 1;
-        mbar_wait_b(&full[buf], (uint32_t)(k & 1));
+        mbar_wait_b(full, (uint32_t)(it & 1));
         if (k >= 1) mbar_wait_b(&acc_empty[buf], (uint32_t)((k - 1) & 1));
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 2 * kC / 64; ++s)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem + buf * kC, make_smem_desc_sw128_k(a_base + buf * kAImg + s * kSlab + ks * 32),
+            umma_bf16(tmem + buf * kC, make_smem_desc_sw128_k(a_base + s * kSlab + ks * 32),
                       make_smem_desc_sw128_k(w_base + s * (kC * 128) + ks * 32), IDESC, (s | ks) != 0);
-        umma_commit(&empty[buf]);
+        umma_commit(empty);
         umma_commit(&acc_full[buf]);
       }
     }
@@ -567,7 +617,7 @@ extern "C" int pcc_gnn_conv1_fwd(const float* x, int F, const int64_t* rowptr, c
                                  float* z_out, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
   PCC_REQUIRE(F >= 1 && F <= 8, "fused conv1 needs input_dim <= 8");
-  int blocks = (int)(cdiv(M, 8) < 1184 ? cdiv(M, 8) : 1184);
+  int blocks = (int)(cdiv(M, 256) < 592 ? cdiv(M, 256) : 592);
   if (blocks < 1) blocks = 1;
   GnnGraph g{rowptr, col, w, mean};
   GNN_ACT_DISPATCH(act, {
@@ -624,7 +674,7 @@ extern "C" int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, co
   const int grid = gnn_grid(p.num_tiles);
   *nblk_out = grid;
   if (grid == 0) return 0;
-  const int smem_bytes = 2 * kAImg + kWImg + (kC + 8 * kC) * 4 + 128;
+  const int smem_bytes = kAImg + kWImg + kLoadWarps * kSlotB + (kC + 8 * kC) * 4 + 256;
   {
     ProfScope prof(3, (cudaStream_t)stream);
     GNN_ACT_DISPATCH(act, {

@@ -32,11 +32,21 @@ __global__ void __launch_bounds__(256) gnn_bn_bwd_finalize_kernel(const float* _
   const int cl = threadIdx.x & 31, gq = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  if (c < Cn)
-    for (int b = gq; b < nblk; b += 8) {
+  if (c < Cn) {
+    int b = gq;
+    for (; b + 24 < nblk; b += 32) {
+      const float a0 = __ldg(partials + (size_t)b * 2 * Cn + c), a1 = __ldg(partials + (size_t)(b + 8) * 2 * Cn + c);
+      const float a2 = __ldg(partials + (size_t)(b + 16) * 2 * Cn + c), a3 = __ldg(partials + (size_t)(b + 24) * 2 * Cn + c);
+      const float q0 = __ldg(partials + (size_t)b * 2 * Cn + Cn + c), q1 = __ldg(partials + (size_t)(b + 8) * 2 * Cn + Cn + c);
+      const float q2 = __ldg(partials + (size_t)(b + 16) * 2 * Cn + Cn + c), q3 = __ldg(partials + (size_t)(b + 24) * 2 * Cn + Cn + c);
+      s1 += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      s2 += ((double)q0 + (double)q1) + ((double)q2 + (double)q3);
+    }
+    for (; b < nblk; b += 8) {
       s1 += (double)__ldg(partials + (size_t)b * 2 * Cn + c);
       s2 += (double)__ldg(partials + (size_t)b * 2 * Cn + Cn + c);
     }
+  }
   red[gq][0][cl] = s1;
   red[gq][1][cl] = s2;
   __syncthreads();
@@ -53,9 +63,14 @@ __global__ void __launch_bounds__(256) gnn_bn_bwd_finalize_kernel(const float* _
 __global__ void gnn_reduce_kernel(const float* __restrict__ part, int nblk, int64_t count, float* __restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * count + i];
-  out[i] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // fixed summation order, four loads in flight
+  int b = 0;
+  for (; b + 3 < nblk; b += 4) {
+    s0 += __ldg(part + (size_t)b * count + i); s1 += __ldg(part + (size_t)(b + 1) * count + i);
+    s2 += __ldg(part + (size_t)(b + 2) * count + i); s3 += __ldg(part + (size_t)(b + 3) * count + i);
+  }
+  for (; b < nblk; ++b) s0 += __ldg(part + (size_t)b * count + i);
+  out[i] = (s0 + s1) + (s2 + s3);
 }
 
 // ====================================================================== fc1 backward
@@ -501,50 +516,85 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
 // dh[j] = droot[j] + sum_{e: src(e) = j} w_e dagg[dst(e)]   (CSR by source; for mean aggregation w already carries
 // 1/deg(dst)); warp per node, lane = 4 channels; writes dh IN PLACE over droot.  Also accumulates sum dh and
 // sum dh xhat of the PREVIOUS block (z_prev, its mean / invstd) per block.
+// The neighbour rows (256 B of bf16) are fetched by the TMA engine into a per-warp shared-memory slot (one
+// cp.async.bulk per row, all of a node's rows in flight at once, no registers tied up), like the forward gather.
+constexpr int kAggSlotRows = 22;
+constexpr uint32_t kAggRowB = kC * 2, kAggSlotB = kAggSlotRows * kAggRowB;
 template <int ACT>
 __global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* __restrict__ dagg, GnnGraph g, float* __restrict__ dh,
                                                           const float* __restrict__ z_prev, const float* __restrict__ mu_prev,
                                                           const float* __restrict__ r_prev, int64_t M, float* __restrict__ partials) {
-  __shared__ float red[8][2][kC];
+  extern __shared__ __align__(128) uint8_t smem_agg[];
+  uint8_t* slots = smem_agg;                                                // [8 warps][22 rows][256 B]
+  float* red = reinterpret_cast<float*>(smem_agg + 8 * kAggSlotB);          // [8][2][C]
+  uint64_t* gbar = reinterpret_cast<uint64_t*>(red + 8 * 2 * kC);           // [8]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 8) mbar_init(&gbar[threadIdx.x], 1);
+  fence_mbar_init();
+  __syncthreads();
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(dagg);
+  uint8_t* slot = slots + warp * kAggSlotB;
+  uint64_t* bar = &gbar[warp];
+  uint32_t gphase = 0;
   const float4 mu = __ldg(reinterpret_cast<const float4*>(mu_prev) + lane), rs = __ldg(reinterpret_cast<const float4*>(r_prev) + lane);
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   const int64_t nwarps = (int64_t)gridDim.x * 8;
-  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < M; node += nwarps) {
-    const int64_t pb = __ldg(g.rowptr + node), pe = __ldg(g.rowptr + node + 1);
+  int64_t node = (int64_t)blockIdx.x * 8 + warp;
+  // ids of the first node's first chunk
+  int64_t pb = 0, pe = 0;
+  if (node < M) { pb = __ldg(g.rowptr + node); pe = __ldg(g.rowptr + node + 1); }
+  int cnt = (int)((pe - pb < kAggSlotRows) ? pe - pb : kAggSlotRows);
+  int myc = lane < cnt ? __ldg(g.col + pb + lane) : 0;
+  float myw = (g.w && lane < cnt) ? __ldg(g.w + pb + lane) : 1.f;
+  for (; node < M; node += nwarps) {
     float4 acc = *(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
     const float4 z = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)node * kC) + lane);
-    for (int64_t p0 = pb; p0 < pe; p0 += 32) {
-      const int cnt = (int)((pe - p0 < 32) ? pe - p0 : 32);
-      const int myc = lane < cnt ? __ldg(g.col + p0 + lane) : 0;
-      const float myw = (g.w && lane < cnt) ? __ldg(g.w + p0 + lane) : 1.f;
-      for (int j = 0; j < cnt; j += 8) {
-        uint2 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int t = __shfl_sync(0xffffffffu, myc, (j + u) & 31);
-          v[u] = (j + u < cnt) ? __ldg(reinterpret_cast<const uint2*>(dagg + (size_t)t * kC) + lane) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float wu = __shfl_sync(0xffffffffu, myw, (j + u) & 31);
-          acc.x = fmaf(wu, bf16_lo(v[u].x), acc.x); acc.y = fmaf(wu, bf16_hi(v[u].x), acc.y);
-          acc.z = fmaf(wu, bf16_lo(v[u].y), acc.z); acc.w = fmaf(wu, bf16_hi(v[u].y), acc.w);
-        }
+    const int64_t deg = pe - pb;
+    int64_t done = 0;
+    for (;;) {
+      if (cnt > 0) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * kAggRowB);
+        __syncwarp();
+        if (lane < cnt) bulk_g2s(slot + lane * kAggRowB, src + (size_t)myc * kAggRowB, kAggRowB, bar);
       }
+      const int ccnt = cnt;
+      const float cw = myw;
+      done += cnt;
+      int64_t npb = pb + done, npe = pe;
+      const bool next_node = done >= deg;
+      if (next_node) {
+        npb = npe = 0;
+        if (node + nwarps < M) { npb = __ldg(g.rowptr + node + nwarps); npe = __ldg(g.rowptr + node + nwarps + 1); }
+      }
+      cnt = (int)((npe - npb < kAggSlotRows) ? npe - npb : kAggSlotRows);
+      myc = lane < cnt ? __ldg(g.col + npb + lane) : 0;
+      myw = (g.w && lane < cnt) ? __ldg(g.w + npb + lane) : 1.f;
+      if (ccnt > 0) {
+        mbar_wait_b(bar, gphase);
+        gphase ^= 1;
+#pragma unroll 2
+        for (int u = 0; u < ccnt; ++u) {
+          const uint2 v = *reinterpret_cast<const uint2*>(slot + u * kAggRowB + lane * 8);
+          const float wu = __shfl_sync(0xffffffffu, cw, u);
+          acc.x = fmaf(wu, bf16_lo(v.x), acc.x); acc.y = fmaf(wu, bf16_hi(v.x), acc.y);
+          acc.z = fmaf(wu, bf16_lo(v.y), acc.z); acc.w = fmaf(wu, bf16_hi(v.y), acc.w);
+        }
+        __syncwarp();
+      }
+      if (next_node) { pb = npb; pe = npe; break; }
     }
     *(reinterpret_cast<float4*>(dh + (size_t)node * kC) + lane) = acc;
     s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
     s2[0] += acc.x * (actf<ACT>(z.x) - mu.x) * rs.x; s2[1] += acc.y * (actf<ACT>(z.y) - mu.y) * rs.y;
     s2[2] += acc.z * (actf<ACT>(z.z) - mu.z) * rs.z; s2[3] += acc.w * (actf<ACT>(z.w) - mu.w) * rs.w;
   }
-  *reinterpret_cast<float4*>(&red[warp][0][4 * lane]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-  *reinterpret_cast<float4*>(&red[warp][1][4 * lane]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+  *reinterpret_cast<float4*>(&red[(warp * 2 + 0) * kC + 4 * lane]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+  *reinterpret_cast<float4*>(&red[(warp * 2 + 1) * kC + 4 * lane]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * kC; i += 256) {
     float s = 0.f;
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][i / kC][i % kC];
+    for (int w8 = 0; w8 < 8; ++w8) s += red[(w8 * 2 + i / kC) * kC + i % kC];
     partials[(size_t)blockIdx.x * 2 * kC + i] = s;
   }
 }
@@ -568,25 +618,40 @@ __global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const float* __restr
 #pragma unroll
     for (int f = 0; f < NA; ++f) acc[j][f] = 0.f;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
-  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < M; node += nwarps) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
-    const float4 zz = __ldg(reinterpret_cast<const float4*>(z + (size_t)node * kC) + lane);
-    float in[2 * FP];
+  // two nodes per iteration: their row loads are independent (the loop is bound by load latency otherwise)
+  for (int64_t node0 = (int64_t)blockIdx.x * 8 + warp; node0 < M; node0 += 2 * nwarps) {
+    float4 g[2], zz[2];
+    float in[2][2 * FP];
+    bool ok[2];
 #pragma unroll
-    for (int f = 0; f < FP; ++f) {
-      in[f] = f < F ? __ldg(agg + node * F + f) : 0.f;
-      in[FP + f] = f < F ? __ldg(x + node * F + f) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int64_t node = node0 + h * nwarps;
+      ok[h] = node < M;
+      g[h] = zz[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int f = 0; f < 2 * FP; ++f) in[h][f] = 0.f;
+      if (ok[h]) {
+        g[h] = __ldg(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
+        zz[h] = __ldg(reinterpret_cast<const float4*>(z + (size_t)node * kC) + lane);
+#pragma unroll
+        for (int f = 0; f < FP; ++f)
+          if (f < F) { in[h][f] = __ldg(agg + node * F + f); in[h][FP + f] = __ldg(x + node * F + f); }
+      }
     }
-    float dz[4], a;
-    a = actf<ACT>(zz.x); dz[0] = sc.x * (g.x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(zz.x, a);
-    a = actf<ACT>(zz.y); dz[1] = sc.y * (g.y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(zz.y, a);
-    a = actf<ACT>(zz.z); dz[2] = sc.z * (g.z - c1.z - (a - mu.z) * rs.z * c2.z) * actg<ACT>(zz.z, a);
-    a = actf<ACT>(zz.w); dz[3] = sc.w * (g.w - c1.w - (a - mu.w) * rs.w * c2.w) * actg<ACT>(zz.w, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int h = 0; h < 2; ++h) {
+      if (!ok[h]) continue;
+      float dz[4], a;
+      a = actf<ACT>(zz[h].x); dz[0] = sc.x * (g[h].x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(zz[h].x, a);
+      a = actf<ACT>(zz[h].y); dz[1] = sc.y * (g[h].y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(zz[h].y, a);
+      a = actf<ACT>(zz[h].z); dz[2] = sc.z * (g[h].z - c1.z - (a - mu.z) * rs.z * c2.z) * actg<ACT>(zz[h].z, a);
+      a = actf<ACT>(zz[h].w); dz[3] = sc.w * (g[h].w - c1.w - (a - mu.w) * rs.w * c2.w) * actg<ACT>(zz[h].w, a);
 #pragma unroll
-      for (int f = 0; f < 2 * FP; ++f) acc[j][f] = fmaf(dz[j], in[f], acc[j][f]);
-      acc[j][2 * FP] += dz[j];
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int f = 0; f < 2 * FP; ++f) acc[j][f] = fmaf(dz[j], in[h][f], acc[j][f]);
+        acc[j][2 * FP] += dz[j];
+      }
     }
   }
 #pragma unroll
@@ -694,16 +759,18 @@ extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src,
                                float* dh_inout, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M,
                                int act, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
-  int blocks = (int)(cdiv(M, 8) < 1184 ? cdiv(M, 8) : 1184);
+  int blocks = (int)(cdiv(M, 8) < 592 ? cdiv(M, 8) : 592);
   if (blocks < 1) blocks = 1;
   *nblk_out = blocks;
   GnnGraph g{rowptr_src, col_src, w_src, 0};
   {
     ProfScope prof(5, (cudaStream_t)stream);
+    const int smem_bytes = 8 * kAggSlotB + 8 * 2 * kC * 4 + 64;
     GNN_ACT_DISPATCH(act, {
       auto kern = gnn_agg_bwd_kernel<A>;
-      PCC_K(kern)<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, dh_inout, z_prev, mu_prev, r_prev, M,
-                                                            partials);
+      PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, dh_inout, z_prev, mu_prev,
+                                                                     r_prev, M, partials);
     });
   }
   return check_launch(__func__);
