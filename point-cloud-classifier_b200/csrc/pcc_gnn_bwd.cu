@@ -74,7 +74,7 @@ __global__ void gnn_reduce_kernel(const float* __restrict__ part, int nblk, int6
 }
 
 // ====================================================================== fc1 backward
-constexpr int kFbLoadWarps = 4, kFbEpiWarp0 = 4, kFbMmaWarp = 12, kFbThreads = 13 * 32;
+constexpr int kFbLoadWarps = 4, kFbEpiWarp0 = 4, kFbEpiWarps = 16, kFbMmaWarp = 20, kFbThreads = 21 * 32;
 constexpr uint32_t kHImgB = kC * kTile * 2;        // 32 KB
 constexpr uint32_t kFcWImgB = kFc * kC * 2;        // 64 KB
 constexpr uint32_t kDzImg = kFc * kTile * 2;       // 64 KB: [128 rows][256 cols]
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kFbLoadWarps); mbar_init(&empty[i], 1); }
-    mbar_init(z_full, 1); mbar_init(z_free, 8); mbar_init(dz_ready, 8); mbar_init(dh_full, 1); mbar_init(dh_free, 8);
+    mbar_init(z_full, 1); mbar_init(z_free, kFbEpiWarps); mbar_init(dz_ready, kFbEpiWarps); mbar_init(dh_full, 1); mbar_init(dh_free, kFbEpiWarps);
     mbar_init(wbar, 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(wbar, kFcWImgB);
@@ -197,15 +197,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
       }
     }
   } else {
-    // ===================== epilogue warps 4-11: lane quarter q, 64-column group cg of every 128-column phase
+    // ===================== epilogue warps 4-19: lane quarter q, 32-column group cg of every 128-column phase
     const int q = warp & 3, cg = (warp - kFbEpiWarp0) >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const float* b3 = cst; const float* kap = cst + kFc; const float* lam = cst + 2 * kFc;
     const float* mu3 = cst + 3 * kFc; const float* r3 = cst + 4 * kFc;
     const float* mu2 = cst + 5 * kFc; const float* r2 = cst + 5 * kFc + kC;
-    float st2[4][2], db3[2][4];
+    float st2[2][2], db3[2][2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { st2[c][0] = st2[c][1] = 0.f; db3[0][c] = db3[1][c] = 0.f; }
+    for (int c = 0; c < 2; ++c) { st2[c][0] = st2[c][1] = 0.f; db3[0][c] = db3[1][c] = 0.f; }
     const int row = q * 32 + lane;
     int it = 0;
     uint32_t use = 0;
@@ -216,19 +216,20 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
       const float* gsr = p.gs + gph * kFc;
 #pragma unroll
       for (int half = 0; half < 2; ++half, ++use) {
+        // this thread's 32 columns of the per-graph gradient term: issued before the wait for the accumulator
+        float gq[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(gsr + half * 128 + cg * 32) + j);
+          gq[4 * j] = t4.x; gq[4 * j + 1] = t4.y; gq[4 * j + 2] = t4.z; gq[4 * j + 3] = t4.w;
+        }
         mbar_wait_b(z_full, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = half * 128 + cg * 64 + c * 16;
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = half * 128 + cg * 32 + c * 16;
           uint32_t v[16];
-          tmem_ld16(lane_base + T_Z + cg * 64 + c * 16, v);
-          float gq[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(gsr + col0) + j);
-            gq[4 * j] = t4.x; gq[4 * j + 1] = t4.y; gq[4 * j + 2] = t4.z; gq[4 * j + 3] = t4.w;
-          }
+          tmem_ld16(lane_base + T_Z + cg * 32 + c * 16, v);
           tmem_wait_ld();
           float dz[16];
 #pragma unroll
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
             const int col = col0 + j;
             const float z = __uint_as_float(v[j]) + b3[col];
             const float a = actf<ACT>(z);
-            const float da = gq[j] - kap[col] - lam[col] * (a - mu3[col]) * r3[col];
+            const float da = gq[c * 16 + j] - kap[col] - lam[col] * (a - mu3[col]) * r3[col];
             dz[j] = valid ? da * actg<ACT>(z, a) : 0.f;
           }
           *reinterpret_cast<uint4*>(Dimg + img_chunk_off(row, col0)) =
@@ -250,31 +251,28 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
       }
       fence_proxy_async();
       mbar_arrive_warp(dz_ready);
-      // ---- dh2 of the tile: TMEM -> HBM (fp32) + the two column sums the bn2 backward needs
+      // ---- dh2 of the tile: TMEM -> HBM (fp32) + the two column sums the bn2 backward needs; the z2 values of this
+      //      thread's columns are fetched while the dh / dW MMAs run
+      float zp[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) t4 = __ldg(reinterpret_cast<const float4*>(p.z_prev + (size_t)node * kC + cg * 32) + j);
+        zp[4 * j] = t4.x; zp[4 * j + 1] = t4.y; zp[4 * j + 2] = t4.z; zp[4 * j + 3] = t4.w;
+      }
       mbar_wait_b(dh_full, (uint32_t)(it & 1));
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = cg * 64 + c * 16;
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = cg * 32 + c * 16;
         uint32_t v[16];
         tmem_ld16(lane_base + T_DH + col0, v);
-        float zp[16];
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.z_prev + (size_t)node * kC + col0) + j);
-            zp[4 * j] = t4.x; zp[4 * j + 1] = t4.y; zp[4 * j + 2] = t4.z; zp[4 * j + 3] = t4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) zp[j] = 0.f;
-        }
         tmem_wait_ld();
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float dh = valid ? __uint_as_float(v[j]) : 0.f;
-          const float xh = (actf<ACT>(zp[j]) - mu2[col0 + j]) * r2[col0 + j];
+          const float xh = (actf<ACT>(zp[c * 16 + j]) - mu2[col0 + j]) * r2[col0 + j];
           s1[j] = dh;
           s2[j] = dh * xh;
         }
@@ -294,38 +292,37 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
     float* sdb = scratch + 4 * 2 * kC;      // [4 q][256]
     if (lane < 16) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        sstat[(q * 2 + 0) * kC + cg * 64 + c * 16 + lane] = st2[c][0];
-        sstat[(q * 2 + 1) * kC + cg * 64 + c * 16 + lane] = st2[c][1];
-        sdb[q * kFc + 0 * 128 + cg * 64 + c * 16 + lane] = db3[0][c];
-        sdb[q * kFc + 1 * 128 + cg * 64 + c * 16 + lane] = db3[1][c];
+      for (int c = 0; c < 2; ++c) {
+        sstat[(q * 2 + 0) * kC + cg * 32 + c * 16 + lane] = st2[c][0];
+        sstat[(q * 2 + 1) * kC + cg * 32 + c * 16 + lane] = st2[c][1];
+        sdb[q * kFc + 0 * 128 + cg * 32 + c * 16 + lane] = db3[0][c];
+        sdb[q * kFc + 1 * 128 + cg * 32 + c * 16 + lane] = db3[1][c];
       }
     }
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    const int t = threadIdx.x - kFbEpiWarp0 * 32;   // 0..255
-    p.stat_part[(size_t)blockIdx.x * 2 * kC + t] = sstat[(0 * 2 + t / kC) * kC + t % kC] + sstat[(1 * 2 + t / kC) * kC + t % kC] +
-                                                   sstat[(2 * 2 + t / kC) * kC + t % kC] + sstat[(3 * 2 + t / kC) * kC + t % kC];
-    p.db_part[(size_t)blockIdx.x * kFc + t] = sdb[t] + sdb[kFc + t] + sdb[2 * kFc + t] + sdb[3 * kFc + t];
+    asm volatile("bar.sync 2, 512;" ::: "memory");
+    const int t = threadIdx.x - kFbEpiWarp0 * 32;   // 0..511
+    if (t < 2 * kC)
+      p.stat_part[(size_t)blockIdx.x * 2 * kC + t] = sstat[(0 * 2 + t / kC) * kC + t % kC] + sstat[(1 * 2 + t / kC) * kC + t % kC] +
+                                                     sstat[(2 * 2 + t / kC) * kC + t % kC] + sstat[(3 * 2 + t / kC) * kC + t % kC];
+    else if (t < 2 * kC + kFc)
+      p.db_part[(size_t)blockIdx.x * kFc + (t - 2 * kC)] = sdb[t - 2 * kC] + sdb[kFc + t - 2 * kC] + sdb[2 * kFc + t - 2 * kC] + sdb[3 * kFc + t - 2 * kC];
     // dW partial [256 out][C in]: TMEM lane = out feature inside its half, column = in feature
-    if (my_tiles > 0) {
-      // the last dh_full commit covered every MMA issued before it, the dW ones included
-      for (int o = 0; o < 2; ++o) {
-        float* dst = p.dw_part + ((size_t)blockIdx.x * kFc + o * 128 + row) * kC + cg * 64;
+    for (int o = 0; o < 2; ++o) {
+      float* dst = p.dw_part + ((size_t)blockIdx.x * kFc + o * 128 + row) * kC + cg * 32;
+      if (my_tiles > 0) {
+        // the last dh_full commit covered every MMA issued before it, the dW ones included
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t v[16];
-          tmem_ld16(lane_base + T_DW + o * kC + cg * 64 + c * 16, v);
+          tmem_ld16(lane_base + T_DW + o * kC + cg * 32 + c * 16, v);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             reinterpret_cast<float4*>(dst + c * 16)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
-      }
-    } else {
-      for (int o = 0; o < 2; ++o) {
-        float* dst = p.dw_part + ((size_t)blockIdx.x * kFc + o * 128 + row) * kC + cg * 64;
-        for (int j = 0; j < 64; ++j) dst[j] = 0.f;
+      } else {
+        for (int j = 0; j < 32; ++j) dst[j] = 0.f;
       }
     }
   }
@@ -398,7 +395,7 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if (it >= 1) mbar_wait_b(empty, (uint32_t)((it - 1) & 1));
-#pragma unroll 2
+#pragma unroll 4
       for (int i = 0; i < kTile / kCbLoadWarps; ++i) {
         const int r = warp + kCbLoadWarps * i;
         const int64_t node = tile * kTile + r;
