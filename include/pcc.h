@@ -305,6 +305,9 @@ int pcc_prof_read(int slot, double* ms_total, int64_t* count);
  *      mode 0 = K-major operands (forward), 1 = MN-major B (dgrad), 2 = MN-major A and B
  *      (wgrad).  Expected values: tests/test_fused_gpu.py. */
 int pcc_selftest_umma(int mode, float* out, int device, void* stream);
+/* FP32 FMA throughput probe (roofline denominator of the kNN kernel): `blocks` blocks of 256 threads, 16 * iters
+ * flops per thread; out[blocks*256].  The caller times it with CUDA events (tools/bench_knn.py). */
+int pcc_selftest_fp32_peak(float* out, int blocks, int iters, int device, void* stream);
 /* ---- fused multi-tensor Adam / AdamW step: torch.optim.Adam / AdamW as constructed at
  *      /root/reference/models/wrapper.py:30-33 (default betas / eps; weight_decay 0 / 0.01), every parameter
  *      tensor in one launch.  table (device, [n_tensors][4] int64): {param pointer, grad pointer (0 = no gradient:

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ pos,
 // queue in shared memory; the queues are drained warp-wide (unrolled compare-exchange chain, ~5 instructions per list
 // slot) only when some lane's queue fills, so the divergent insertion cost is paid once per ~5 accepted candidates
 // instead of once per candidate.  Distances use the oracle's arithmetic (no FMA contraction): results are bit-exact.
-constexpr int kKnnTile = 1024, kKnnQ = 8;
+constexpr int kKnnTile = 1024, kKnnQ = 16;
 template <int K>
 __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict__ pos, int64_t pos_stride,
                                                         const int64_t* __restrict__ offsets, int64_t n, int64_t B, int k,

@@ -109,3 +109,22 @@ extern "C" int pcc_selftest_umma(int mode, float* out, int device, void* stream)
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, out);
   return check_launch(__func__);
 }
+
+// ---- FP32 FMA peak (the roofline denominator of the kNN kernel, SURVEY.md section 8d: "must be measured on the box"):
+// 8 independent FMA chains per thread, 2 x iters x 8 flops per thread, grid = 8 blocks of 256 threads per SM.
+namespace pcc {
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+    x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+  }
+  out[blockIdx.x * 256 + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace pcc
+
+extern "C" int pcc_selftest_fp32_peak(float* out, int blocks, int iters, int device, void* stream) {
+  PCC_ENTER(device);
+  fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+  return check_launch(__func__);
+}

@@ -93,6 +93,7 @@ _SIGS = {
     "pcc_debug_set_fwd_pair": [_i32],
     "pcc_debug_set_pdl": [_i32],
     "pcc_selftest_umma": [_i32, _vp, _i32, _vp],
+    "pcc_selftest_fp32_peak": [_vp, _i32, _i32, _i32, _vp],
     "pcc_phi_fused_supported": [C.POINTER(PhiDesc)],
     "pcc_phi_fused_workspace_bytes": [C.POINTER(PhiDesc), _i64, _i64],
     "pcc_phi_packed_bytes": [C.POINTER(PhiDesc)],
