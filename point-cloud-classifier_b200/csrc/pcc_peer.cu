@@ -69,7 +69,11 @@ __global__ void __launch_bounds__(kPeerThreads, 1) peer_allreduce_kernel(const P
   }
   if (threadIdx.x < p.world) {
     const unsigned int* flag = reinterpret_cast<const unsigned int*>(p.stage[p.rank]) + threadIdx.x;
+    // bounded: a peer that died or never launched this step makes the kernel TRAP (a CUDA error on every healthy
+    // rank) after ~10 s instead of spinning forever and hanging the node
+    const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+      if (clock64() - t0 > 20000000000ll) __trap();
     }
   }
   __syncthreads();
