@@ -715,7 +715,7 @@ extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const 
   if (grid == 0) return 0;
   const int smem_bytes = 2 * kHImgB + kFcWImgB + kDzImg + (5 * kFc + 2 * kC + 8 * kC + 4 * kFc) * 4 + 128;
   {
-    ProfScope prof(4, (cudaStream_t)stream);
+    ProfScope prof(7, (cudaStream_t)stream);
     GNN_ACT_DISPATCH(act, {
       auto kern = gnn_fc1_bwd_kernel<A>;
       PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

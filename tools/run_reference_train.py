@@ -49,6 +49,27 @@ def write_synthetic_s2ppc(data_dir, events=24, seed=0):
                  position_z=rows[:, 4], time=np.abs(rows[:, 5]), label=label)
 
 
+def write_synthetic_s2pg(data_dir, graphs=24, seed=0, k=6):
+    """per-graph npz schema of utils/data.py:1112-1121 (read back at :1183-1196): features [n,4] fp32 (col 0 energy,
+    cols 1:4 xyz), edges [2,E] int64 (source; target), weights [E] fp32, label, event_id"""
+    rng = np.random.default_rng(seed)
+    for split in ("train", "val", "test"):
+        d = os.path.join(data_dir, "S2PG", split)
+        os.makedirs(d, exist_ok=True)
+        for i in range(graphs):
+            n = int(rng.integers(30, 120))
+            f = rng.normal(size=(n, 4)).astype(np.float32)
+            f[:, 0] = rng.random(n).astype(np.float32)
+            d2 = ((f[:, None, 1:4] - f[None, :, 1:4]) ** 2).sum(-1)
+            np.fill_diagonal(d2, np.inf)
+            nbr = np.argsort(d2, axis=1)[:, :k]
+            edges = np.stack([nbr.reshape(-1), np.repeat(np.arange(n), k)]).astype(np.int64)
+            dist = np.sqrt(d2[edges[1], edges[0]]).astype(np.float32)
+            w = np.exp(-dist ** 2 / (2 * (np.median(dist) + 1e-6) ** 2)).astype(np.float32)
+            np.savez(os.path.join(d, f"graph_{i:05d}.npz"), features=f, edges=edges, weights=w,
+                     label=np.float32(i % 2), event_id=np.int64(i))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default=os.environ.get("PCC_REFERENCE", "/root/reference"))
@@ -64,13 +85,18 @@ def main():
     if not os.path.exists(os.path.join(args.workdir, "configs")):
         os.symlink(os.path.join(args.reference, "configs"), os.path.join(args.workdir, "configs"))
     write_synthetic_s2ppc(os.path.join(args.workdir, "data", "continuous"))
+    write_synthetic_s2pg(os.path.join(args.workdir, "data", "continuous"))
     os.chdir(args.workdir)
     import train  # the reference's train.py
     import models.deep_sets as ds
     assert "pcc_b200" in ds.DeepSets.__module__, "models.deep_sets did not resolve to the B200 package"
     cfg = train.load_config("configs/base.yaml", f"configs/{args.model}.yaml")
     cfg["trainer"]["epochs"] = args.epochs
-    train.train_model(args.model, args.dataset, cfg)
+    import torch
+    log_dir = train.train_model(args.model, args.dataset, cfg, return_log_dir=True)
+    sd = torch.load(os.path.join(log_dir, "model.pt"), map_location="cpu")
+    print(f"REFERENCE_TRAIN_OK model={args.model} dataset={args.dataset} device={'cuda' if torch.cuda.is_available() else 'cpu'} "
+          f"log_dir={log_dir} state_dict_keys={len(sd)} first_key={next(iter(sd))}")
 
 
 if __name__ == "__main__":
