@@ -187,6 +187,68 @@ __device__ __forceinline__ float act_t(float z) {
   return z;
 }
 
+// ---- packed-pair (f32x2) activation math.  The gelu / silu epilogues are bound by instruction issue (a trace of the
+// backward chain: 19k of 29k cycles per tile are activation math at ~20 scalar instructions per element); Blackwell's
+// packed fp32 pipe evaluates the polynomial parts of two elements per instruction, the tanh stays one MUFU op per element.
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t splat2(float v) { return f32x2(v, v); }
+__device__ __forceinline__ uint64_t tanh2(uint64_t x) {
+  float lo, hi;
+  f32x2_unpack(x, lo, hi);
+  return f32x2(tanh_approx(lo), tanh_approx(hi));
+}
+// a = act(z), da = act'(z) for a pair; same functions of z as act_and_grad_t (identical operation order up to fma contraction)
+template <int ACT>
+__device__ __forceinline__ void act_and_grad2(uint64_t z, uint64_t& a, uint64_t& da) {
+  if (ACT == PCC_ACT_GELU) {
+    constexpr float c0 = 0.7978845608028654f;
+    const uint64_t z2 = fmul2(z, z);
+    const uint64_t t = tanh2(fmul2(z, ffma2(splat2(c0 * 0.044715f), z2, splat2(c0))));
+    const uint64_t h = ffma2(splat2(0.5f), t, splat2(0.5f));
+    a = fmul2(z, h);
+    // da = h + 2 z h (1 - h) u',  u' = c0 (1 + 0.134145 z^2)      (1 - t^2 = 4 h (1 - h))
+    const uint64_t up2 = ffma2(splat2(2.f * c0 * 0.134145f), z2, splat2(2.f * c0));
+    const uint64_t omh = ffma2(h, splat2(-1.f), splat2(1.f));
+    da = ffma2(fmul2(a, omh), up2, h);
+  } else if (ACT == PCC_ACT_SILU) {
+    const uint64_t s = ffma2(splat2(0.5f), tanh2(fmul2(z, splat2(0.5f))), splat2(0.5f));
+    a = fmul2(z, s);
+    da = ffma2(a, ffma2(s, splat2(-1.f), splat2(1.f)), s);   // s + z s (1 - s)
+  } else {
+    float lo, hi;
+    f32x2_unpack(z, lo, hi);
+    a = f32x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+    da = f32x2(lo > 0.f ? 1.f : 0.f, hi > 0.f ? 1.f : 0.f);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ uint64_t act2(uint64_t z) {
+  if (ACT == PCC_ACT_GELU) {
+    constexpr float c0 = 0.7978845608028654f;
+    const uint64_t t = tanh2(fmul2(z, ffma2(splat2(c0 * 0.044715f), fmul2(z, z), splat2(c0))));
+    return fmul2(z, ffma2(splat2(0.5f), t, splat2(0.5f)));
+  }
+  if (ACT == PCC_ACT_SILU) return fmul2(z, ffma2(splat2(0.5f), tanh2(fmul2(z, splat2(0.5f))), splat2(0.5f)));
+  float lo, hi;
+  f32x2_unpack(z, lo, hi);
+  return f32x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
+  float lo, hi;
+  f32x2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) { return f32x2(bf16_lo(u), bf16_hi(u)); }
+
 __device__ __forceinline__ uint32_t float_ordered(float v) {
   uint32_t b = __float_as_uint(v);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);

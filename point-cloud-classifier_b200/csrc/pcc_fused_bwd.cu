@@ -252,55 +252,56 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
     auto wait_A = [&]() { mbar_wait(accA_ready, phA); phA ^= 1; tc_fence_after(); };
     auto wait_B = [&]() { mbar_wait(accB_ready, phB); phB ^= 1; tc_fence_after(); };
     auto arrive_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive_warp(a_ready); };
-    // h = [old +] act(z + b) for one 8-column group
+    // h = [old +] act(z + b) for one 8-column group (packed-pair math: two columns per instruction)
     auto h_chunk8 = [&](const uint32_t* z, const float* bl, uint8_t* dst, bool res) {
       const float4 b0 = *reinterpret_cast<const float4*>(bl);
       const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
-      float o[8];
-      o[0] = act_t<ACT>(__uint_as_float(z[0]) + b0.x); o[1] = act_t<ACT>(__uint_as_float(z[1]) + b0.y);
-      o[2] = act_t<ACT>(__uint_as_float(z[2]) + b0.z); o[3] = act_t<ACT>(__uint_as_float(z[3]) + b0.w);
-      o[4] = act_t<ACT>(__uint_as_float(z[4]) + b1.x); o[5] = act_t<ACT>(__uint_as_float(z[5]) + b1.y);
-      o[6] = act_t<ACT>(__uint_as_float(z[6]) + b1.z); o[7] = act_t<ACT>(__uint_as_float(z[7]) + b1.w);
-      if (res) {
-        const uint4 old = *reinterpret_cast<const uint4*>(dst);
-        o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
-        o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+      const uint64_t bb[4] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w), f32x2(b1.x, b1.y), f32x2(b1.z, b1.w)};
+      uint4 old = make_uint4(0u, 0u, 0u, 0u);
+      if (res) old = *reinterpret_cast<const uint4*>(dst);
+      const uint32_t oo[4] = {old.x, old.y, old.z, old.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint64_t o = act2<ACT>(fadd2(f32x2(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])), bb[j]));
+        if (res) o = fadd2(o, bf16x2_to_f32x2(oo[j]));
+        pk[j] = pack_bf16x2_pair(o);
       }
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     };
     // dZ = dH * act'(z + b) for one 8-column group
     auto dz_chunk8 = [&](const uint32_t* z, const uint32_t* g, const float* bl, uint8_t* dst) {
       const float4 b0 = *reinterpret_cast<const float4*>(bl);
       const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      const uint64_t bb[4] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w), f32x2(b1.x, b1.y), f32x2(b1.z, b1.w)};
+      uint32_t pk[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(g[j]) * act_grad_t<ACT>(__uint_as_float(z[j]) + bb[j]);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                  pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      for (int j = 0; j < 4; ++j) {
+        uint64_t a, da;
+        act_and_grad2<ACT>(fadd2(f32x2(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])), bb[j]), a, da);
+        pk[j] = pack_bf16x2_pair(fmul2(f32x2(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])), da));
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     };
     // both at once (the activation and its derivative share their transcendental)
     auto hdz_chunk8 = [&](const uint32_t* z, const uint32_t* g, const float* bl, uint8_t* hdst, uint8_t* gdst, bool res) {
       const float4 b0 = *reinterpret_cast<const float4*>(bl);
       const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8], q[8];
+      const uint64_t bb[4] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w), f32x2(b1.x, b1.y), f32x2(b1.z, b1.w)};
+      uint4 old = make_uint4(0u, 0u, 0u, 0u);
+      if (res) old = *reinterpret_cast<const uint4*>(hdst);
+      const uint32_t oo[4] = {old.x, old.y, old.z, old.w};
+      uint32_t ph[4], pg[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float da;
-        act_and_grad_t<ACT>(__uint_as_float(z[j]) + bb[j], o[j], da);
-        q[j] = __uint_as_float(g[j]) * da;
+      for (int j = 0; j < 4; ++j) {
+        uint64_t a, da;
+        act_and_grad2<ACT>(fadd2(f32x2(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])), bb[j]), a, da);
+        if (res) a = fadd2(a, bf16x2_to_f32x2(oo[j]));
+        ph[j] = pack_bf16x2_pair(a);
+        pg[j] = pack_bf16x2_pair(fmul2(f32x2(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1])), da));
       }
-      if (res) {
-        const uint4 old = *reinterpret_cast<const uint4*>(hdst);
-        o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
-        o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
-      }
-      *reinterpret_cast<uint4*>(hdst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                   pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-      *reinterpret_cast<uint4*>(gdst) = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]),
-                                                   pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
+      *reinterpret_cast<uint4*>(hdst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(gdst) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
     };
 
     load_x(blockIdx.x);

@@ -80,16 +80,17 @@ __device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t
           pack_bf16x2_relu(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
       continue;
     }
-    float o[8];
+    uint4 old = make_uint4(0u, 0u, 0u, 0u);
+    if (res) old = *reinterpret_cast<const uint4*>(dst);
+    const uint32_t oo[4] = {old.x, old.y, old.z, old.w};
+    uint32_t pk[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(__uint_as_float(v[q * 8 + j]));
-    if (res) {
-      const uint4 old = *reinterpret_cast<const uint4*>(dst);
-      o[0] += bf16_lo(old.x); o[1] += bf16_hi(old.x); o[2] += bf16_lo(old.y); o[3] += bf16_hi(old.y);
-      o[4] += bf16_lo(old.z); o[5] += bf16_hi(old.z); o[6] += bf16_lo(old.w); o[7] += bf16_hi(old.w);
+    for (int j = 0; j < 4; ++j) {   // packed-pair math: two columns per instruction
+      uint64_t o = act2<ACT>(f32x2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1])));
+      if (res) o = fadd2(o, bf16x2_to_f32x2(oo[j]));
+      pk[j] = pack_bf16x2_pair(o);
     }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
           for (int pi = 0; pi < 4; ++pi) {
             float lo, hi;
             f32x2_unpack(z[i][pi], lo, hi);
-            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
+            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2_pair(act2<ACT>(z[i][pi]));
           }
           *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, s * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -775,7 +776,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) phi
           for (int pi = 0; pi < 4; ++pi) {
             float lo, hi;
             f32x2_unpack(z[i][pi], lo, hi);
-            o[i][pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(act_t<ACT>(lo), act_t<ACT>(hi));
+            o[i][pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2_pair(act2<ACT>(z[i][pi]));
           }
         // The image is free once the previous final layer has completed (multicast commit).  The first slab of the
         // new tile has been computed in registers by now: its math hides under the tail of that final layer.

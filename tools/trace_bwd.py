@@ -4,8 +4,10 @@ sys.path.insert(0, os.path.join(ROOT, "point-cloud-classifier_b200"))
 import pcc_b200
 from pcc_b200 import _lib
 pool = sys.argv[1] if len(sys.argv) > 1 else "sum"
+act = sys.argv[2] if len(sys.argv) > 2 else "relu"
+res = len(sys.argv) > 3 and sys.argv[3] == "res"
 B, N = 256, 1024
-m = pcc_b200.DeepSets(3, [256, 256], [256], 10, "relu", layer_norm=False, pooling=pool, precision="bf16").cuda()
+m = pcc_b200.DeepSets(3, [256, 256], [256], 10, act, layer_norm=False, residual_block=res, pooling=pool, precision="bf16").cuda()
 x = torch.randn(B * N, 3, device="cuda"); idx = torch.arange(B, device="cuda").repeat_interleave(N)
 y = (torch.rand(B, 10, device="cuda") > 0.5).float(); lf = torch.nn.BCEWithLogitsLoss()
 buf = torch.zeros(4 * 4096, dtype=torch.int64, device="cuda")
