@@ -116,6 +116,11 @@ int pcc_batchnorm_bwd(const float* dy, const float* x, const float* gamma, const
 int64_t pcc_csr_workspace_bytes(int64_t n, int64_t E);
 int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t* rowptr, int32_t* perm, void* ws, int device,
                   void* stream);
+/* transpose of a CSR by target with int32 neighbour ids (col_d[p] = source of slot p; slots of target i =
+ * [rowptr_d[i], rowptr_d[i+1]) or, with k_uniform > 0, [i k, (i+1) k) — a kNN graph): rowptr_s[n+1], col_s[E] = target ids
+ * grouped by source, ascending inside a row.  ws: pcc_csr_workspace_bytes(n, E).  Feeds pcc_gnn_agg_bwd. */
+int pcc_csr_transpose(const int32_t* col_d, const int64_t* rowptr_d, int64_t E, int64_t n, int k_uniform, int64_t* rowptr_s,
+                      int32_t* col_s, void* ws, int device, void* stream);
 /* out[i,:] = aggr_{e in in(i)} w_e * x[src(e),:]   (aggr: PCC_POOL_ADD / MEAN / MAX);
  * rowptr/perm = CSR by TARGET.  arg_edge[n,C] (int32 edge id, -1 if none) for MAX only. */
 int pcc_graph_aggregate_fwd(const float* x, const int64_t* src, const float* w, const int64_t* rowptr,

@@ -74,6 +74,39 @@ __global__ void __launch_bounds__(256) csr_sort_rows_kernel(const int64_t* __res
   }
 }
 
+// ------------------------------------------------------------------ CSR transpose (by target -> by source)
+// Input: CSR by target with int32 neighbour ids (col_d[p] = source of slot p; the slots of target i are
+// [rowptr_d[i], rowptr_d[i+1]), or [i k, (i+1) k) when k_uniform > 0, e.g. a kNN graph).  Output: rowptr_s[n+1] and
+// col_s[E] = TARGET ids grouped by source, ascending inside a row (deterministic).  No edge-id permutation, no int64
+// index traffic: the backward aggregation of the fused GraphNet path reads exactly these two arrays.
+__global__ void csrt_count_kernel(const int32_t* __restrict__ col_d, int64_t E, int64_t n, unsigned long long* __restrict__ counts) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p < E) {
+    const int s = col_d[p];
+    if (s >= 0 && s < n) atomicAdd(&counts[s], 1ull);
+  }
+}
+__global__ void csrt_fill_kernel(const int32_t* __restrict__ col_d, const int64_t* __restrict__ rowptr_d, int64_t E, int64_t n,
+                                 int k_uniform, unsigned long long* __restrict__ cursor, int32_t* __restrict__ col_s) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= E) return;
+  const int s = col_d[p];
+  if (s < 0 || s >= n) return;
+  int64_t t;
+  if (k_uniform > 0) {
+    t = p / k_uniform;
+  } else {   // target of slot p: last i with rowptr_d[i] <= p
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(rowptr_d + mid) <= p) lo = mid; else hi = mid;
+    }
+    t = lo;
+  }
+  const unsigned long long pos = atomicAdd(&cursor[s], 1ull);
+  col_s[pos] = (int32_t)t;
+}
+
 // ------------------------------------------------------------------ aggregation
 // tpn threads per node, each owning float4 channel groups c = 4*(lane + it*tpn)
 template <bool VEC4>
@@ -399,6 +432,25 @@ extern "C" int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t*
     PCC_K(csr_copy_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr, cursor, n);
     PCC_K(csr_fill_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(keys, E, n, cursor, perm);
     PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(rowptr, perm, n);
+  }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_csr_transpose(const int32_t* col_d, const int64_t* rowptr_d, int64_t E, int64_t n, int k_uniform,
+                                 int64_t* rowptr_s, int32_t* col_s, void* ws, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(E < (int64_t)0x7fffffff && n < (int64_t)0x7fffffff, "edge / node count exceeds int32 range");
+  PCC_REQUIRE(k_uniform > 0 || rowptr_d != nullptr, "rowptr_d required unless every target has k_uniform slots");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* scan_ws = (int64_t*)ws;
+  unsigned long long* cursor = (unsigned long long*)(scan_ws + cdiv(n + 1, 1024) + 4);
+  PCC_K(csr_zero_kernel)<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(rowptr_s, n + 1);
+  if (E > 0) PCC_K(csrt_count_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(col_d, E, n, (unsigned long long*)rowptr_s);
+  exclusive_scan_i64(rowptr_s, n + 1, scan_ws, st);
+  if (E > 0 && n > 0) {
+    PCC_K(csr_copy_kernel)<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(rowptr_s, cursor, n);
+    PCC_K(csrt_fill_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(col_d, rowptr_d, E, n, k_uniform, cursor, col_s);
+    PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(rowptr_s, col_s, n);
   }
   return check_launch(__func__);
 }

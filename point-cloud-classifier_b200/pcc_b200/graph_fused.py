@@ -27,10 +27,11 @@ class FusedGraph:
     """CSR views of a batched edge list in the layout the fused kernels read: rowptr int64 [n+1], col int32 [E]
     (neighbour node per slot), w fp32 [E] or None.  by_dst feeds the forward aggregation, by_src its transpose."""
 
-    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None):
+    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None, k_uniform: int = 0):
         from .functional import GraphCSR
         self.n, self.aggr = n, aggr
         self.E = edges.shape[1]
+        self.k_uniform = k_uniform
         csr = None
         if by_dst is not None:                       # e.g. a kNN graph: k consecutive edges per target, already grouped
             self.rowptr_d, self.col_d = by_dst
@@ -46,6 +47,15 @@ class FusedGraph:
         self._src = None
 
     def by_src(self):
+        if self._src is None and self._weights is None and self.aggr == "add":
+            # unweighted sum aggregation: transpose the int32 CSR directly (no edge-id permutation, no int64 index ops)
+            dev = L.require_cuda(self.col_d)
+            rowptr_s = torch.empty(self.n + 1, dtype=torch.int64, device=self.col_d.device)
+            col_s = torch.empty(max(self.E, 1), dtype=torch.int32, device=self.col_d.device)
+            ws = torch.empty(call("pcc_csr_workspace_bytes", self.n, self.E), dtype=torch.uint8, device=self.col_d.device)
+            call("pcc_csr_transpose", ptr(self.col_d), ptr(self.rowptr_d), self.E, self.n, int(self.k_uniform), ptr(rowptr_s),
+                 ptr(col_s), ptr(ws), dev, L.stream_ptr(dev))
+            self._src = (rowptr_s, col_s, None)
         if self._src is None:
             from .functional import GraphCSR
             csr = self._csr or GraphCSR(self._edges, self.n)

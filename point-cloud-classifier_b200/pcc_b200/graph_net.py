@@ -151,11 +151,11 @@ def _fused_methods():
         """bf16 tcgen05 path (graph_fused.py): one autograd Function for everything before fc2"""
         n, E = x.shape[0], edges.shape[1]
         edges = edges if edges.dtype == torch.int64 else edges.long()
-        by_dst = None
+        by_dst, k = None, 0
         if sorted_by_target and n > 0 and E % n == 0:      # kNN graph: k consecutive edges per target node
             k = E // n
             by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, edges[0].to(torch.int32))
-        graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst)
+        graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst, k_uniform=k)
         counts = offsets[1:] - offsets[:-1]
         bns = (self.bn1, self.bn2, self.bn3)
         bufs = [(b.running_mean, b.running_var) for b in bns]
