@@ -64,7 +64,7 @@ int pcc_segment_pool_bwd(const float* dpooled, const int64_t* offsets, const int
  * (x = hi + lo split, error ~2^-21 per product: the parity mode), 1 = single TF32 (operands rounded to 10 mantissa
  * bits, ~1e-3 relative, 3x fewer MMAs).  Library-wide switch; the small-tile (batch-sized) kernels stay exact fp32. */
 int pcc_set_dense_precision(int mode);
-/* ---- dense layer, fp32 SIMT path: replaces nn.Linear (+ fused activation / residual)
+/* ---- dense layer, fp32-grade path (3xTF32 `mma.sync` with a hi / lo operand split; small shapes exact fp32 FFMA): replaces nn.Linear (+ fused activation / residual)
  *      inside phi / rho (deep_sets.py:89,112), GraphConv's lin_rel / lin_root and fc1 /
  *      fc2 (graph_net.py:73,82,87,98,102).
  *      y[M,N] = residual[M,N]? + act( x[M,K] · w[N,K]^T + bias[N]? + pre_add[M,N]? );

@@ -10,7 +10,7 @@ Two execution paths behind the same module:
   precision="bf16" (default, env PCC_PRECISION): phi + pooling run in ONE fused
       tcgen05/TMEM kernel (bf16 operands, fp32 accumulate; activations never reach HBM),
       backward in one fused recompute kernel.  Taken when pcc_phi_fused_supported().
-  precision="fp32": exact-fp32 SIMT kernels layer by layer (parity mode; also the path
+  precision="fp32": fp32-grade kernels layer by layer (3xTF32 mma.sync with a hi/lo split; parity mode; also the path
       for LayerNorm-in-phi and widths the fused kernel does not take).
 """
 from __future__ import annotations

@@ -85,7 +85,7 @@ def segment_pool(x, offsets, pooling: str, return_argmax: bool = False):
     return SegmentPoolFn.apply(x, offsets, pooling)
 
 
-# ------------------------------------------------------------------ dense layers (fp32 SIMT)
+# ------------------------------------------------------------------ dense layers (fp32-grade: 3xTF32 mma.sync)
 class LinearActFn(torch.autograd.Function):
     """y = residual? + act(x W^T + b + pre_add?): nn.Linear + activation (+ ResidualBlock
     add), deep_sets.py:48-53,64-68,156-160; graph_net.py lin_rel/lin_root/fc1/fc2."""
