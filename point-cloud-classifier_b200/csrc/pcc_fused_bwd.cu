@@ -131,6 +131,11 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
   // same per-tile flow as mode 1 with the dH image built from G; h_lh is not needed by any weight gradient.
   const bool virt = p.virt != 0;     // no per-point dgrad / wgrad GEMM for the final Linear
   const bool vmax = p.virt == 1, bcast = p.virt == 2;
+  // bcast3 (sum / mean pooling commuted with the final Linear, two hidden layers): the pooled gradient of a row is read
+  // straight from the [B,H] matrix G in the dZ_1 pass, which leaves the gradient image buffer free during the h_0
+  // epilogue: that epilogue also stores act'(z_0) there (bf16), so the tile needs neither a second z_0 GEMM nor a second
+  // activation evaluation for dZ_0; dZ_1 is written over h_0 (already staged) and feeds the dgrad from there.
+  const bool bcast3 = bcast && p.L == 3;
 
   if (warp == kProdWarp) {
     // ===================== producer: weight slabs in consumption order
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         if (L == 3) {
           push_layer(p.w_off[1]);                               // z_1
           push_layer(p.wt_off[1]);                              // dgrad of layer 1
-          push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);      // z_0 again
+          if (!bcast3) push(p.wpack + p.w_off[0], (kK0 / 8) * W0_LBO);      // z_0 again
         }
       }
     }
@@ -196,12 +201,14 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           wait_a();                                 // h_0 image written
           gemm(h_base, ACC_A, false);               // z_1
           umma_commit(accA_ready);
-          wait_a();                                 // dZ_1 image written
-          gemm(g_base, ACC_B, (p.res_mask >> 1) & 1);  // dH_0 (+ dH_1)
+          wait_a();                                 // dZ_1 image written (bcast3: into bufH, over h_0)
+          gemm(bcast3 ? h_base : g_base, ACC_B, (p.res_mask >> 1) & 1);  // dH_0 (+ dH_1)
           umma_commit(accB_ready);
-          wait_a();                                 // x tile staged again
-          gemm0();                                  // z_0 again
-          umma_commit(accA_ready);
+          if (!bcast3) {
+            wait_a();                               // x tile staged again
+            gemm0();                                // z_0 again
+            umma_commit(accA_ready);
+          }
         }
       }
     }
@@ -269,6 +276,22 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       }
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     };
+    // h = act(z + b) -> hdst and act'(z + b) -> dadst (both bf16) for one 8-column group
+    auto hda_chunk8 = [&](const uint32_t* z, const float* bl, uint8_t* hdst, uint8_t* dadst) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bl);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + 4);
+      const uint64_t bb[4] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w), f32x2(b1.x, b1.y), f32x2(b1.z, b1.w)};
+      uint32_t ph[4], pd[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint64_t a, da;
+        act_and_grad2<ACT>(fadd2(f32x2(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])), bb[j]), a, da);
+        ph[j] = pack_bf16x2_pair(a);
+        pd[j] = pack_bf16x2_pair(da);
+      }
+      *reinterpret_cast<uint4*>(hdst) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(dadst) = make_uint4(pd[0], pd[1], pd[2], pd[3]);
+    };
     // dZ = dH * act'(z + b) for one 8-column group
     auto dz_chunk8 = [&](const uint32_t* z, const uint32_t* g, const float* bl, uint8_t* dst) {
       const float4 b0 = *reinterpret_cast<const float4*>(bl);
@@ -335,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           for (int s = 0; s < NSLAB; ++s)
             bulk_g2s(bufG + s * kActSlab, p.wpack + p.w_off[L - 1] + (size_t)s * SLAB + (size_t)f0 * 128, kActSlab, wf_ready);
         }
-      } else {
+      } else if (!bcast3) {
         // the pooled-gradient rows of the sets that intersect this tile are staged one set at a time in a
         // scratch area of bufH (free until the h_0 epilogue) and broadcast from shared memory; a thread
         // writes its row when its own set is staged.  (Per-thread global loads here were latency bound:
@@ -387,7 +410,26 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       TRE(4);
 
       // ---- L = 3: h_0 = act(z_0 + b_0) -> bufH (over the x tile), staged; TMEM loads one chunk ahead
-      if (L == 3) {
+      if (bcast3) {
+        wait_A();
+        TRE(5);
+        const float* bl = biasS;
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 2) {
+          uint32_t z[32];
+          tmem_ld32(lane_base + ACC_A + c * 32, z);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t off = act_chunk_off(r, c * 32 + q * 8);
+            hda_chunk8(z + q * 8, bl + c * 32 + q * 8, bufH + off, bufG + off);
+          }
+          store_slabs(p.stage_h[0] + (size_t)tile * BLOB, bufH, c >> 1, 1, nullptr, nullptr);
+        }
+        TRE(6);
+        arrive_a();
+        TRE(7);
+      } else if (L == 3) {
         wait_A();
         TRE(5);
         const float* bl = biasS;
@@ -421,7 +463,39 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
       TRE(9);
       acquire();  // staging stores of h_0 (bufH) and dZ_{L-1} (bufG) have finished reading
       TRE(10);
-      if (virt) {
+      if (bcast3) {
+        const bool res = (p.res_mask >> lh) & 1;
+        const float* bl = biasS + lh * H;
+        const float* grow = p.dpooled + (myset < 0 ? 0 : myset) * H;   // G row of this thread's set ([B,H] fp32, L2 resident)
+        const float sc = myset < 0 ? 0.f : scale;
+        uint32_t gn[32];
+        auto load_g = [&](int c, uint32_t (&dst)[32]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + j);   // raw: scaled at use, so the
+            dst[4 * j] = __float_as_uint(t4.x); dst[4 * j + 1] = __float_as_uint(t4.y);    // loads stay in flight
+            dst[4 * j + 2] = __float_as_uint(t4.z); dst[4 * j + 3] = __float_as_uint(t4.w);
+          }
+        };
+        load_g(grp, gn);
+#pragma unroll 1
+        for (int c = grp; c < NCHUNK; c += 2) {
+          uint32_t z[32], g[32];
+          tmem_ld32(lane_base + ACC_A + c * 32, z);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(sc * __uint_as_float(gn[j]));
+          if (c + 2 < NCHUNK) load_g(c + 2, gn);     // next chunk's gradient row in flight during this chunk's math
+          if (res) tmem_st32(lane_base + ACC_B + c * 32, g);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufH + act_chunk_off(r, c * 32 + q * 8));
+          // (one 64 KB store per image instead of slab-wise stores was tried: the passes get shorter but the store then
+          // competes with the GEMM that reads the same buffer — z_1 wait 2.2k -> 3.7k cycles — and the step got slower)
+          store_slabs(p.stage_g[lh] + (size_t)tile * BLOB, bufH, c >> 1, 1, nullptr, nullptr);
+        }
+        if (res) tmem_wait_st();
+      } else if (virt) {
         if (vmax) {
           mbar_wait(wf_ready, wf_phase);
           wf_phase ^= 1;
@@ -480,6 +554,31 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
         if (threadIdx.x == 0) bulk_wait_read0();  // slab-wise stores: only the last slab pair can still be in flight
         asm volatile("bar.sync 1, 256;" ::: "memory");
         TRE(13);
+        if (bcast3) {
+          // ---- dZ_0 = dH_0 * act'(z_0) with act'(z_0) kept (bf16) in bufG by the h_0 epilogue: in place
+          wait_B();
+          TRE(14);
+          TRE(15);
+#pragma unroll 1
+          for (int c = grp; c < NCHUNK; c += 2) {
+            uint32_t g[32];
+            tmem_ld32(lane_base + ACC_B + c * 32, g);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint8_t* dst = bufG + act_chunk_off(r, c * 32 + q * 8);
+              const uint4 da = *reinterpret_cast<const uint4*>(dst);
+              const uint32_t dd[4] = {da.x, da.y, da.z, da.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                pk[j] = pack_bf16x2_pair(fmul2(f32x2(__uint_as_float(g[q * 8 + 2 * j]), __uint_as_float(g[q * 8 + 2 * j + 1])),
+                                               bf16x2_to_f32x2(dd[j])));
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            store_slabs(p.stage_g[0] + (size_t)tile * BLOB, bufG, c >> 1, 1, nullptr, nullptr);
+          }
+        } else {
         stage_x();
         arrive_a();
         // ---- dZ_0 = dH_0 * act'(z_0 + b_0) -> bufG, staged
@@ -499,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_bwd_chain_kernel(const BwdPar
           for (int q = 0; q < 4; ++q)
             dz_chunk8(z + q * 8, g + q * 8, bl + c * 32 + q * 8, bufG + act_chunk_off(r, c * 32 + q * 8));
           store_slabs(p.stage_g[0] + (size_t)tile * BLOB, bufG, c >> 1, 1, nullptr, nullptr);
+        }
         }
         TRE(16);
         TRE(17);
