@@ -234,7 +234,9 @@ int pcc_mlp_head_bwd(const pcc_head_desc* d, const float* x, const float* zsave,
  *   pcc_gnn_bn_apply     : h = bf16(act(z)*scale + shift)            (activation BEFORE BatchNorm, graph_net.py:75-76)
  *   pcc_gnn_conv_fwd     : GraphConv 2 (:82) in ONE kernel: CSR gather-reduce of bf16 neighbour rows into the shared-
  *                          memory A image [agg | h], tcgen05 GEMM with [W_rel ; W_root], z (fp32) + BatchNorm partial
- *                          sums in the epilogue; agg_out keeps the aggregate for the weight gradient.
+ *                          sums in the epilogue; agg_out keeps the aggregate for the weight gradient.  Optional
+ *                          membership + psum[B,128]: per-graph sums of act(z) (deepchem_style = false pools right after
+ *                          the block, graph_net.py:96: mean pooling commutes with the BatchNorm affine).
  *   pcc_gnn_fc1_pool_fwd : fc1 + act + bn3 statistics + global_mean_pool (:87-92): psum[B,256] = per-graph sums of
  *                          act(fc1(h)), partials [nblk][2][256]; the per-node [M,256] tensor never reaches HBM. */
 int64_t pcc_gnn_packed_bytes(void);
@@ -252,7 +254,8 @@ int pcc_gnn_bn_apply(const float* z, const float* scale, const float* shift, int
                      void* stream);
 int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, const int32_t* col, const float* w, int mean,
                      const void* packed, const float* bias, int64_t M, int act, void* agg_out_bf16, float* z_out,
-                     float* partials, int* nblk_out, int device, void* stream);
+                     float* partials, const int64_t* membership, float* psum, int64_t B, int* nblk_out, int device,
+                     void* stream);
 int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership, int64_t M,
                          int64_t B, int act, float* psum, float* partials, int* nblk_out, int device, void* stream);
 /*   backward (autograd of the above).  One block z = A W^T + b, a = act(z), h = a*scale + shift has
@@ -263,7 +266,8 @@ int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float*
  *   pcc_gnn_fc1_bwd         : recomputes z3 per tile; dz3 = (gs[graph] - kap - lam*xhat3) act'(z3) (gs / kap / lam carry the
  *                             mean-pool + bn3 backward, computed by the caller from [B,256]-sized data); dh_out = dz3 Wfc1
  *                             (fp32) + its bn2 sums; dw_part [nblk][256][128], db_part [nblk][256].
- *   pcc_gnn_conv_bwd        : dz in the operand prologue; dagg_out (bf16) | droot_out (fp32) = dz [W_rel | W_root];
+ *   pcc_gnn_conv_bwd        : dz in the operand prologue (dh [M,128], or dh_graph [B,128] + membership when the gradient is
+ *                             the same row for every node of a graph: mean pooling straight after the block); dagg_out (bf16) | droot_out (fp32) = dz [W_rel | W_root];
  *                             dw_part [nblk][128][256] = dz^T [agg | h_in] accumulated in TMEM; db_part [nblk][128].
  *   pcc_gnn_agg_bwd         : dh_inout[j] += sum_{e: src(e)=j} w_e dagg[dst(e)] (CSR by source) + the bn sums of the
  *                             previous block (z_prev, its mean / invstd).
@@ -275,7 +279,7 @@ int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const float* bias
                     const float* kap, const float* lam, const float* mu3, const float* r3, const float* z_prev,
                     const float* mu_prev, const float* r_prev, int64_t M, int act, float* dh_out, float* stat_part,
                     float* dw_part, float* db_part, int* nblk_out, int device, void* stream);
-int pcc_gnn_conv_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
+int pcc_gnn_conv_bwd(const float* dh, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
                      const float* bn_c1, const float* bn_c2, const void* agg_bf16, const void* h_in_bf16, const void* packed,
                      int64_t M, int act, void* dagg_out_bf16, float* droot_out, float* dw_part, float* db_part, int* nblk_out,
                      int device, void* stream);

@@ -110,9 +110,10 @@ def graphnet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x, membership, edge
                      operand_rounding: Optional[str] = None) -> torch.Tensor:
     """cfg keys = the reference ctor kwargs (graph_net.py:10-22); only the
     use_gat=False, sag_pool=False branch (configs/graph_net.yaml:6,8) is restated.
-    operand_rounding="bf16": the STATED arithmetic of the product's bf16 GraphNet mode (deepchem_style only) — the
-    normalised activations h1 / h2, the conv2 aggregate and the conv2 / fc1 weights are rounded to bf16, products and
-    sums, pre-activations, BatchNorm statistics and conv1 stay fp32.  Same algorithm, stated operand precision."""
+    operand_rounding="bf16": the STATED arithmetic of the product's bf16 GraphNet mode — the normalised activations h1
+    (and h2 when fc1 runs per node, deepchem_style), the conv2 aggregate and the conv2 (/ fc1) weights are rounded to
+    bf16; products and sums, pre-activations, BatchNorm statistics, conv1, the pooled tensors and the graph-level layers
+    stay fp32.  Same algorithm, stated operand precision."""
     if cfg.get("use_gat", False) or cfg.get("sag_pool", False):
         raise NotImplementedError("GATConv / SAGPooling branches are out of scope (SURVEY.md §2 row 3)")
     act = cfg["activation"]
@@ -124,8 +125,8 @@ def graphnet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x, membership, edge
         h = q(h)
     h = graphconv(sd, "conv2", h, edges, weights, aggr, q)
     h = _bn(sd, "bn2", _act(act, h), training, stats_out)
-    if q is not None:
-        h = q(h)
+    if q is not None and cfg.get("deepchem_style", False):
+        h = q(h)     # h2 feeds the fc1 tensor-core contraction (deepchem); otherwise it is pooled in fp32, never rounded
     if cfg.get("deepchem_style", False):
         h = F.linear(h, q(sd["fc1.weight"]) if q is not None else sd["fc1.weight"], sd["fc1.bias"])
         h = _bn(sd, "bn3", _act(act, h), training, stats_out)

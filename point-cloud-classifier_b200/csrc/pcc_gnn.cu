@@ -224,6 +224,8 @@ struct ConvFwdParams {
   __nv_bfloat16* agg_out;
   float* z_out;
   float* partials;   // [grid][2][C]
+  const int64_t* membership;   // optional (with psum): graph of every node
+  float* psum;                 // optional [B,C]: per-graph sums of act(z) (global_mean_pool straight after the block)
   int64_t M, num_tiles;
 };
 
@@ -380,6 +382,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
       tc_fence_after();
       const int64_t node = tile * kTile + q * 32 + lane;
       const bool valid = node < p.M;
+      // optional per-graph sums (the block is followed by global_mean_pool): like the fc1 kernel, one atomic per column
+      // when the warp's 32 rows belong to one graph, per-row atomics otherwise
+      int64_t gph = -1, g0 = -1;
+      bool uniform = false;
+      if (p.psum) {
+        gph = valid ? __ldg(p.membership + node) : -1;
+        g0 = __shfl_sync(0xffffffffu, gph, 0);
+        uniform = __all_sync(0xffffffffu, gph == g0) && g0 >= 0;
+      }
 #pragma unroll
       for (int c = 0; c < kC / 16; ++c) {
         uint32_t v[16];
@@ -400,8 +411,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
           for (int j = 0; j < 4; ++j)
             dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
-        st[c][0] += warp_transpose_sum16(a1, lane);
+        if (p.psum && !uniform && valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(p.psum + gph * kC + c * 16 + j, a1[j]);
+        }
+        const float cs = warp_transpose_sum16(a1, lane);
+        st[c][0] += cs;
         st[c][1] += warp_transpose_sum16(a2, lane);
+        if (p.psum && uniform && lane < 16) atomicAdd(p.psum + g0 * kC + c * 16 + lane, cs);
       }
       tc_fence_before();
       mbar_arrive_warp(&acc_empty[buf]);
@@ -659,9 +676,14 @@ extern "C" int pcc_gnn_bn_apply(const float* z, const float* scale, const float*
 
 extern "C" int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, const int32_t* col, const float* w, int mean,
                                 const void* packed, const float* bias, int64_t M, int act, void* agg_out_bf16, float* z_out,
-                                float* partials, int* nblk_out, int device, void* stream) {
+                                float* partials, const int64_t* membership, float* psum, int64_t B, int* nblk_out, int device,
+                                void* stream) {
   PCC_ENTER(device);
+  PCC_REQUIRE(psum == nullptr || membership != nullptr, "psum needs the membership vector");
+  if (psum) PCC_CUDA(cudaMemsetAsync(psum, 0, (size_t)B * kC * sizeof(float), (cudaStream_t)stream));
   ConvFwdParams p{};
+  p.membership = membership;
+  p.psum = psum;
   p.h_in = (const __nv_bfloat16*)h_in_bf16;
   p.g = GnnGraph{rowptr, col, w, mean};
   p.wimg = (const uint8_t*)packed;

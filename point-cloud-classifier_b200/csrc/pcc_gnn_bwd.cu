@@ -338,6 +338,8 @@ constexpr uint32_t kAinImg = 2 * kC * kTile * 2;      // 64 KB: [128 rows][2C co
 constexpr uint32_t kCwImg = 2 * kC * kC * 2;          // 64 KB
 
 struct ConvBwdParams {
+  const int64_t* membership;   // with dh_graph: graph of every node
+  const float* dh_graph;       // optional [B,C]: dL/dh is the same row for every node of a graph (global_mean_pool follows the block)
   const float* dh;             // dL/dh of this block's output [M,C] fp32
   const float* z;              // pre-activation of this block [M,C]
   BnBack bn;                   // [C] arrays
@@ -402,7 +404,8 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
         float dz[4] = {0.f, 0.f, 0.f, 0.f};
         uint2 ag = make_uint2(0u, 0u), hr = make_uint2(0u, 0u);
         if (node < p.M) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.dh + (size_t)node * kC) + lane);
+          const float4 g = p.dh_graph ? __ldg(reinterpret_cast<const float4*>(p.dh_graph + (size_t)__ldg(p.membership + node) * kC) + lane)
+                                      : __ldg(reinterpret_cast<const float4*>(p.dh + (size_t)node * kC) + lane);
           const float4 z = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)node * kC) + lane);
           ag = __ldg(reinterpret_cast<const uint2*>(p.agg + (size_t)node * kC) + lane);
           hr = __ldg(reinterpret_cast<const uint2*>(p.h_in + (size_t)node * kC) + lane);
@@ -725,13 +728,15 @@ extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const 
   return check_launch(__func__);
 }
 
-extern "C" int pcc_gnn_conv_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd,
+extern "C" int pcc_gnn_conv_bwd(const float* dh, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd,
                                 const float* bn_scale, const float* bn_c1, const float* bn_c2, const void* agg_bf16,
                                 const void* h_in_bf16, const void* packed, int64_t M, int act, void* dagg_out_bf16,
                                 float* droot_out, float* dw_part, float* db_part, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
+  PCC_REQUIRE((dh != nullptr) != (dh_graph != nullptr), "exactly one of dh / dh_graph");
+  PCC_REQUIRE(dh_graph == nullptr || membership != nullptr, "dh_graph needs the membership vector");
   ConvBwdParams p{};
-  p.dh = dh; p.z = z;
+  p.dh = dh; p.z = z; p.membership = membership; p.dh_graph = dh_graph;
   p.bn = BnBack{bn_mean, bn_invstd, bn_scale, bn_c1, bn_c2};
   p.agg = (const __nv_bfloat16*)agg_bf16; p.h_in = (const __nv_bfloat16*)h_in_bf16;
   p.wimg = (const uint8_t*)packed;

@@ -79,12 +79,12 @@ _SIGS = {
     "pcc_gnn_bn_finalize": [_vp, _i32, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "pcc_gnn_bn_eval": [_vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _i32, _vp],
     "pcc_gnn_bn_apply": [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
-    "pcc_gnn_conv_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_conv_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(C.c_int), _i32, _vp],
     "pcc_gnn_fc1_pool_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
     "pcc_gnn_bn_bwd_finalize": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "pcc_gnn_reduce": [_vp, _i32, _i64, _vp, _i32, _vp],
     "pcc_gnn_fc1_bwd": [_vp] * 12 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
-    "pcc_gnn_conv_bwd": [_vp] * 10 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_conv_bwd": [_vp] * 12 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
     "pcc_gnn_agg_bwd": [_vp] * 8 + [_i64, _i32, _vp, C.POINTER(C.c_int), _i32, _vp],
     "pcc_gnn_conv1_bwd": [_vp] * 9 + [_i32, _i64, _i32, _vp, C.POINTER(C.c_int), _i32, _vp],
     "pcc_launch_count": [_i32],

@@ -159,17 +159,27 @@ def _fused_methods():
         counts = offsets[1:] - offsets[:-1]
         bns = (self.bn1, self.bn2, self.bn3)
         bufs = [(b.running_mean, b.running_var) for b in bns]
-        meta = (self._act_name, self.training, float(self.bn1.eps), float(self.bn1.momentum))
+        hidden = self.conv2.out_channels
+        meta = (self._act_name, self.training, float(self.bn1.eps), float(self.bn1.momentum), bool(self.deepchem_style), hidden)
         params = (self.conv1.lin_rel.weight, self.conv1.lin_rel.bias, self.conv1.lin_root.weight,
                   self.conv2.lin_rel.weight, self.conv2.lin_rel.bias, self.conv2.lin_root.weight,
-                  self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias,
-                  self.fc1.weight, self.fc1.bias, self.bn3.weight, self.bn3.bias)
-        y3 = GF.GraphNetFusedFn.apply(x, membership, graph, counts, meta, bufs, *params)
-        if self.training:
-            for b in bns:
-                b.num_batches_tracked.add_(1)
+                  self.bn1.weight, self.bn1.bias, self.bn2.weight, self.bn2.bias)
         self.last_path = "fused-bf16"
-        return PF.linear_act(y3, self.fc2.weight, self.fc2.bias, None, "none")
+        if self.deepchem_style:
+            params += (self.fc1.weight, self.fc1.bias, self.bn3.weight, self.bn3.bias)
+            y3 = GF.GraphNetFusedFn.apply(x, membership, graph, counts, meta, bufs, *params)
+            if self.training:
+                for b in bns:
+                    b.num_batches_tracked.add_(1)
+            return PF.linear_act(y3, self.fc2.weight, self.fc2.bias, None, "none")
+        # deepchem_style=False (graph_net.py:94-100): pool first, then fc1 -> act -> bn3 on [B, .] (layer-wise ops)
+        pooled = GF.GraphNetFusedFn.apply(x, membership, graph, counts, meta, bufs[:2], *params)
+        if self.training:
+            for b in bns[:2]:
+                b.num_batches_tracked.add_(1)
+        h = PF.linear_act(pooled, self.fc1.weight, self.fc1.bias, None, self._act_name)
+        h = PF.batchnorm(h, self.bn3)
+        return PF.linear_act(h, self.fc2.weight, self.fc2.bias, None, "none")
 
     GraphNet.fused_supported = fused_supported
     GraphNet._forward_fused = _forward_fused

@@ -36,19 +36,24 @@ def _clouds(sizes, seed, F=4):
     return feats, memb, off
 
 
-def _cfg(act, aggr, F=4):
-    return dict(input_dim=F, hidden_dim=128, output_dim=1, activation=act, use_gat=False, gat_heads=4, sag_pool=False,
-                pool_ratio=0.5, local_pooling=aggr, global_pooling="mean", deepchem_style=True)
+def _cfg(act, aggr, F=4, hidden=128, deepchem=True):
+    return dict(input_dim=F, hidden_dim=hidden, output_dim=1, activation=act, use_gat=False, gat_heads=4, sag_pool=False,
+                pool_ratio=0.5, local_pooling=aggr, global_pooling="mean", deepchem_style=deepchem)
 
 
-@pytest.mark.parametrize("act,aggr,use_w,F,sizes,k", [
-    ("tanh", "add", False, 4, [300, 200, 400, 256], 8),       # configs/graph_net.yaml
-    ("relu", "mean", True, 4, [129, 1000, 77], 6),
-    ("gelu", "add", True, 1, [64, 64, 500], 5),
-    ("tanh", "add", False, 4, [1024] * 20, 20),               # more tiles than SMs: several tiles per CTA
+@pytest.mark.parametrize("act,aggr,use_w,F,sizes,k,hidden,deepchem", [
+    ("tanh", "add", False, 4, [300, 200, 400, 256], 8, 128, True),       # configs/graph_net.yaml
+    ("relu", "mean", True, 4, [129, 1000, 77], 6, 128, True),
+    ("gelu", "add", True, 1, [64, 64, 500], 5, 128, True),
+    ("tanh", "add", False, 4, [1024] * 20, 20, 128, True),               # more tiles than SMs: several tiles per CTA
+    ("tanh", "add", False, 4, [300, 200, 400, 256], 8, 128, False),      # deepchem_style=False: pool straight after conv2
+    ("gelu", "mean", True, 4, [129, 500, 77, 40], 6, 128, False),
+    ("tanh", "add", False, 4, [300, 200, 400, 256], 8, 64, True),        # hidden_dim 64 (zero-padded to the 128-wide kernels)
+    # (deepchem_style=False normalises over GRAPHS in bn3: 24 graphs keep that BatchNorm well conditioned)
+    ("relu", "add", True, 1, [60, 45, 80, 33] * 6, 6, 64, False),
 ])
-def test_fused_graphnet_train_step_matches_oracle(act, aggr, use_w, F, sizes, k):
-    cfg = _cfg(act, aggr, F)
+def test_fused_graphnet_train_step_matches_oracle(act, aggr, use_w, F, sizes, k, hidden, deepchem):
+    cfg = _cfg(act, aggr, F, hidden, deepchem)
     feats, memb, off = _clouds(sizes, seed=21, F=max(F, 4))
     nbr, _ = KO.knn_neighbours(feats[:, 1:4].numpy(), off, k)
     edges = torch.from_numpy(KO.knn_edges(nbr))
@@ -80,7 +85,7 @@ def test_fused_graphnet_train_step_matches_oracle(act, aggr, use_w, F, sizes, k)
             worst = (kname, e)
         if eq > worstq[1]:
             worstq = (kname, eq)
-    print(f"fused graphnet {act}/{aggr}/w={use_w}/F={F}/n={sum(sizes)}: logits {e_logq:.1e}/{e_log:.1e} (vs bf16-operand oracle / "
+    print(f"fused graphnet {act}/{aggr}/w={use_w}/F={F}/C={hidden}/deepchem={deepchem}/n={sum(sizes)}: logits {e_logq:.1e}/{e_log:.1e} (vs bf16-operand oracle / "
           f"fp32 oracle); worst grad {worstq[0]} {worstq[1]:.1e} / {worst[0]} {worst[1]:.1e}; " + " ".join(rows))
     assert e_logq < LOGIT_TOL_Q and e_log < LOGIT_TOL
     assert worstq[1] < (GRAD_TOL_Q_RELU if act == "relu" else GRAD_TOL_Q), worstq
