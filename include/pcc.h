@@ -121,6 +121,11 @@ int pcc_csr_build(const int64_t* keys, int64_t E, int64_t n, int64_t* rowptr, in
  * grouped by source, ascending inside a row.  ws: pcc_csr_workspace_bytes(n, E).  Feeds pcc_gnn_agg_bwd. */
 int pcc_csr_transpose(const int32_t* col_d, const int64_t* rowptr_d, int64_t E, int64_t n, int k_uniform, int64_t* rowptr_s,
                       int32_t* col_s, void* ws, int device, void* stream);
+/* the same transpose for a block-diagonal simple graph with k slots per target (a kNN graph over a batch of clouds:
+ * offsets[B+1] = node range of every cloud, all neighbours of a node in the node's cloud, no repeated edge — violations
+ * trap): one CTA per cloud in shared memory, no workspace, no sort. */
+int pcc_csr_transpose_blocks(const int32_t* col_d, int k, const int64_t* offsets, int64_t B, int64_t n, int64_t* rowptr_s,
+                             int32_t* col_s, int device, void* stream);
 /* out[i,:] = aggr_{e in in(i)} w_e * x[src(e),:]   (aggr: PCC_POOL_ADD / MEAN / MAX);
  * rowptr/perm = CSR by TARGET.  arg_edge[n,C] (int32 edge id, -1 if none) for MAX only. */
 int pcc_graph_aggregate_fwd(const float* x, const int64_t* src, const float* w, const int64_t* rowptr,
@@ -260,14 +265,16 @@ int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float*
                          int64_t B, int act, float* psum, float* partials, int* nblk_out, int device, void* stream);
 /*   backward (autograd of the above).  One block z = A W^T + b, a = act(z), h = a*scale + shift has
  *      dz = scale (dh - c1 - xhat c2) act'(z),  c1 = sum(dh)/M,  c2 = sum(dh xhat)/M,  xhat = (a - mean) invstd;
- *   the kernel that produces a gradient tensor dh also accumulates the two sums (partials [nblk][2][128]).
+ *   the kernel that produces a gradient tensor dh also accumulates the two sums (partials [nblk][2][128]) — from its fp32
+ *   values; the [M,128] gradient tensors themselves travel between the kernels in bf16 (they are GEMM / gather operands,
+ *   rounded to bf16 by their consumer anyway; the traffic, not the arithmetic, bounds these kernels).
  *   pcc_gnn_bn_bwd_finalize : partial sums -> c1, c2, dgamma, dbeta.
  *   pcc_gnn_reduce          : out[i] = sum_b part[b*count + i] (weight-gradient partials).
  *   pcc_gnn_fc1_bwd         : recomputes z3 per tile; dz3 = (gs[graph] - kap - lam*xhat3) act'(z3) (gs / kap / lam carry the
  *                             mean-pool + bn3 backward, computed by the caller from [B,256]-sized data); dh_out = dz3 Wfc1
- *                             (fp32) + its bn2 sums; dw_part [nblk][256][128], db_part [nblk][256].
- *   pcc_gnn_conv_bwd        : dz in the operand prologue (dh [M,128], or dh_graph [B,128] + membership when the gradient is
- *                             the same row for every node of a graph: mean pooling straight after the block); dagg_out (bf16) | droot_out (fp32) = dz [W_rel | W_root];
+ *                             (bf16) + its bn2 sums; dw_part [nblk][256][128], db_part [nblk][256].
+ *   pcc_gnn_conv_bwd        : dz in the operand prologue (dh [M,128] bf16, or dh_graph [B,128] fp32 + membership when the gradient is
+ *                             the same row for every node of a graph: mean pooling straight after the block); dagg_out | droot_out (bf16) = dz [W_rel | W_root];
  *                             dw_part [nblk][128][256] = dz^T [agg | h_in] accumulated in TMEM; db_part [nblk][128].
  *   pcc_gnn_agg_bwd         : dh_inout[j] += sum_{e: src(e)=j} w_e dagg[dst(e)] (CSR by source) + the bn sums of the
  *                             previous block (z_prev, its mean / invstd).
@@ -277,16 +284,16 @@ int pcc_gnn_bn_bwd_finalize(const float* partials, int nblk, int Cn, int64_t row
 int pcc_gnn_reduce(const float* part, int nblk, int64_t count, float* out, int device, void* stream);
 int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership, const float* gs,
                     const float* kap, const float* lam, const float* mu3, const float* r3, const float* z_prev,
-                    const float* mu_prev, const float* r_prev, int64_t M, int act, float* dh_out, float* stat_part,
+                    const float* mu_prev, const float* r_prev, int64_t M, int act, void* dh_out_bf16, float* stat_part,
                     float* dw_part, float* db_part, int* nblk_out, int device, void* stream);
-int pcc_gnn_conv_bwd(const float* dh, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
+int pcc_gnn_conv_bwd(const void* dh_bf16, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
                      const float* bn_c1, const float* bn_c2, const void* agg_bf16, const void* h_in_bf16, const void* packed,
-                     int64_t M, int act, void* dagg_out_bf16, float* droot_out, float* dw_part, float* db_part, int* nblk_out,
+                     int64_t M, int act, void* dagg_out_bf16, void* droot_out_bf16, float* dw_part, float* db_part, int* nblk_out,
                      int device, void* stream);
 int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src, const int32_t* col_src, const float* w_src,
-                    float* dh_inout, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M, int act,
+                    void* dh_inout_bf16, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M, int act,
                     float* partials, int* nblk_out, int device, void* stream);
-int pcc_gnn_conv1_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
+int pcc_gnn_conv1_bwd(const void* dh_bf16, const float* z, const float* bn_mean, const float* bn_invstd, const float* bn_scale,
                       const float* bn_c1, const float* bn_c2, const float* agg, const float* x, int F, int64_t M, int act,
                       float* partials, int* nblk_out, int device, void* stream);
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) gnn_bn_apply_kernel(const float* __restri
 constexpr int kLoadWarps = 16, kEpiWarp0 = 16, kMmaWarpG = 20, kConvThreads = 21 * 32;
 constexpr uint32_t kAImg = 2 * kC * kTile * 2;   // [128 rows][2C cols] bf16 = 64 KB
 constexpr uint32_t kWImg = 2 * kC * kC * 2;      // 64 KB
-constexpr int kSlotRows = 22;                    // neighbour rows per gather slot (k = 20 fits in one round)
+constexpr int kSlotRows = 21;                    // neighbour rows per gather slot (k = 20 fits in one round)
 constexpr uint32_t kRowB = kC * 2;               // 256 B
 constexpr uint32_t kSlotB = kSlotRows * kRowB;
 
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Aimg = smem;                       // 64 KB (single buffer: the MMA of a tile takes ~0.5k cycles, its gather >10k)
   uint8_t* Wimg = smem + kAImg;               // 64 KB
-  uint8_t* slots = smem + kAImg + kWImg;      // 16 x 22 rows x 256 B
+  uint8_t* slots = smem + kAImg + kWImg;      // 16 x 21 rows x 256 B
   float* biasS = reinterpret_cast<float*>(slots + kLoadWarps * kSlotB);     // [C]
   float* scratch = biasS + kC;                                              // [4][2][C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 4 * 2 * kC);
@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
   uint64_t* wbar = bars + 6;
   uint64_t* gbar = bars + 7;      // [16] gather slot of warp w landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + kLoadWarps);
+  uint32_t* stage_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [4 warps] 2 KB staging tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -320,13 +321,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
           if (ccnt > 0) {
             mbar_wait_b(bar, gphase);
             gphase ^= 1;
-#pragma unroll 2
-            for (int u = 0; u < ccnt; ++u) {
-              const uint2 v = *reinterpret_cast<const uint2*>(slot + u * kRowB + lane * 8);
-              const float wu = __shfl_sync(0xffffffffu, cw, u);
-              acc[0] = fmaf(wu, bf16_lo(v.x), acc[0]); acc[1] = fmaf(wu, bf16_hi(v.x), acc[1]);
-              acc[2] = fmaf(wu, bf16_lo(v.y), acc[2]); acc[3] = fmaf(wu, bf16_hi(v.y), acc[3]);
-            }
+            slot_reduce<(int)kRowB>(slot, ccnt, lane, p.g.w != nullptr, cw, acc);
             __syncwarp();   // every lane has read the slot before the next chunk's copies overwrite it
           }
           if (next_node) { pb = npb; pe = npe; break; }
@@ -375,13 +370,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
     float st[kC / 16][2];
 #pragma unroll
     for (int c = 0; c < kC / 16; ++c) st[c][0] = st[c][1] = 0.f;
+    uint32_t* stage = stage_all + q * kStage16Words;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1, k = it >> 1;
       mbar_wait_b(&acc_full[buf], (uint32_t)(k & 1));
       tc_fence_after();
-      const int64_t node = tile * kTile + q * 32 + lane;
+      const int64_t node0 = tile * kTile + q * 32;
+      const int64_t node = node0 + lane;
       const bool valid = node < p.M;
+      const int rows_valid = (int)((p.M - node0) < 32 ? (p.M - node0 < 0 ? 0 : p.M - node0) : 32);
       // optional per-graph sums (the block is followed by global_mean_pool): like the fc1 kernel, one atomic per column
       // when the warp's 32 rows belong to one graph, per-row atomics otherwise
       int64_t gph = -1, g0 = -1;
@@ -405,12 +403,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
           a1[j] = a;
           a2[j] = a * a;
         }
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(p.z_out + (size_t)node * kC + c * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
+        warp_store_rows16(stage, v, reinterpret_cast<uint32_t*>(p.z_out) + (size_t)node0 * kC + c * 16, kC, rows_valid, lane);
         if (p.psum && !uniform && valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(p.psum + gph * kC + c * 16 + j, a1[j]);
@@ -696,7 +689,7 @@ extern "C" int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, co
   const int grid = gnn_grid(p.num_tiles);
   *nblk_out = grid;
   if (grid == 0) return 0;
-  const int smem_bytes = kAImg + kWImg + kLoadWarps * kSlotB + (kC + 8 * kC) * 4 + 256;
+  const int smem_bytes = kAImg + kWImg + kLoadWarps * kSlotB + (kC + 8 * kC) * 4 + 256 + 4 * kStage16Words * 4;
   {
     ProfScope prof(3, (cudaStream_t)stream);
     GNN_ACT_DISPATCH(act, {

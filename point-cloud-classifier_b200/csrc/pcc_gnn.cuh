@@ -57,6 +57,59 @@ __device__ __forceinline__ float actg(float z, float a) {
   return 1.f;
 }
 
+// ---- the same activations on packed pairs (f32x2): the polynomial parts of two elements per instruction, the tanh one
+// MUFU op per element.  Same formulas as actf / actg, so forward, backward and both code shapes agree.
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t spl2(float v) { return f32x2(v, v); }
+__device__ __forceinline__ uint64_t tanh2_fast(uint64_t x) {
+  float lo, hi;
+  f32x2_unpack(x, lo, hi);
+  return f32x2(tanh_fast(lo), tanh_fast(hi));
+}
+template <int ACT>
+__device__ __forceinline__ uint64_t actf2(uint64_t z) {
+  if (ACT == PCC_ACT_TANH) return tanh2_fast(z);
+  if (ACT == PCC_ACT_GELU) {
+    constexpr float c0 = 0.7978845608028654f;
+    const uint64_t t = tanh2_fast(mul2(z, ffma2(spl2(c0 * 0.044715f), mul2(z, z), spl2(c0))));
+    return mul2(z, ffma2(spl2(0.5f), t, spl2(0.5f)));
+  }
+  float lo, hi;
+  f32x2_unpack(z, lo, hi);
+  if (ACT == PCC_ACT_RELU) return f32x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+  return z;
+}
+// a = act(z), g = act'(z)
+template <int ACT>
+__device__ __forceinline__ void act_grad2(uint64_t z, uint64_t& a, uint64_t& g) {
+  if (ACT == PCC_ACT_TANH) {
+    a = tanh2_fast(z);
+    g = ffma2(mul2(a, spl2(-1.f)), a, spl2(1.f));
+  } else if (ACT == PCC_ACT_GELU) {
+    constexpr float c0 = 0.7978845608028654f;
+    const uint64_t z2 = mul2(z, z);
+    const uint64_t t = tanh2_fast(mul2(z, ffma2(spl2(c0 * 0.044715f), z2, spl2(c0))));
+    const uint64_t h = ffma2(spl2(0.5f), t, spl2(0.5f));                       // 0.5 (1 + t)
+    a = mul2(z, h);
+    // 0.5 z (1 - t^2) u' with u' = c0 (1 + 0.134145 z^2);  0.5 (1 - t^2) = 2 h (1 - h)
+    const uint64_t up2 = ffma2(spl2(2.f * c0 * 0.134145f), z2, spl2(2.f * c0));
+    const uint64_t omh = ffma2(h, spl2(-1.f), spl2(1.f));
+    g = ffma2(mul2(a, omh), up2, h);
+  } else if (ACT == PCC_ACT_RELU) {
+    float lo, hi;
+    f32x2_unpack(z, lo, hi);
+    a = f32x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+    g = f32x2(lo > 0.f ? 1.f : 0.f, hi > 0.f ? 1.f : 0.f);
+  } else {
+    a = z;
+    g = spl2(1.f);
+  }
+}
+
 // Sum over the 32 lanes of a warp of 32 per-lane values, transposed: afterwards v[0] of lane l holds the sum over
 // all lanes of their v[l] (31 shuffles instead of 160).
 template <int HALF>
@@ -94,12 +147,134 @@ __device__ __forceinline__ uint32_t img_chunk_off(int r, int col0) {
 
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
 
+// ---- reduction of the landed rows of a gather slot (conv forward, aggregation backward): lane owns 4 channels = 8
+// bytes of every 256-byte row.  Both gather kernels are issue bound (ncu: 60-65 % issue-slot utilisation, half of the
+// samples in this loop), so the loop is written for instruction count: packed f32x2 adds (3 instructions per bf16
+// pair: two unpacks, one add), two independent chains, and no weight broadcast when the graph is unweighted.
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bf2_to_f32x2(uint32_t u) { return f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)); }
+template <int ROWB>
+__device__ __forceinline__ void slot_reduce(const uint8_t* slot, int cnt, int lane, bool weighted, float cw, float (&acc)[4]) {
+  uint64_t a01 = f32x2(acc[0], acc[1]), a23 = f32x2(acc[2], acc[3]);
+  const uint8_t* p = slot + lane * 8;
+  if (!weighted) {
+    uint64_t b01 = 0ull, b23 = 0ull;
+    int u = 0;
+#pragma unroll 1
+    for (; u + 4 <= cnt; u += 4) {
+      const uint2 v0 = *reinterpret_cast<const uint2*>(p + u * ROWB);
+      const uint2 v1 = *reinterpret_cast<const uint2*>(p + (u + 1) * ROWB);
+      const uint2 v2 = *reinterpret_cast<const uint2*>(p + (u + 2) * ROWB);
+      const uint2 v3 = *reinterpret_cast<const uint2*>(p + (u + 3) * ROWB);
+      a01 = add2(a01, bf2_to_f32x2(v0.x)); a23 = add2(a23, bf2_to_f32x2(v0.y));
+      b01 = add2(b01, bf2_to_f32x2(v1.x)); b23 = add2(b23, bf2_to_f32x2(v1.y));
+      a01 = add2(a01, bf2_to_f32x2(v2.x)); a23 = add2(a23, bf2_to_f32x2(v2.y));
+      b01 = add2(b01, bf2_to_f32x2(v3.x)); b23 = add2(b23, bf2_to_f32x2(v3.y));
+    }
+#pragma unroll 1
+    for (; u < cnt; ++u) {
+      const uint2 v0 = *reinterpret_cast<const uint2*>(p + u * ROWB);
+      a01 = add2(a01, bf2_to_f32x2(v0.x)); a23 = add2(a23, bf2_to_f32x2(v0.y));
+    }
+    a01 = add2(a01, b01); a23 = add2(a23, b23);
+  } else {
+#pragma unroll 2
+    for (int u = 0; u < cnt; ++u) {
+      const uint2 v = *reinterpret_cast<const uint2*>(p + u * ROWB);
+      const float wu = __shfl_sync(0xffffffffu, cw, u);
+      const uint64_t w2 = f32x2(wu, wu);
+      a01 = ffma2(w2, bf2_to_f32x2(v.x), a01); a23 = ffma2(w2, bf2_to_f32x2(v.y), a23);
+    }
+  }
+  f32x2_unpack(a01, acc[0], acc[1]);
+  f32x2_unpack(a23, acc[2], acc[3]);
+}
+
 // bounded mbarrier wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 20000000000ll) __trap();
   }
+}
+
+// Coalesced row stores / loads for "thread = row" epilogues.  A lane that writes 32 consecutive words of its own row
+// straight to global memory makes every store instruction touch 32 different 128-byte lines (32 L1 wavefronts per
+// instruction — the epilogues of the first version were bound by exactly that).  Staged through a per-warp 4 KB shared
+// tile ([32 rows][8 chunks of 16 B], chunk index XOR-ed with row & 7), 8 lanes cover one row's 128 bytes and an
+// instruction touches 4 lines.  Both sides of the tile are bank-conflict free.
+constexpr int kStageWords = 32 * 32;
+__device__ __forceinline__ uint4* stage_chunk(uint32_t* stage, int r, int c) {
+  return reinterpret_cast<uint4*>(stage + r * 32 + ((c ^ (r & 7)) << 2));
+}
+// the lane's 32 words of row `lane` -> tile
+__device__ __forceinline__ void stage_put_row(uint32_t* stage, const uint32_t (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *stage_chunk(stage, lane, j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_get_row(uint32_t* stage, uint32_t (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 t = *stage_chunk(stage, lane, j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+// v[32]: the lane's 32 words of row `lane`; gdst: row 0 of the warp, first column of the chunk; ld in words
+__device__ __forceinline__ void warp_store_rows32(uint32_t* stage, const uint32_t (&v)[32], uint32_t* gdst, size_t ld,
+                                                  int rows_valid, int lane) {
+  stage_put_row(stage, v, lane);
+  __syncwarp();
+  const int rsub = lane >> 3, c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    const uint4 t = *stage_chunk(stage, r, c);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gdst + (size_t)r * ld + 4 * c) = t;
+  }
+  __syncwarp();
+}
+// 16-word rows (2 KB tile) for kernels without 4 KB of shared memory per epilogue warp: 4 lanes per row, 8 lines per
+// instruction
+constexpr int kStage16Words = 32 * 16;
+__device__ __forceinline__ uint4* stage16_chunk(uint32_t* stage, int r, int c) {
+  return reinterpret_cast<uint4*>(stage + r * 16 + ((c ^ ((r >> 1) & 3)) << 2));
+}
+__device__ __forceinline__ void warp_store_rows16(uint32_t* stage, const uint32_t (&v)[16], uint32_t* gdst, size_t ld,
+                                                  int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *stage16_chunk(stage, lane, j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + rsub;
+    const uint4 t = *stage16_chunk(stage, r, c);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gdst + (size_t)r * ld + 4 * c) = t;
+  }
+  __syncwarp();
+}
+// the mirror, in two steps so that the global loads can be issued early: (1) coalesced loads into registers
+// (pre[i] = 16 bytes of row 4i + lane/8), (2) through the tile to the lane that owns the row
+__device__ __forceinline__ void warp_prefetch_rows32(uint4 (&pre)[8], const uint32_t* gsrc, size_t ld, int rows_valid, int lane) {
+  const int rsub = lane >> 3, c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) pre[i] = __ldg(reinterpret_cast<const uint4*>(gsrc + (size_t)r * ld + 4 * c));
+  }
+}
+__device__ __forceinline__ void warp_deliver_rows32(uint32_t* stage, const uint4 (&pre)[8], uint32_t (&v)[32], int lane) {
+  const int rsub = lane >> 3, c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *stage_chunk(stage, 4 * i + rsub, c) = pre[i];
+  __syncwarp();
+  stage_get_row(stage, v, lane);
+  __syncwarp();
 }
 
 struct GnnGraph {

@@ -92,7 +92,7 @@ struct Fc1BwdParams {
   const float* z_prev;         // z2 [M,C]
   const float* mu_prev;        // bn2 mean [C]
   const float* r_prev;         // bn2 invstd [C]
-  float* dh_out;               // dh2 [M,C] fp32
+  __nv_bfloat16* dh_out;       // dh2 [M,C] bf16 (a GEMM-operand-like gradient: conv_bwd rounds dz to bf16 right after)
   float* stat_part;            // [grid][2][C]
   float* dw_part;              // [grid][256][C]
   float* db_part;              // [grid][256]
@@ -126,11 +126,16 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
     mbar_arrive_expect_tx(wbar, kFcWImgB);
     for (int s = 0; s < 4; ++s) bulk_g2s(Wimg + s * (kFcWImgB / 4), p.wimg + (size_t)s * (kFcWImgB / 4), kFcWImgB / 4, wbar);
   }
+  // folded constants: da3 = gs - kap - lam (a - mu3) r3 = gs - K1 - K2 a  with K2 = lam r3, K1 = kap - K2 mu3;
+  //                   xhat2 = (a - mu2) r2 = a r2 + M2               with M2 = -mu2 r2        (stored: b, -K1, -K2, M2, r2)
   for (int i = threadIdx.x; i < kFc; i += kFbThreads) {
-    cst[i] = __ldg(p.bias + i); cst[kFc + i] = __ldg(p.kap + i); cst[2 * kFc + i] = __ldg(p.lam + i);
-    cst[3 * kFc + i] = __ldg(p.mu3 + i); cst[4 * kFc + i] = __ldg(p.r3 + i);
+    const float k2 = __ldg(p.lam + i) * __ldg(p.r3 + i);
+    cst[i] = __ldg(p.bias + i); cst[kFc + i] = k2 * __ldg(p.mu3 + i) - __ldg(p.kap + i); cst[2 * kFc + i] = -k2;
   }
-  for (int i = threadIdx.x; i < kC; i += kFbThreads) { cst[5 * kFc + i] = __ldg(p.mu_prev + i); cst[5 * kFc + kC + i] = __ldg(p.r_prev + i); }
+  for (int i = threadIdx.x; i < kC; i += kFbThreads) {
+    const float r = __ldg(p.r_prev + i);
+    cst[5 * kFc + i] = -__ldg(p.mu_prev + i) * r; cst[5 * kFc + kC + i] = r;
+  }
   if (warp == kFbMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -200,13 +205,13 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
     // ===================== epilogue warps 4-19: lane quarter q, 32-column group cg of every 128-column phase
     const int q = warp & 3, cg = (warp - kFbEpiWarp0) >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const float* b3 = cst; const float* kap = cst + kFc; const float* lam = cst + 2 * kFc;
-    const float* mu3 = cst + 3 * kFc; const float* r3 = cst + 4 * kFc;
-    const float* mu2 = cst + 5 * kFc; const float* r2 = cst + 5 * kFc + kC;
+    const float* b3 = cst; const float* nK1 = cst + kFc; const float* nK2 = cst + 2 * kFc;   // -K1, -K2
+    const float* M2 = cst + 5 * kFc; const float* r2 = cst + 5 * kFc + kC;
     float st2[2][2], db3[2][2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) { st2[c][0] = st2[c][1] = 0.f; db3[0][c] = db3[1][c] = 0.f; }
     const int row = q * 32 + lane;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(Dimg + cg * kSlab + q * 32 * 128);   // 4 KB: rows of this quarter, slab cg
     int it = 0;
     uint32_t use = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -233,12 +238,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
           tmem_wait_ld();
           float dz[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 16; j += 2) {
             const int col = col0 + j;
-            const float z = __uint_as_float(v[j]) + b3[col];
-            const float a = actf<ACT>(z);
-            const float da = gq[c * 16 + j] - kap[col] - lam[col] * (a - mu3[col]) * r3[col];
-            dz[j] = valid ? da * actg<ACT>(z, a) : 0.f;
+            const uint64_t z = add2(f32x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), *reinterpret_cast<const uint64_t*>(b3 + col));
+            uint64_t a, g;
+            act_grad2<ACT>(z, a, g);
+            const uint64_t da = ffma2(*reinterpret_cast<const uint64_t*>(nK2 + col), a,
+                                      add2(f32x2(gq[c * 16 + j], gq[c * 16 + j + 1]), *reinterpret_cast<const uint64_t*>(nK1 + col)));
+            f32x2_unpack(mul2(da, g), dz[j], dz[j + 1]);
+            if (!valid) dz[j] = dz[j + 1] = 0.f;
           }
           *reinterpret_cast<uint4*>(Dimg + img_chunk_off(row, col0)) =
               make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
@@ -251,17 +259,19 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
       }
       fence_proxy_async();
       mbar_arrive_warp(dz_ready);
-      // ---- dh2 of the tile: TMEM -> HBM (fp32) + the two column sums the bn2 backward needs; the z2 values of this
-      //      thread's columns are fetched while the dh / dW MMAs run
-      float zp[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) t4 = __ldg(reinterpret_cast<const float4*>(p.z_prev + (size_t)node * kC + cg * 32) + j);
-        zp[4 * j] = t4.x; zp[4 * j + 1] = t4.y; zp[4 * j + 2] = t4.z; zp[4 * j + 3] = t4.w;
-      }
+      // ---- dh2 of the tile: TMEM -> HBM (fp32) + the two column sums the bn2 backward needs.  The z2 values are
+      //      fetched coalesced (8 lanes per row) while the dh / dW MMAs run and handed to the row's lane through the
+      //      warp's staging tile; dh2 leaves the same way.  The tile lives in the dZ image, which is idle between the
+      //      MMAs of this tile (dh_full) and the next tile's dz stores; the warps of a lane quarter write each other's
+      //      staging bytes then, hence the quarter barrier at the end.
+      const int64_t node0 = tile * kTile + q * 32;
+      const int rows_valid = (int)((p.M - node0) < 32 ? (p.M - node0 < 0 ? 0 : p.M - node0) : 32);
+      uint4 pre[8];
+      warp_prefetch_rows32(pre, reinterpret_cast<const uint32_t*>(p.z_prev) + (size_t)node0 * kC + cg * 32, kC, rows_valid, lane);
       mbar_wait_b(dh_full, (uint32_t)(it & 1));
       tc_fence_after();
+      uint32_t zp[32], out[32];
+      warp_deliver_rows32(stage, pre, zp, lane);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = cg * 32 + c * 16;
@@ -270,20 +280,25 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
         tmem_wait_ld();
         float s1[16], s2[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float dh = valid ? __uint_as_float(v[j]) : 0.f;
-          const float xh = (actf<ACT>(zp[c * 16 + j]) - mu2[col0 + j]) * r2[col0 + j];
-          s1[j] = dh;
-          s2[j] = dh * xh;
-        }
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(p.dh_out + (size_t)node * kC + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_float4(s1[4 * j], s1[4 * j + 1], s1[4 * j + 2], s1[4 * j + 3]);
+        for (int j = 0; j < 16; j += 2) {
+          const uint64_t dh = valid ? f32x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])) : 0ull;
+          const uint64_t a = actf2<ACT>(f32x2(__uint_as_float(zp[c * 16 + j]), __uint_as_float(zp[c * 16 + j + 1])));
+          const uint64_t xh = ffma2(a, *reinterpret_cast<const uint64_t*>(r2 + col0 + j), *reinterpret_cast<const uint64_t*>(M2 + col0 + j));
+          f32x2_unpack(dh, s1[j], s1[j + 1]);
+          f32x2_unpack(mul2(dh, xh), s2[j], s2[j + 1]);
+          out[c * 16 + j] = __float_as_uint(s1[j]);
+          out[c * 16 + j + 1] = __float_as_uint(s1[j + 1]);
         }
         st2[c][0] += warp_transpose_sum16(s1, lane);
         st2[c][1] += warp_transpose_sum16(s2, lane);
       }
+      {
+        uint32_t w16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w16[j] = pack_bf16x2(__uint_as_float(out[2 * j]), __uint_as_float(out[2 * j + 1]));
+        warp_store_rows16(stage, w16, reinterpret_cast<uint32_t*>(p.dh_out) + (size_t)node0 * (kC / 2) + cg * 16, kC / 2, rows_valid, lane);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + q) : "memory");
       tc_fence_before();
       mbar_arrive_warp(dh_free);
     }
@@ -332,22 +347,26 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
 }
 
 // ====================================================================== conv2 backward
-constexpr int kCbLoadWarps = 16, kCbEpiWarp0 = 16, kCbMmaWarp = 20, kCbThreads = 21 * 32;
+// 8 prologue warps (16 rows of every tile each, register-pipelined loads) + 4 epilogue warps (the first one also issues
+// the MMAs): 384 threads, so that a prologue thread can hold two batches of 4 rows (96 registers of operands) in flight
+constexpr int kCbLoadWarps = 8, kCbMmaWarp = 8, kCbThreads = 12 * 32;
+constexpr int kCbBatch = 4, kCbBatches = kTile / kCbLoadWarps / kCbBatch;   // 4 batches of 4 rows per warp and tile
 constexpr uint32_t kDz2Img = kC * kTile * 2;          // 32 KB: [128 rows][C cols]
 constexpr uint32_t kAinImg = 2 * kC * kTile * 2;      // 64 KB: [128 rows][2C cols]
 constexpr uint32_t kCwImg = 2 * kC * kC * 2;          // 64 KB
 
 struct ConvBwdParams {
   const int64_t* membership;   // with dh_graph: graph of every node
-  const float* dh_graph;       // optional [B,C]: dL/dh is the same row for every node of a graph (global_mean_pool follows the block)
-  const float* dh;             // dL/dh of this block's output [M,C] fp32
+  const float* dh_graph;       // optional [B,C] fp32: dL/dh is the same row for every node of a graph (global_mean_pool follows
+                               // the block).  Kept in fp32: a rounding error shared by all nodes of a graph does not average out.
+  const __nv_bfloat16* dh;     // dL/dh of this block's output [M,C] bf16
   const float* z;              // pre-activation of this block [M,C]
   BnBack bn;                   // [C] arrays
   const __nv_bfloat16* agg;    // [M,C] kept aggregate (A operand, left half)
   const __nv_bfloat16* h_in;   // [M,C] block input (A operand, right half)
   const uint8_t* wimg;         // [C][2C] image
   __nv_bfloat16* dagg_out;     // [M,C] bf16
-  float* droot_out;            // [M,C] fp32
+  __nv_bfloat16* droot_out;    // [M,C] bf16
   float* dw_part;              // [grid][C][2C]
   float* db_part;              // [grid][C]
   int64_t M, num_tiles;
@@ -360,14 +379,15 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
   uint8_t* Aimg = smem + kDz2Img;                  // 64 KB
   uint8_t* Wimg = smem + kDz2Img + kAinImg;        // 64 KB
   float* cst = reinterpret_cast<float*>(smem + kDz2Img + kAinImg + kCwImg);   // [5][C]
-  float* scratch = cst + 5 * kC;                                              // [16][C] db
+  float* scratch = cst + 5 * kC;                                              // [kCbLoadWarps][C] db
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kCbLoadWarps * kC);
-  uint64_t* full = bars;        // 16 warps
+  uint64_t* full = bars;        // prologue warps
   uint64_t* empty = bars + 1;   // MMA commit
   uint64_t* dx_full = bars + 2;
   uint64_t* dx_free = bars + 3; // 4 warps
   uint64_t* wbar = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint32_t* stage_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [4 warps] 4 KB staging tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(full, kCbLoadWarps); mbar_init(empty, 1); mbar_init(dx_full, 1); mbar_init(dx_free, 4); mbar_init(wbar, 1);
@@ -394,21 +414,37 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
     const float4 sc = *reinterpret_cast<const float4*>(cst + 2 * kC + col), c1 = *reinterpret_cast<const float4*>(cst + 3 * kC + col);
     const float4 c2 = *reinterpret_cast<const float4*>(cst + 4 * kC + col);
     float db[4] = {0.f, 0.f, 0.f, 0.f};
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      if (it >= 1) mbar_wait_b(empty, (uint32_t)((it - 1) & 1));
-#pragma unroll 4
-      for (int i = 0; i < kTile / kCbLoadWarps; ++i) {
-        const int r = warp + kCbLoadWarps * i;
+    // The loop is bound by load latency, not by bytes or instructions (ncu of the first version: 13 % issue utilisation,
+    // half of the samples on the first use of a loaded value, and no load in flight while the warps waited for the MMAs to
+    // release the images).  So the operands of a batch of 4 rows are loaded into registers one batch AHEAD of their use,
+    // across the wait for the images: batch 0 of the next tile is in flight while this tile's MMAs run.
+    struct Rows { float4 z[kCbBatch]; uint2 g[kCbBatch], ag[kCbBatch], hr[kCbBatch]; };
+    auto load_batch = [&](int64_t tile, int b, Rows& R) {
+#pragma unroll
+      for (int j = 0; j < kCbBatch; ++j) {
+        const int r = warp + kCbLoadWarps * (b * kCbBatch + j);
+        const int64_t node = tile * kTile + r;
+        R.z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.g[j] = R.ag[j] = R.hr[j] = make_uint2(0u, 0u);
+        if (node < p.M) {
+          if (p.dh_graph) R.g[j].x = (uint32_t)__ldg(p.membership + node);   // the row itself is read at use (L1-resident table)
+          else R.g[j] = __ldg(reinterpret_cast<const uint2*>(p.dh + (size_t)node * kC) + lane);
+          R.z[j] = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)node * kC) + lane);
+          R.ag[j] = __ldg(reinterpret_cast<const uint2*>(p.agg + (size_t)node * kC) + lane);
+          R.hr[j] = __ldg(reinterpret_cast<const uint2*>(p.h_in + (size_t)node * kC) + lane);
+        }
+      }
+    };
+    auto process_batch = [&](int64_t tile, int b, const Rows& R) {
+#pragma unroll
+      for (int j = 0; j < kCbBatch; ++j) {
+        const int r = warp + kCbLoadWarps * (b * kCbBatch + j);
         const int64_t node = tile * kTile + r;
         float dz[4] = {0.f, 0.f, 0.f, 0.f};
-        uint2 ag = make_uint2(0u, 0u), hr = make_uint2(0u, 0u);
         if (node < p.M) {
-          const float4 g = p.dh_graph ? __ldg(reinterpret_cast<const float4*>(p.dh_graph + (size_t)__ldg(p.membership + node) * kC) + lane)
-                                      : __ldg(reinterpret_cast<const float4*>(p.dh + (size_t)node * kC) + lane);
-          const float4 z = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)node * kC) + lane);
-          ag = __ldg(reinterpret_cast<const uint2*>(p.agg + (size_t)node * kC) + lane);
-          hr = __ldg(reinterpret_cast<const uint2*>(p.h_in + (size_t)node * kC) + lane);
+          const float4 z = R.z[j];
+          const float4 g = p.dh_graph ? __ldg(reinterpret_cast<const float4*>(p.dh_graph + (size_t)R.g[j].x * kC) + lane)
+                                      : make_float4(bf16_lo(R.g[j].x), bf16_hi(R.g[j].x), bf16_lo(R.g[j].y), bf16_hi(R.g[j].y));
           float a;
           a = actf<ACT>(z.x); dz[0] = sc.x * (g.x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(z.x, a);
           a = actf<ACT>(z.y); dz[1] = sc.y * (g.y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(z.y, a);
@@ -418,74 +454,84 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
         db[0] += dz[0]; db[1] += dz[1]; db[2] += dz[2]; db[3] += dz[3];
         *reinterpret_cast<uint2*>(Dimg + img_chunk_off(r, col) + ((col & 7) << 1)) =
             make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
-        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, col) + ((col & 7) << 1)) = ag;
-        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, kC + col) + ((col & 7) << 1)) = hr;
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, col) + ((col & 7) << 1)) = R.ag[j];
+        *reinterpret_cast<uint2*>(Aimg + img_chunk_off(r, kC + col) + ((col & 7) << 1)) = R.hr[j];
       }
+    };
+    static_assert(kCbBatches == 4, "the pipeline below is written for 4 batches per tile");
+    Rows RA, RB;
+    if ((int64_t)blockIdx.x < p.num_tiles) load_batch(blockIdx.x, 0, RA);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (it >= 1) mbar_wait_b(empty, (uint32_t)((it - 1) & 1));
+      load_batch(tile, 1, RB); process_batch(tile, 0, RA);
+      load_batch(tile, 2, RA); process_batch(tile, 1, RB);
+      load_batch(tile, 3, RB); process_batch(tile, 2, RA);
+      if (tile + gridDim.x < p.num_tiles) load_batch(tile + gridDim.x, 0, RA);
+      process_batch(tile, 3, RB);
       fence_proxy_async();
       mbar_arrive_warp(full);
     }
     *reinterpret_cast<float4*>(scratch + warp * kC + col) = make_float4(db[0], db[1], db[2], db[3]);
-    asm volatile("bar.sync 3, 512;" ::: "memory");
+    asm volatile("bar.sync 3, %0;" ::"n"(kCbLoadWarps * 32) : "memory");
     for (int i = threadIdx.x; i < kC; i += kCbLoadWarps * 32) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < kCbLoadWarps; ++w) s += scratch[w * kC + i];
       p.db_part[(size_t)blockIdx.x * kC + i] = s;
     }
-  } else if (warp == kCbMmaWarp) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC_DX = make_idesc_bf16(128, 2 * kC, 0, 1);   // [128 rows] x [2C in]: dZ (K-major) x W viewed [in x out]
-      constexpr uint32_t IDESC_DW = make_idesc_bf16(128, 2 * kC, 1, 1);   // [C out] x [2C in]: dZ^T x [agg | h]
-      mbar_wait_b(wbar, 0);
-      const uint32_t d_base = smem_u32(Dimg), a_base = smem_u32(Aimg), w_base = smem_u32(Wimg);
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait_b(full, (uint32_t)(it & 1));
-        if (it >= 1) mbar_wait_b(dx_free, (uint32_t)((it - 1) & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < kC / 16; ++ks)
-          umma_bf16(tmem + T_DX, make_smem_desc_sw128_k(d_base + (ks >> 2) * kSlab + (ks & 3) * 32),
-                    make_smem_desc_sw128_mn(w_base + ks * 2048, kC * 128), IDESC_DX, ks != 0);
-#pragma unroll
-        for (int ks = 0; ks < kTile / 16; ++ks)
-          umma_bf16(tmem + T_DW, make_smem_desc_sw128_mn(d_base + ks * 2048, kSlab),
-                    make_smem_desc_sw128_mn(a_base + ks * 2048, kSlab), IDESC_DW, (it | ks) != 0);
-        umma_commit(empty);
-        umma_commit(dx_full);
-      }
-    }
   } else {
-    // ===================== epilogue warps 16-19: dX accumulator -> dagg (bf16) | droot (fp32)
+    // ===================== epilogue warps 8-11: dX accumulator -> dagg (bf16) | droot (fp32)
     const int q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int row = q * 32 + lane;
+    uint32_t* stage = stage_all + q * kStageWords;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int64_t node = tile * kTile + row;
-      const bool valid = node < p.M;
+      const int64_t node0 = tile * kTile + q * 32;
+      const int rows_valid = (int)((p.M - node0) < 32 ? (p.M - node0 < 0 ? 0 : p.M - node0) : 32);
+      if (warp == kCbMmaWarp) {
+        // The dX accumulator is single-buffered, so the MMAs of a tile can only start after the epilogue of the previous
+        // one: the first epilogue warp issues them itself (a dedicated issuer warp would only push the CTA over 12 warps
+        // and the prologue threads under the registers their load pipeline needs).
+        if (lane == 0) {
+          constexpr uint32_t IDESC_DX = make_idesc_bf16(128, 2 * kC, 0, 1);   // [128 rows] x [2C in]: dZ (K-major) x W viewed [in x out]
+          constexpr uint32_t IDESC_DW = make_idesc_bf16(128, 2 * kC, 1, 1);   // [C out] x [2C in]: dZ^T x [agg | h]
+          const uint32_t d_base = smem_u32(Dimg), a_base = smem_u32(Aimg), w_base = smem_u32(Wimg);
+          if (it == 0) mbar_wait_b(wbar, 0);
+          mbar_wait_b(full, (uint32_t)(it & 1));
+          if (it >= 1) mbar_wait_b(dx_free, (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < kC / 16; ++ks)
+            umma_bf16(tmem + T_DX, make_smem_desc_sw128_k(d_base + (ks >> 2) * kSlab + (ks & 3) * 32),
+                      make_smem_desc_sw128_mn(w_base + ks * 2048, kC * 128), IDESC_DX, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < kTile / 16; ++ks)
+            umma_bf16(tmem + T_DW, make_smem_desc_sw128_mn(d_base + ks * 2048, kSlab),
+                      make_smem_desc_sw128_mn(a_base + ks * 2048, kSlab), IDESC_DW, (it | ks) != 0);
+          umma_commit(empty);
+          umma_commit(dx_full);
+        }
+        __syncwarp();
+      }
       mbar_wait_b(dx_full, (uint32_t)(it & 1));
       tc_fence_after();
+      // [dagg | droot]: 64 columns (two TMEM chunks) -> 32 packed bf16 words per row, stored through the warp's staging
+      // tile so that an instruction writes whole 128-byte row segments.
 #pragma unroll
-      for (int c = 0; c < 2 * kC / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + T_DX + c * 32, v);
+      for (int c = 0; c < 2 * kC / 64; ++c) {
+        uint32_t v[32], w[32];
+        tmem_ld32(lane_base + T_DX + c * 64, v);
         tmem_wait_ld();
-        if (!valid) continue;
-        if (c < kC / 32) {
-          uint4* dst = reinterpret_cast<uint4*>(p.dagg_out + (size_t)node * kC + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-        } else {
-          float4* dst = reinterpret_cast<float4*>(p.droot_out + (size_t)node * kC + (c - kC / 32) * 32);
+        for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        tmem_ld32(lane_base + T_DX + c * 64 + 32, v);
+        tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
+        for (int j = 0; j < 16; ++j) w[16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        __nv_bfloat16* dst = (c < kC / 64) ? p.dagg_out : p.droot_out;
+        warp_store_rows32(stage, w, reinterpret_cast<uint32_t*>(dst) + (size_t)node0 * (kC / 2) + (c & 1) * 32, kC / 2, rows_valid, lane);
       }
       tc_fence_before();
       mbar_arrive_warp(dx_free);
@@ -498,10 +544,7 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
         uint32_t v[32];
         tmem_ld32(lane_base + T_DW + c * 32, v);
         tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<float4*>(dst + c * 32)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        warp_store_rows32(stage, v, reinterpret_cast<uint32_t*>(dst - (size_t)lane * (2 * kC)) + c * 32, 2 * kC, 32, lane);
       }
     } else {
       for (int j = 0; j < 2 * kC; ++j) dst[j] = 0.f;
@@ -521,7 +564,7 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
 constexpr int kAggSlotRows = 22;
 constexpr uint32_t kAggRowB = kC * 2, kAggSlotB = kAggSlotRows * kAggRowB;
 template <int ACT>
-__global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* __restrict__ dagg, GnnGraph g, float* __restrict__ dh,
+__global__ void __launch_bounds__(256, 3) gnn_agg_bwd_kernel(const __nv_bfloat16* __restrict__ dagg, GnnGraph g, __nv_bfloat16* __restrict__ dh,
                                                           const float* __restrict__ z_prev, const float* __restrict__ mu_prev,
                                                           const float* __restrict__ r_prev, int64_t M, float* __restrict__ partials) {
   extern __shared__ __align__(128) uint8_t smem_agg[];
@@ -540,17 +583,35 @@ __global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* _
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   int64_t node = (int64_t)blockIdx.x * 8 + warp;
-  // ids of the first node's first chunk
-  int64_t pb = 0, pe = 0;
-  if (node < M) { pb = __ldg(g.rowptr + node); pe = __ldg(g.rowptr + node + 1); }
-  int cnt = (int)((pe - pb < kAggSlotRows) ? pe - pb : kAggSlotRows);
+  // Software pipeline over the warp's nodes (the loop is a chain of dependent global loads otherwise — row pointers ->
+  // neighbour ids -> rows, and the node's own dh / z rows; ncu showed ~20 % of the samples on their first uses): the row
+  // pointers are loaded TWO nodes ahead, the node's dh / z rows and the neighbour ids ONE node ahead.
+  int pb = 0, pe = 0, nb = 0, ne = 0;     // [pb, pe): this node's CSR slots, [nb, ne): the next node's  (E < 2^31)
+  if (node < M) { pb = (int)__ldg(g.rowptr + node); pe = (int)__ldg(g.rowptr + node + 1); }
+  if (node + nwarps < M) { nb = (int)__ldg(g.rowptr + node + nwarps); ne = (int)__ldg(g.rowptr + node + nwarps + 1); }
+  int cnt = (pe - pb < kAggSlotRows) ? pe - pb : kAggSlotRows;
   int myc = lane < cnt ? __ldg(g.col + pb + lane) : 0;
   float myw = (g.w && lane < cnt) ? __ldg(g.w + pb + lane) : 1.f;
+  uint2 dh_next = make_uint2(0u, 0u);
+  float4 z_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (node < M) {
+    dh_next = *(reinterpret_cast<const uint2*>(dh + (size_t)node * kC) + lane);
+    z_next = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)node * kC) + lane);
+  }
   for (; node < M; node += nwarps) {
-    float4 acc = *(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
-    const float4 z = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)node * kC) + lane);
-    const int64_t deg = pe - pb;
-    int64_t done = 0;
+    const uint2 acc0 = dh_next;
+    const float4 z = z_next;
+    int n2b = 0, n2e = 0;
+    if (node + nwarps < M) {
+      // (every node is read and written by exactly one warp, once: the early read of the next node's dh is safe)
+      dh_next = *(reinterpret_cast<const uint2*>(dh + (size_t)(node + nwarps) * kC) + lane);
+      z_next = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)(node + nwarps) * kC) + lane);
+      if (node + 2 * nwarps < M) { n2b = (int)__ldg(g.rowptr + node + 2 * nwarps); n2e = (int)__ldg(g.rowptr + node + 2 * nwarps + 1); }
+    }
+    float acc[4];
+    bool first = true;
+    const int deg = pe - pb;
+    int done = 0;
     for (;;) {
       if (cnt > 0) {
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * kAggRowB);
@@ -560,33 +621,27 @@ __global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* _
       const int ccnt = cnt;
       const float cw = myw;
       done += cnt;
-      int64_t npb = pb + done, npe = pe;
       const bool next_node = done >= deg;
-      if (next_node) {
-        npb = npe = 0;
-        if (node + nwarps < M) { npb = __ldg(g.rowptr + node + nwarps); npe = __ldg(g.rowptr + node + nwarps + 1); }
-      }
-      cnt = (int)((npe - npb < kAggSlotRows) ? npe - npb : kAggSlotRows);
+      const int npb = next_node ? nb : pb + done, npe = next_node ? ne : pe;
+      cnt = (npe - npb < kAggSlotRows) ? npe - npb : kAggSlotRows;
       myc = lane < cnt ? __ldg(g.col + npb + lane) : 0;
       myw = (g.w && lane < cnt) ? __ldg(g.w + npb + lane) : 1.f;
+      if (first) {
+        acc[0] = bf16_lo(acc0.x); acc[1] = bf16_hi(acc0.x); acc[2] = bf16_lo(acc0.y); acc[3] = bf16_hi(acc0.y);
+        first = false;
+      }
       if (ccnt > 0) {
         mbar_wait_b(bar, gphase);
         gphase ^= 1;
-#pragma unroll 2
-        for (int u = 0; u < ccnt; ++u) {
-          const uint2 v = *reinterpret_cast<const uint2*>(slot + u * kAggRowB + lane * 8);
-          const float wu = __shfl_sync(0xffffffffu, cw, u);
-          acc.x = fmaf(wu, bf16_lo(v.x), acc.x); acc.y = fmaf(wu, bf16_hi(v.x), acc.y);
-          acc.z = fmaf(wu, bf16_lo(v.y), acc.z); acc.w = fmaf(wu, bf16_hi(v.y), acc.w);
-        }
+        slot_reduce<(int)kAggRowB>(slot, ccnt, lane, g.w != nullptr, cw, acc);
         __syncwarp();
       }
-      if (next_node) { pb = npb; pe = npe; break; }
+      if (next_node) { pb = nb; pe = ne; nb = n2b; ne = n2e; break; }
     }
-    *(reinterpret_cast<float4*>(dh + (size_t)node * kC) + lane) = acc;
-    s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
-    s2[0] += acc.x * (actf<ACT>(z.x) - mu.x) * rs.x; s2[1] += acc.y * (actf<ACT>(z.y) - mu.y) * rs.y;
-    s2[2] += acc.z * (actf<ACT>(z.z) - mu.z) * rs.z; s2[3] += acc.w * (actf<ACT>(z.w) - mu.w) * rs.w;
+    *(reinterpret_cast<uint2*>(dh + (size_t)node * kC) + lane) = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
+    s1[0] += acc[0]; s1[1] += acc[1]; s1[2] += acc[2]; s1[3] += acc[3];
+    s2[0] += acc[0] * (actf<ACT>(z.x) - mu.x) * rs.x; s2[1] += acc[1] * (actf<ACT>(z.y) - mu.y) * rs.y;
+    s2[2] += acc[2] * (actf<ACT>(z.z) - mu.z) * rs.z; s2[3] += acc[3] * (actf<ACT>(z.w) - mu.w) * rs.w;
   }
   *reinterpret_cast<float4*>(&red[(warp * 2 + 0) * kC + 4 * lane]) = make_float4(s1[0], s1[1], s1[2], s1[3]);
   *reinterpret_cast<float4*>(&red[(warp * 2 + 1) * kC + 4 * lane]) = make_float4(s2[0], s2[1], s2[2], s2[3]);
@@ -603,7 +658,7 @@ __global__ void __launch_bounds__(256) gnn_agg_bwd_kernel(const __nv_bfloat16* _
 // dz1 = s (dh - c1 - xhat c2) act'(z1);  dW_rel1[c,f] += dz1[c] agg1[f],  dW_root1[c,f] += dz1[c] x[f],  db1[c] += dz1[c]
 // per-block partial [C][2F+1] (rel | root | bias).
 template <int ACT, int FP>
-__global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z, BnBack bn,
+__global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ z, BnBack bn,
                                                             const float* __restrict__ agg, const float* __restrict__ x, int F,
                                                             int64_t M, float* __restrict__ partials) {
   extern __shared__ float red1[];   // [8][C][2 FP + 1]
@@ -621,17 +676,19 @@ __global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const float* __restr
   // two nodes per iteration: their row loads are independent (the loop is bound by load latency otherwise)
   for (int64_t node0 = (int64_t)blockIdx.x * 8 + warp; node0 < M; node0 += 2 * nwarps) {
     float4 g[2], zz[2];
+    uint2 gb[2];
     float in[2][2 * FP];
     bool ok[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int64_t node = node0 + h * nwarps;
       ok[h] = node < M;
-      g[h] = zz[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zz[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gb[h] = make_uint2(0u, 0u);
 #pragma unroll
       for (int f = 0; f < 2 * FP; ++f) in[h][f] = 0.f;
       if (ok[h]) {
-        g[h] = __ldg(reinterpret_cast<const float4*>(dh + (size_t)node * kC) + lane);
+        gb[h] = __ldg(reinterpret_cast<const uint2*>(dh + (size_t)node * kC) + lane);
         zz[h] = __ldg(reinterpret_cast<const float4*>(z + (size_t)node * kC) + lane);
 #pragma unroll
         for (int f = 0; f < FP; ++f)
@@ -641,6 +698,7 @@ __global__ void __launch_bounds__(256) gnn_conv1_bwd_kernel(const float* __restr
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (!ok[h]) continue;
+      g[h] = make_float4(bf16_lo(gb[h].x), bf16_hi(gb[h].x), bf16_lo(gb[h].y), bf16_hi(gb[h].y));
       float dz[4], a;
       a = actf<ACT>(zz[h].x); dz[0] = sc.x * (g[h].x - c1.x - (a - mu.x) * rs.x * c2.x) * actg<ACT>(zz[h].x, a);
       a = actf<ACT>(zz[h].y); dz[1] = sc.y * (g[h].y - c1.y - (a - mu.y) * rs.y * c2.y) * actg<ACT>(zz[h].y, a);
@@ -703,7 +761,7 @@ extern "C" int pcc_gnn_reduce(const float* part, int nblk, int64_t count, float*
 extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership,
                                const float* gs, const float* kap, const float* lam, const float* mu3, const float* r3,
                                const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M, int act,
-                               float* dh_out, float* stat_part, float* dw_part, float* db_part, int* nblk_out, int device,
+                               void* dh_out_bf16, float* stat_part, float* dw_part, float* db_part, int* nblk_out, int device,
                                void* stream) {
   PCC_ENTER(device);
   Fc1BwdParams p{};
@@ -711,7 +769,7 @@ extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const 
   p.wimg = (const uint8_t*)packed + 2 * kC * kC * 2;
   p.bias = bias; p.membership = membership; p.gs = gs; p.kap = kap; p.lam = lam; p.mu3 = mu3; p.r3 = r3;
   p.z_prev = z_prev; p.mu_prev = mu_prev; p.r_prev = r_prev;
-  p.dh_out = dh_out; p.stat_part = stat_part; p.dw_part = dw_part; p.db_part = db_part;
+  p.dh_out = (__nv_bfloat16*)dh_out_bf16; p.stat_part = stat_part; p.dw_part = dw_part; p.db_part = db_part;
   p.M = M; p.num_tiles = cdiv(M, kTile);
   const int grid = gnn_grid(p.num_tiles);
   *nblk_out = grid;
@@ -728,24 +786,24 @@ extern "C" int pcc_gnn_fc1_bwd(const void* h_in_bf16, const void* packed, const 
   return check_launch(__func__);
 }
 
-extern "C" int pcc_gnn_conv_bwd(const float* dh, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd,
+extern "C" int pcc_gnn_conv_bwd(const void* dh_bf16, const int64_t* membership, const float* dh_graph, const float* z, const float* bn_mean, const float* bn_invstd,
                                 const float* bn_scale, const float* bn_c1, const float* bn_c2, const void* agg_bf16,
                                 const void* h_in_bf16, const void* packed, int64_t M, int act, void* dagg_out_bf16,
-                                float* droot_out, float* dw_part, float* db_part, int* nblk_out, int device, void* stream) {
+                                void* droot_out_bf16, float* dw_part, float* db_part, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
-  PCC_REQUIRE((dh != nullptr) != (dh_graph != nullptr), "exactly one of dh / dh_graph");
+  PCC_REQUIRE((dh_bf16 != nullptr) != (dh_graph != nullptr), "exactly one of dh / dh_graph");
   PCC_REQUIRE(dh_graph == nullptr || membership != nullptr, "dh_graph needs the membership vector");
   ConvBwdParams p{};
-  p.dh = dh; p.z = z; p.membership = membership; p.dh_graph = dh_graph;
+  p.dh = (const __nv_bfloat16*)dh_bf16; p.z = z; p.membership = membership; p.dh_graph = dh_graph;
   p.bn = BnBack{bn_mean, bn_invstd, bn_scale, bn_c1, bn_c2};
   p.agg = (const __nv_bfloat16*)agg_bf16; p.h_in = (const __nv_bfloat16*)h_in_bf16;
   p.wimg = (const uint8_t*)packed;
-  p.dagg_out = (__nv_bfloat16*)dagg_out_bf16; p.droot_out = droot_out; p.dw_part = dw_part; p.db_part = db_part;
+  p.dagg_out = (__nv_bfloat16*)dagg_out_bf16; p.droot_out = (__nv_bfloat16*)droot_out_bf16; p.dw_part = dw_part; p.db_part = db_part;
   p.M = M; p.num_tiles = cdiv(M, kTile);
   const int grid = gnn_grid(p.num_tiles);
   *nblk_out = grid;
   if (grid == 0) return 0;
-  const int smem_bytes = kDz2Img + kAinImg + kCwImg + (5 * kC + kCbLoadWarps * kC) * 4 + 128;
+  const int smem_bytes = kDz2Img + kAinImg + kCwImg + (5 * kC + kCbLoadWarps * kC) * 4 + 128 + 4 * kStageWords * 4;
   {
     ProfScope prof(4, (cudaStream_t)stream);
     GNN_ACT_DISPATCH(act, {
@@ -758,7 +816,7 @@ extern "C" int pcc_gnn_conv_bwd(const float* dh, const int64_t* membership, cons
 }
 
 extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src, const int32_t* col_src, const float* w_src,
-                               float* dh_inout, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M,
+                               void* dh_inout_bf16, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M,
                                int act, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
   int blocks = (int)(cdiv(M, 8) < 592 ? cdiv(M, 8) : 592);
@@ -771,14 +829,14 @@ extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src,
     GNN_ACT_DISPATCH(act, {
       auto kern = gnn_agg_bwd_kernel<A>;
       PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, dh_inout, z_prev, mu_prev,
+      PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, (__nv_bfloat16*)dh_inout_bf16, z_prev, mu_prev,
                                                                      r_prev, M, partials);
     });
   }
   return check_launch(__func__);
 }
 
-extern "C" int pcc_gnn_conv1_bwd(const float* dh, const float* z, const float* bn_mean, const float* bn_invstd,
+extern "C" int pcc_gnn_conv1_bwd(const void* dh_bf16, const float* z, const float* bn_mean, const float* bn_invstd,
                                  const float* bn_scale, const float* bn_c1, const float* bn_c2, const float* agg, const float* x,
                                  int F, int64_t M, int act, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
@@ -791,7 +849,7 @@ extern "C" int pcc_gnn_conv1_bwd(const float* dh, const float* z, const float* b
   GNN_ACT_DISPATCH(act, {
     auto kern = F <= 4 ? gnn_conv1_bwd_kernel<A, 4> : gnn_conv1_bwd_kernel<A, 8>;
     PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>(dh, z, bn, agg, x, F, M, partials);
+    PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dh_bf16, z, bn, agg, x, F, M, partials);
   });
   return check_launch(__func__);
 }

@@ -107,6 +107,149 @@ __global__ void csrt_fill_kernel(const int32_t* __restrict__ col_d, const int64_
   col_s[pos] = (int32_t)t;
 }
 
+// ---- block-diagonal simple graphs (a kNN graph over a batch of clouds): one CTA per cloud, everything in shared memory.
+// Preconditions: uniform k slots per target, every neighbour of a node lies in the node's own cloud, no repeated edge
+// (violations trap: the caller built the graph).  Then the cloud's edges occupy the same slot range [o k, (o + nc) k)
+// in both CSRs and the transpose is local to the cloud:
+//   1. in-degree of every source: shared-memory histogram, block scan -> rowptr_s;
+//   2. for blocks of S sources: a bitmap [S][nc bits] over the targets, one atomicOr per edge, then warp = source
+//      enumerates the set bits of its row — ascending target order for free, no sort, no global atomics.  S = all sources of the cloud
+//      when nc <= ~1250 (one pass), fewer for larger clouds (several passes over the cloud's edge slots).
+// 256 clouds of 1024 points, k = 20: ~20 us against ~180 us for count + scan + fill + row sort in global memory.
+constexpr int kCsrtBlkThreads = 1024;
+constexpr int kCsrtMaxK = 32;
+constexpr int kCsrtBlkSmem = 200 * 1024;
+__global__ void __launch_bounds__(kCsrtBlkThreads, 1) csrt_block_kernel(const int32_t* __restrict__ col_d, int k,
+                                                                         const int64_t* __restrict__ offsets, int64_t n,
+                                                                         int64_t* __restrict__ rowptr_s, int32_t* __restrict__ col_s) {
+  extern __shared__ __align__(16) uint32_t csrt_smem[];
+  __shared__ int warp_tot[32];
+  const int64_t o = offsets[blockIdx.x];
+  const int nc = (int)(offsets[blockIdx.x + 1] - o);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) rowptr_s[n] = n * (int64_t)k;
+  if (nc <= 0) return;
+  const int W = (nc + 31) >> 5;                       // bitmap words per source row
+  int* cnt = reinterpret_cast<int*>(csrt_smem);       // [nc + 1] in-degree, then exclusive offsets
+  uint32_t* bm = csrt_smem + ((nc + 1 + 3) & ~3);
+  const int avail_words = kCsrtBlkSmem / 4 - ((nc + 1 + 3) & ~3);
+  if (avail_words < W) __trap();                      // cloud beyond ~50k points
+  const int S = avail_words / W < nc ? avail_words / W : nc;
+  const int tid = threadIdx.x;
+  const int64_t e0 = o * (int64_t)k;
+  // ---- 1. in-degrees
+  for (int i = tid; i <= nc; i += kCsrtBlkThreads) cnt[i] = 0;
+  __syncthreads();
+  // thread = target: its k <= 32 slots are loaded in one go (all loads in flight before the first shared-memory atomic;
+  // a load-atomic-load-atomic loop exposes every load's latency) and, for clouds of up to 1024 points, stay in
+  // registers for the bitmap pass
+  int v[kCsrtMaxK];
+  for (int t = tid; t < nc; t += kCsrtBlkThreads) {
+    const int32_t* slots = col_d + e0 + (int64_t)t * k;
+#pragma unroll
+    for (int j = 0; j < kCsrtMaxK; ++j) v[j] = (j < k) ? slots[j] - (int)o : 0;
+#pragma unroll
+    for (int j = 0; j < kCsrtMaxK; ++j) {
+      if (j < k) {
+        if (v[j] < 0 || v[j] >= nc) __trap();         // neighbour outside the cloud (or a missing neighbour)
+        atomicAdd(&cnt[v[j]], 1);
+      }
+    }
+  }
+  __syncthreads();
+  // block exclusive scan, thread = contiguous range of `per` sources
+  {
+    const int per = (nc + kCsrtBlkThreads - 1) / kCsrtBlkThreads;
+    const int b = tid * per, e = (b + per < nc) ? b + per : nc;
+    int local = 0;
+    for (int i = b; i < e; ++i) local += cnt[i];
+    int incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= d) t += u;
+      }
+      warp_tot[lane] = t;   // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - local + (warp > 0 ? warp_tot[warp - 1] : 0);
+    for (int i = b; i < e; ++i) {
+      const int c = cnt[i];
+      cnt[i] = run;
+      rowptr_s[o + i] = e0 + run;
+      run += c;
+    }
+    if (tid == kCsrtBlkThreads - 1) cnt[nc] = warp_tot[31];
+    __syncthreads();
+  }
+  // ---- 2. bitmap passes
+  for (int s0 = 0; s0 < nc; s0 += S) {
+    const int sn = (s0 + S < nc) ? S : nc - s0;
+    for (int i = tid; i < sn * W; i += kCsrtBlkThreads) bm[i] = 0u;
+    __syncthreads();
+    // thread = target (its k slots are consecutive: no division by k; the 32-byte sectors are reused across j)
+    for (int t = tid; t < nc; t += kCsrtBlkThreads) {
+      if (nc > kCsrtBlkThreads) {                      // (otherwise v still holds this thread's only target)
+        const int32_t* slots = col_d + e0 + (int64_t)t * k;
+#pragma unroll
+        for (int j = 0; j < kCsrtMaxK; ++j) v[j] = (j < k) ? slots[j] - (int)o : 0;
+      }
+      const int tw = t >> 5;
+      const uint32_t bit = 1u << (t & 31);
+#pragma unroll
+      for (int j = 0; j < kCsrtMaxK; ++j) {
+        const int r = v[j] - s0;
+        if (j < k && r >= 0 && r < sn) {
+          int w = tw + (W == 32 ? (r & 31) : r % W);   // word index rotated by the row: the lanes of a warp (same word
+          if (w >= W) w -= W;                          // column, different rows) hit different banks
+          atomicOr(&bm[r * W + w], bit);
+        }
+      }
+    }
+    __syncthreads();
+    // warp = source row: lane j takes words j, j + 32, ...; a warp scan of the popcounts gives every lane the slot of its
+    // first target, so a row's targets leave as one contiguous (coalesced) run in ascending order
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < sn; r += kCsrtBlkThreads / 32) {
+      int pos = cnt[s0 + r];
+      const int end = cnt[s0 + r + 1];
+      const uint32_t* row = bm + r * W;
+      const int rot = (W == 32) ? (r & 31) : r % W;
+      for (int j0 = 0; j0 < W; j0 += 32) {
+        int w = j0 + lane + rot;
+        if (w >= W) w -= W;
+        uint32_t word = (j0 + lane < W) ? row[w] : 0u;
+        const int c = __popc(word);
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += u;
+        }
+        int mine = pos + incl - c;
+        while (word) {
+          const int b = __ffs(word) - 1;
+          word &= word - 1;
+          if (mine < end) col_s[e0 + mine] = (int32_t)(o + (j0 + lane) * 32 + b);
+          ++mine;
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (pos != end) __trap();                       // repeated edge
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ aggregation
 // tpn threads per node, each owning float4 channel groups c = 4*(lane + it*tpn)
 template <bool VEC4>
@@ -452,6 +595,20 @@ extern "C" int pcc_csr_transpose(const int32_t* col_d, const int64_t* rowptr_d, 
     PCC_K(csrt_fill_kernel)<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(col_d, rowptr_d, E, n, k_uniform, cursor, col_s);
     PCC_K(csr_sort_rows_kernel)<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(rowptr_s, col_s, n);
   }
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_csr_transpose_blocks(const int32_t* col_d, int k, const int64_t* offsets, int64_t B, int64_t n,
+                                        int64_t* rowptr_s, int32_t* col_s, int device, void* stream) {
+  PCC_ENTER(device);
+  PCC_REQUIRE(k >= 1 && k <= kCsrtMaxK, "k must be in [1,32]");
+  PCC_REQUIRE(n * (int64_t)k < (int64_t)0x7fffffff, "edge count exceeds int32 range");
+  if (B == 0) {
+    PCC_K(csr_zero_kernel)<<<1, 32, 0, (cudaStream_t)stream>>>(rowptr_s, n + 1);
+    return check_launch(__func__);
+  }
+  PCC_CUDA(cudaFuncSetAttribute(csrt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsrtBlkSmem));
+  PCC_K(csrt_block_kernel)<<<(unsigned)B, kCsrtBlkThreads, kCsrtBlkSmem, (cudaStream_t)stream>>>(col_d, k, offsets, n, rowptr_s, col_s);
   return check_launch(__func__);
 }
 

@@ -52,6 +52,7 @@ _SIGS = {
     "pcc_csr_workspace_bytes": [_i64, _i64],
     "pcc_csr_build": [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp],
     "pcc_csr_transpose": [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
+    "pcc_csr_transpose_blocks": [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _vp],
     "pcc_graph_aggregate_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
     "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],

@@ -29,11 +29,15 @@ class FusedGraph:
     """CSR views of a batched edge list in the layout the fused kernels read: rowptr int64 [n+1], col int32 [E]
     (neighbour node per slot), w fp32 [E] or None.  by_dst feeds the forward aggregation, by_src its transpose."""
 
-    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None, k_uniform: int = 0):
+    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None, k_uniform: int = 0,
+                 block_offsets: Optional[torch.Tensor] = None):
         from .functional import GraphCSR
         self.n, self.aggr = n, aggr
         self.E = edges.shape[1]
+        if self.E >= 2 ** 31 or n >= 2 ** 31:
+            raise ValueError("the fused GraphNet kernels index nodes and edges with int32")
         self.k_uniform = k_uniform
+        self.block_offsets = block_offsets           # [B+1] node range per cloud of a block-diagonal simple graph, or None
         csr = None
         if by_dst is not None:                       # e.g. a kNN graph: k consecutive edges per target, already grouped
             self.rowptr_d, self.col_d = by_dst
@@ -49,6 +53,17 @@ class FusedGraph:
         self._src = None
 
     def by_src(self):
+        if self._src is None and self._weights is None and self.block_offsets is not None and self.k_uniform > 0:
+            # kNN graph: per-cloud transpose in shared memory (pcc_csr_transpose_blocks); mean folds 1 / deg = 1 / k
+            dev = L.require_cuda(self.col_d, self.block_offsets)
+            rowptr_s = torch.empty(self.n + 1, dtype=torch.int64, device=self.col_d.device)
+            col_s = torch.empty(max(self.E, 1), dtype=torch.int32, device=self.col_d.device)
+            call("pcc_csr_transpose_blocks", ptr(self.col_d), int(self.k_uniform), ptr(self.block_offsets),
+                 self.block_offsets.numel() - 1, self.n, ptr(rowptr_s), ptr(col_s), dev, L.stream_ptr(dev))
+            w_s = None
+            if self.aggr == "mean":
+                w_s = torch.full((max(self.E, 1),), 1.0 / self.k_uniform, dtype=torch.float32, device=self.col_d.device)
+            self._src = (rowptr_s, col_s, w_s)
         if self._src is None and self._weights is None and self.aggr == "add":
             # unweighted sum aggregation: transpose the int32 CSR directly (no edge-id permutation, no int64 index ops)
             dev = L.require_cuda(self.col_d)
@@ -191,7 +206,7 @@ class GraphNetFusedFn(torch.autograd.Function):
         nb = _nblk()
         stat = torch.empty(nmax * 2 * Ch, **f32)
         dagg2 = torch.empty((M, Ch), dtype=torch.bfloat16, device=G.device)
-        droot = torch.empty((M, Ch), **f32)
+        droot = torch.empty((M, Ch), dtype=torch.bfloat16, device=G.device)   # becomes dh1 in place (pcc_gnn_agg_bwd)
         cw_part = torch.empty(148 * Ch * 2 * Ch, **f32)
         cb_part = torch.empty(148 * Ch, **f32)
         if deepchem:
@@ -205,7 +220,7 @@ class GraphNetFusedFn(torch.autograd.Function):
             kap = (s3 * sumG / M).contiguous()
             lam = (s3 * sumGx / M).contiguous()
             # ---- fc1 backward (+ bn2 sums)
-            dh2 = torch.empty((M, Ch), **f32)
+            dh2 = torch.empty((M, Ch), dtype=torch.bfloat16, device=G.device)
             dw_part = torch.empty(148 * C_FC * Ch, **f32)
             db_part = torch.empty(148 * C_FC, **f32)
             call("pcc_gnn_fc1_bwd", ptr(h2), ptr(packed), ptr(b_fc1), ptr(membership), ptr(gs), ptr(kap), ptr(lam), ptr(mu3), ptr(r3),

@@ -93,7 +93,10 @@ class GraphNet(nn.Module):
         self.last_path = None   # "fused-bf16" | "fp32": which kernels the last forward used
 
     def forward(self, x, membership, edges, weights=None, num_graphs: Optional[int] = None,
-                edges_sorted_by_target: bool = False):
+                edges_sorted_by_target: bool = False, simple_graph: bool = False):
+        """edges_sorted_by_target: the edge list holds the same number of consecutive edges for every target node, in node
+        order (a kNN graph).  simple_graph: additionally no edge is repeated (lets the bf16 path transpose the graph per
+        cloud in shared memory; a violation traps)."""
         if not x.is_cuda:
             raise RuntimeError("pcc_b200.GraphNet runs on CUDA tensors only (sm_100a kernels, no CPU fallback)")
         if not hasattr(self, "activation"):
@@ -104,7 +107,7 @@ class GraphNet(nn.Module):
             num_graphs = PF.index_max(membership) + 1
         offsets = PF.segment_offsets(membership, num_graphs)
         if self.precision == "bf16" and self.fused_supported(x.shape[1]):
-            return self._forward_fused(x, membership, edges, weights, offsets, edges_sorted_by_target)
+            return self._forward_fused(x, membership, edges, weights, offsets, edges_sorted_by_target, simple_graph)
         self.last_path = "fp32"
         csr = PF.GraphCSR(edges, n)
 
@@ -138,7 +141,7 @@ class KnnGraphNet(nn.Module):
         if num_graphs is None:
             num_graphs = PF.index_max(membership) + 1
         edges, _ = knn_graph(features, membership, self.k, self.pos_cols, num_graphs)
-        return self.net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True)
+        return self.net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True, simple_graph=True)
 
 
 def _fused_methods():
@@ -147,7 +150,7 @@ def _fused_methods():
         return GF.supported(F, self.conv2.out_channels, self._act_name, self.local_pooling, self.deepchem_style) and \
             all(isinstance(b.momentum, float) for b in (self.bn1, self.bn2, self.bn3))
 
-    def _forward_fused(self, x, membership, edges, weights, offsets, sorted_by_target):
+    def _forward_fused(self, x, membership, edges, weights, offsets, sorted_by_target, simple_graph=False):
         """bf16 tcgen05 path (graph_fused.py): one autograd Function for everything before fc2"""
         n, E = x.shape[0], edges.shape[1]
         edges = edges if edges.dtype == torch.int64 else edges.long()
@@ -155,7 +158,8 @@ def _fused_methods():
         if sorted_by_target and n > 0 and E % n == 0:      # kNN graph: k consecutive edges per target node
             k = E // n
             by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, edges[0].to(torch.int32))
-        graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst, k_uniform=k)
+        graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst, k_uniform=k,
+                              block_offsets=offsets if (simple_graph and by_dst is not None) else None)
         counts = offsets[1:] - offsets[:-1]
         bns = (self.bn1, self.bn2, self.bn3)
         bufs = [(b.running_mean, b.running_var) for b in bns]

@@ -4,10 +4,10 @@ and consumer prologues) against the pinned oracle (oracle/graphnet_oracle.py, fp
 Stated bf16 tolerance: the normalised activations h1 / h2, the aggregates and the conv2 / fc1 weights are rounded to bf16
 (8-bit mantissa) before every tensor-core contraction; accumulation, pre-activations and BatchNorm statistics are fp32.
 Two comparisons, per tensor, printed by the tests (measured on B200, profiles/r2/graph_fused_err.txt):
- (1) oracle with the SAME stated operand rounding (graphnet_oracle operand_rounding="bf16"): logits <= 2.1e-4 of max|ref|;
-     gradients (relative Frobenius) <= 8.7e-3 for tanh / gelu, <= 3.3e-2 for relu (the backward additionally rounds the
-     gradient operands dz / dagg to bf16, which the oracle does not model; bias gradients are near-cancelling sums).
-     Tolerances 2x measured: logits 2e-3 (10x, floor), gradients 2e-2 (7e-2 relu).
+ (1) oracle with the SAME stated operand rounding (graphnet_oracle operand_rounding="bf16"): logits <= 1.5e-3 of max|ref|;
+     gradients (relative Frobenius) <= 1.5e-2 for tanh / gelu, <= 3.3e-2 for relu (the backward additionally rounds the
+     gradient tensors dz / dagg / dh that travel between its kernels to bf16, which the oracle does not model; bias
+     gradients are near-cancelling sums).  Tolerances 2x measured: logits 3e-3, gradients 3e-2 (7e-2 relu).
  (2) the fp32 oracle: logits <= 7.3e-3 -> 1.5e-2; gradients <= 2.6e-2 (tanh / gelu) -> 5e-2, <= 0.14 (relu: ReLU masks
      flip where |z| is below the bf16 rounding noise, as in tests/test_fused_gpu.py) -> 0.3.
 The fp32 mode of the same module stays at rtol 1e-4 (tests/test_graph_gpu.py)."""
@@ -22,7 +22,7 @@ from oracle import knn_oracle as KO
 import pcc_b200
 
 pytestmark = pytest.mark.gpu
-LOGIT_TOL_Q, GRAD_TOL_Q, GRAD_TOL_Q_RELU = 2e-3, 2e-2, 7e-2   # vs the oracle with the stated bf16 operand rounding
+LOGIT_TOL_Q, GRAD_TOL_Q, GRAD_TOL_Q_RELU = 3e-3, 3e-2, 7e-2   # vs the oracle with the stated bf16 operand rounding
 LOGIT_TOL, GRAD_TOL, GRAD_TOL_RELU = 1.5e-2, 5e-2, 0.3   # vs the fp32 oracle
 
 
@@ -121,3 +121,41 @@ def test_knn_graphnet_module_uses_fused_path_and_matches_fp32_mode():
     assert rel_err(outs[0][0], outs[1][0]) < LOGIT_TOL
     for k, g in outs[1][1].items():
         assert rel_l2(outs[0][1][k], g) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("sizes,k", [
+    ([300, 200, 400, 256], 8),
+    ([1024] * 5, 20),
+    ([33, 1300, 21, 2900], 20),          # clouds beyond one bitmap pass (> ~1250 points)
+    ([64], 5),
+])
+def test_csr_transpose_blocks_matches_numpy(sizes, k):
+    """pcc_csr_transpose_blocks (per-cloud shared-memory transpose of a kNN graph) is bit-exact against a stable numpy
+    transposition: rowptr by source, targets ascending inside a row — and equal to the generic pcc_csr_transpose."""
+    import ctypes as C
+    from pcc_b200 import _lib as L
+    feats, memb, off = _clouds(sizes, seed=5)
+    nbr, _ = KO.knn_neighbours(feats[:, 1:4].numpy(), off, k)
+    n = feats.shape[0]
+    src = nbr.reshape(-1).astype(np.int64)                 # slot p = (target p // k) <- source nbr
+    tgt = np.repeat(np.arange(n, dtype=np.int64), k)
+    order = np.lexsort((tgt, src))
+    ref_col = tgt[order].astype(np.int32)
+    ref_rowptr = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=n))]).astype(np.int64)
+    dev = torch.device("cuda:0")
+    col_d = torch.from_numpy(src.astype(np.int32)).to(dev)
+    offs = torch.from_numpy(off).to(dev)
+    rowptr_s = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col_s = torch.empty(n * k, dtype=torch.int32, device=dev)
+    L.call("pcc_csr_transpose_blocks", L.ptr(col_d), k, L.ptr(offs), len(sizes), n, L.ptr(rowptr_s), L.ptr(col_s), 0,
+           L.stream_ptr(0))
+    torch.cuda.synchronize()
+    assert np.array_equal(rowptr_s.cpu().numpy(), ref_rowptr)
+    assert np.array_equal(col_s.cpu().numpy(), ref_col)
+    # the generic transpose gives the same arrays
+    rowptr_g = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col_g = torch.empty(n * k, dtype=torch.int32, device=dev)
+    ws = torch.empty(L.call("pcc_csr_workspace_bytes", n, n * k), dtype=torch.uint8, device=dev)
+    L.call("pcc_csr_transpose", L.ptr(col_d), None, n * k, n, k, L.ptr(rowptr_g), L.ptr(col_g), L.ptr(ws), 0, L.stream_ptr(0))
+    torch.cuda.synchronize()
+    assert torch.equal(rowptr_g, rowptr_s) and torch.equal(col_g, col_s)
