@@ -620,13 +620,13 @@ KERNEL_SYMBOL = {"phi_pool_fwd_kernel": "phi_pool_fwd_pair_kernel"}   # H = 256 
 
 
 def GRAPH_KERNEL_BYTES_PT(wl):
-    """algorithmic bytes per node of the fused bf16 kernels: gathered rows are bf16 (2 B / channel),
-    pre-activations and gradients fp32"""
+    """algorithmic bytes per node of the fused bf16 kernels: gathered rows and the gradient tensors
+    between the backward kernels are bf16 (2 B / channel), pre-activations fp32"""
     k, Cc = wl.k, wl.hidden
     return {"gnn_conv_fwd_kernel": k * Cc * 2 + Cc * 2 + Cc * 2 + Cc * 4 + k * 4,      # rows + root + agg out + z out + ids
-            "gnn_conv_bwd_kernel": 2 * Cc * 4 + 2 * Cc * 2 + Cc * 2 + Cc * 4,        # dh, z, agg, h in; dagg, droot out
-            "gnn_agg_bwd_kernel": k * Cc * 2 + 3 * Cc * 4 + k * 4,                    # rows + droot in / dh out + z1 + ids
-            "gnn_fc1_bwd_kernel": Cc * 2 + Cc * 4 + Cc * 4}
+            "gnn_conv_bwd_kernel": Cc * 2 + Cc * 4 + 2 * Cc * 2 + 2 * Cc * 2,        # dh, z, agg, h in; dagg, droot out
+            "gnn_agg_bwd_kernel": k * Cc * 2 + 2 * Cc * 2 + Cc * 4 + k * 4,           # rows + droot in / dh out + z1 + ids
+            "gnn_fc1_bwd_kernel": Cc * 2 + Cc * 4 + Cc * 2}                           # h2, z2 in; dh2 out
 
 
 # ---------------------------------------------------------------------------- configs[4]: point-count sweep

@@ -439,11 +439,12 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ pos,
 // CTA = 256 consecutive query points; for every cloud the CTA's queries belong to, the cloud's points stream through a
 // shared-memory tile ({x, y, z} as float4, 1024 candidates) that ALL warps read (one broadcast LDS.128 per candidate
 // instead of per-lane global loads).  Thread = one query: its running top-K lives in REGISTERS as a sorted list of
-// 64-bit keys (fp32 bits of d2 << 32 | candidate id: d2 >= 0, so the unsigned order is the (d2, id) order the oracle
-// defines, ties -> lower id).  A candidate that beats the thread's current K-th key is appended to a small per-thread
-// queue in shared memory; the queues are drained warp-wide (unrolled compare-exchange chain, ~5 instructions per list
-// slot) only when some lane's queue fills, so the divergent insertion cost is paid once per ~5 accepted candidates
-// instead of once per candidate.  Distances use the oracle's arithmetic (no FMA contraction): results are bit-exact.
+// (fp32 bits of d2, candidate id) — d2 >= 0, so the unsigned order of the bits is the order of the distances, and the
+// ascending scan order makes a stable insertion reproduce the oracle's (d2, id) order (ties -> lower id).  A candidate that
+// beats the thread's current K-th distance is appended to a small per-thread queue in shared memory; the queues are
+// drained warp-wide (unrolled insertion chain, ~5 instructions per list slot) only when some lane's queue fills, so the
+// divergent insertion cost is paid once per several accepted candidates instead of once per candidate.  Distances use
+// the oracle's arithmetic (no FMA contraction): results are bit-exact.
 constexpr int kKnnTile = 1024, kKnnQ = 16;
 template <int K>
 __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict__ pos, int64_t pos_stride,
@@ -465,22 +466,30 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict_
   const int64_t q_first = (int64_t)blockIdx.x * 256;
   const int64_t q_last = (q_first + 255 < n - 1) ? q_first + 255 : n - 1;
   const int64_t b_first = cloud_of(q_first), b_last = cloud_of(q_last);
-  unsigned long long list[K];
+  // Sorted top-K list as two register arrays (distance bits, candidate id).  Candidates arrive in ASCENDING id order (tiles
+  // and slots are scanned in order, a lane's queue is drained in order), so a candidate's id is larger than every id
+  // already in the list: the (d2, id) order the oracle defines reduces to "insert after every entry with d2 <= mine"
+  // — compares on the 32-bit distance bits only, and a stable insertion keeps equal distances in id order.
+  unsigned ld[K], li[K];
 #pragma unroll
-  for (int s = 0; s < K; ++s) list[s] = ~0ull;
+  for (int s = 0; s < K; ++s) { ld[s] = 0xffffffffu; li[s] = 0xffffffffu; }
   int cnt = 0;
   auto drain = [&]() {
     const int m = __reduce_max_sync(0xffffffffu, cnt);
     for (int i = 0; i < m; ++i) {
       const unsigned long long key = (i < cnt) ? queue[i][tid] : ~0ull;
-      if (key < list[K - 1]) {
-        list[K - 1] = key;
+      const unsigned kd = (unsigned)(key >> 32), ki = (unsigned)key;
+      if (kd < ld[K - 1]) {
+        // new[s] = (kd < ld[s-1]) ? old[s-1] : ((kd < ld[s]) ? key : old[s]), from the bottom up
+        bool below = true;   // kd < ld[s] (true for s = K-1 by the test above)
 #pragma unroll
         for (int s = K - 1; s >= 1; --s) {
-          const unsigned long long a = list[s - 1], b = list[s];
-          list[s - 1] = a < b ? a : b;
-          list[s] = a < b ? b : a;
+          const bool above = kd < ld[s - 1];
+          ld[s] = above ? ld[s - 1] : (below ? kd : ld[s]);
+          li[s] = above ? li[s - 1] : (below ? ki : li[s]);
+          below = above;
         }
+        if (below) { ld[0] = kd; li[0] = ki; }
       }
     }
     cnt = 0;
@@ -503,23 +512,38 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict_
       __syncthreads();
       if (!warp_active) continue;
       const unsigned self = (unsigned)(q - t0);   // position of the query inside this tile (or out of range)
-      for (int j0 = 0; j0 < tn; j0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u;
-          if (j < tn) {
-            const float4 c = tile[j];
-            const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(unsigned)(t0 + j);
-            if (active && (unsigned)j != self && key < list[K - 1]) {
-              queue[cnt][tid] = key;
-              ++cnt;
-            }
-          }
+      // Per candidate: one broadcast LDS.128, the oracle's 8 flops and ONE compare of the distance bits against the bits
+      // of the K-th distance (0 for an inactive lane: never taken); the self test and the queue append sit behind that
+      // rarely taken branch.
+      unsigned thr1 = 0u;
+      auto refresh = [&]() { thr1 = active ? ld[K - 1] : 0u; };
+      refresh();
+      auto dist_bits = [&](int j) {
+        const float4 c = tile[j];
+        const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+        return __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      };
+      auto accept = [&](int j, unsigned bits) {
+        if (bits < thr1 && (unsigned)j != self) {
+          queue[cnt][tid] = ((unsigned long long)bits << 32) | (unsigned long long)(unsigned)(t0 + j);
+          ++cnt;
         }
-        if (__any_sync(0xffffffffu, cnt > kKnnQ - 4)) drain();
+      };
+      auto consider = [&](int j) {
+        const unsigned bits = dist_bits(j);
+        if (bits < thr1) accept(j, bits);
+      };
+      const int tn4 = tn & ~3;
+      for (int j0 = 0; j0 < tn4; j0 += 4) {
+        // four candidates per branch: the distances are independent, one test covers the group
+        const unsigned b0 = dist_bits(j0), b1 = dist_bits(j0 + 1), b2 = dist_bits(j0 + 2), b3 = dist_bits(j0 + 3);
+        if ((b0 < thr1) | (b1 < thr1) | (b2 < thr1) | (b3 < thr1)) {
+          accept(j0, b0); accept(j0 + 1, b1); accept(j0 + 2, b2); accept(j0 + 3, b3);
+        }
+        if (__any_sync(0xffffffffu, cnt > kKnnQ - 4)) { drain(); refresh(); }
       }
+      for (int j = tn4; j < tn; ++j) consider(j);
+      if (__any_sync(0xffffffffu, cnt > kKnnQ - 4)) { drain(); refresh(); }
     }
     if (warp_active) drain();
   }
@@ -527,9 +551,9 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict_
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       if (s < k) {
-        const bool ok = list[s] != ~0ull;
-        nbr[q * k + s] = ok ? (int64_t)(list[s] & 0xffffffffull) : -1;
-        d2o[q * k + s] = ok ? __uint_as_float((unsigned)(list[s] >> 32)) : INFINITY;
+        const bool ok = li[s] != 0xffffffffu;
+        nbr[q * k + s] = ok ? (int64_t)li[s] : -1;
+        d2o[q * k + s] = ok ? __uint_as_float(ld[s]) : INFINITY;
       }
     }
   }
