@@ -26,13 +26,27 @@ def _clouds(sizes, seed, F=4):
 
 
 @pytest.mark.parametrize("sizes,k", [([64, 100, 33], 20), ([1024, 1024], 20), ([21, 22, 500], 20), ([5, 3, 1, 40], 4),
-                                     ([300], 32), ([10, 15], 20)])
+                                     ([300], 32), ([10, 15], 20), ([2500, 1500, 90], 20), ([5000, 700], 8)])
 def test_knn_bit_exact(sizes, k):
+    """identical neighbour ids and identical fp32 distance bits; clouds of several 1024-candidate tiles included"""
     feats, memb, off = _clouds(sizes, seed=7)
     ref_nbr, ref_d2 = KO.knn_neighbours(feats[:, 1:4].numpy(), off, k)
     nbr, d2 = PF.knn(feats.cuda()[:, 1:4], torch.from_numpy(off).cuda(), k)
     assert np.array_equal(nbr.cpu().numpy(), ref_nbr)
     assert np.array_equal(d2.cpu().numpy(), ref_d2)  # identical fp32 bits (no FMA contraction)
+
+
+def test_knn_ties_break_by_lower_id():
+    """points on a coarse integer lattice (many exactly equal distances, repeated points): the (d2, id) order of the oracle
+    (the kernel compares distance bits only and relies on the ascending scan order for the ids)"""
+    g = torch.Generator().manual_seed(11)
+    sizes = [400, 257]
+    pos = torch.randint(0, 4, (sum(sizes), 3), generator=g).float()
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ref_nbr, ref_d2 = KO.knn_neighbours(pos.numpy(), off, 20)
+    nbr, d2 = PF.knn(pos.cuda(), torch.from_numpy(off).cuda(), 20)
+    assert np.array_equal(nbr.cpu().numpy(), ref_nbr)
+    assert np.array_equal(d2.cpu().numpy(), ref_d2)
 
 
 def test_knn_graph_edge_convention():
