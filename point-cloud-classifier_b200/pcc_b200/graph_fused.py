@@ -29,11 +29,13 @@ class FusedGraph:
     """CSR views of a batched edge list in the layout the fused kernels read: rowptr int64 [n+1], col int32 [E]
     (neighbour node per slot), w fp32 [E] or None.  by_dst feeds the forward aggregation, by_src its transpose."""
 
-    def __init__(self, edges: torch.Tensor, n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None, k_uniform: int = 0,
+    def __init__(self, edges: Optional[torch.Tensor], n: int, weights: Optional[torch.Tensor], aggr: str, by_dst=None, k_uniform: int = 0,
                  block_offsets: Optional[torch.Tensor] = None):
         from .functional import GraphCSR
         self.n, self.aggr = n, aggr
-        self.E = edges.shape[1]
+        if edges is None and (by_dst is None or block_offsets is None or weights is not None):
+            raise ValueError("a graph without an edge list needs by_dst and block_offsets (an unweighted kNN neighbour table)")
+        self.E = edges.shape[1] if edges is not None else by_dst[1].numel()
         if self.E >= 2 ** 31 or n >= 2 ** 31:
             raise ValueError("the fused GraphNet kernels index nodes and edges with int32")
         self.k_uniform = k_uniform

@@ -140,8 +140,14 @@ class KnnGraphNet(nn.Module):
     def forward(self, features, membership, num_graphs: Optional[int] = None):
         if num_graphs is None:
             num_graphs = PF.index_max(membership) + 1
+        net = self.net
+        if features.is_cuda and net.precision == "bf16" and net.fused_supported(features.shape[1]):
+            # fused path: the [n, k] neighbour table IS the CSR by target (k slots per node); no edge list is materialised
+            offsets = PF.segment_offsets(membership, num_graphs)
+            nbr, _ = PF.knn(features[:, self.pos_cols[0]:self.pos_cols[1]], offsets, self.k)
+            return net._forward_fused(features, membership, None, None, offsets, True, True, nbr=nbr)
         edges, _ = knn_graph(features, membership, self.k, self.pos_cols, num_graphs)
-        return self.net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True, simple_graph=True)
+        return net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True, simple_graph=True)
 
 
 def _fused_methods():
@@ -150,14 +156,20 @@ def _fused_methods():
         return GF.supported(F, self.conv2.out_channels, self._act_name, self.local_pooling, self.deepchem_style) and \
             all(isinstance(b.momentum, float) for b in (self.bn1, self.bn2, self.bn3))
 
-    def _forward_fused(self, x, membership, edges, weights, offsets, sorted_by_target, simple_graph=False):
-        """bf16 tcgen05 path (graph_fused.py): one autograd Function for everything before fc2"""
-        n, E = x.shape[0], edges.shape[1]
-        edges = edges if edges.dtype == torch.int64 else edges.long()
+    def _forward_fused(self, x, membership, edges, weights, offsets, sorted_by_target, simple_graph=False, nbr=None):
+        """bf16 tcgen05 path (graph_fused.py): one autograd Function for everything before fc2.  Either an edge list
+        [2, E] or (KnnGraphNet) the neighbour table nbr[n, k] of a kNN graph."""
+        n = x.shape[0]
         by_dst, k = None, 0
-        if sorted_by_target and n > 0 and E % n == 0:      # kNN graph: k consecutive edges per target node
-            k = E // n
-            by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, edges[0].to(torch.int32))
+        if nbr is not None:
+            k = nbr.shape[1]
+            by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, nbr.reshape(-1).to(torch.int32))
+        else:
+            E = edges.shape[1]
+            edges = edges if edges.dtype == torch.int64 else edges.long()
+            if sorted_by_target and n > 0 and E % n == 0:      # kNN graph: k consecutive edges per target node
+                k = E // n
+                by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, edges[0].to(torch.int32))
         graph = GF.FusedGraph(edges, n, weights, self.local_pooling, by_dst=by_dst, k_uniform=k,
                               block_offsets=offsets if (simple_graph and by_dst is not None) else None)
         counts = offsets[1:] - offsets[:-1]
