@@ -194,10 +194,16 @@ __device__ __forceinline__ void slot_reduce(const uint8_t* slot, int cnt, int la
   f32x2_unpack(a23, acc[2], acc[3]);
 }
 
-// bounded mbarrier wait: a protocol bug traps instead of hanging the GPU
+// bounded mbarrier wait: a protocol bug traps instead of hanging the GPU.  The clock is read once per 1024 failed
+// polls only: with a clock read in every iteration the wait loops were 15 % of ALL instructions the conv forward kernel
+// executed (ncu, profiles/r2/ncu_gnn_r2e.txt) — issue slots taken from the warps that had work.
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
     if (clock64() - t0 > 20000000000ll) __trap();
   }
 }
