@@ -94,6 +94,53 @@ __device__ __forceinline__ void epi_store_chunk(const uint32_t (&v)[32], uint8_t
   }
 }
 
+// layer 0 of one 128-point tile on the FP32 pipe, slabs [s0, s1) of 64 columns: h_0 = act(W_0 x + b_0) -> bf16 activation
+// image.  256 threads (t = 0..255): thread = 8 columns (cg) x 4 rows (rw + 32 i) of a slab, so the weights sit in
+// registers and every shared-memory read is shared by 8 (x) or 4 (weights) lanes; column pairs as packed fp32 pairs
+// (FFMA2 does two columns per issue slot with the row's input broadcast).  Every finished slab is handed to the MMA warp
+// at once (8 warp arrivals on slab_ready[s]).
+template <int ACT, int Q, int NSLAB>
+__device__ __forceinline__ void layer0_slabs(const float* xT, const ulonglong2* w0S, uint8_t* bufA, uint64_t* slab_ready, int s0,
+                                             int s1, int t, long long* trace, int tn, bool tr0) {
+  constexpr int XW = 4 * Q;
+  const int cg = t & 7, rw = t >> 3;
+#pragma unroll 1
+  for (int s = s0; s < s1; ++s) {
+    uint64_t z[4][4];
+#pragma unroll
+    for (int qq = 0; qq < Q; ++qq) {
+      ulonglong2 w[8];  // [pair][half]: {t0, t1} / {t2, t3} of quad qq, each a packed column pair
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = w0S[(qq * NSLAB + s) * 64 + e * 8 + cg];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 xv = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
+        const uint64_t x0 = f32x2(xv.x, xv.x), x1 = f32x2(xv.y, xv.y), x2 = f32x2(xv.z, xv.z), x3 = f32x2(xv.w, xv.w);
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) {
+          if (qq == 0) z[i][pi] = ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, w[2 * pi].x)));
+          else z[i][pi] = ffma2(w[2 * pi].x, x0, ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, z[i][pi]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t o[4];
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        float lo, hi;
+        f32x2_unpack(z[i][pi], lo, hi);
+        o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2_pair(act2<ACT>(z[i][pi]));
+      }
+      *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, s * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (tr0) trace_ev(trace, 0, tn, 50 + s);
+    fence_proxy_async();
+    mbar_arrive_warp(&slab_ready[s]);
+    if (tr0) trace_ev(trace, 0, tn, 60 + s);
+  }
+}
+
 // ------------------------------------------------------------------ forward kernel
 // L = 2 (phi = Linear, final Linear) or 3 (one H x H hidden layer / ResidualBlock in between).
 // TMEM: L = 3: hidden accumulator = columns [0,256), final accumulator = [256,512);
@@ -295,9 +342,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     const int r = quarter * 32 + lane;  // tile row (hidden-layer epilogue)
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     const int d = p.d;
-    // layer 0: thread = 8 columns (cg) x 4 rows (rw + 32 i) of a 64-column slab, so the weights sit in
-    // registers and every shared-memory read is shared by 8 (x) or 4 (weights) lanes
-    const int cg = threadIdx.x & 7, rw = threadIdx.x >> 3;
     // x tile -> registers -> xS (padded rows, bf16-rounded like every MMA operand: the backward recomputes
     // this layer with MMAs): slot s = tid + 256 k covers row s / XW, column s % XW - 1
     float xp[2 * Q];
@@ -317,6 +361,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
     };
     load_x(blockIdx.x);
     store_x(0);
+    // (poolh: the pool warps compute half of layer 0 and wait on barrier 4 for the staged inputs of their tile)
+    if (POOLH && (int64_t)blockIdx.x < p.num_tiles) asm volatile("bar.arrive 4, 512;" ::: "memory");
     int tn = 0;
     uint32_t acch_phase = 0;
     const bool tr0 = (threadIdx.x == 0);
@@ -338,43 +384,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
       // next tile's inputs: issued here so that they have landed before the first fence below (the proxy fence
       // drains every outstanding memory operation of the thread, global loads included)
       load_x(tile + gridDim.x);
-#pragma unroll 1
-      for (int s = 0; s < NSLAB; ++s) {
-        // column pairs (2 pi, 2 pi + 1) of the thread's 8 columns as packed fp32 pairs: FFMA2 does two columns
-        // per issue slot with the row's input broadcast
-        uint64_t z[4][4];
-#pragma unroll
-        for (int qq = 0; qq < Q; ++qq) {
-          ulonglong2 w[8];  // [pair][half]: {t0, t1} / {t2, t3} of quad qq, each a packed column pair
-#pragma unroll
-          for (int e = 0; e < 8; ++e) w[e] = w0S[(qq * NSLAB + s) * 64 + e * 8 + cg];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 xv = *reinterpret_cast<const float4*>(xT + (rw + 32 * i) * XW + 4 * qq);
-            const uint64_t x0 = f32x2(xv.x, xv.x), x1 = f32x2(xv.y, xv.y), x2 = f32x2(xv.z, xv.z), x3 = f32x2(xv.w, xv.w);
-#pragma unroll
-            for (int pi = 0; pi < 4; ++pi) {
-              if (qq == 0) z[i][pi] = ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, w[2 * pi].x)));
-              else z[i][pi] = ffma2(w[2 * pi].x, x0, ffma2(w[2 * pi].y, x1, ffma2(w[2 * pi + 1].x, x2, ffma2(w[2 * pi + 1].y, x3, z[i][pi]))));
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t o[4];
-#pragma unroll
-          for (int pi = 0; pi < 4; ++pi) {
-            float lo, hi;
-            f32x2_unpack(z[i][pi], lo, hi);
-            o[pi] = (ACT == PCC_ACT_RELU) ? pack_bf16x2_relu(lo, hi) : pack_bf16x2_pair(act2<ACT>(z[i][pi]));
-          }
-          *reinterpret_cast<uint4*>(bufA + act_chunk_off(rw + 32 * i, s * 64 + cg * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        if (tr0) trace_ev(p.trace, 0, tn, 50 + s);
-        fence_proxy_async();
-        mbar_arrive_warp(&slab_ready[s]);
-        if (tr0) trace_ev(p.trace, 0, tn, 60 + s);
-      }
+      // (sum / mean pooling: the pool warps have almost nothing to do per tile, so they take the second half of the slabs
+      //  and of the hidden epilogue below — the tile period of the yaml model was 17k cycles, 9.1k of them this layer on
+      //  8 warps and 4.6k the epilogue, all serial)
+      layer0_slabs<ACT, Q, NSLAB>(xT, w0S, bufA, slab_ready, 0, POOLH ? NSLAB / 2 : NSLAB, threadIdx.x, p.trace, tn, tr0);
       if (tr0) trace_ev(p.trace, 0, tn, 5);
 
       // ---- hidden layer: TMEM -> bias/act/residual -> bf16 image (in place); TMEM loads run one chunk
@@ -386,6 +399,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
         if (tr0) trace_ev(p.trace, 0, tn, 11);
         const bool res = (p.res_mask >> 1) & 1;
         uint32_t va[32], vb[32];
+        if (POOLH) {
+          // four warp groups (two of them pool warps): chunks grp, grp + 4
+          tmem_ld32(lane_base + grp * 32, va);
+          if (grp + 4 < NCHUNK) tmem_ld32(lane_base + (grp + 4) * 32, vb);
+          tmem_wait_ld();
+          epi_store_chunk<ACT>(va, bufA, r, grp, res);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive_warp(&slab_ready[grp >> 1]);
+          if (grp + 4 < NCHUNK) {
+            epi_store_chunk<ACT>(vb, bufA, r, grp + 4, res);
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive_warp(&slab_ready[(grp + 4) >> 1]);
+          }
+        } else {
         tmem_ld32(lane_base + grp * 32, va);
 #pragma unroll 1
         for (int c = grp; c < NCHUNK; c += 4) {
@@ -404,9 +433,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
             mbar_arrive_warp(&slab_ready[(c + 2) >> 1]);
           }
         }
+        }
         if (tr0) trace_ev(p.trace, 0, tn, 21);
       }
       store_x((nt + 1) & 1);  // buffer last read by h_0 of the previous tile; every warp is past it (barrier above)
+      if (POOLH && tile + gridDim.x < p.num_tiles) asm volatile("bar.arrive 4, 512;" ::: "memory");
     }
   } else if (warp < kFwdHidWarps + kFwdPoolWarps) {
     // ===================== pool warps 8-15: thread = feature, TMEM columns = the tile's points
@@ -421,55 +452,108 @@ __global__ void __launch_bounds__(kFwdThreads, 1) phi_pool_fwd_kernel(const PhiP
       float* hsum = reinterpret_cast<float*>(p.pool_acc);
       int tn = 0;
       uint32_t use = 0;  // running count of final-accumulator uses, in step with the MMA thread
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int64_t r0 = tile * kTileM;
-        const int b_first0 = __ldg(p.tile_first + tile), b_last = __ldg(p.tile_last + tile);
+      int nt = 0;
+      uint32_t acch_phase = 0;
+      // indicator operand of sets [b_first, b_first + nsets) over the tile's points
+      auto build_indicator = [&](int64_t r0, int b_first, int nsets, uint32_t N) {
+        for (uint32_t q = pt; q < N * 16; q += 32 * kFwdPoolWarps) {
+          const uint32_t sidx = q >> 4, kc = q & 15;   // set slot, 8-point chunk
+          int64_t lo = 0, hi = 0;
+          if ((int)sidx < nsets) { lo = __ldg(p.offsets + b_first + sidx); hi = __ldg(p.offsets + b_first + sidx + 1); }
+          const int64_t p0 = r0 + kc * 8;
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t b0 = (p0 + 2 * j >= lo && p0 + 2 * j < hi) ? 0x3F80u : 0u;          // bf16 1.0
+            const uint32_t b1 = (p0 + 2 * j + 1 >= lo && p0 + 2 * j + 1 < hi) ? 0x3F80u : 0u;
+            w[j] = b0 | (b1 << 16);
+          }
+          *reinterpret_cast<uint4*>(indS + (kc >> 3) * (N * 128) + sidx * 128 + (((kc & 7) ^ (sidx & 7)) << 4)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (pt == 0) *nsetsS = N;
+        fence_proxy_async();
+        mbar_arrive_warp(ind_ready);
+      };
+      // pooled columns of one chunk: final accumulator -> [B,H] sums
+      auto read_pooled = [&](int b_first, int nsets, uint32_t N) {
+        const int slot = (L == 2) ? (int)(use & 1) : 0;
+        const uint32_t k = (L == 2) ? (use >> 1) : use;
+        mbar_wait(&acc_f[slot], k & 1);
+        tc_fence_after();
+        if (tr0) trace_ev(p.trace, 2, tn, 30);
+        if (h < HALVES) {
+          const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
+          for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(accT + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((int)(c0 + j) < nsets) atomicAdd(hsum + (int64_t)(b_first + c0 + j) * H + f, __uint_as_float(v[j]));
+          }
+          tc_fence_before();
+          mbar_arrive_warp(&pool_done[slot]);
+        }
+        if (tr0) trace_ev(p.trace, 2, tn, 40);
+        ++use;
+      };
+      // chunks of <= 128 sets (a tile of 128 one-point sets plus interior empty sets holds more than 128): the first
+      // chunk's indicator is built right after this group's layer-0 share, the pooled columns are read at the start of
+      // the next tile
+      auto finish_tile = [&](int64_t tile_f) {
+        const int64_t r0 = tile_f * kTileM;
+        const int b_first0 = __ldg(p.tile_first + tile_f), b_last = __ldg(p.tile_last + tile_f);
         const int nsets_t = b_last - b_first0 + 1;
-        // chunks of <= 128 sets (a tile of 128 one-point sets plus interior empty sets holds more than 128)
-        for (int c0s = 0; c0s < nsets_t; c0s += 128, ++use) {
+        for (int c0s = 0; c0s < nsets_t; c0s += 128) {
           const int b_first = b_first0 + c0s;
           const int nsets = (nsets_t - c0s < 128) ? nsets_t - c0s : 128;
           const uint32_t N = (uint32_t)((nsets + 15) & ~15);   // MMA N: multiple of 16, >= 16, <= 128
-          // the previous pooling MMA (which read the indicator) is complete: this warp waited for its accumulator below
-          for (uint32_t q = pt; q < N * 16; q += 32 * kFwdPoolWarps) {
-            const uint32_t sidx = q >> 4, kc = q & 15;   // set slot, 8-point chunk
-            int64_t lo = 0, hi = 0;
-            if ((int)sidx < nsets) { lo = __ldg(p.offsets + b_first + sidx); hi = __ldg(p.offsets + b_first + sidx + 1); }
-            const int64_t p0 = r0 + kc * 8;
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t b0 = (p0 + 2 * j >= lo && p0 + 2 * j < hi) ? 0x3F80u : 0u;          // bf16 1.0
-              const uint32_t b1 = (p0 + 2 * j + 1 >= lo && p0 + 2 * j + 1 < hi) ? 0x3F80u : 0u;
-              w[j] = b0 | (b1 << 16);
-            }
-            *reinterpret_cast<uint4*>(indS + (kc >> 3) * (N * 128) + sidx * 128 + (((kc & 7) ^ (sidx & 7)) << 4)) =
-                make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          if (pt == 0) *nsetsS = N;
-          fence_proxy_async();
-          mbar_arrive_warp(ind_ready);
-          const int slot = (L == 2) ? (int)(use & 1) : 0;
-          const uint32_t k = (L == 2) ? (use >> 1) : use;
-          mbar_wait(&acc_f[slot], k & 1);
-          tc_fence_after();
-          if (tr0) trace_ev(p.trace, 2, tn, 30);
-          if (h < HALVES) {
-            const uint32_t accT = lane_base + ((L == 2) ? slot * 256 : 256) + h * 128;
-            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(accT + c0, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if ((int)(c0 + j) < nsets) atomicAdd(hsum + (int64_t)(b_first + c0 + j) * H + f, __uint_as_float(v[j]));
-            }
-            tc_fence_before();
-            mbar_arrive_warp(&pool_done[slot]);
-          }
-          if (tr0) trace_ev(p.trace, 2, tn, 40);
+          if (c0s > 0) build_indicator(r0, b_first, nsets, N);
+          read_pooled(b_first, nsets, N);
         }
+      };
+      int64_t pending = -1;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++nt) {
+        // ---- this group's share of the per-point work: the second half of layer 0's slabs (the hidden warps staged
+        //      the tile's inputs: barrier 4; the image is free once the previous tile's pooling MMAs have read it)
+        if (pending >= 0) finish_tile(pending);   // pooled columns of the previous tile (measured: reading them after
+                                                  // this tile's layer-0 share instead only moves the wait to the MMA)
+        if (nt >= 1) mbar_wait(img_free, (uint32_t)((nt - 1) & 1));
+        asm volatile("bar.sync 4, 512;" ::: "memory");
+        layer0_slabs<ACT, Q, NSLAB>(xS + (nt & 1) * (kTileM * XW), w0S, bufA, slab_ready, NSLAB / 2, NSLAB, pt, nullptr, 0, false);
+        // ---- first chunk's indicator of this tile (the previous pooling MMA, which read the indicator, is complete)
+        {
+          const int b_first0 = __ldg(p.tile_first + tile), b_last = __ldg(p.tile_last + tile);
+          const int nsets_t = b_last - b_first0 + 1;
+          const int nsets = nsets_t < 128 ? nsets_t : 128;
+          build_indicator(tile * kTileM, b_first0, nsets, (uint32_t)((nsets + 15) & ~15));
+        }
+        if (L == 3) {
+          // ---- and of the hidden-layer epilogue: warp groups 2, 3 of four (chunks grp, grp + 4)
+          mbar_wait(acc_h, acch_phase);
+          acch_phase ^= 1;
+          tc_fence_after();
+          const bool res = (p.res_mask >> 1) & 1;
+          const int grp = 2 + h, r = quarter * 32 + lane;
+          uint32_t va[32], vb[32];
+          tmem_ld32(lane_base + grp * 32, va);
+          if (grp + 4 < NCHUNK) tmem_ld32(lane_base + (grp + 4) * 32, vb);
+          tmem_wait_ld();
+          epi_store_chunk<ACT>(va, bufA, r, grp, res);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive_warp(&slab_ready[grp >> 1]);
+          if (grp + 4 < NCHUNK) {
+            epi_store_chunk<ACT>(vb, bufA, r, grp + 4, res);
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive_warp(&slab_ready[(grp + 4) >> 1]);
+          }
+        }
+        pending = tile;
       }
+      if (pending >= 0) finish_tile(pending);
     } else if (h < HALVES) {
       const int r = quarter * 32 + lane;
       const int f = h * 128 + r;

@@ -4,14 +4,20 @@ sys.path.insert(0, os.path.join(ROOT, "point-cloud-classifier_b200"))
 import pcc_b200
 from pcc_b200 import _lib, functional as PF, fused as FZ
 B, N = 256, 1024
-m = pcc_b200.DeepSets(3, [256, 256], [256], 10, "relu", layer_norm=False, pooling="max", precision="bf16").cuda()
-x = torch.randn(B * N, 3, device="cuda"); idx = torch.arange(B, device="cuda").repeat_interleave(N)
+CFG = sys.argv[1] if len(sys.argv) > 1 else "deepsets"      # deepsets (relu + max, d = 3) | yaml (gelu + res + mean, d = 6)
+if CFG == "yaml":
+    D, ACT_, POOL_ = 6, "gelu", "mean"
+    m = pcc_b200.DeepSets(6, [256, 256], [256], 1, "gelu", layer_norm=False, residual_block=True, pooling="mean", precision="bf16").cuda()
+else:
+    D, ACT_, POOL_ = 3, "relu", "max"
+    m = pcc_b200.DeepSets(3, [256, 256], [256], 10, "relu", layer_norm=False, pooling="max", precision="bf16").cuda()
+x = torch.randn(B * N, D, device="cuda"); idx = torch.arange(B, device="cuda").repeat_interleave(N)
 off = PF.segment_offsets(idx, B)
 buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
 with torch.no_grad():
-    for _ in range(2): FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
+    for _ in range(2): FZ.phi_pool(x, off, m._phi_plan, ACT_, POOL_)
     _lib.call("pcc_debug_set_trace", _lib.ptr(buf))
-    FZ.phi_pool(x, off, m._phi_plan, "relu", "max")
+    FZ.phi_pool(x, off, m._phi_plan, ACT_, POOL_)
     torch.cuda.synchronize()
     _lib.call("pcc_debug_set_trace", None)
 t = buf.cpu().numpy().reshape(3, 2048, 2)
