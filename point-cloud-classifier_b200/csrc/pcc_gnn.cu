@@ -441,7 +441,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) gnn_conv_fwd_kernel(const Con
 // per-graph sums of a3 leave the SM — global_mean_pool(bn3(a3)) = bn3_affine(mean_graph(a3)) (graph_net.py:88-92).
 // Warps 0-3: h2 tile (bf16 rows) -> SW128 image, double buffered; warp 12: MMA (two 256-column accumulators);
 // warps 4-11: epilogue (lane quarter = warp & 3, column half = (warp - 4) >> 2).
-constexpr int kFcLoadWarps = 4, kFcEpiWarp0 = 4, kFcMmaWarp = 12, kFcThreads = 13 * 32;
+// 4 loader warps, 16 epilogue warps (lane quarter x 64-column part: the kernel is bound by its epilogue — activation, two
+// transposed column sums and the per-graph sums of 128 x 256 outputs per tile), 1 MMA warp
+constexpr int kFcLoadWarps = 4, kFcEpiWarp0 = 4, kFcEpiWarps = 16, kFcMmaWarp = 20, kFcThreads = 21 * 32;
+constexpr int kFcChunks = kFc / 16 / (kFcEpiWarps / 4);   // 16-column chunks per epilogue warp
 constexpr uint32_t kHImg = kC * kTile * 2;       // 32 KB
 constexpr uint32_t kFcWImg = kFc * kC * 2;       // 64 KB
 
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) gnn_fc1_pool_fwd_kernel(const F
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kFcLoadWarps); mbar_init(&empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], kFcLoadWarps); mbar_init(&empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kFcEpiWarps); }
     mbar_init(wbar, 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(wbar, kFcWImg);
@@ -527,11 +530,11 @@ __global__ void __launch_bounds__(kFcThreads, 1) gnn_fc1_pool_fwd_kernel(const F
       }
     }
   } else {
-    const int q = warp & 3, half = (warp - kFcEpiWarp0) >> 2;   // column half of 128
+    const int q = warp & 3, part = (warp - kFcEpiWarp0) >> 2;   // column part of kFcChunks * 16
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float st[8][2];
+    float st[kFcChunks][2];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) st[c][0] = st[c][1] = 0.f;
+    for (int c = 0; c < kFcChunks; ++c) st[c][0] = st[c][1] = 0.f;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1, k = it >> 1;
@@ -545,8 +548,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) gnn_fc1_pool_fwd_kernel(const F
       mbar_wait_b(&acc_full[buf], (uint32_t)(k & 1));
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int col0 = half * 128 + c * 16;
+      for (int c = 0; c < kFcChunks; ++c) {
+        const int col0 = (part * kFcChunks + c) * 16;
         uint32_t v[16];
         tmem_ld16(lane_base + buf * kFc + col0, v);
         tmem_wait_ld();
@@ -571,14 +574,14 @@ __global__ void __launch_bounds__(kFcThreads, 1) gnn_fc1_pool_fwd_kernel(const F
     }
     if (lane < 16) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        scratch[(q * 2 + 0) * kFc + half * 128 + c * 16 + lane] = st[c][0];
-        scratch[(q * 2 + 1) * kFc + half * 128 + c * 16 + lane] = st[c][1];
+      for (int c = 0; c < kFcChunks; ++c) {
+        scratch[(q * 2 + 0) * kFc + (part * kFcChunks + c) * 16 + lane] = st[c][0];
+        scratch[(q * 2 + 1) * kFc + (part * kFcChunks + c) * 16 + lane] = st[c][1];
       }
     }
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    const int t = threadIdx.x - kFcEpiWarp0 * 32;   // 0..255
-    for (int i = t; i < 2 * kFc; i += 256) {
+    asm volatile("bar.sync 2, %0;" ::"n"(kFcEpiWarps * 32) : "memory");
+    const int t = threadIdx.x - kFcEpiWarp0 * 32;   // 0..511
+    for (int i = t; i < 2 * kFc; i += kFcEpiWarps * 32) {
       const int which = i / kFc, c = i % kFc;
       p.partials[(size_t)blockIdx.x * 2 * kFc + i] = scratch[(0 * 2 + which) * kFc + c] + scratch[(1 * 2 + which) * kFc + c] +
                                                       scratch[(2 * 2 + which) * kFc + c] + scratch[(3 * 2 + which) * kFc + c];
