@@ -141,9 +141,10 @@ int pcc_graph_aggregate_bwd(const float* g, const int64_t* dst, const float* w, 
 /* kNN graph build (north_star; no reference counterpart — semantics defined by
  * oracle/knn_oracle.py).  pos: row r at pos + r*pos_stride floats, 3 coordinates.
  * nbr[n,k] global neighbour ids (-1 pad), d2[n,k] squared distances (inf pad), both
- * ascending by (d2, id).  k <= 32. */
+ * ascending by (d2, id).  k <= 32.  nbr32 (optional): the same table as int32 — the CSR-by-target column array the fused
+ * GraphNet kernels read (k slots per node), written by the same launch. */
 int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offsets, int64_t n, int64_t B, int k, int64_t* nbr,
-            float* d2, int device, void* stream);
+            float* d2, int32_t* nbr32, int device, void* stream);
 /* edge_index[2,n*k] from nbr (row0 = neighbour, row1 = centre); all slots must be valid */
 int pcc_knn_edges(const int64_t* nbr, int64_t n, int k, int64_t* edge_index, int device, void* stream);
 /* Gaussian edge weights of the reference's graph dataset (/root/reference/utils/data.py:835-845,
@@ -261,6 +262,9 @@ int pcc_gnn_conv_fwd(const void* h_in_bf16, const int64_t* rowptr, const int32_t
                      const void* packed, const float* bias, int64_t M, int act, void* agg_out_bf16, float* z_out,
                      float* partials, const int64_t* membership, float* psum, int64_t B, int* nblk_out, int device,
                      void* stream);
+/* graph-sized glue of the pooled outputs: P = psum / max(n_g, 1), y = P * scale + shift (mean pool commuted with the affine) */
+int pcc_gnn_pool_affine(const float* psum, const int64_t* counts, const float* scale, const float* shift, int64_t B, int Cn,
+                        float* P, float* y, int device, void* stream);
 int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float* bias, const int64_t* membership, int64_t M,
                          int64_t B, int act, float* psum, float* partials, int* nblk_out, int device, void* stream);
 /*   backward (autograd of the above).  One block z = A W^T + b, a = act(z), h = a*scale + shift has
@@ -279,6 +283,11 @@ int pcc_gnn_fc1_pool_fwd(const void* h_in_bf16, const void* packed, const float*
  *   pcc_gnn_agg_bwd         : dh_inout[j] += sum_{e: src(e)=j} w_e dagg[dst(e)] (CSR by source) + the bn sums of the
  *                             previous block (z_prev, its mean / invstd).
  *   pcc_gnn_conv1_bwd       : partials [nblk][128][2F+1] = (dW_rel | dW_root | db) of GraphConv 1. */
+/* backward of the same glue from G = dL/dy [B, Cn]: gs = G f / n_g, kap = f sum(G) / M, lam = f sum(G xhat(P)) / M,
+ * dgamma = sum(G xhat), dbeta = sum(G)   (f = s, or 1 with use_scale = 0) */
+int pcc_gnn_pool_bwd_prep(const float* G, const float* P, const float* mu, const float* rinv, const float* s,
+                          const int64_t* counts, int64_t B, int Cn, int64_t M, int use_scale, float* gs, float* kap, float* lam,
+                          float* dgamma, float* dbeta, int device, void* stream);
 int pcc_gnn_bn_bwd_finalize(const float* partials, int nblk, int Cn, int64_t rows, float* c1, float* c2, float* dgamma,
                             float* dbeta, int device, void* stream);
 int pcc_gnn_reduce(const float* part, int nblk, int64_t count, float* out, int device, void* stream);

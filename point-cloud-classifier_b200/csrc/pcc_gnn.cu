@@ -178,6 +178,21 @@ __global__ void gnn_bn_eval_kernel(const float* __restrict__ running_mean, const
   shift[c] = beta[c] - running_mean[c] * gamma[c] * invstd;
 }
 
+// per-graph mean + BatchNorm affine of the pooled sums: P = psum / max(n_g, 1), y = P * scale + shift   ([B, Cn] tensors;
+// global_mean_pool commutes with the affine, graph_net.py:89-92 / :96)
+__global__ void gnn_pool_affine_kernel(const float* __restrict__ psum, const int64_t* __restrict__ counts,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int64_t B, int Cn,
+                                       float* __restrict__ P, float* __restrict__ y) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B * Cn) return;
+  const int64_t b = i / Cn;
+  const int c = (int)(i % Cn);
+  const int64_t n = counts[b];
+  const float pv = psum[i] / (float)(n > 0 ? n : 1);
+  P[i] = pv;
+  y[i] = fmaf(pv, scale[c], shift[c]);
+}
+
 // h = bf16( act(z) * scale + shift ), 8 elements per thread
 template <int ACT>
 __global__ void __launch_bounds__(256) gnn_bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale,
@@ -655,6 +670,14 @@ extern "C" int pcc_gnn_bn_eval(const float* running_mean, const float* running_v
                                float eps, int Cn, float* scale, float* shift, int device, void* stream) {
   PCC_ENTER(device);
   PCC_K(gnn_bn_eval_kernel)<<<cdiv(Cn, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta, eps, Cn, scale, shift);
+  return check_launch(__func__);
+}
+
+extern "C" int pcc_gnn_pool_affine(const float* psum, const int64_t* counts, const float* scale, const float* shift, int64_t B,
+                                   int Cn, float* P, float* y, int device, void* stream) {
+  PCC_ENTER(device);
+  if (B * Cn == 0) return 0;
+  PCC_K(gnn_pool_affine_kernel)<<<(unsigned)cdiv(B * Cn, 256), 256, 0, (cudaStream_t)stream>>>(psum, counts, scale, shift, B, Cn, P, y);
   return check_launch(__func__);
 }
 

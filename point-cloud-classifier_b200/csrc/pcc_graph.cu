@@ -449,7 +449,8 @@ constexpr int kKnnTile = 1024;
 template <int K, int kKnnQ>
 __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict__ pos, int64_t pos_stride,
                                                         const int64_t* __restrict__ offsets, int64_t n, int64_t B, int k,
-                                                        int64_t* __restrict__ nbr, float* __restrict__ d2o) {
+                                                        int64_t* __restrict__ nbr, float* __restrict__ d2o,
+                                                        int32_t* __restrict__ nbr32) {
   __shared__ float4 tile[kKnnTile];
   __shared__ unsigned long long queue[kKnnQ][256];
   const int tid = threadIdx.x;
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(256) knn_tiled_kernel(const float* __restrict_
         const bool ok = li[s] != 0xffffffffu;
         nbr[q * k + s] = ok ? (int64_t)li[s] : -1;
         d2o[q * k + s] = ok ? __uint_as_float(ld[s]) : INFINITY;
+        if (nbr32) nbr32[q * k + s] = ok ? (int32_t)li[s] : -1;
       }
     }
   }
@@ -667,7 +669,7 @@ extern "C" int pcc_graph_aggregate_bwd(const float* g, const int64_t* dst, const
 }
 
 extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offsets, int64_t n, int64_t B, int k,
-                       int64_t* nbr, float* d2, int device, void* stream) {
+                       int64_t* nbr, float* d2, int32_t* nbr32, int device, void* stream) {
   PCC_ENTER(device);
   PCC_REQUIRE(k >= 1 && k <= 32, "k must be in [1,32]");
   PCC_REQUIRE(n < (int64_t)0x7fffffff, "point count exceeds int32 range");
@@ -677,6 +679,7 @@ extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offs
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof(6, st);
   if (legacy) {
+    PCC_REQUIRE(nbr32 == nullptr, "the legacy kNN kernel has no int32 neighbour output");
     constexpr int QW = 4;
     const int64_t warps = cdiv(n, QW);
     pcc::note_launch(1), knn_kernel<QW><<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
@@ -685,10 +688,10 @@ extern "C" int pcc_knn(const float* pos, int64_t pos_stride, const int64_t* offs
   const unsigned grid = (unsigned)cdiv(n, 256);
   pcc::note_launch(1);
   // queue depth 16 (measured at N = 1024: depth 8 0.478 ms, 12 0.440 ms, 16 0.430 ms)
-  if (k <= 8) knn_tiled_kernel<8, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
-  else if (k <= 16) knn_tiled_kernel<16, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
-  else if (k <= 20) knn_tiled_kernel<20, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
-  else knn_tiled_kernel<32, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2);
+  if (k <= 8) knn_tiled_kernel<8, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2, nbr32);
+  else if (k <= 16) knn_tiled_kernel<16, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2, nbr32);
+  else if (k <= 20) knn_tiled_kernel<20, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2, nbr32);
+  else knn_tiled_kernel<32, 16><<<grid, 256, 0, st>>>(pos, pos_stride, offsets, n, B, k, nbr, d2, nbr32);
   return check_launch(__func__);
 }
 

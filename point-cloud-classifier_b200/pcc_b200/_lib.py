@@ -55,7 +55,7 @@ _SIGS = {
     "pcc_csr_transpose_blocks": [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _vp],
     "pcc_graph_aggregate_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
     "pcc_graph_aggregate_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp],
-    "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp],
+    "pcc_knn": [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
     "pcc_knn_edges": [_vp, _i64, _i32, _vp, _i32, _vp],
     "pcc_expand_segments": [_vp, _i64, _i64, _vp, _i32, _vp],
     "pcc_offset_edges": [_vp, _i64, _vp, _vp, _i64, _vp, _i32, _vp],
@@ -82,6 +82,8 @@ _SIGS = {
     "pcc_gnn_bn_apply": [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
     "pcc_gnn_conv_fwd": [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(C.c_int), _i32, _vp],
     "pcc_gnn_fc1_pool_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],
+    "pcc_gnn_pool_affine": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp],
+    "pcc_gnn_pool_bwd_prep": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "pcc_gnn_bn_bwd_finalize": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "pcc_gnn_reduce": [_vp, _i32, _i64, _vp, _i32, _vp],
     "pcc_gnn_fc1_bwd": [_vp] * 12 + [_i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _i32, _vp],

@@ -302,8 +302,9 @@ def graph_aggregate(x, w, csr: GraphCSR, aggr: str):
 
 
 # ------------------------------------------------------------------ kNN
-def knn(pos: torch.Tensor, offsets: torch.Tensor, k: int):
-    """pos[n,>=3] fp32 view with unit inner stride (e.g. features[:, 1:4]) -> (nbr[n,k] i64, d2[n,k] f32)."""
+def knn(pos: torch.Tensor, offsets: torch.Tensor, k: int, with_int32: bool = False):
+    """pos[n,>=3] fp32 view with unit inner stride (e.g. features[:, 1:4]) -> (nbr[n,k] i64, d2[n,k] f32)
+    [, nbr32[n,k] i32 from the same launch with with_int32=True]."""
     if pos.dtype != torch.float32 or pos.stride(1) != 1:
         pos = pos.float().contiguous()
     dev, st = _ctx(pos, offsets)
@@ -311,8 +312,9 @@ def knn(pos: torch.Tensor, offsets: torch.Tensor, k: int):
     B = offsets.numel() - 1
     nbr = torch.empty((n, k), dtype=torch.int64, device=pos.device)
     d2 = torch.empty((n, k), dtype=torch.float32, device=pos.device)
-    call("pcc_knn", ptr(pos), pos.stride(0), ptr(offsets), n, B, int(k), ptr(nbr), ptr(d2), dev, st)
-    return nbr, d2
+    nbr32 = torch.empty((n, k), dtype=torch.int32, device=pos.device) if with_int32 else None
+    call("pcc_knn", ptr(pos), pos.stride(0), ptr(offsets), n, B, int(k), ptr(nbr), ptr(d2), ptr(nbr32), dev, st)
+    return (nbr, d2, nbr32) if with_int32 else (nbr, d2)
 
 
 def knn_edges(nbr: torch.Tensor) -> torch.Tensor:

@@ -170,13 +170,13 @@ class GraphNetFusedFn(torch.autograd.Function):
         call("pcc_gnn_conv_fwd", ptr(h1), ptr(graph.rowptr_d), ptr(graph.col_d), ptr(graph.w_d), mean, ptr(packed), ptr(b_rel2), M, A,
              ptr(agg2), ptr(z2), ptr(part), ptr(membership) if not deepchem else None, ptr(psum2), B, C.byref(nb), dev, st)
         s2, t2, mu2, r2 = bn(1, Ch, g2, be2, nb.value, M)
-        nb_f = counts.to(torch.float32).clamp(min=1.0).unsqueeze(1)
+        counts = L.i64c(counts)
         ctx.graph, ctx.meta, ctx.shapes = graph, meta, (M, F, B)
         if not deepchem:
             # global_mean_pool(bn2(a2)) = bn2_affine(mean_graph(a2)): graph_net.py:96 with the pool commuted with the affine
-            P2 = psum2 / nb_f
-            out = P2 * s2 + t2
-            ctx.save_for_backward(x, membership, agg1, z1, h1, agg2, z2, P2, nb_f, packed, s1, mu1, r1, s2, mu2, r2)
+            P2, out = torch.empty((B, Ch), **f32), torch.empty((B, Ch), **f32)
+            call("pcc_gnn_pool_affine", ptr(psum2), ptr(counts), ptr(s2), ptr(t2), B, Ch, ptr(P2), ptr(out), dev, st)
+            ctx.save_for_backward(x, membership, agg1, z1, h1, agg2, z2, P2, counts, packed, s1, mu1, r1, s2, mu2, r2)
             return out[:, :Cr].contiguous() if Cr != Ch else out
         h2 = torch.empty((M, Ch), **bf)
         call("pcc_gnn_bn_apply", ptr(z2), ptr(s2), ptr(t2), M, A, ptr(h2), dev, st)
@@ -185,9 +185,9 @@ class GraphNetFusedFn(torch.autograd.Function):
         call("pcc_gnn_fc1_pool_fwd", ptr(h2), ptr(packed), ptr(b_fc1), ptr(membership), M, B, A, ptr(psum), ptr(part), C.byref(nb),
              dev, st)
         s3, t3, mu3, r3 = bn(2, C_FC, g3, be3, nb.value, M)
-        P = psum / nb_f
-        y3 = P * s3 + t3
-        ctx.save_for_backward(x, membership, agg1, z1, h1, agg2, z2, h2, P, nb_f, packed, b_fc1,
+        P, y3 = torch.empty((B, C_FC), **f32), torch.empty((B, C_FC), **f32)
+        call("pcc_gnn_pool_affine", ptr(psum), ptr(counts), ptr(s3), ptr(t3), B, C_FC, ptr(P), ptr(y3), dev, st)
+        ctx.save_for_backward(x, membership, agg1, z1, h1, agg2, z2, h2, P, counts, packed, b_fc1,
                               s1, mu1, r1, s2, mu2, r2, s3, mu3, r3)
         return y3
 
@@ -212,15 +212,13 @@ class GraphNetFusedFn(torch.autograd.Function):
         cw_part = torch.empty(148 * Ch * 2 * Ch, **f32)
         cb_part = torch.empty(148 * Ch, **f32)
         if deepchem:
-            (x, membership, agg1, z1, h1, agg2, z2, h2, P, nb_f, packed, b_fc1,
+            (x, membership, agg1, z1, h1, agg2, z2, h2, P, counts, packed, b_fc1,
              s1, mu1, r1, s2, mu2, r2, s3, mu3, r3) = ctx.saved_tensors
-            # ---- bn3 + mean-pool backward: per-graph / per-channel terms (graph-sized tensors)
-            xhatP = (P - mu3) * r3
-            sumG, sumGx = G.sum(0), (G * xhatP).sum(0)
-            d_g3, d_be3 = sumGx, sumG
-            gs = (G * s3 / nb_f).contiguous()
-            kap = (s3 * sumG / M).contiguous()
-            lam = (s3 * sumGx / M).contiguous()
+            # ---- bn3 + mean-pool backward: per-graph / per-channel terms (graph-sized tensors, one launch)
+            gs = torch.empty((B, C_FC), **f32)
+            kap, lam, d_g3, d_be3 = (torch.empty(C_FC, **f32) for _ in range(4))
+            call("pcc_gnn_pool_bwd_prep", ptr(G), ptr(P), ptr(mu3), ptr(r3), ptr(s3), ptr(counts), B, C_FC, M, 1, ptr(gs), ptr(kap),
+                 ptr(lam), ptr(d_g3), ptr(d_be3), dev, st)
             # ---- fc1 backward (+ bn2 sums)
             dh2 = torch.empty((M, Ch), dtype=torch.bfloat16, device=G.device)
             dw_part = torch.empty(148 * C_FC * Ch, **f32)
@@ -237,15 +235,15 @@ class GraphNetFusedFn(torch.autograd.Function):
             call("pcc_gnn_conv_bwd", ptr(dh2), None, None, ptr(z2), ptr(mu2), ptr(r2), ptr(s2), ptr(c1), ptr(c2), ptr(agg2), ptr(h1),
                  ptr(packed), M, A, ptr(dagg2), ptr(droot), ptr(cw_part), ptr(cb_part), C.byref(nb), dev, st)
         else:
-            (x, membership, agg1, z1, h1, agg2, z2, P2, nb_f, packed, s1, mu1, r1, s2, mu2, r2) = ctx.saved_tensors
+            (x, membership, agg1, z1, h1, agg2, z2, P2, counts, packed, s1, mu1, r1, s2, mu2, r2) = ctx.saved_tensors
             if Cr != Ch:
                 G = _pad(G, (B, Ch))
             # the gradient of h2 is the same row for every node of a graph: dh2[i] = G[g(i)] / n_g, so the two bn2 sums are
             # graph-sized reductions and the conv backward reads the row through the membership vector
-            d_be2 = G.sum(0)
-            d_g2 = (G * ((P2 - mu2) * r2)).sum(0)
-            c1, c2 = (d_be2 / M).contiguous(), (d_g2 / M).contiguous()
-            gsb = (G / nb_f).contiguous()
+            gsb = torch.empty((B, Ch), **f32)
+            c1, c2, d_g2, d_be2 = (torch.empty(Ch, **f32) for _ in range(4))
+            call("pcc_gnn_pool_bwd_prep", ptr(G), ptr(P2), ptr(mu2), ptr(r2), ptr(s2), ptr(counts), B, Ch, M, 0, ptr(gsb), ptr(c1),
+                 ptr(c2), ptr(d_g2), ptr(d_be2), dev, st)
             call("pcc_gnn_conv_bwd", None, ptr(membership), ptr(gsb), ptr(z2), ptr(mu2), ptr(r2), ptr(s2), ptr(c1), ptr(c2), ptr(agg2),
                  ptr(h1), ptr(packed), M, A, ptr(dagg2), ptr(droot), ptr(cw_part), ptr(cb_part), C.byref(nb), dev, st)
         d_w2 = torch.empty((Ch, 2 * Ch), **f32)

@@ -144,8 +144,8 @@ class KnnGraphNet(nn.Module):
         if features.is_cuda and net.precision == "bf16" and net.fused_supported(features.shape[1]):
             # fused path: the [n, k] neighbour table IS the CSR by target (k slots per node); no edge list is materialised
             offsets = PF.segment_offsets(membership, num_graphs)
-            nbr, _ = PF.knn(features[:, self.pos_cols[0]:self.pos_cols[1]], offsets, self.k)
-            return net._forward_fused(features, membership, None, None, offsets, True, True, nbr=nbr)
+            _, _, nbr32 = PF.knn(features[:, self.pos_cols[0]:self.pos_cols[1]], offsets, self.k, with_int32=True)
+            return net._forward_fused(features, membership, None, None, offsets, True, True, nbr=nbr32)
         edges, _ = knn_graph(features, membership, self.k, self.pos_cols, num_graphs)
         return net(features, membership, edges, num_graphs=num_graphs, edges_sorted_by_target=True, simple_graph=True)
 
@@ -163,7 +163,9 @@ def _fused_methods():
         by_dst, k = None, 0
         if nbr is not None:
             k = nbr.shape[1]
-            by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k, nbr.reshape(-1).to(torch.int32))
+            col = nbr.reshape(-1)
+            by_dst = (torch.arange(n + 1, device=x.device, dtype=torch.int64) * k,
+                      col if col.dtype == torch.int32 else col.to(torch.int32))
         else:
             E = edges.shape[1]
             edges = edges if edges.dtype == torch.int64 else edges.long()
