@@ -350,21 +350,21 @@ __global__ void __launch_bounds__(kFbThreads, 1) gnn_fc1_bwd_kernel(const Fc1Bwd
 // y = P * s + t with P = per-graph mean of a (graph_net.py:89-92 / :96).  From G = dL/dy [B, Cn]:
 //   sumG[c] = sum_b G, sumGx[c] = sum_b G xhat(P)      -> dbeta = sumG, dgamma = sumGx,
 //   gs[b, c] = G * f / n_b,  kap[c] = f * sumG / M,  lam[c] = f * sumGx / M      (f = s[c], or 1 when use_scale = 0)
-// are everything the node-level backward kernels need (da = gs[graph] - kap - lam xhat).  One CTA per 32 columns,
-// fixed summation order.
-__global__ void __launch_bounds__(256) gnn_pool_bwd_prep_kernel(const float* __restrict__ G, const float* __restrict__ P,
+// are everything the node-level backward kernels need (da = gs[graph] - kap - lam xhat).  One CTA per 32 columns (32 row
+// slices per column, reduced through shared memory in a fixed order).
+__global__ void __launch_bounds__(1024) gnn_pool_bwd_prep_kernel(const float* __restrict__ G, const float* __restrict__ P,
                                                                 const float* __restrict__ mu, const float* __restrict__ rinv,
                                                                 const float* __restrict__ s, const int64_t* __restrict__ counts,
                                                                 int64_t B, int Cn, int64_t M, int use_scale, float* __restrict__ gs,
                                                                 float* __restrict__ kap, float* __restrict__ lam,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red[2][8][32];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  __shared__ float red[2][32][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;   // column of the block's 32, row slice of 32
   const int c = blockIdx.x * 32 + cl;
   float a0 = 0.f, a1 = 0.f;
   if (c < Cn) {
     const float f = use_scale ? s[c] : 1.f, m = mu[c], r = rinv[c];
-    for (int64_t b = sl; b < B; b += 8) {
+    for (int64_t b = sl; b < B; b += 32) {
       const float g = G[b * Cn + c];
       const int64_t n = counts[b];
       gs[b * Cn + c] = g * f / (float)(n > 0 ? n : 1);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) gnn_pool_bwd_prep_kernel(const float* __r
   if (sl == 0 && c < Cn) {
     float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { t0 += red[0][k][cl]; t1 += red[1][k][cl]; }
+    for (int k = 0; k < 32; ++k) { t0 += red[0][k][cl]; t1 += red[1][k][cl]; }
     const float f = use_scale ? s[c] : 1.f;
     dbeta[c] = t0;
     dgamma[c] = t1;
@@ -832,7 +832,7 @@ extern "C" int pcc_gnn_pool_bwd_prep(const float* G, const float* P, const float
                                      float* lam, float* dgamma, float* dbeta, int device, void* stream) {
   PCC_ENTER(device);
   PCC_REQUIRE(Cn > 0 && M > 0, "empty problem");
-  PCC_K(gnn_pool_bwd_prep_kernel)<<<(unsigned)cdiv(Cn, 32), 256, 0, (cudaStream_t)stream>>>(G, P, mu, rinv, s, counts, B, Cn, M, use_scale,
+  PCC_K(gnn_pool_bwd_prep_kernel)<<<(unsigned)cdiv(Cn, 32), 1024, 0, (cudaStream_t)stream>>>(G, P, mu, rinv, s, counts, B, Cn, M, use_scale,
                                                                                         gs, kap, lam, dgamma, dbeta);
   return check_launch(__func__);
 }
