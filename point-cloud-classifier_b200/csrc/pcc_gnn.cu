@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) gnn_bn_apply_kernel(const float* __restri
 // ====================================================================== conv2: gather + tcgen05 GEMM + BatchNorm partials
 // Persistent, one CTA per SM, 128-node tiles.
 //   warps 0-15 : CSR gather-reduce.  The neighbour rows (256 B of bf16 each) are fetched by the TMA engine: the lanes of
-//                a warp issue one cp.async.bulk per neighbour into the warp's shared-memory slot (22 rows) and wait on
+//                a warp issue one cp.async.bulk per neighbour into the warp's shared-memory slot (21 rows) and wait on
 //                the slot's mbarrier, so a node's rows are ALL in flight at once and no register holds in-flight data
 //                (ncu on the register-gather version: every memory unit below 25 % of peak, the loop was bound by the
 //                ~1.2k-cycle L2 latency times the few loads a thread can keep in registers).  The next node's neighbour

@@ -10,6 +10,8 @@
 //   conv bwd (tcgen05): dz2 in the prologue, [dagg2 | droot] = dz2 [W_rel | W_root], dW += dz2^T [agg2 | h1] in TMEM
 //   agg bwd  (CUDA cores): dh1 = droot + A^T dagg2 (CSR by source, bf16 rows), sums for bn1
 //   conv1 bwd (CUDA cores): dz1, dW_rel1 / dW_root1 / db1 (K = 2F)
+// The [M,128] gradient tensors between these kernels (dh2, dagg2, droot -> dh1) are bf16; the BatchNorm sums are taken
+// from the fp32 values before the store.
 #include "pcc_gnn.cuh"
 
 namespace pcc {
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(kCbThreads, 1) gnn_conv_bwd_kernel(const ConvB
       p.db_part[(size_t)blockIdx.x * kC + i] = s;
     }
   } else {
-    // ===================== epilogue warps 8-11: dX accumulator -> dagg (bf16) | droot (fp32)
+    // ===================== epilogue warps 8-11: dX accumulator -> dagg (bf16) | droot (bf16)
     const int q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int row = q * 32 + lane;
