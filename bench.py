@@ -293,7 +293,7 @@ def eager_gpu_baseline(wl, dev, steps=5, warmup=2):
     """The reference's "existing GPU path": its algorithm as stock PyTorch eager ops on the same B200 (oracle port
     moved to cuda:0, fp32, TF32 off — the port runs at the reference module's speed)."""
     if wl.kind != "deepsets":
-        return None
+        return eager_gpu_baseline_graph(wl, dev, steps, warmup)
     from oracle import deepsets_oracle as O
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -316,6 +316,38 @@ def eager_gpu_baseline(wl, dev, steps=5, warmup=2):
     return {"value": wl.B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": steps,
             "what": "reference algorithm as stock PyTorch eager ops on cuda:0 (oracle port, fp32, TF32 off): cuBLAS sgemm + "
                     "B-iteration pooling loop + counts.tolist() sync, same batch shape"}
+
+
+def eager_gpu_baseline_graph(wl, dev, steps=5, warmup=2):
+    """GraphNet: the reference algorithm as stock PyTorch eager ops on cuda:0 (oracle port: index_add scatter for GraphConv,
+    torch BatchNorm arithmetic, fp32, TF32 off).  The kNN graph is built once OUTSIDE the timed region (the reference builds
+    its edges offline, utils/data.py:847-929), so this arm times less work than the step it is compared with."""
+    from oracle import graphnet_oracle as GO
+    import pcc_b200
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {k: v.to(dev) for k, v in wl.cpu_state().items()}
+        (inputs, y), = wl.make_batches(1, seed=3, pin=False)
+        f, memb, y = inputs[0].to(dev), inputs[1].to(dev), y.to(dev)
+        edges, _ = pcc_b200.knn_graph(f, memb, wl.k, num_graphs=wl.B)
+        for _ in range(warmup):
+            GO.graphnet_train_step(sd, wl.cfg, f, memb, edges, None, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            GO.graphnet_train_step(sd, wl.cfg, f, memb, edges, None, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    except Exception as e:   # the arm is a comparator, not the product: report instead of failing the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return {"value": wl.B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+            "what": "reference GraphNet algorithm as stock PyTorch eager ops on cuda:0 (oracle port, fp32, TF32 off), kNN edge list "
+                    "prebuilt outside the timed region"}
 
 
 def wrapper_loop_e2e(wl, dev, precision, steps=20, warmup=5):

@@ -59,7 +59,7 @@ def graph_aggregate(x: torch.Tensor, edges: torch.Tensor, weights: Optional[torc
         out = out.index_add(0, dst, msg)
     elif aggr == "mean":
         out = out.index_add(0, dst, msg)
-        deg = torch.zeros(n, dtype=x.dtype).index_add(0, dst, torch.ones_like(dst, dtype=x.dtype))
+        deg = torch.zeros(n, dtype=x.dtype, device=x.device).index_add(0, dst, torch.ones_like(dst, dtype=x.dtype))
         out = out / deg.clamp(min=1.0).view(-1, 1)
     elif aggr == "max":
         out = out.scatter_reduce(0, dst.view(-1, 1).expand(-1, C), msg, reduce="amax", include_self=False)
@@ -85,7 +85,7 @@ def graphconv(sd, prefix: str, x, edges, weights, aggr: str, q=None) -> torch.Te
 def global_mean_pool(x: torch.Tensor, membership: torch.Tensor) -> torch.Tensor:
     B = int(membership.max()) + 1
     out = x.new_zeros((B, x.shape[1])).index_add(0, membership, x)
-    cnt = torch.zeros(B, dtype=x.dtype).index_add(0, membership, torch.ones_like(membership, dtype=x.dtype))
+    cnt = torch.zeros(B, dtype=x.dtype, device=x.device).index_add(0, membership, torch.ones_like(membership, dtype=x.dtype))
     return out / cnt.clamp(min=1.0).view(-1, 1)
 
 
