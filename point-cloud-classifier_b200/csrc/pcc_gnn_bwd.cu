@@ -17,6 +17,8 @@
 namespace pcc {
 namespace gnn {
 
+int gnn_resident_blocks(const void* kern, int threads, int smem_bytes, int64_t want);   // pcc_gnn.cu
+
 // bnb arrays: [5][Cn] = {mean, invstd, scale, c1 = dbeta/M, c2 = dgamma/M}
 struct BnBack {
   const float* mean;
@@ -872,9 +874,7 @@ extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src,
                                void* dh_inout_bf16, const float* z_prev, const float* mu_prev, const float* r_prev, int64_t M,
                                int act, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
-  int blocks = (int)(cdiv(M, 8) < 592 ? cdiv(M, 8) : 592);
-  if (blocks < 1) blocks = 1;
-  *nblk_out = blocks;
+  int blocks = 1;
   GnnGraph g{rowptr_src, col_src, w_src, 0};
   {
     ProfScope prof(5, (cudaStream_t)stream);
@@ -882,6 +882,8 @@ extern "C" int pcc_gnn_agg_bwd(const void* dagg_bf16, const int64_t* rowptr_src,
     GNN_ACT_DISPATCH(act, {
       auto kern = gnn_agg_bwd_kernel<A>;
       PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      blocks = gnn_resident_blocks((const void*)kern, 256, smem_bytes, cdiv(M, 8));
+      *nblk_out = blocks;
       PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dagg_bf16, g, (__nv_bfloat16*)dh_inout_bf16, z_prev, mu_prev,
                                                                      r_prev, M, partials);
     });
@@ -894,14 +896,14 @@ extern "C" int pcc_gnn_conv1_bwd(const void* dh_bf16, const float* z, const floa
                                  int F, int64_t M, int act, float* partials, int* nblk_out, int device, void* stream) {
   PCC_ENTER(device);
   PCC_REQUIRE(F >= 1 && F <= 8, "fused conv1 needs input_dim <= 8");
-  int blocks = (int)(cdiv(M, 8 * 16) < 592 ? cdiv(M, 8 * 16) : 592);
-  if (blocks < 1) blocks = 1;
-  *nblk_out = blocks;
+  int blocks = 1;
   BnBack bn{bn_mean, bn_invstd, bn_scale, bn_c1, bn_c2};
   const int smem_bytes = 8 * kC * (F <= 4 ? 9 : 17) * 4;
   GNN_ACT_DISPATCH(act, {
     auto kern = F <= 4 ? gnn_conv1_bwd_kernel<A, 4> : gnn_conv1_bwd_kernel<A, 8>;
     PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    blocks = gnn_resident_blocks((const void*)kern, 256, smem_bytes, cdiv(M, 8 * 16) < 592 ? cdiv(M, 8 * 16) : 592);   // (caller: 592 partials)
+    *nblk_out = blocks;
     PCC_K(kern)<<<blocks, 256, smem_bytes, (cudaStream_t)stream>>>((const __nv_bfloat16*)dh_bf16, z, bn, agg, x, F, M, partials);
   });
   return check_launch(__func__);
