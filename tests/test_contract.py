@@ -87,3 +87,37 @@ def test_yaml_default_param_count():
     assert list(m.state_dict().keys()) == ["phi.0.weight", "phi.0.bias", "phi.2.linear.weight", "phi.2.linear.bias",
                                            "phi.3.weight", "phi.3.bias", "rho.0.weight", "rho.0.bias",
                                            "rho.2.weight", "rho.2.bias"]
+
+
+def test_recorded_bench_lines_carry_the_contract_keys():
+    """The bench lines committed under profiles/r2 (what bench.py printed on a B200 at the end of the round) carry every
+    key of the bench contract: base line, e2e with its copy sizes, roofline, cpu_baseline, launches, clocks; the reference
+    arm marks itself and reports zero copies."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r2", "bench_r2*.json")))
+    assert files, "no recorded headline bench line"
+    d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["roofline"]["bound"] in ("hbm", "tensor")
+    for k in ("achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-6
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["cpu_baseline"]["kind"] in ("port", "reference")
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"], k
+    refs = sorted(glob.glob(os.path.join(root, "profiles", "r2", "bench_ref_r2*.json")))
+    r = json.loads(open(refs[-1]).read().strip().splitlines()[-1])
+    assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"]
+    assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["d2h_bytes_per_step"] == 0
+    assert r["config"]["workload"] == d["config"]["workload"]
